@@ -1,0 +1,103 @@
+"""ctypes binding of libippgpu (include/ippgpu.h) — the C-ABI drop-in boundary.
+
+There is deliberately no fallback: if the shared library is missing or a call
+fails, an exception is raised.  Error codes map to the exception class the
+reference's transform would raise for the same mistake.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_NAME = "libippgpu.so"
+_lib = None
+
+
+class IppError(RuntimeError):
+    """A CUDA runtime error reported by libippgpu (positive return code)."""
+
+
+def lib_path() -> Path:
+    env = os.environ.get("IPPGPU_LIB")
+    return Path(env) if env else Path(__file__).resolve().parent / _LIB_NAME
+
+
+class HsvRange(C.Structure):
+    _fields_ = [("lo", C.c_int32 * 3), ("hi", C.c_int32 * 3), ("zone", C.c_int32 * 4)]
+
+
+IPP_MAX_HSV_RANGES = 16
+
+
+class ChainGeom(C.Structure):
+    _fields_ = [("frame_w", C.c_int32), ("frame_h", C.c_int32),
+                ("crop_l", C.c_int32), ("crop_t", C.c_int32), ("crop_w", C.c_int32), ("crop_h", C.c_int32),
+                ("bg_w", C.c_int32), ("bg_h", C.c_int32),
+                ("n_ranges", C.c_int32),
+                ("ranges", HsvRange * IPP_MAX_HSV_RANGES)]
+
+
+_u8p = C.c_void_p      # device pointers travel as integers
+_i32p = C.c_void_p
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+
+# name -> (restype, argtypes); mirrors include/ippgpu.h declaration by declaration
+PROTOTYPES = {
+    "ipp_version": (_int, []),
+    "ipp_last_error_string": (C.c_char_p, []),
+    "ipp_sm_count": (_int, [C.POINTER(C.c_int)]),
+    "ipp_remap_u8": (_int, [_u8p, _i64, _int, _int, _int, _int, _int, _int, _int, _int, _int,
+                            _u8p, _i64, _int, _i64, _i64, _vp]),
+    "ipp_symmetries_u8": (_int, [_u8p, _i64, _int, _int, _int, _u8p, _u8p, _u8p, _u8p, _i64, _int, _i64, _i64, _vp]),
+    "ipp_to_rgba_u8": (_int, [_u8p, _i64, _int, _int, _int, _int, _u8p, _i64, _vp]),
+    "ipp_rot90_rgba_u8": (_int, [_u8p, _i64, _int, _int, _int, _u8p, _i64, _vp]),
+    "ipp_alpha_bbox_u8": (_int, [_u8p, _i64, _int, _int, _int, _int, _i32p, _vp]),
+    "ipp_bbox_reset": (_int, [_i32p, _int, _vp]),
+    "ipp_rotate_rgba_u8": (_int, [_u8p, _i64, _int, _int, _int, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                  _u8p, _i64, _int, _int, _i32p, _vp]),
+    "ipp_resample_rgba_u8": (_int, [_u8p, _i64, _int, _int, _u8p, _i64, _int, _int,
+                                    _i32p, _i32p, _int, _i32p, _i32p, _int, _u8p, _vp]),
+    "ipp_lanczos_ksize": (_int, [_int, _int]),
+    "ipp_lanczos_coeffs_host": (_int, [_int, _int, _vp, _vp]),
+    "ipp_paste_rgba_on_rgb_u8": (_int, [_u8p, _i64, _int, _int, _u8p, _i64, _int, _int, _int, _int,
+                                        _int, _int, _int, _int, _u8p, _i64, _vp]),
+    "ipp_hsv_ranges_to_alpha_u8": (_int, [_u8p, _i64, _int, _int, C.POINTER(HsvRange), _int, _u8p, _i64,
+                                          _int, _i64, _i64, _vp]),
+    "ipp_keep_largest_workspace_bytes": (_i64, [_int, _int, _int]),
+    "ipp_keep_largest_cc_u8": (_int, [_u8p, _i64, _int, _int, _i32p, _vp, _i64, _int, _i64, _vp]),
+    "ipp_boxes_square_crop_f32": (_int, [_vp, _i32p, _i32p, _vp, _i32p, _int, _vp]),
+    "ipp_boxes_xyxy2xywhn_f32": (_int, [_i32p, _i32p, _vp, _int, _vp]),
+}
+
+EXCEPTION_FOR_CODE = {-1: ValueError, -2: ValueError, -3: MemoryError, -4: NotImplementedError}
+
+
+def load():
+    """Load libippgpu.so and declare every prototype.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.is_file():
+        raise ImportError(
+            f"{path} not found: build it with `python -m image_processor_pipeline_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = ""):
+    if code == 0:
+        return
+    msg = load().ipp_last_error_string().decode("utf-8", "replace")
+    if code < 0:
+        raise EXCEPTION_FOR_CODE.get(code, RuntimeError)(msg or what)
+    raise IppError(f"{what}: CUDA error {code}: {msg}")

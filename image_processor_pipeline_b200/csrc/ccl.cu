@@ -1,0 +1,413 @@
+// ccl.cu — keep the largest 8-connected component (see ccl.cuh for the design).
+#include "ccl.cuh"
+
+namespace ipp {
+
+constexpr uint64_t kEven = 0x5555555555555555ull;
+
+__device__ __forceinline__ uint32_t compress_even(uint64_t x) {
+    x &= kEven;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+    x = (x | (x >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)x;
+}
+
+// pixels 64k .. 64k+63 of one mask row
+__device__ __forceinline__ uint64_t load_px64(const uint32_t* row, int k, int wpr) {
+    const uint32_t lo = (2 * k < wpr) ? row[2 * k] : 0u;
+    const uint32_t hi = (2 * k + 1 < wpr) ? row[2 * k + 1] : 0u;
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+// first block of the run that contains block gbx (row-local block column)
+__device__ __forceinline__ int run_start(const uint32_t* crow, int gbx) {
+    int k = gbx >> 5;
+    const int i = gbx & 31;
+    uint32_t m = ~crow[k] & (0xffffffffu >> (31 - i));
+    while (m == 0u) {
+        --k;
+        m = ~crow[k];
+    }
+    return (k << 5) + 31 - __clz(m);
+}
+
+__device__ __forceinline__ int find_root(const int32_t* L, int x) {
+    int p;
+    while ((p = __ldcg(L + x)) != x) x = p;
+    return x;
+}
+
+__device__ __forceinline__ void unite(int32_t* L, int a, int b) {
+    bool done;
+    do {
+        a = find_root(L, a);
+        b = find_root(L, b);
+        if (a < b) {
+            const int old = atomicMin(&L[b], a);
+            done = (old == b);
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(&L[a], b);
+            done = (old == a);
+            a = old;
+        } else {
+            done = true;
+        }
+    } while (!done);
+}
+
+struct GroupIdx {
+    int img, by, k;
+    bool ok;
+};
+__device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n) {
+    GroupIdx r;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)g.bh * g.bww;
+    r.ok = t < per * n;
+    r.img = (int)(t / per);
+    const int rem = (int)(t - (int64_t)r.img * per);
+    r.by = rem / g.bww;
+    r.k = rem - r.by * g.bww;
+    return r;
+}
+
+// ---- phase 1: block bits, horizontal connectivity, initialise run-start entries
+__global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const GroupIdx t = group_index(g, n);
+    if (!t.ok) return;
+    const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+    const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+    const bool has1 = (2 * t.by + 1) < g.h;
+    const uint32_t* r1 = r0 + g.wpr;
+    const uint64_t any = load_px64(r0, t.k, g.wpr) | (has1 ? load_px64(r1, t.k, g.wpr) : 0ull);
+    const uint32_t Lc = compress_even(any), Rc = compress_even(any >> 1);
+    const uint32_t F = Lc | Rc;
+    uint32_t carry = 0;
+    if (t.k > 0) carry = (r0[2 * t.k - 1] | (has1 ? r1[2 * t.k - 1] : 0u)) >> 31;
+    const uint32_t C = ((Rc << 1) | carry) & Lc;
+    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
+    b.cbits[cf] = C;
+    b.fbits[cf] = F;
+    uint32_t S = F & ~C;
+    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+    int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+    const int base = t.by * g.bw + (t.k << 5);
+    while (S) {
+        const int i = __ffs(S) - 1;
+        S &= S - 1;
+        L[base + i] = base + i;
+        A[base + i] = 0;
+    }
+    if (t.by == 0 && t.k == 0) {
+        b.best[t.img] = 0ull;
+        int32_t* acc = b.acc + 8 * t.img;
+        acc[0] = INT_MAX; acc[1] = INT_MAX; acc[2] = 0; acc[3] = 0; acc[4] = 0; acc[5] = 0; acc[6] = 0; acc[7] = 0;
+    }
+}
+
+// ---- phase 2: unions between runs of adjacent block rows (once per contact segment)
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const GroupIdx t = group_index(g, n);
+    if (!t.ok || t.by == 0) return;
+    const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+    const uint32_t* rowT = bits + (int64_t)(2 * t.by) * g.wpr;
+    const uint32_t* rowB = rowT - g.wpr;
+    const uint64_t T = load_px64(rowT, t.k, g.wpr);
+    if (T == 0ull) return;
+    const uint64_t B = load_px64(rowB, t.k, g.wpr);
+    const uint64_t bprev = (t.k > 0) ? (uint64_t)(rowB[2 * t.k - 1] >> 31) : 0ull;
+    const uint64_t bnext = (2 * t.k + 2 < g.wpr) ? (uint64_t)(rowB[2 * t.k + 2] & 1u) : 0ull;
+    if ((B | bprev | bnext) == 0ull) return;
+    const uint64_t Tl = T & kEven, Tr = (T >> 1) & kEven, Bl = B & kEven, Br = (B >> 1) & kEven;
+    const uint32_t cU = compress_even((Tl | Tr) & (Bl | Br));
+    const uint32_t cUL = compress_even(Tl & ((Br << 2) | bprev));
+    const uint32_t cUR = compress_even(Tr & ((Bl >> 2) | (bnext << 62)));
+    if ((cU | cUL | cUR) == 0u) return;
+    const uint32_t* crow = b.cbits + (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
+    const uint32_t* crowU = crow - g.bww;
+    const uint32_t C = crow[t.k], Cu = crowU[t.k];
+    const uint32_t cu_next0 = (t.k + 1 < g.bww) ? (crowU[t.k + 1] & 1u) : 0u;
+    const uint32_t Cush = (Cu >> 1) | (cu_next0 << 31);
+    uint32_t nU = cU & ~(C & ((cUR << 1) | (Cu & (cU << 1))));
+    uint32_t nUL = cUL & ~(cU & Cu) & ~(C & (cU << 1));
+    uint32_t nUR = cUR & ~(cU & Cush);
+    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+    const int rowbase = t.by * g.bw, rowbaseU = rowbase - g.bw, gb0 = t.k << 5;
+    while (nU) {
+        const int i = __ffs(nU) - 1;
+        nU &= nU - 1;
+        unite(L, rowbase + run_start(crow, gb0 + i), rowbaseU + run_start(crowU, gb0 + i));
+    }
+    while (nUL) {
+        const int i = __ffs(nUL) - 1;
+        nUL &= nUL - 1;
+        unite(L, rowbase + run_start(crow, gb0 + i), rowbaseU + run_start(crowU, gb0 + i - 1));
+    }
+    while (nUR) {
+        const int i = __ffs(nUR) - 1;
+        nUR &= nUR - 1;
+        unite(L, rowbase + run_start(crow, gb0 + i), rowbaseU + run_start(crowU, gb0 + i + 1));
+    }
+}
+
+// first zero of C strictly above bit i (32 if none): end (exclusive) of the segment that starts at i
+__device__ __forceinline__ int segment_end(uint32_t C, int i) {
+    const uint32_t above = (i == 31) ? 0u : (~C & (0xffffffffu << (i + 1)));
+    return above ? (__ffs(above) - 1) : 32;
+}
+
+// ---- phase 3: per-segment pixel counts onto the root, compress run-start entries
+__global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const GroupIdx t = group_index(g, n);
+    if (!t.ok) return;
+    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
+    const uint32_t F = b.fbits[cf + t.k];
+    if (F == 0u) return;
+    const uint32_t C = b.cbits[cf + t.k];
+    const uint32_t* crow = b.cbits + cf;
+    const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+    const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+    const uint64_t p0 = load_px64(r0, t.k, g.wpr);
+    const uint64_t p1 = ((2 * t.by + 1) < g.h) ? load_px64(r0 + g.wpr, t.k, g.wpr) : 0ull;
+    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+    int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+    const int rowbase = t.by * g.bw, gb0 = t.k << 5;
+    uint32_t starts = F & (~C | 1u);
+    int nfg = 0;
+    while (starts) {
+        const int i = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const int e = segment_end(C, i);
+        const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
+        const int cnt = __popcll(p0 & pm) + __popcll(p1 & pm);
+        const bool own = ((C >> i) & 1u) == 0u;
+        const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
+        const int root = find_root(L, rowbase + s);
+        atomicAdd(&A[root], cnt);
+        if (own) L[rowbase + gb0 + i] = root;
+        nfg += cnt;
+    }
+    if (nfg) atomicAdd(&b.acc[8 * t.img + 4], nfg);
+}
+
+// ---- phase 4: argmax over roots of (area, smallest block index)
+__global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const GroupIdx t = group_index(g, n);
+    if (!t.ok) return;
+    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
+    uint32_t S = b.fbits[cf] & ~b.cbits[cf];
+    if (S == 0u) return;
+    const int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+    const int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+    const int base = t.by * g.bw + (t.k << 5);
+    unsigned long long best = 0ull;
+    while (S) {
+        const int i = __ffs(S) - 1;
+        S &= S - 1;
+        const int bi = base + i;
+        if (L[bi] == bi) {
+            const unsigned long long key = ((unsigned long long)(uint32_t)A[bi] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
+            best = key > best ? key : best;
+        }
+    }
+    if (best) atomicMax(&b.best[t.img], best);
+}
+
+// ---- phase 5: keep-mask (in place) + bounding box of the kept pixels
+__global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)g.h * g.wpr;
+    int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
+    int img = 0;
+    const bool ok = tt < per * n;
+    if (ok) {
+        img = (int)(tt / per);
+        const int rem = (int)(tt - (int64_t)img * per);
+        const int y = rem / g.wpr, kx = rem - y * g.wpr;
+        uint32_t* pw = b.bits + (int64_t)img * g.bits_stride + (int64_t)y * g.wpr + kx;
+        const uint32_t bits = *pw;
+        if (bits) {
+            const unsigned long long bk = b.best[img];
+            const int best_root = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
+            const int by = y >> 1, k = kx >> 1, half = (kx & 1) * 16;
+            const uint32_t* crow = b.cbits + (int64_t)img * g.cf_stride + (int64_t)by * g.bww;
+            const uint32_t C = crow[k];
+            const int32_t* L = b.label + (int64_t)img * g.lab_stride;
+            const int rowbase = by * g.bw;
+            uint32_t rem_bits = bits, keep = 0;
+            while (rem_bits) {
+                const int px = __ffs(rem_bits) - 1;
+                const int i = half + (px >> 1);
+                const int e = segment_end(C, i);
+                const int lo = 2 * (i - half);
+                const int hi = min(32, 2 * (e - half));
+                const uint32_t pm = ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                const int s = run_start(crow, (k << 5) + i);
+                if (L[rowbase + s] == best_root) keep |= bits & pm;
+                rem_bits &= ~pm;
+            }
+            if (keep != bits) *pw = keep;
+            if (keep) {
+                minx = 32 * kx + __ffs(keep) - 1;
+                maxx1 = 32 * kx + 32 - __clz(keep);
+                miny = y;
+                maxy1 = y + 1;
+            }
+        }
+    }
+    // a CTA may straddle two images only at image boundaries; reduce per warp, then atomics
+    const int wimg = __shfl_sync(0xffffffffu, img, 0);
+    const bool uniform = __all_sync(0xffffffffu, img == wimg || !ok);
+    if (uniform) {
+        minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
+        if ((threadIdx.x & 31) == 0 && maxx1 > 0) {
+            int32_t* acc = b.acc + 8 * wimg;
+            atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
+        }
+    } else if (ok && maxx1 > 0) {
+        int32_t* acc = b.acc + 8 * img;
+        atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
+    }
+}
+
+int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
+    const int64_t groups = (int64_t)g.bh * g.bww * n;
+    const int gb = ceil_div(groups, 256);
+    ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    IPP_LAUNCH_CHECK();
+    ccl_merge_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    IPP_LAUNCH_CHECK();
+    ccl_area_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    IPP_LAUNCH_CHECK();
+    ccl_best_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    IPP_LAUNCH_CHECK();
+    const int64_t words = (int64_t)g.h * g.wpr * n;
+    ccl_keep_kernel<<<ceil_div(words, 256), 256, 0, st>>>(g, b, n);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+// ================================================================== stand-alone op
+// alpha > 1 -> pixel mask.  One warp per 1024 pixels of a row: lane l tests pixels
+// l, l+32, ... so every ballot is one finished mask word and the byte loads of a warp
+// cover contiguous memory.
+__global__ void __launch_bounds__(256) alpha_to_bits_kernel(const uint8_t* __restrict__ img, int64_t pitch, int64_t img_stride,
+                                                            const CclGeom g, uint32_t* bits, int n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int wpr32 = (g.wpr + 31) / 32;                    // warps per row
+    const int64_t per = (int64_t)g.h * wpr32;
+    if (warp >= per * n) return;
+    const int im = (int)(warp / per);
+    const int rem = (int)(warp - (int64_t)im * per);
+    const int y = rem / wpr32, seg = rem - y * wpr32;
+    const uint8_t* row = img + (int64_t)im * img_stride + (int64_t)y * pitch;
+    uint32_t* out = bits + (int64_t)im * g.bits_stride + (int64_t)y * g.wpr;
+    const int w0 = seg * 32;
+    uint32_t mine = 0;
+    for (int j = 0; j < 32 && w0 + j < g.wpr; ++j) {
+        const int x = (w0 + j) * 32 + lane;
+        const bool fg = (x < g.w) && (row[(int64_t)x * 4 + 3] > 1);
+        const uint32_t word = __ballot_sync(0xffffffffu, fg);
+        if (lane == j) mine = word;
+    }
+    if (w0 + lane < g.wpr) out[w0 + lane] = mine;
+}
+
+// alpha[not kept] = 0 when any foreground exists; bbox of alpha != 0 afterwards
+__global__ void __launch_bounds__(256) apply_keep_kernel(uint8_t* img, int64_t pitch, int64_t img_stride, const CclGeom g,
+                                                         const CclBuffers b, int n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t per = (int64_t)g.h * g.wpr;
+    if (warp >= per * n) return;
+    const int im = (int)(warp / per);
+    const int rem = (int)(warp - (int64_t)im * per);
+    const int y = rem / g.wpr, kx = rem - y * g.wpr;
+    const int x = kx * 32 + lane;
+    const bool any_fg = b.acc[8 * im + 4] > 0;
+    const uint32_t keep = b.bits[(int64_t)im * g.bits_stride + (int64_t)y * g.wpr + kx];
+    bool nz = false;
+    if (x < g.w) {
+        uint8_t* pa = img + (int64_t)im * img_stride + (int64_t)y * pitch + (int64_t)x * 4 + 3;
+        const uint8_t a = *pa;
+        if (any_fg) {
+            const bool kept = (keep >> lane) & 1u;
+            if (!kept && a != 0) *pa = 0;
+            nz = kept;            // kept pixels have alpha > 1
+        } else {
+            nz = a != 0;          // no component: image unchanged (alpha == 1 pixels count)
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0 && m && !any_fg) {
+        int32_t* acc = b.acc + 8 * im;
+        atomicMin(&acc[0], 32 * kx + __ffs(m) - 1);
+        atomicMax(&acc[2], 32 * kx + 32 - __clz(m));
+        atomicMin(&acc[1], y);
+        atomicMax(&acc[3], y + 1);
+    }
+}
+
+__global__ void ccl_info_kernel(const CclBuffers b, int32_t* info, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* acc = b.acc + 8 * i;
+    int32_t* o = info + 8 * i;
+    const bool any = acc[2] > 0;
+    o[0] = any ? acc[0] : 0;
+    o[1] = any ? acc[1] : 0;
+    o[2] = any ? acc[2] - acc[0] : 0;
+    o[3] = any ? acc[3] - acc[1] : 0;
+    o[4] = (int32_t)(b.best[i] >> 32);
+    o[5] = acc[4];
+    o[6] = 0;
+    o[7] = 0;
+}
+
+}  // namespace ipp
+
+extern "C" {
+
+int64_t ipp_keep_largest_workspace_bytes(int w, int h, int n) {
+    if (w <= 0 || h <= 0 || n <= 0) return 0;
+    return ipp::ccl_workspace_bytes(ipp::make_ccl_geom(w, h), n);
+}
+
+int ipp_keep_largest_cc_u8(uint8_t* bgra, int64_t pitch, int w, int h,
+                           int32_t* info_out, void* workspace, int64_t workspace_bytes,
+                           int n, int64_t image_stride, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(bgra && info_out, IPP_ERR_BAD_ARG, "ipp_keep_largest_cc_u8: NULL pointer");
+    IPP_REQUIRE(w > 0 && h > 0 && n >= 1 && pitch >= (int64_t)w * 4, IPP_ERR_BAD_SHAPE,
+                "ipp_keep_largest_cc_u8: bad geometry %dx%d n=%d", w, h, n);
+    IPP_REQUIRE((int64_t)((w + 1) / 2) * ((h + 1) / 2) < (1LL << 31), IPP_ERR_UNSUPPORTED, "image too large");
+    const CclGeom g = make_ccl_geom(w, h);
+    IPP_REQUIRE(workspace && workspace_bytes >= ccl_workspace_bytes(g, n) && (((uintptr_t)workspace) & 255) == 0,
+                IPP_ERR_WORKSPACE, "ipp_keep_largest_cc_u8: workspace too small or not 256-byte aligned (need %lld bytes)",
+                (long long)ccl_workspace_bytes(g, n));
+    const CclBuffers b = carve_ccl(workspace, g, n);
+    {
+        const int wpr32 = (g.wpr + 31) / 32;
+        const int64_t warps = (int64_t)g.h * wpr32 * n;
+        alpha_to_bits_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b.bits, n);
+        IPP_LAUNCH_CHECK();
+    }
+    const int rc = ccl_run(g, b, n, st);
+    if (rc != IPP_OK) return rc;
+    {
+        const int64_t warps = (int64_t)g.h * g.wpr * n;
+        apply_keep_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b, n);
+        IPP_LAUNCH_CHECK();
+    }
+    ccl_info_kernel<<<ceil_div(n, 128), 128, 0, st>>>(b, info_out, n);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+}  // extern "C"

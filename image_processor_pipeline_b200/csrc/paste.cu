@@ -1,0 +1,167 @@
+// paste.cu — alpha paste of an RGBA sprite onto an RGB background with the final
+// crop folded into the same pass.
+//
+// Reference behaviour replaced: bg.copy().paste(sprite, (x, y), sprite)
+// (transforms/overlays.py:138-139; libImaging paste_mask_RGBA:
+// out = DIV255(bg*(255-a) + spr*a)) followed by image[y0:y0+cs, x0:x0+cs]
+// (transforms/crop_square.py:196).
+//
+// Streaming kernel: one CTA owns a few output rows; the bulk-copy engine stages the
+// background row windows (arbitrary byte alignment: crop_x0*3) into shared memory;
+// each thread emits aligned 16-byte output vectors, blending only the vectors that
+// intersect the sprite rectangle (the sprite is small and L2 resident).
+#include "staging.cuh"
+
+namespace ipp {
+
+struct PasteParams {
+    const uint8_t* bg;
+    int64_t bg_pitch;
+    const uint8_t* sprite;
+    int64_t sprite_pitch;
+    int sprite_w, sprite_h, pos_x, pos_y;
+    int crop_x0, crop_y0, crop_w, crop_h;
+    uint8_t* dst;
+    int64_t dst_pitch;
+    int rows_per_cta;
+    uint32_t smem_row_stride;
+};
+
+constexpr int kPasteThreads = 256;
+
+__device__ __forceinline__ uint32_t sprite_px(const PasteParams& p, int sx, int sy) {
+    return __ldg(reinterpret_cast<const uint32_t*>(p.sprite + (int64_t)sy * p.sprite_pitch) + sx);
+}
+
+// blend `cnt` output bytes starting at output byte ob of the row whose sprite row is sy
+__device__ __forceinline__ void blend_bytes(const PasteParams& p, uint8_t* bytes, uint32_t ob, int cnt, int sy) {
+    uint32_t q = ob / 3u;
+    uint32_t c = ob - q * 3u;
+    int sx = (int)q + p.crop_x0 - p.pos_x;
+    uint32_t spx = 0;
+    bool have = false;
+    for (int k = 0; k < cnt; ++k) {
+        if (sx >= 0 && sx < p.sprite_w) {
+            if (!have) {
+                spx = sprite_px(p, sx, sy);
+                have = true;
+            }
+            const uint32_t a = spx >> 24;
+            const uint32_t s = (spx >> (8 * c)) & 255u;
+            bytes[k] = (uint8_t)div255((uint32_t)bytes[k] * (255u - a) + s * a);
+        }
+        if (++c == 3u) {
+            c = 0;
+            ++sx;
+            have = false;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPasteThreads) paste_kernel(const PasteParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, p.crop_h - row0);
+    const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
+            total += make_window(s, rowbytes).bytes;
+        }
+        mbar_expect_tx(&bar, total);
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
+            const Window w = make_window(s, rowbytes);
+            bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    // output byte range of a row that can intersect the sprite
+    const int spr_q0 = max(p.pos_x - p.crop_x0, 0);
+    const int spr_q1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w);   // exclusive
+    const uint32_t cpr = (rowbytes >> 4) + 2;
+    const uint32_t items = (uint32_t)nrows * cpr;
+    for (uint32_t it = tid; it < items; it += kPasteThreads) {
+        const uint32_t r = it / cpr;
+        const uint32_t c = it - r * cpr;
+        const int y = row0 + (int)r;
+        uint8_t* d = p.dst + (int64_t)y * p.dst_pitch;
+        const uint8_t* win = smem + (size_t)r * p.smem_row_stride;
+        const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + y) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
+        const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
+        const RowSplit sp = split_row(d, rowbytes);
+        const int sy = p.crop_y0 + y - p.pos_y;
+        const bool row_hit = (sy >= 0 && sy < p.sprite_h && spr_q1 > spr_q0);
+        if (c < sp.nb) {
+            const uint32_t ob = sp.head + (c << 4);
+            uint4 val = window_load16(win, shift + ob);
+            if (row_hit && (int)(ob + 15u) >= spr_q0 * 3 && (int)ob < spr_q1 * 3) {
+                __align__(16) uint8_t bytes[16];
+                *reinterpret_cast<uint4*>(bytes) = val;
+                blend_bytes(p, bytes, ob, 16, sy);
+                val = *reinterpret_cast<uint4*>(bytes);
+            }
+            stg_stream16(d + ob, val);
+        } else if (c >= cpr - 2) {
+            const uint32_t b0 = (c == cpr - 2) ? 0u : sp.head + (sp.nb << 4);
+            const int cnt = (int)((c == cpr - 2) ? sp.head : sp.tail);
+            if (cnt > 0) {
+                uint8_t bytes[16];
+                for (int k = 0; k < cnt; ++k) bytes[k] = win[shift + b0 + k];
+                if (row_hit) blend_bytes(p, bytes, b0, cnt, sy);
+                for (int k = 0; k < cnt; ++k) d[b0 + k] = bytes[k];
+            }
+        }
+    }
+}
+
+}  // namespace ipp
+
+extern "C" int ipp_paste_rgba_on_rgb_u8(const uint8_t* bg, int64_t bg_pitch, int bg_w, int bg_h,
+                                        const uint8_t* sprite, int64_t sprite_pitch, int sprite_w, int sprite_h,
+                                        int pos_x, int pos_y,
+                                        int crop_x0, int crop_y0, int crop_w, int crop_h,
+                                        uint8_t* dst, int64_t dst_pitch, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(bg && dst, IPP_ERR_BAD_ARG, "ipp_paste_rgba_on_rgb_u8: NULL image pointer");
+    IPP_REQUIRE(sprite || sprite_w == 0 || sprite_h == 0, IPP_ERR_BAD_ARG, "ipp_paste_rgba_on_rgb_u8: NULL sprite");
+    IPP_REQUIRE(bg_w > 0 && bg_h > 0 && crop_x0 >= 0 && crop_y0 >= 0 && crop_w >= 0 && crop_h >= 0 &&
+                    crop_x0 + crop_w <= bg_w && crop_y0 + crop_h <= bg_h,
+                IPP_ERR_BAD_SHAPE, "ipp_paste_rgba_on_rgb_u8: crop (%d,%d,%d,%d) outside %dx%d", crop_x0, crop_y0,
+                crop_w, crop_h, bg_w, bg_h);
+    IPP_REQUIRE(bg_pitch >= (int64_t)bg_w * 3 && dst_pitch >= (int64_t)crop_w * 3, IPP_ERR_BAD_SHAPE,
+                "ipp_paste_rgba_on_rgb_u8: pitch smaller than a row");
+    IPP_REQUIRE(sprite_w == 0 || sprite_h == 0 ||
+                    ((sprite_pitch & 3) == 0 && (((uintptr_t)sprite) & 3) == 0 && sprite_pitch >= (int64_t)sprite_w * 4),
+                IPP_ERR_BAD_ARG, "ipp_paste_rgba_on_rgb_u8: sprite must be 4-byte aligned RGBA");
+    if (crop_w == 0 || crop_h == 0) return IPP_OK;
+    PasteParams p{};
+    p.bg = bg; p.bg_pitch = bg_pitch;
+    p.sprite = sprite; p.sprite_pitch = sprite_pitch;
+    p.sprite_w = sprite_w > 0 ? sprite_w : 0; p.sprite_h = sprite_h > 0 ? sprite_h : 0;
+    p.pos_x = pos_x; p.pos_y = pos_y;
+    p.crop_x0 = crop_x0; p.crop_y0 = crop_y0; p.crop_w = crop_w; p.crop_h = crop_h;
+    p.dst = dst; p.dst_pitch = dst_pitch;
+    const uint32_t rowbytes = (uint32_t)crop_w * 3u;
+    p.smem_row_stride = staged_row_stride(rowbytes);
+    IPP_REQUIRE(p.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_paste_rgba_on_rgb_u8: row too long");
+    int rows = (int)(16384 / p.smem_row_stride);
+    if (rows < 1) rows = 1;
+    if (rows > crop_h) rows = crop_h;
+    const int sms = sm_count();
+    while (rows > 1 && ceil_div(crop_h, rows) < 4 * sms) rows = (rows + 1) / 2;
+    p.rows_per_cta = rows;
+    const size_t smem = (size_t)rows * p.smem_row_stride;
+    if (smem > 48 * 1024)
+        IPP_CUDA(cudaFuncSetAttribute(paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    paste_kernel<<<ceil_div(crop_h, rows), kPasteThreads, smem, (cudaStream_t)stream>>>(p);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}

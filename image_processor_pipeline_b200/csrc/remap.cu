@@ -1,0 +1,289 @@
+// remap.cu — flip x crop x copy as a load-address remap; fused symmetries; to-RGBA.
+//
+// Reference behaviour replaced: cv2.flip / ndarray.copy (transforms/symmetry.py:114-119),
+// ndarray slicing crops (recadrages.py:46, crop_square.py:196, pixels_isolés.py:81),
+// PIL crop (rotations.py:101) and convert("RGBA") (rotations.py:55).
+//
+// One CTA owns a few consecutive source rows.  The bulk-copy engine stages the
+// 16-byte-aligned window of each row that covers [x0*bpp, (x0+out_w)*bpp) into shared
+// memory (one read of the source, whatever its alignment); the CTA then emits up to
+// four variants from that single staging: o (as is), v (mirrored row index),
+// h and hv (pixel order reversed inside the row).  Destination rows are written as
+// aligned 16-byte vectors (head/tail bytes individually), so any pitch works.
+#include "staging.cuh"
+
+namespace ipp {
+
+struct RowsParams {
+    const uint8_t* src;
+    int64_t src_pitch, src_img_stride;
+    int bpp, x0, y0, out_w, out_h;
+    uint8_t* dst[4];  // 0 = o, 1 = h, 2 = v, 3 = hv
+    int64_t dst_pitch, dst_img_stride;
+    int rows_per_cta;
+    uint32_t smem_row_stride;
+};
+
+constexpr int kRowsThreads = 256;
+
+// 16 output bytes of a horizontally mirrored row, starting at output byte ob0.
+__device__ __forceinline__ uint4 gather_reversed16(const uint8_t* win, uint32_t shift, uint32_t ob0,
+                                                   int out_w, int bpp) {
+    uint32_t q = ob0 / (uint32_t)bpp;
+    uint32_t rr = ob0 - q * (uint32_t)bpp;
+    int sp = (int)shift + (out_w - 1 - (int)q) * bpp + (int)rr;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc |= (uint32_t)win[sp] << (8 * k);
+            ++rr;
+            ++sp;
+            if (rr == (uint32_t)bpp) {
+                rr = 0;
+                sp -= 2 * bpp;
+            }
+        }
+        w[i] = acc;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int img = blockIdx.y;
+    const int row0 = blockIdx.x * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, p.out_h - row0);
+    const uint32_t rowbytes = (uint32_t)p.out_w * (uint32_t)p.bpp;
+    const uint8_t* src_img = p.src + (int64_t)img * p.src_img_stride;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = src_img + (int64_t)(p.y0 + row0 + r) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            total += make_window(s, rowbytes).bytes;
+        }
+        mbar_expect_tx(&bar, total);
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = src_img + (int64_t)(p.y0 + row0 + r) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            const Window w = make_window(s, rowbytes);
+            bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    const uint32_t cpr = (rowbytes >> 4) + 2;  // body chunks (+1 slack), head, tail
+    const uint32_t items = (uint32_t)nrows * cpr;
+#pragma unroll 1
+    for (int v = 0; v < 4; ++v) {
+        uint8_t* dimg = p.dst[v];
+        if (dimg == nullptr) continue;
+        dimg += (int64_t)img * p.dst_img_stride;
+        const bool rev = (v & 1) != 0;
+        for (uint32_t it = tid; it < items; it += kRowsThreads) {
+            const uint32_t r = it / cpr;
+            const uint32_t c = it - r * cpr;
+            const int y = row0 + (int)r;
+            const int drow = (v & 2) ? (p.out_h - 1 - y) : y;
+            uint8_t* d = dimg + (int64_t)drow * p.dst_pitch;
+            const uint8_t* win = smem + (size_t)r * p.smem_row_stride;
+            const uint8_t* s = src_img + (int64_t)(p.y0 + y) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
+            const RowSplit sp = split_row(d, rowbytes);
+            if (c < sp.nb) {
+                const uint32_t ob = sp.head + (c << 4);
+                uint4 val;
+                if (!rev) {
+                    val = window_load16(win, shift + ob);
+                } else if (p.bpp == 4 && ((shift | ob) & 3u) == 0) {
+                    const uint32_t q = ob >> 2;
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(win + shift);
+                    const int last = p.out_w - 1 - (int)q;
+                    val = make_uint4(w32[last], w32[last - 1], w32[last - 2], w32[last - 3]);
+                } else {
+                    val = gather_reversed16(win, shift, ob, p.out_w, p.bpp);
+                }
+                stg_stream16(d + ob, val);
+            } else if (c == cpr - 2 || c == cpr - 1) {
+                // head bytes (c == cpr-2) or tail bytes (c == cpr-1)
+                const uint32_t b0 = (c == cpr - 2) ? 0u : sp.head + (sp.nb << 4);
+                const uint32_t cnt = (c == cpr - 2) ? sp.head : sp.tail;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const uint32_t ob = b0 + k;
+                    uint32_t sb;
+                    if (!rev) {
+                        sb = shift + ob;
+                    } else {
+                        const uint32_t q = ob / (uint32_t)p.bpp;
+                        const uint32_t rr = ob - q * (uint32_t)p.bpp;
+                        sb = shift + (uint32_t)(p.out_w - 1 - (int)q) * (uint32_t)p.bpp + rr;
+                    }
+                    d[ob] = win[sb];
+                }
+            }
+        }
+    }
+}
+
+static int launch_rows(RowsParams& p, int n, cudaStream_t st) {
+    const uint32_t rowbytes = (uint32_t)p.out_w * (uint32_t)p.bpp;
+    p.smem_row_stride = staged_row_stride(rowbytes);
+    IPP_REQUIRE(p.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED,
+                "remap: a row of %u bytes does not fit the shared-memory staging buffer", rowbytes);
+    // ~16 KB of rows per CTA: enough bytes in flight per SM with several resident CTAs
+    int rows = (int)(16384 / p.smem_row_stride);
+    if (rows < 1) rows = 1;
+    if (rows > p.out_h) rows = p.out_h;
+    // keep the grid at >= ~4 waves of CTAs when the image is small
+    const int sms = sm_count();
+    while (rows > 1 && (int64_t)ceil_div(p.out_h, rows) * n < 4LL * sms) rows = (rows + 1) / 2;
+    p.rows_per_cta = rows;
+    const size_t smem = (size_t)rows * p.smem_row_stride;
+    if (smem > 48 * 1024) {
+        IPP_CUDA(cudaFuncSetAttribute(rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(ceil_div(p.out_h, rows), n);
+    rows_kernel<<<grid, kRowsThreads, smem, st>>>(p);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+// ------------------------------------------------------------------ to RGBA
+__global__ void __launch_bounds__(256) to_rgba_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int w, int h,
+                                                      int ch, int swap_rb, uint8_t* __restrict__ dst, int64_t dst_pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* s = src + (int64_t)y * src_pitch + (int64_t)x * ch;
+    uint32_t c0, c1, c2, a = 255;
+    if (ch == 1) {
+        c0 = c1 = c2 = s[0];
+    } else {
+        c0 = s[0];
+        c1 = s[1];
+        c2 = s[2];
+        if (ch == 4) a = s[3];
+    }
+    if (swap_rb) {
+        const uint32_t t = c0;
+        c0 = c2;
+        c2 = t;
+    }
+    const uint32_t px = c0 | (c1 << 8) | (c2 << 16) | (a << 24);
+    uint8_t* d = dst + (int64_t)y * dst_pitch + (int64_t)x * 4;
+    if ((((uintptr_t)d) & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(d) = px;
+    } else {
+        d[0] = (uint8_t)c0; d[1] = (uint8_t)c1; d[2] = (uint8_t)c2; d[3] = (uint8_t)a;
+    }
+}
+
+// ------------------------------------------------------------------ quarter turns (PIL transpose fast paths)
+// ROTATE_90 (counter-clockwise): out[y][x] = in[x][w-1-y];  ROTATE_270: out[y][x] = in[h-1-x][y].
+// 32x32 tiles through shared memory so that both the loads and the stores are row-contiguous.
+__global__ void __launch_bounds__(256) rot90_rgba_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int w, int h,
+                                                         uint8_t* __restrict__ dst, int64_t dst_pitch, int ccw) {
+    __shared__ uint32_t tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // destination tile origin (dst is h wide, w high)
+    const int dx0 = blockIdx.x * 32, dy0 = blockIdx.y * 32;
+    // source tile origin
+    const int sx0 = ccw ? (w - 32 - dy0) : dy0;
+    const int sy0 = ccw ? dx0 : (h - 32 - dx0);
+    for (int r = ty; r < 32; r += 8) {
+        const int sx = sx0 + tx, sy = sy0 + r;
+        if (sx >= 0 && sx < w && sy >= 0 && sy < h)
+            tile[r][tx] = *reinterpret_cast<const uint32_t*>(src + (int64_t)sy * src_pitch + (int64_t)sx * 4);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int dx = dx0 + tx, dy = dy0 + r;
+        if (dx < h && dy < w) {
+            // ccw: in[x][w-1-y] -> source row = dx - sy0 ... expressed in tile coordinates
+            const int srow = ccw ? (dx - sy0) : (h - 1 - dx - sy0);
+            const int scol = ccw ? (w - 1 - dy - sx0) : (dy - sx0);
+            *reinterpret_cast<uint32_t*>(dst + (int64_t)dy * dst_pitch + (int64_t)dx * 4) = tile[srow][scol];
+        }
+    }
+}
+
+}  // namespace ipp
+
+extern "C" {
+
+int ipp_rot90_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int counter_clockwise,
+                      uint8_t* dst, int64_t dst_pitch, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(src && dst, IPP_ERR_BAD_ARG, "ipp_rot90_rgba_u8: NULL image pointer");
+    IPP_REQUIRE(w > 0 && h > 0 && src_pitch >= (int64_t)w * 4 && dst_pitch >= (int64_t)h * 4, IPP_ERR_BAD_SHAPE,
+                "ipp_rot90_rgba_u8: bad geometry");
+    IPP_REQUIRE(((src_pitch | dst_pitch) & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 3) == 0, IPP_ERR_BAD_ARG,
+                "ipp_rot90_rgba_u8: RGBA images must be 4-byte aligned");
+    dim3 grid(ceil_div(h, 32), ceil_div(w, 32));
+    rot90_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, dst, dst_pitch, counter_clockwise);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_remap_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src_h, int bpp,
+                 int x0, int y0, int out_w, int out_h, int flip_h, int flip_v,
+                 uint8_t* dst, int64_t dst_pitch,
+                 int n, int64_t src_image_stride, int64_t dst_image_stride, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(src && dst, IPP_ERR_BAD_ARG, "ipp_remap_u8: NULL image pointer");
+    IPP_REQUIRE(bpp >= 1 && bpp <= 16, IPP_ERR_BAD_ARG, "ipp_remap_u8: bpp=%d not in 1..16", bpp);
+    IPP_REQUIRE(n >= 1, IPP_ERR_BAD_ARG, "ipp_remap_u8: n=%d", n);
+    IPP_REQUIRE(out_w >= 0 && out_h >= 0 && x0 >= 0 && y0 >= 0 && x0 + out_w <= src_w && y0 + out_h <= src_h,
+                IPP_ERR_BAD_SHAPE, "ipp_remap_u8: crop (%d,%d,%d,%d) outside %dx%d", x0, y0, out_w, out_h, src_w, src_h);
+    IPP_REQUIRE(src_pitch >= (int64_t)src_w * bpp && dst_pitch >= (int64_t)out_w * bpp, IPP_ERR_BAD_SHAPE,
+                "ipp_remap_u8: pitch smaller than a row");
+    if (out_w == 0 || out_h == 0) return IPP_OK;
+    RowsParams p{};
+    p.src = src; p.src_pitch = src_pitch; p.src_img_stride = src_image_stride;
+    p.bpp = bpp; p.x0 = x0; p.y0 = y0; p.out_w = out_w; p.out_h = out_h;
+    p.dst[(flip_h ? 1 : 0) | (flip_v ? 2 : 0)] = dst;
+    p.dst_pitch = dst_pitch; p.dst_img_stride = dst_image_stride;
+    return launch_rows(p, n, (cudaStream_t)stream);
+}
+
+int ipp_symmetries_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int bpp,
+                      uint8_t* dst_o, uint8_t* dst_h, uint8_t* dst_v, uint8_t* dst_hv,
+                      int64_t dst_pitch,
+                      int n, int64_t src_image_stride, int64_t dst_image_stride, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(src, IPP_ERR_BAD_ARG, "ipp_symmetries_u8: NULL source");
+    IPP_REQUIRE(bpp >= 1 && bpp <= 16, IPP_ERR_BAD_ARG, "ipp_symmetries_u8: bpp=%d not in 1..16", bpp);
+    IPP_REQUIRE(n >= 1 && w >= 0 && h >= 0, IPP_ERR_BAD_ARG, "ipp_symmetries_u8: bad n/size");
+    IPP_REQUIRE(src_pitch >= (int64_t)w * bpp && dst_pitch >= (int64_t)w * bpp, IPP_ERR_BAD_SHAPE,
+                "ipp_symmetries_u8: pitch smaller than a row");
+    if (w == 0 || h == 0 || (!dst_o && !dst_h && !dst_v && !dst_hv)) return IPP_OK;
+    RowsParams p{};
+    p.src = src; p.src_pitch = src_pitch; p.src_img_stride = src_image_stride;
+    p.bpp = bpp; p.x0 = 0; p.y0 = 0; p.out_w = w; p.out_h = h;
+    p.dst[0] = dst_o; p.dst[1] = dst_h; p.dst[2] = dst_v; p.dst[3] = dst_hv;
+    p.dst_pitch = dst_pitch; p.dst_img_stride = dst_image_stride;
+    return launch_rows(p, n, (cudaStream_t)stream);
+}
+
+int ipp_to_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int src_channels,
+                   int swap_rb, uint8_t* dst, int64_t dst_pitch, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(src && dst, IPP_ERR_BAD_ARG, "ipp_to_rgba_u8: NULL image pointer");
+    IPP_REQUIRE(src_channels == 1 || src_channels == 3 || src_channels == 4, IPP_ERR_BAD_ARG,
+                "ipp_to_rgba_u8: channels=%d not in {1,3,4}", src_channels);
+    IPP_REQUIRE(w >= 0 && h >= 0 && src_pitch >= (int64_t)w * src_channels && dst_pitch >= (int64_t)w * 4,
+                IPP_ERR_BAD_SHAPE, "ipp_to_rgba_u8: bad size/pitch");
+    if (w == 0 || h == 0) return IPP_OK;
+    dim3 grid(ceil_div(w, 256), h);
+    to_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, src_channels, swap_rb, dst, dst_pitch);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+/*
+ * ippgpu.h — C ABI of the B200-native per-image transform chain.
+ *
+ * Drop-in boundary for the hot path of Tezahc/image_processor_pipeline: the
+ * arithmetic executed inside one "process function" call
+ * (reference pipeline.py:332-336 -> transforms/*.py) between "pixels decoded"
+ * and "pixels ready to encode".  The reference has no FFI of its own (it is pure
+ * Python over cv2 / Pillow); each entry point below replaces the library call
+ * sequence of the cited reference lines.  INTEGRATION.md shows the ctypes stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C symbols, no C++/torch types; every image pointer is a DEVICE pointer
+ *    owned by the caller (the library never allocates or frees user-visible
+ *    memory); `*_host` parameters are HOST pointers read during the call;
+ *  - images are interleaved HWC uint8 with an explicit row pitch in bytes;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    all work is enqueued asynchronously on it; calls are re-entrant per stream;
+ *  - return value: 0 = ok; negative = IPP_ERR_* (invalid argument class, mapped
+ *    to the Python exception the reference function raises); positive = the
+ *    cudaError_t of a failed runtime call.  ipp_last_error_string() describes
+ *    the last failure on the calling thread.  No exceptions cross the ABI.
+ *  - sm_100a only.  There is no CPU fallback.
+ */
+#ifndef IPPGPU_H
+#define IPPGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPP_VERSION 100
+
+#define IPP_OK 0
+#define IPP_ERR_BAD_ARG (-1)      /* -> ValueError   */
+#define IPP_ERR_BAD_SHAPE (-2)    /* -> ValueError   */
+#define IPP_ERR_WORKSPACE (-3)    /* -> MemoryError  */
+#define IPP_ERR_UNSUPPORTED (-4)  /* -> NotImplementedError */
+
+#define IPP_MAX_HSV_RANGES 16
+#define IPP_MAX_TAPS_NOTE "resample taps are unbounded; tables are caller-provided"
+
+int ipp_version(void);
+const char* ipp_last_error_string(void);
+/* number of SMs of the current device (grid sizing on the host side) */
+int ipp_sm_count(int* out_host);
+
+/* ---------------------------------------------------------------------------------
+ * 1. flip x crop x copy as one load-address remap.
+ *    Replaces cv2.flip / ndarray.copy (reference transforms/symmetry.py:114-119),
+ *    ndarray slicing crops (recadrages.py:46, crop_square.py:196, pixels_isolés.py:81)
+ *    and PIL crop (rotations.py:101, recadrages.py:77).
+ *    dst[y, x, :] = src[y0 + (flip_v ? out_h-1-y : y), x0 + (flip_h ? out_w-1-x : x), :]
+ *    bpp = bytes per pixel (1..16).  n images of identical geometry are processed
+ *    when n > 1 (image i at src + i*src_image_stride / dst + i*dst_image_stride).
+ * --------------------------------------------------------------------------------- */
+int ipp_remap_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src_h, int bpp,
+                 int x0, int y0, int out_w, int out_h, int flip_h, int flip_v,
+                 uint8_t* dst, int64_t dst_pitch,
+                 int n, int64_t src_image_stride, int64_t dst_image_stride, void* stream);
+
+/*    Fused symmetries: ONE read of the source, up to four writes
+ *    (reference transforms/symmetry.py:128-137 writes each selected variant).
+ *    Any of dst_o / dst_h / dst_v / dst_hv may be NULL (variant not wanted). */
+int ipp_symmetries_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int bpp,
+                      uint8_t* dst_o, uint8_t* dst_h, uint8_t* dst_v, uint8_t* dst_hv,
+                      int64_t dst_pitch,
+                      int n, int64_t src_image_stride, int64_t dst_image_stride, void* stream);
+
+/*    gray/RGB -> RGBA with A=255 (PIL convert("RGBA"), reference rotations.py:55,
+ *    overlays.py:85) and channel-order swap BGR(A)<->RGB(A) between cv2 and PIL
+ *    conventions.  src_channels in {1,3,4}; dst is always 4 channels. */
+int ipp_to_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int src_channels,
+                   int swap_rb, uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/*    Quarter turns of an RGBA image: PIL Image.rotate fast paths for 90 / 270 degrees
+ *    (PIL/Image.py:2509-2521 -> transpose(ROTATE_90 | ROTATE_270)).  dst is h x w. */
+int ipp_rot90_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int counter_clockwise,
+                      uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 2. bounding box of non-zero pixels.
+ *    PIL getbbox() (rotations.py:99, recadrages.py:73: alpha band for 2/4-channel
+ *    images, any band otherwise) and cv2.findNonZero+boundingRect on the alpha
+ *    plane (pixels_isolés.py:77-79).
+ *    bbox_out (device int32[4]) = {x0, y0, x1, y1} exclusive; empty <=> x1 == 0
+ *    (then x0 = y0 = INT_MAX).
+ * --------------------------------------------------------------------------------- */
+int ipp_alpha_bbox_u8(const uint8_t* img, int64_t pitch, int w, int h, int channels,
+                      int alpha_only, int32_t* bbox_out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 3. inverse-mapped rotation warp (reference transforms/rotations.py:96,
+ *    PIL Image.rotate(expand=True) -> libImaging affine_fixed / bilinear).
+ *    mode 0: NEAREST, 16.16 fixed point: xin=(a2+y*a1+x*a0)>>16, yin=(a5+y*a4+x*a3)>>16
+ *            (coef_fixed_host = int32[6] {a0..a5}); bit-exact.
+ *    mode 1: BILINEAR on premultiplied alpha, double-precision coordinates
+ *            (coef_f64_host = double[6] PIL matrix); <= 1 LSB (documented).
+ *    The canvas (dst_w x dst_h, 4 channels) is fully written (0 outside the
+ *    source).  If bbox_out != NULL the bbox {x0,y0,x1,y1} of alpha != 0 is reduced
+ *    in the same launch (PIL getbbox, rotations.py:99); it must be pre-set by the
+ *    caller to {INT_MAX, INT_MAX, 0, 0} (ipp_bbox_reset does that).
+ * --------------------------------------------------------------------------------- */
+int ipp_bbox_reset(int32_t* bbox, int n, void* stream);
+int ipp_rotate_rgba_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src_h,
+                       int mode, const int32_t* coef_fixed_host, const double* coef_f64_host,
+                       uint8_t* dst, int64_t dst_pitch, int dst_w, int dst_h,
+                       int32_t* bbox_out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 4. Pillow-compatible 8bpc separable resample of an RGBA image
+ *    (reference transforms/overlays.py:129, Image.resize(LANCZOS): RGBA -> RGBa
+ *    premultiply, horizontal pass, vertical pass, un-premultiply; bit-exact).
+ *    Coefficient tables are computed on the host exactly as libImaging
+ *    precompute_coeffs + normalize_coeffs_8bpc do and passed as DEVICE arrays:
+ *      h_bounds int32[dst_w][2] = {xmin, count}, h_kk int32[dst_w][h_ksize]
+ *      v_bounds int32[dst_h][2],                  v_kk int32[dst_h][v_ksize]
+ *    A pass is skipped when its size is unchanged (h_ksize == 0 / v_ksize == 0).
+ *    tmp: device scratch of at least src_h * dst_w * 4 bytes.
+ * --------------------------------------------------------------------------------- */
+/* host helpers: ksize = 2*ceil(3*max(in/out,1))+1; tables as Pillow computes them
+ * (C library sin(), double precision, same operation order).  bounds_host is
+ * int32[out_size][2], kk_host int32[out_size][ksize] — both HOST arrays. */
+int ipp_lanczos_ksize(int in_size, int out_size);
+int ipp_lanczos_coeffs_host(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host);
+int ipp_resample_rgba_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src_h,
+                         uint8_t* dst, int64_t dst_pitch, int dst_w, int dst_h,
+                         const int32_t* h_bounds, const int32_t* h_kk, int h_ksize,
+                         const int32_t* v_bounds, const int32_t* v_kk, int v_ksize,
+                         uint8_t* tmp, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 5. alpha paste of an RGBA sprite onto an RGB background, optionally cropped
+ *    (reference transforms/overlays.py:138-139: bg.copy().paste(spr, pos, spr);
+ *    libImaging paste_mask_RGBA: out = DIV255(bg*(255-a) + spr*a); bit-exact).
+ *    dst (crop_w x crop_h x 3) = composite[crop_y0 : crop_y0+crop_h, crop_x0 : ...]
+ *    — crop = (0, 0, bg_w, bg_h) reproduces the plain paste; a square crop
+ *    (reference crop_square.py:196) folds into the same pass.
+ * --------------------------------------------------------------------------------- */
+int ipp_paste_rgba_on_rgb_u8(const uint8_t* bg, int64_t bg_pitch, int bg_w, int bg_h,
+                             const uint8_t* sprite, int64_t sprite_pitch, int sprite_w, int sprite_h,
+                             int pos_x, int pos_y,
+                             int crop_x0, int crop_y0, int crop_w, int crop_h,
+                             uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 6. HSV range keying (reference transforms/filtres_liste.py:90-134:
+ *    cvtColor(BGR2HSV) -> OR_k(inRange_k & zone_k) -> alpha = ~mask; bit-exact).
+ *    Bounds are integers already rounded like cv2.inRange rounds scalars on CV_8U
+ *    (half-to-even); zone = margins {top, bottom, left, right}.
+ * --------------------------------------------------------------------------------- */
+typedef struct ipp_hsv_range {
+    int32_t lo[3];   /* H, S, V lower bounds (inclusive) */
+    int32_t hi[3];   /* H, S, V upper bounds (inclusive) */
+    int32_t zone[4]; /* top, bottom, left, right margins in pixels */
+} ipp_hsv_range;
+
+int ipp_hsv_ranges_to_alpha_u8(const uint8_t* bgr, int64_t src_pitch, int w, int h,
+                               const ipp_hsv_range* ranges_host, int n_ranges,
+                               uint8_t* bgra, int64_t dst_pitch,
+                               int n, int64_t src_image_stride, int64_t dst_image_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 7. keep the largest 8-connected component of alpha > 1
+ *    (reference transforms/pixels_isolés.py:32-55 + _crop_fit :74-81:
+ *    cv2.threshold + connectedComponentsWithStats(8) + argmax area (ties: first
+ *    label in OpenCV's order = smallest 2x2-block raster key) + alpha[not kept]=0
+ *    + bounding rect of alpha != 0; bit-exact).
+ *    The alpha channel of the 4-channel image is rewritten in place; colour bytes
+ *    are untouched.  info_out (device int32[8] per image) =
+ *    {x, y, w, h of alpha != 0 after cleaning (0,0,0,0 if none), area, n_fg_pixels, 0, 0}.
+ *    workspace: ipp_keep_largest_workspace_bytes(w, h, n) bytes of device scratch.
+ * --------------------------------------------------------------------------------- */
+int64_t ipp_keep_largest_workspace_bytes(int w, int h, int n);
+int ipp_keep_largest_cc_u8(uint8_t* bgra, int64_t pitch, int w, int h,
+                           int32_t* info_out, void* workspace, int64_t workspace_bytes,
+                           int n, int64_t image_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 8. YOLO box arithmetic, one warp per image (float32 store semantics of
+ *    ultralytics.utils.ops as the reference uses them).
+ *    ipp_boxes_square_crop_f32: reference crop_square.py:167,201-217 —
+ *      xywhn -> xyxy (float32) -> shift by (x0,y0) -> clip to [0,cs] -> keep
+ *      x1<x2 && y1<y2 -> xyxy -> xywhn(cs,cs) (float32).
+ *      boxes_in/out: float64[n_boxes][4] in, float32[n_boxes][4] out, valid_out
+ *      int32[n_boxes]; boxes of image i are rows box_offsets[i] .. box_offsets[i+1].
+ *      params int32[n_images][5] = {img_w, img_h, x0, y0, crop_size}.
+ *    ipp_boxes_xyxy2xywhn_f32: reference overlays.py:143-146 — int box
+ *      {x1,y1,x2,y2} -> float32 {cx,cy,w,h} normalised by (img_w, img_h).
+ * --------------------------------------------------------------------------------- */
+int ipp_boxes_square_crop_f32(const double* boxes_in, const int32_t* box_offsets, const int32_t* params,
+                              float* boxes_out, int32_t* valid_out, int n_images, void* stream);
+int ipp_boxes_xyxy2xywhn_f32(const int32_t* xyxy, const int32_t* img_wh, float* xywhn_out,
+                             int n_boxes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 9. Fused chain (batched, device-resident): frame -> border crop -> HSV key ->
+ *    keep largest component + fit -> rotate (nearest) + fit -> flip -> LANCZOS
+ *    resize -> paste on background -> square crop (+ YOLO label).
+ *    Reference order of steps: SURVEY.md §7.2 (video.py:42 -> recadrages.py:23 ->
+ *    filtres_liste.py:138 -> pixels_isolés.py:16 -> rotations.py:55 -> symmetry ->
+ *    overlays.py -> crop_square.py).  The chain is split where data-dependent
+ *    sizes must reach the host RNG: stage A, stage B1, stage
+ *    B2+C.  All frames of a batch share one geometry.
+ * --------------------------------------------------------------------------------- */
+typedef struct ipp_chain_geom {
+    int32_t frame_w, frame_h;            /* decoded frame size (BGR, 3 bytes/px)      */
+    int32_t crop_l, crop_t, crop_w, crop_h; /* border crop rect (recadrages.py:46)    */
+    int32_t bg_w, bg_h;                  /* background size (RGB, 3 bytes/px)          */
+    int32_t n_ranges;
+    ipp_hsv_range ranges[IPP_MAX_HSV_RANGES];
+} ipp_chain_geom;
+
+/* per-image record living in DEVICE memory, filled stage by stage (int32 fields) */
+typedef struct ipp_chain_item {
+    /* stage A out: component bbox inside the cropped frame + area */
+    int32_t cc_x, cc_y, cc_w, cc_h, cc_area, n_fg, _pad0, _pad1;
+    /* stage B1 in (host): rotation kind (0 affine,1 copy,2 rot180,3 rot90,4 rot270),
+       fixed-point coefficients, canvas size */
+    int32_t rot_kind, a0, a1, a2, a3, a4, a5, canvas_w, canvas_h;
+    /* stage B1 out: alpha bbox on the canvas {x0,y0,x1,y1} (INT_MAX,INT_MAX,0,0 if empty) */
+    int32_t rb_x0, rb_y0, rb_x1, rb_y1;
+    /* stage B2/C in (host): flips, resized sprite size, paste position, final crop */
+    int32_t flip_h, flip_v, spr_w, spr_h, new_w, new_h, pos_x, pos_y, sq_x0, sq_y0, sq_size;
+    /* offsets (in int32 elements) of this image's coefficient tables in the tables buffer */
+    int32_t h_bounds_off, h_kk_off, h_ksize, v_bounds_off, v_kk_off, v_ksize;
+    /* offsets (bytes) of this image's scratch in the sprite workspace */
+    int64_t rot_off, tmp_off, spr_off;
+} ipp_chain_item;
+
+int64_t ipp_chain_workspace_bytes(const ipp_chain_geom* geom_host, int n);
+/* stage A: frames (n x frame_h x frame_w x 3, BGR) -> keep bitmask + items[i].cc_* */
+int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
+                      const ipp_chain_geom* geom_host, ipp_chain_item* items,
+                      void* workspace, int64_t workspace_bytes, int n, void* stream);
+/* stage B1: alpha bbox of every rotated sprite canvas -> items[i].rb_* */
+int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, ipp_chain_item* items,
+                       void* workspace, int64_t workspace_bytes, int n, int max_canvas_w, int max_canvas_h,
+                       void* stream);
+/* stage B2: rotate∘fit∘flip gather + premultiply -> LANCZOS h/v passes -> sprites */
+int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
+                       const ipp_chain_geom* geom_host, ipp_chain_item* items, const int32_t* tables,
+                       void* workspace, int64_t workspace_bytes,
+                       uint8_t* sprite_ws, int n, int max_spr_w, int max_spr_h, int max_new_w, int max_new_h,
+                       void* stream);
+/* stage C: background crop + alpha paste -> out (n x sq x sq x 3, RGB) */
+int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
+                      const ipp_chain_geom* geom_host, const ipp_chain_item* items,
+                      const uint8_t* sprite_ws,
+                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPPGPU_H */

@@ -1,0 +1,265 @@
+"""Parity of every CUDA operator (through the C ABI) against the oracle on seeded
+inputs.  Integer paths: bit-exact.  Bilinear rotation: <= 1 LSB (tolerance stated in
+the test; measured 0 here because the kernel evaluates in double like libImaging)."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import intmodels as M, libcalls as L
+
+pytestmark = pytest.mark.gpu
+
+ops = pytest.importorskip("image_processor_pipeline_b200.ops")
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------ flip / crop / symmetries
+@pytest.mark.parametrize("shape", [(37, 53, 3), (20, 31, 4), (16, 16), (64, 1024, 3), (5, 7, 1), (33, 40, 2),
+                                   (1080, 1920, 3), (1024, 1024, 3), (3, 17000, 3)])
+def test_symmetries(shape):
+    img = rng(1).integers(0, 256, shape, dtype=np.uint8)
+    syms = ["hv", "o", "h", "v"]
+    outs = ops.symmetries(dev(img), syms)
+    for o, ref in zip(outs, L.symmetries(img, syms)):
+        assert np.array_equal(host(o), ref.reshape(host(o).shape))
+
+
+@pytest.mark.parametrize("case", [((50, 80, 3), 7, 3, 41, 33), ((1080, 1920, 3), 413, 0, 1080, 1080),
+                                  ((90, 60, 4), 0, 13, 60, 60), ((64, 64, 1), 5, 5, 1, 1), ((100, 333, 3), 1, 2, 331, 97)])
+@pytest.mark.parametrize("fh", [False, True])
+@pytest.mark.parametrize("fv", [False, True])
+def test_flip_crop(case, fh, fv):
+    shape, x0, y0, w, h = case
+    img = rng(2).integers(0, 256, shape, dtype=np.uint8)
+    ref = img[y0:y0 + h, x0:x0 + w]
+    if fh:
+        ref = ref[:, ::-1]
+    if fv:
+        ref = ref[::-1]
+    out = ops.flip_crop(dev(img), x0, y0, w, h, fh, fv)
+    assert np.array_equal(host(out), ref)
+
+
+def test_flip_crop_strided_source_and_batch_contract():
+    big = rng(3).integers(0, 256, (70, 90, 3), dtype=np.uint8)
+    view = dev(big)[5:60, 10:75]            # non-dense rows: pitch = 270, width = 65 px
+    out = ops.flip_crop(view, 3, 4, 50, 40, True, False)
+    assert np.array_equal(host(out), big[5:60, 10:75][4:44, 3:53][:, ::-1])
+
+
+@pytest.mark.parametrize("shape", [(31, 40, 3), (24, 18, 4), (9, 9)])
+def test_to_rgba(shape):
+    img = rng(4).integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(host(ops.to_rgba(dev(img))), L.to_rgba(img))
+    if img.ndim == 3:
+        sw = host(ops.to_rgba(dev(img), swap_rb=True))
+        ref = L.to_rgba(img).copy()
+        ref[..., [0, 2]] = ref[..., [2, 0]]
+        assert np.array_equal(sw, ref)
+
+
+# ------------------------------------------------------------------ bbox
+def test_nonzero_bbox():
+    img = np.zeros((40, 50, 4), np.uint8)
+    assert ops.nonzero_bbox(dev(img)) is None
+    img[5:9, 7:30, 3] = 3
+    img[20, 45, 3] = 1
+    img[0, 0, 0] = 200
+    assert ops.nonzero_bbox(dev(img)) == Image.fromarray(img, "RGBA").getbbox()
+    rgb = np.zeros((10, 12, 3), np.uint8)
+    rgb[3, 4, 1] = 1
+    rgb[8, 11, 2] = 9
+    assert ops.nonzero_bbox(dev(rgb)) == Image.fromarray(rgb, "RGB").getbbox()
+    big = np.zeros((1080, 1920, 4), np.uint8)
+    big[1079, 1919, 3] = 1
+    big[17, 3, 3] = 255
+    assert ops.nonzero_bbox(dev(big)) == (3, 17, 1920, 1080)
+
+
+# ------------------------------------------------------------------ rotation
+@pytest.mark.parametrize("wh", [(64, 48), (333, 217), (640, 360)])
+@pytest.mark.parametrize("angle", [17.3, 45.0, 90.0, 180.0, 270.0, 359.0, 1.0, 123.456, 200.2, 360.0, -30.0])
+def test_rotate_nearest_bit_exact(wh, angle):
+    w, h = wh
+    img = rng(5).integers(0, 256, (h, w, 4), dtype=np.uint8)
+    img[..., 3] = np.where(rng(6).random((h, w)) < 0.3, 0, img[..., 3])
+    out, bbox = ops.rotate_expand(dev(img), angle, with_bbox=True)
+    ref = L.rotate_expand(img, angle)
+    assert np.array_equal(host(out), ref)
+    assert bbox == Image.fromarray(ref, "RGBA").getbbox()
+
+
+def test_rotate_nearest_1080p_and_fit():
+    img = np.asarray(Image.fromarray(rng(7).integers(0, 256, (1080, 1920, 3), dtype=np.uint8), "RGB").convert("RGBA"))
+    for angle in (17.3, 211.9):
+        out, bbox = ops.rotate_and_fit(dev(img), angle)
+        ref, rbbox = L.rotate_and_fit(img, angle)
+        assert bbox == rbbox and np.array_equal(host(out), ref)
+
+
+@pytest.mark.parametrize("angle", [17.3, 45.0, 123.456, 200.2, 301.0])
+def test_rotate_bilinear_within_1_lsb(angle):
+    img = rng(8).integers(0, 256, (217, 333, 4), dtype=np.uint8)
+    out = host(ops.rotate_expand(dev(img), angle, resample="bilinear"))
+    ref = L.rotate_expand(img, angle, Image.Resampling.BILINEAR)
+    assert out.shape == ref.shape
+    diff = np.abs(out.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1, "north_star tolerance: at most 1 LSB per channel for bilinear rotation"
+
+
+# ------------------------------------------------------------------ resize / paste
+@pytest.mark.parametrize("dims", [(80, 60, 48, 36), (50, 40, 75, 60), (200, 150, 31, 23), (64, 64, 64, 32), (64, 64, 20, 64),
+                                  (33, 77, 33, 77), (512, 384, 300, 225), (7, 5, 1, 1), (3, 3, 20, 30), (640, 480, 333, 250)])
+def test_resize_lanczos_bit_exact(dims):
+    w, h, nw, nh = dims
+    sp = rng(9).integers(0, 256, (h, w, 4), dtype=np.uint8)
+    assert np.array_equal(host(ops.resize_lanczos(dev(sp), (nw, nh))), L.resize_lanczos(sp, (nw, nh)))
+
+
+@pytest.mark.parametrize("pos", [(0, 0), (10, 20), (70, 60), (-5, -7), (100, 90), (119, 99), (200, 5)])
+def test_paste_bit_exact(pos):
+    bg = rng(10).integers(0, 256, (100, 120, 3), dtype=np.uint8)
+    sp = rng(11).integers(0, 256, (40, 50, 4), dtype=np.uint8)
+    assert np.array_equal(host(ops.paste(dev(bg), dev(sp), pos)), L.paste(bg, sp, pos))
+
+
+def test_paste_with_square_crop_1080p():
+    bg = rng(12).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    sp = rng(13).integers(0, 256, (300, 411, 4), dtype=np.uint8)
+    comp = L.paste(bg, sp, (500, 333))
+    for x0 in (0, 413, 840):
+        out = ops.paste(dev(bg), dev(sp), (500, 333), crop=(x0, 0, 1080, 1080))
+        assert np.array_equal(host(out), comp[:, x0:x0 + 1080])
+
+
+# ------------------------------------------------------------------ HSV keying
+FILTERS = [(0, 0, 0, 180, 255, 150), (15, 60, 200, 35, 255, 255),
+           (15, 30 * 2.55, 55 * 2.55, 30, 60 * 2.55, 80 * 2.55), (15, 60 * 2.55, 60 * 2.55, 30, 75 * 2.55, 90 * 2.55)]
+
+
+@pytest.mark.parametrize("shape", [(64, 80, 3), (512, 512, 3), (37, 53, 3), (1080, 1920, 3)])
+def test_color_masks(shape):
+    img = rng(14).integers(0, 256, shape, dtype=np.uint8)
+    zones = [(0, 0, 0, 0), (3, 4, 5, 6), None, (10, 0, 0, 20)]
+    assert np.array_equal(host(ops.color_masks_to_alpha(dev(img), FILTERS, zones)), L.color_masks_to_alpha(img, FILTERS, zones))
+    assert np.array_equal(host(ops.color_masks_to_alpha(dev(img), FILTERS)), L.color_masks_to_alpha(img, FILTERS))
+
+
+def test_color_masks_all_colours_and_gimp_and_batch():
+    c = np.arange(1 << 24, dtype=np.uint32)
+    bgr = np.stack([c & 255, (c >> 8) & 255, (c >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    gimp = [(40, 20, 30, 120, 90, 100), (300, 0, 50, 360, 100, 100)]
+    for filt, g in ((FILTERS, False), (gimp, True)):
+        assert np.array_equal(host(ops.color_masks_to_alpha(dev(bgr), filt, None, g)), L.color_masks_to_alpha(bgr, filt, None, g))
+    batch = rng(15).integers(0, 256, (5, 48, 52, 3), dtype=np.uint8)
+    out = host(ops.color_masks_to_alpha(dev(batch), FILTERS))
+    for i in range(5):
+        assert np.array_equal(out[i], L.color_masks_to_alpha(batch[i], FILTERS))
+
+
+# ------------------------------------------------------------------ largest component
+def _blob_alpha(h, w, seed, p_speck):
+    r = rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.zeros((h, w), np.uint8)
+    for _ in range(4):
+        cy, cx = r.integers(0, h), r.integers(0, w)
+        ry, rx = r.integers(3, max(4, h // 3)), r.integers(3, max(4, w // 3))
+        a[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = r.integers(2, 256)
+    sp = r.random((h, w)) < p_speck
+    a[sp] = r.integers(0, 256, (h, w), dtype=np.uint8)[sp]
+    a[r.random((h, w)) < 0.01] = 1
+    return a
+
+
+def _check_keep_largest(alpha, seed=0):
+    h, w = alpha.shape
+    img = np.dstack([rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8), alpha])
+    cleaned, info = ops.keep_largest_component(dev(img))
+    if alpha.max() > 0:
+        _, ref_cleaned, bbox, area = L.keep_largest_component(img, with_info=True)
+        assert np.array_equal(host(cleaned), ref_cleaned)
+        assert tuple(info[0, :4]) == tuple(bbox)
+        if (alpha > 1).any():
+            assert info[0, 4] == area
+    else:
+        assert np.array_equal(host(cleaned), img) and tuple(info[0, :4]) == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (45, 77), (33, 20), (1, 1), (2, 130), (131, 3), (512, 512), (200, 333)])
+@pytest.mark.parametrize("p", [0.0, 0.02, 0.3])
+def test_keep_largest_blobs(hw, p):
+    _check_keep_largest(_blob_alpha(hw[0], hw[1], hw[0] * 1000 + hw[1], p))
+
+
+@pytest.mark.parametrize("p", [0.3, 0.45, 0.5, 0.55, 0.6, 0.75])
+def test_keep_largest_noise(p):
+    r = rng(int(p * 100))
+    for hw in [(40, 40), (97, 65), (64, 193)]:
+        alpha = (r.random(hw) < p).astype(np.uint8) * r.integers(2, 256, hw).astype(np.uint8)
+        _check_keep_largest(alpha)
+
+
+def test_keep_largest_edge_cases():
+    _check_keep_largest(np.zeros((10, 12), np.uint8))                       # nothing at all
+    a = np.zeros((10, 12), np.uint8); a[2, 3] = 1; a[7, 9] = 1
+    _check_keep_largest(a)                                                  # only alpha == 1: image unchanged
+    _check_keep_largest(np.full((9, 70), 255, np.uint8))                    # one full component
+    a = np.zeros((4, 8), np.uint8); a[1, 6] = a[1, 7] = 200; a[2, 0] = a[3, 0] = 200; a[0, 2] = 50
+    _check_keep_largest(a)                                                  # tie: block-raster order decides
+    a = np.zeros((66, 130), np.uint8); a[::2, :] = 255; a[:, 64] = 255      # comb joined by one column
+    _check_keep_largest(a)
+    a = np.zeros((65, 129), np.uint8)
+    for i in range(64):                                                      # long diagonal (8-connectivity only)
+        a[i, 2 * i] = 255; a[i, 2 * i + 1] = 255
+    _check_keep_largest(a)
+    a = np.zeros((80, 80), np.uint8)                                         # spiral
+    a[10, 10:70] = 255; a[10:70, 69] = 255; a[69, 20:70] = 255; a[30:70, 20] = 255; a[30, 20:50] = 255
+    a[0, 0] = 255; a[79, 79] = 200; a[79, 78] = 200
+    _check_keep_largest(a)
+
+
+def test_keep_largest_1080p_batch():
+    alphas = [_blob_alpha(1080, 1920, 77 + i, 0.01) for i in range(2)]
+    imgs = np.stack([np.dstack([rng(i).integers(0, 256, (1080, 1920, 3), dtype=np.uint8), a]) for i, a in enumerate(alphas)])
+    cleaned, info = ops.keep_largest_component(dev(imgs))
+    for i in range(2):
+        _, ref_cleaned, bbox, area = L.keep_largest_component(imgs[i], with_info=True)
+        assert np.array_equal(host(cleaned[i]), ref_cleaned)
+        assert tuple(info[i, :4]) == tuple(bbox) and info[i, 4] == area
+
+
+# ------------------------------------------------------------------ boxes
+def test_square_crop_boxes_and_overlay_label():
+    r = rng(20)
+    for _ in range(20):
+        W, H = int(r.integers(50, 2000)), int(r.integers(50, 2000))
+        n = int(r.integers(1, 6))
+        boxes = np.column_stack([r.uniform(.3, .7, n), r.uniform(.3, .7, n), r.uniform(.05, .3, n), r.uniform(.05, .3, n)])
+        cls = np.arange(n)
+        try:
+            _, cs, (lbx, ubx), (lby, uby) = L.square_crop_bounds(boxes, W, H)
+        except RuntimeError:
+            continue
+        x0, y0 = int(r.integers(lbx, ubx + 1)), int(r.integers(lby, uby + 1))
+        img = np.zeros((H, W, 3), np.uint8)
+        _, ncls, nboxes, _ = L.square_crop(img, cls, boxes, x0, y0)
+        out, valid = ops.square_crop_boxes(boxes, W, H, x0, y0, cs, DEV)
+        assert np.array_equal(cls[valid], ncls)
+        assert np.array_equal(out[valid].view(np.uint32), nboxes.view(np.uint32))      # float32 bit patterns
+    xyxy = np.array([[413, 77, 413 + 300, 77 + 211], [0, 0, 1920, 1080], [5, 6, 7, 9]])
+    got = ops.xyxy2xywhn(xyxy, 1920, 1080, DEV)
+    assert np.array_equal(got.view(np.uint32), L.xyxy2xywhn(xyxy, 1920, 1080).view(np.uint32))
