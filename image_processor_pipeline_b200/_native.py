@@ -70,6 +70,12 @@ PROTOTYPES = {
     "ipp_keep_largest_cc_u8": (_int, [_u8p, _i64, _int, _int, _i32p, _vp, _i64, _int, _i64, _vp]),
     "ipp_boxes_square_crop_f32": (_int, [_vp, _i32p, _i32p, _vp, _i32p, _int, _vp]),
     "ipp_boxes_xyxy2xywhn_f32": (_int, [_i32p, _i32p, _vp, _int, _vp]),
+    "ipp_chain_mask_workspace_bytes": (_i64, [C.POINTER(ChainGeom), _int]),
+    "ipp_chain_stage_a": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _i32p, _vp, _i64, _int, _vp]),
+    "ipp_chain_stage_b1": (_int, [C.POINTER(ChainGeom), _vp, _int, _int, _vp, _i32p, _vp]),
+    "ipp_chain_stage_b2": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _int, _int, _int,
+                                  _i32p, _vp, _u8p, _vp]),
+    "ipp_chain_stage_c": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _u8p, _u8p, _i64, _i64, _int, _vp]),
 }
 
 EXCEPTION_FOR_CODE = {-1: ValueError, -2: ValueError, -3: MemoryError, -4: NotImplementedError}

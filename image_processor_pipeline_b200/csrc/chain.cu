@@ -1,0 +1,502 @@
+// chain.cu — the fused, batched, device-resident transform chain (include/ippgpu.h §9).
+//
+//   stage A   frame -> (border crop folded into addressing) -> HSV key -> 1-bit mask
+//             -> largest 8-connected component (ccl.cu) -> keep-mask + bbox/area
+//   stage B1  per rotated sprite: bbox of the rotated keep-mask (PIL getbbox)
+//   stage B2  gather: rotate∘fit∘flip folded into one inverse map frame -> premultiplied
+//             sprite; LANCZOS horizontal pass; vertical pass + un-premultiply
+//   stage C   background crop + alpha blend + final square crop in one streaming pass
+//
+// Per frame the 6.2 MB of pixels are read from HBM exactly once at full resolution
+// (stage A); everything between A and C works on bits or on the small sprite.
+#include "ccl.cuh"
+#include "hsv.cuh"
+#include "staging.cuh"
+
+namespace ipp {
+
+// ===================================================================== stage A: mask
+struct MaskParams {
+    const uint8_t* frames;
+    int64_t pitch, stride;
+    int crop_l, crop_t, w, h;     // w, h = cropped size
+    int wpr;
+    uint32_t* bits;
+    int64_t bits_stride;          // words per image
+    int rows_per_cta;
+    uint32_t smem_row_stride;
+    HsvFilterSet f;
+};
+
+constexpr int kMaskThreads = 256;
+
+// One CTA = a few cropped rows of one frame, staged by the bulk-copy engine.  A lane
+// converts 4 pixels (12 staged bytes, conflict-free 12-byte lane stride) into a nibble;
+// 8 lanes are OR-combined by shuffles into one mask word.
+__global__ void __launch_bounds__(kMaskThreads) chain_mask_kernel(const MaskParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ int sdiv[256], hdiv[256];
+    const int tid = threadIdx.x;
+    const int img = blockIdx.y;
+    const int row0 = blockIdx.x * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, p.h - row0);
+    const uint32_t rowbytes = (uint32_t)p.w * 3u;
+    const uint8_t* src = p.frames + (int64_t)img * p.stride + (int64_t)p.crop_t * p.pitch + (int64_t)p.crop_l * 3;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; ++r) total += make_window(src + (int64_t)(row0 + r) * p.pitch, rowbytes).bytes;
+        mbar_expect_tx(&bar, total);
+        for (int r = 0; r < nrows; ++r) {
+            const Window w = make_window(src + (int64_t)(row0 + r) * p.pitch, rowbytes);
+            bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
+        }
+    }
+    fill_hsv_tables(sdiv, hdiv, tid, kMaskThreads);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const int gpr = p.wpr * 8;            // groups of 4 pixels per row, padded to whole words
+    const int items = nrows * gpr;
+    uint32_t* out_img = p.bits + (int64_t)img * p.bits_stride;
+    for (int base = 0; base < items; base += kMaskThreads) {
+        const int it = base + tid;
+        uint32_t nib = 0;
+        int r = 0, gi = 0;
+        if (it < items) {
+            r = it / gpr;
+            gi = it - r * gpr;
+            const int x = gi * 4;
+            if (x < p.w) {
+                const int y = row0 + r;
+                const uint8_t* s = src + (int64_t)y * p.pitch;
+                const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
+                const uint4 raw = window_load16(smem + (size_t)r * p.smem_row_stride, shift + (uint32_t)x * 3u);
+                uint32_t bgr[4];
+                bgr[0] = raw.x & 0x00ffffffu;
+                bgr[1] = __funnelshift_r(raw.x, raw.y, 24) & 0x00ffffffu;
+                bgr[2] = __funnelshift_r(raw.y, raw.z, 16) & 0x00ffffffu;
+                bgr[3] = raw.z >> 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (x + k < p.w) {
+                        const uint32_t X = bgr_to_hsv_packed(bgr[k] & 255u, (bgr[k] >> 8) & 255u, bgr[k] >> 16, sdiv, hdiv);
+                        if (!hsv_excluded(X, x + k, y, p.f)) nib |= 1u << k;     // kept by the key => alpha 255 => foreground
+                    }
+                }
+            }
+        }
+        uint32_t v = nib << (4 * (gi & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        if (it < items && (gi & 7) == 0) out_img[(int64_t)(row0 + r) * p.wpr + (gi >> 3)] = v;
+    }
+}
+
+// ===================================================================== shared: inverse map
+struct SrcMap {
+    int kind, a0, a1, a2, a3, a4, a5, w, h;     // w, h = source sprite (component rect) size
+};
+// canvas pixel (cx, cy) -> source sprite pixel; false when outside the source
+__device__ __forceinline__ bool map_canvas(const SrcMap& m, int cx, int cy, int& xin, int& yin) {
+    switch (m.kind) {
+        case 0:
+            xin = (m.a2 + cy * m.a1 + cx * m.a0) >> 16;
+            yin = (m.a5 + cy * m.a4 + cx * m.a3) >> 16;
+            break;
+        case 1: xin = cx; yin = cy; break;
+        case 2: xin = m.w - 1 - cx; yin = m.h - 1 - cy; break;
+        case 3: xin = m.w - 1 - cy; yin = cx; break;          // ROTATE_90: out[y][x] = in[x][w-1-y]
+        default: xin = cy; yin = m.h - 1 - cx; break;         // ROTATE_270: out[y][x] = in[h-1-x][y]
+    }
+    return xin >= 0 && xin < m.w && yin >= 0 && yin < m.h;
+}
+
+// flat tile index -> (record index, tile inside the record) by binary search on tile_start
+template <typename Rec, typename GetStart>
+__device__ __forceinline__ int find_record(const Rec* recs, int n, int tile, GetStart start_of) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (start_of(recs[mid]) <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ===================================================================== stage B1: rotated bbox
+__global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot* __restrict__ rots, int n_rot,
+                                                             const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
+                                                             int32_t* bbox_out) {
+    __shared__ int s_rec;
+    __shared__ int s_box[4];
+    if (threadIdx.x == 0) {
+        s_rec = find_record(rots, n_rot, (int)blockIdx.x, [](const ipp_chain_rot& r) { return r.tile_start; });
+        s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = 0; s_box[3] = 0;
+    }
+    __syncthreads();
+    const ipp_chain_rot rec = rots[s_rec];
+    const int tile = (int)blockIdx.x - rec.tile_start;
+    const int tiles_x = (rec.canvas_w + 31) >> 5;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = tx * 32 + lane;
+    const SrcMap m{rec.kind, rec.a0, rec.a1, rec.a2, rec.a3, rec.a4, rec.a5, rec.cc_w, rec.cc_h};
+    const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride;
+    int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int y = ty * 32 + warp * 4 + j;
+        bool on = false;
+        if (x < rec.canvas_w && y < rec.canvas_h) {
+            int xin, yin;
+            if (map_canvas(m, x, y, xin, yin)) {
+                const int fx = rec.cc_x + xin, fy = rec.cc_y + yin;
+                on = (fb[(int64_t)fy * wpr + (fx >> 5)] >> (fx & 31)) & 1u;
+            }
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, on);
+        if (mask) {
+            minx = min(minx, tx * 32 + __ffs(mask) - 1);
+            maxx1 = max(maxx1, tx * 32 + 32 - __clz(mask));
+            miny = min(miny, y);
+            maxy1 = max(maxy1, y + 1);
+        }
+    }
+    if (lane == 0 && maxx1 > 0) {
+        atomicMin(&s_box[0], minx); atomicMin(&s_box[1], miny); atomicMax(&s_box[2], maxx1); atomicMax(&s_box[3], maxy1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_box[2] > 0) {
+        int32_t* o = bbox_out + 4 * s_rec;
+        atomicMin(&o[0], s_box[0]); atomicMin(&o[1], s_box[1]); atomicMax(&o[2], s_box[2]); atomicMax(&o[3], s_box[3]);
+    }
+}
+
+// ===================================================================== stage B2
+struct B2Common {
+    const uint8_t* frames;
+    int64_t pitch, stride;
+    int crop_l, crop_t;
+    const uint32_t* bits;
+    int64_t bits_stride;
+    int wpr;
+    const ipp_chain_item* items;
+    int n_items;
+    const int32_t* tables;
+    uint8_t* sprite_ws;
+};
+
+// gather: sprite pixel (X, Y) after flip <- canvas (X' + fit_x0, Y' + fit_y0) <- frame pixel.
+// Stored premultiplied (alpha is 0 or 255 here): RGB order, R in byte 0.
+__global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
+    __shared__ int s_rec;
+    if (threadIdx.x == 0)
+        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+    __syncthreads();
+    const ipp_chain_item& it = c.items[s_rec];
+    const int spr_w = it.spr_w, spr_h = it.spr_h;
+    const int tile = (int)blockIdx.x - it.gather_tile_start;
+    const int tiles_x = (spr_w + 31) >> 5;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int X = tx * 32 + lane;
+    if (X >= spr_w) return;
+    const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, it.cc_w, it.cc_h};
+    const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride;
+    const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.rot_off);
+    const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int Y = ty * 32 + warp * 4 + j;
+        if (Y >= spr_h) break;
+        const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
+        uint32_t px = 0;
+        int xin, yin;
+        if (map_canvas(m, cx, cy, xin, yin)) {
+            const int fx = it.cc_x + xin, fy = it.cc_y + yin;
+            if ((fb[(int64_t)fy * c.wpr + (fx >> 5)] >> (fx & 31)) & 1u) {
+                const uint8_t* s = frame + (int64_t)(c.crop_t + fy) * c.pitch + (int64_t)(c.crop_l + fx) * 3;
+                px = (uint32_t)s[2] | ((uint32_t)s[1] << 8) | ((uint32_t)s[0] << 16) | 0xff000000u;   // BGR -> RGBA
+            }
+        }
+        dst[(int64_t)Y * spr_w + X] = px;
+    }
+}
+
+constexpr int kPrec = 32 - 8 - 2;
+__device__ __forceinline__ uint32_t c_clip8(int v) {
+    v >>= kPrec;
+    return (uint32_t)min(max(v, 0), 255);
+}
+__device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
+    const uint32_t a = v >> 24;
+    if (a == 0u || a == 255u) return v;
+    const uint32_t c0 = min(255u, (255u * (v & 255u)) / a);
+    const uint32_t c1 = min(255u, (255u * ((v >> 8) & 255u)) / a);
+    const uint32_t c2 = min(255u, (255u * ((v >> 16) & 255u)) / a);
+    return c0 | (c1 << 8) | (c2 << 16) | (a << 24);
+}
+
+// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles)
+__global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
+    __shared__ int s_rec;
+    if (threadIdx.x == 0)
+        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.h_tile_start; });
+    __syncthreads();
+    const ipp_chain_item& it = c.items[s_rec];
+    const int tile = (int)blockIdx.x - it.h_tile_start;
+    const int tiles_x = (it.new_w + 31) >> 5;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int X = tx * 32 + (threadIdx.x & 31);
+    const int y = ty * 8 + (threadIdx.x >> 5);
+    if (X >= it.new_w || y >= it.spr_h) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.rot_off) + (int64_t)y * it.spr_w;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.tmp_off) + (int64_t)y * it.new_w;
+    if (it.h_ksize == 0) {          // width unchanged: Pillow skips the horizontal pass
+        dst[X] = src[X];
+        return;
+    }
+    const int32_t* bounds = c.tables + it.hb_off;
+    const int xmin = bounds[2 * X], n = bounds[2 * X + 1];
+    const int32_t* k = c.tables + it.hk_off + (int64_t)X * it.h_ksize;
+    int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t v = src[xmin + i];
+        const int w = __ldg(k + i);
+        s0 += (int)(v & 255u) * w;
+        s1 += (int)((v >> 8) & 255u) * w;
+        s2 += (int)((v >> 16) & 255u) * w;
+        s3 += (int)(v >> 24) * w;
+    }
+    dst[X] = c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24);
+}
+
+// vertical pass + un-premultiply: spr[Y][x], Y < new_h, x < new_w   (32 x 8 tiles)
+__global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
+    __shared__ int s_rec;
+    if (threadIdx.x == 0)
+        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+    __syncthreads();
+    const ipp_chain_item& it = c.items[s_rec];
+    const int tile = (int)blockIdx.x - it.v_tile_start;
+    const int tiles_x = (it.new_w + 31) >> 5;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x = tx * 32 + (threadIdx.x & 31);
+    const int Y = ty * 8 + (threadIdx.x >> 5);
+    if (x >= it.new_w || Y >= it.new_h) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.tmp_off);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off) + (int64_t)Y * it.new_w;
+    if (it.v_ksize == 0) {
+        dst[x] = c_unpremultiply(src[(int64_t)Y * it.new_w + x]);
+        return;
+    }
+    const int32_t* bounds = c.tables + it.vb_off;
+    const int ymin = bounds[2 * Y], n = bounds[2 * Y + 1];
+    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;
+    int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t v = src[(int64_t)(ymin + i) * it.new_w + x];
+        const int w = __ldg(k + i);
+        s0 += (int)(v & 255u) * w;
+        s1 += (int)((v >> 8) & 255u) * w;
+        s2 += (int)((v >> 16) & 255u) * w;
+        s3 += (int)(v >> 24) * w;
+    }
+    dst[x] = c_unpremultiply(c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24));
+}
+
+// ===================================================================== stage C
+struct CParams {
+    const uint8_t* bgs;
+    int64_t bg_pitch, bg_stride;
+    const ipp_chain_item* items;
+    const uint8_t* sprite_ws;
+    uint8_t* out;
+    int64_t out_pitch, out_stride;
+    int out_size;
+    int rows_per_cta;
+    uint32_t smem_row_stride;
+};
+
+__global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParams c) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const ipp_chain_item& it = c.items[blockIdx.y];
+    PasteParams p;
+    p.bg = c.bgs + (int64_t)it.bg * c.bg_stride;
+    p.bg_pitch = c.bg_pitch;
+    p.sprite = c.sprite_ws + it.spr_off;
+    p.sprite_pitch = (int64_t)it.new_w * 4;
+    p.sprite_w = it.new_w; p.sprite_h = it.new_h; p.pos_x = it.pos_x; p.pos_y = it.pos_y;
+    p.crop_x0 = it.sq_x0; p.crop_y0 = it.sq_y0; p.crop_w = it.sq_size; p.crop_h = it.sq_size;
+    p.dst = c.out + (int64_t)blockIdx.y * c.out_stride;
+    p.dst_pitch = c.out_pitch;
+    const int row0 = blockIdx.x * c.rows_per_cta;
+    if (row0 >= p.crop_h) return;
+    const int nrows = min(c.rows_per_cta, p.crop_h - row0);
+    const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; ++r)
+            total += make_window(p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes).bytes;
+        mbar_expect_tx(&bar, total);
+        for (int r = 0; r < nrows; ++r) {
+            const Window w = make_window(p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes);
+            bulk_g2s(smem + (size_t)r * c.smem_row_stride, w.base, w.bytes, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+    paste_rows_from_smem(p, smem, c.smem_row_stride, row0, nrows, tid);
+}
+
+}  // namespace ipp
+
+// ===================================================================== C ABI
+extern "C" {
+
+int64_t ipp_chain_mask_workspace_bytes(const ipp_chain_geom* g, int n_frames) {
+    if (!g || n_frames <= 0 || g->crop_w <= 0 || g->crop_h <= 0) return 0;
+    return ipp::ccl_workspace_bytes(ipp::make_ccl_geom(g->crop_w, g->crop_h), n_frames);
+}
+
+static int chain_check_geom(const ipp_chain_geom* g) {
+    using namespace ipp;
+    IPP_REQUIRE(g != nullptr, IPP_ERR_BAD_ARG, "chain: geometry is NULL");
+    IPP_REQUIRE(g->frame_w > 0 && g->frame_h > 0 && g->crop_l >= 0 && g->crop_t >= 0 && g->crop_w > 0 && g->crop_h > 0 &&
+                    g->crop_l + g->crop_w <= g->frame_w && g->crop_t + g->crop_h <= g->frame_h,
+                IPP_ERR_BAD_SHAPE, "chain: border crop outside the frame");
+    IPP_REQUIRE(g->n_ranges >= 1 && g->n_ranges <= IPP_MAX_HSV_RANGES, IPP_ERR_BAD_ARG, "chain: n_ranges=%d", g->n_ranges);
+    return IPP_OK;
+}
+
+int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
+                      const ipp_chain_geom* g, int32_t* info_out,
+                      void* workspace, int64_t workspace_bytes, int n_frames, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chain_check_geom(g);
+    if (rc != IPP_OK) return rc;
+    IPP_REQUIRE(frames && info_out && n_frames >= 1, IPP_ERR_BAD_ARG, "ipp_chain_stage_a: bad arguments");
+    IPP_REQUIRE(frame_pitch >= (int64_t)g->frame_w * 3, IPP_ERR_BAD_SHAPE, "ipp_chain_stage_a: pitch smaller than a row");
+    const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
+    IPP_REQUIRE(workspace && workspace_bytes >= ccl_workspace_bytes(cg, n_frames) && (((uintptr_t)workspace) & 255) == 0,
+                IPP_ERR_WORKSPACE, "ipp_chain_stage_a: workspace too small or misaligned (need %lld bytes)",
+                (long long)ccl_workspace_bytes(cg, n_frames));
+    const int te = ensure_hsv_tables();
+    IPP_REQUIRE(te == 0, te, "ipp_chain_stage_a: table upload failed (%d)", te);
+    const CclBuffers b = carve_ccl(workspace, cg, n_frames);
+    MaskParams p{};
+    p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
+    p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
+    p.wpr = cg.wpr; p.bits = b.bits; p.bits_stride = cg.bits_stride;
+    p.f = pack_filters(g->ranges, g->n_ranges, g->crop_w, g->crop_h);
+    const uint32_t rowbytes = (uint32_t)g->crop_w * 3u;
+    p.smem_row_stride = staged_row_stride(rowbytes);
+    IPP_REQUIRE(p.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_a: row too long");
+    int rows = (int)(24576 / p.smem_row_stride);
+    if (rows < 1) rows = 1;
+    if (rows > g->crop_h) rows = g->crop_h;
+    p.rows_per_cta = rows;
+    const size_t smem = (size_t)rows * p.smem_row_stride;
+    if (smem > 40 * 1024)
+        IPP_CUDA(cudaFuncSetAttribute(chain_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(g->crop_h, rows), n_frames);
+    chain_mask_kernel<<<grid, kMaskThreads, smem, st>>>(p);
+    IPP_LAUNCH_CHECK();
+    rc = ccl_run(cg, b, n_frames, st);
+    if (rc != IPP_OK) return rc;
+    ccl_info_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(b, info_out, n_frames);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n_rot, int total_tiles,
+                       const void* workspace, int32_t* bbox_out, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chain_check_geom(g);
+    if (rc != IPP_OK) return rc;
+    IPP_REQUIRE(rots && workspace && bbox_out && n_rot >= 0 && total_tiles >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b1: bad arguments");
+    if (n_rot == 0) return IPP_OK;
+    const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
+    bbox_reset_kernel<<<ceil_div(n_rot, 256), 256, 0, st>>>(bbox_out, n_rot);
+    IPP_LAUNCH_CHECK();
+    if (total_tiles == 0) return IPP_OK;
+    chain_rot_bbox_kernel<<<total_tiles, 256, 0, st>>>(rots, n_rot, (const uint32_t*)workspace, cg.bits_stride, cg.wpr, bbox_out);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
+                       const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
+                       int gather_tiles, int h_tiles, int v_tiles,
+                       const int32_t* tables, const void* workspace, uint8_t* sprite_ws, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chain_check_geom(g);
+    if (rc != IPP_OK) return rc;
+    IPP_REQUIRE(frames && items && workspace && sprite_ws && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: bad arguments");
+    IPP_REQUIRE((((uintptr_t)sprite_ws) & 15) == 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: sprite workspace must be 16-byte aligned");
+    if (n_items == 0) return IPP_OK;
+    const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
+    B2Common c{};
+    c.frames = frames; c.pitch = frame_pitch; c.stride = frame_stride;
+    c.crop_l = g->crop_l; c.crop_t = g->crop_t;
+    c.bits = (const uint32_t*)workspace; c.bits_stride = cg.bits_stride; c.wpr = cg.wpr;
+    c.items = items; c.n_items = n_items; c.tables = tables; c.sprite_ws = sprite_ws;
+    if (gather_tiles > 0) {
+        chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c);
+        IPP_LAUNCH_CHECK();
+    }
+    if (h_tiles > 0) {
+        chain_hpass_kernel<<<h_tiles, 256, 0, st>>>(c);
+        IPP_LAUNCH_CHECK();
+    }
+    if (v_tiles > 0) {
+        chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c);
+        IPP_LAUNCH_CHECK();
+    }
+    return IPP_OK;
+}
+
+int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
+                      const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
+                      const uint8_t* sprite_ws,
+                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_size, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(g && backgrounds && items && sprite_ws && out && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_c: bad arguments");
+    IPP_REQUIRE(out_size > 0 && out_size <= g->bg_w && out_size <= g->bg_h && bg_pitch >= (int64_t)g->bg_w * 3 &&
+                    out_pitch >= (int64_t)out_size * 3,
+                IPP_ERR_BAD_SHAPE, "ipp_chain_stage_c: bad geometry");
+    if (n_items == 0) return IPP_OK;
+    CParams c{};
+    c.bgs = backgrounds; c.bg_pitch = bg_pitch; c.bg_stride = bg_stride;
+    c.items = items; c.sprite_ws = sprite_ws;
+    c.out = out; c.out_pitch = out_pitch; c.out_stride = out_stride; c.out_size = out_size;
+    const uint32_t rowbytes = (uint32_t)out_size * 3u;
+    c.smem_row_stride = staged_row_stride(rowbytes);
+    IPP_REQUIRE(c.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
+    int rows = (int)(24576 / c.smem_row_stride);
+    if (rows < 1) rows = 1;
+    if (rows > out_size) rows = out_size;
+    c.rows_per_cta = rows;
+    const size_t smem = (size_t)rows * c.smem_row_stride;
+    if (smem > 48 * 1024)
+        IPP_CUDA(cudaFuncSetAttribute(chain_paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(out_size, rows), n_items);
+    chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c);
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+}  // extern "C"

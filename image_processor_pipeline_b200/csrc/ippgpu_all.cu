@@ -8,3 +8,4 @@
 #include "hsv.cu"
 #include "ccl.cu"
 #include "boxes.cu"
+#include "chain.cu"

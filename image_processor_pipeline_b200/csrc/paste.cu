@@ -58,31 +58,10 @@ __device__ __forceinline__ void blend_bytes(const PasteParams& p, uint8_t* bytes
     }
 }
 
-__global__ void __launch_bounds__(kPasteThreads) paste_kernel(const PasteParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
-    const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * p.rows_per_cta;
-    const int nrows = min(p.rows_per_cta, p.crop_h - row0);
+// emit rows [row0, row0+nrows) of the cropped composite from staged background windows
+__device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const uint8_t* smem, uint32_t smem_row_stride,
+                                                     int row0, int nrows, int tid) {
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
-
-    if (tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int r = 0; r < nrows; ++r) {
-            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
-            total += make_window(s, rowbytes).bytes;
-        }
-        mbar_expect_tx(&bar, total);
-        for (int r = 0; r < nrows; ++r) {
-            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
-            const Window w = make_window(s, rowbytes);
-            bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
-        }
-    }
-    mbar_wait(&bar, 0);
-
     // output byte range of a row that can intersect the sprite
     const int spr_q0 = max(p.pos_x - p.crop_x0, 0);
     const int spr_q1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w);   // exclusive
@@ -93,7 +72,7 @@ __global__ void __launch_bounds__(kPasteThreads) paste_kernel(const PasteParams 
         const uint32_t c = it - r * cpr;
         const int y = row0 + (int)r;
         uint8_t* d = p.dst + (int64_t)y * p.dst_pitch;
-        const uint8_t* win = smem + (size_t)r * p.smem_row_stride;
+        const uint8_t* win = smem + (size_t)r * smem_row_stride;
         const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + y) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
         const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
         const RowSplit sp = split_row(d, rowbytes);
@@ -120,6 +99,34 @@ __global__ void __launch_bounds__(kPasteThreads) paste_kernel(const PasteParams 
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(kPasteThreads) paste_kernel(const PasteParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, p.crop_h - row0);
+    const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
+            total += make_window(s, rowbytes).bytes;
+        }
+        mbar_expect_tx(&bar, total);
+        for (int r = 0; r < nrows; ++r) {
+            const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
+            const Window w = make_window(s, rowbytes);
+            bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    paste_rows_from_smem(p, smem, p.smem_row_stride, row0, nrows, tid);
 }
 
 }  // namespace ipp

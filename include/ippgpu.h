@@ -198,58 +198,74 @@ int ipp_boxes_xyxy2xywhn_f32(const int32_t* xyxy, const int32_t* img_wh, float* 
 /* ---------------------------------------------------------------------------------
  * 9. Fused chain (batched, device-resident): frame -> border crop -> HSV key ->
  *    keep largest component + fit -> rotate (nearest) + fit -> flip -> LANCZOS
- *    resize -> paste on background -> square crop (+ YOLO label).
+ *    resize -> paste on background -> square crop.
  *    Reference order of steps: SURVEY.md §7.2 (video.py:42 -> recadrages.py:23 ->
- *    filtres_liste.py:138 -> pixels_isolés.py:16 -> rotations.py:55 -> symmetry ->
- *    overlays.py -> crop_square.py).  The chain is split where data-dependent
- *    sizes must reach the host RNG: stage A, stage B1, stage
- *    B2+C.  All frames of a batch share one geometry.
+ *    filtres_liste.py:138 -> pixels_isolés.py:16 -> rotations.py:55 -> symmetry.py ->
+ *    overlays.py -> crop_square.py).  Intermediate images are never materialised at
+ *    full size: the frame is read once into a 1-bit keep-mask, the sprite is gathered
+ *    once (rotate∘fit∘flip folded into the addressing), and the background crop,
+ *    the alpha blend and the final square crop are one streaming pass.
+ *    The chain is split only where data-dependent sizes must reach the host RNG
+ *    (randint bounds depend on the sprite size): stage A | B1 | B2+C.
+ *    All frames of a batch share one geometry; all backgrounds share one geometry.
  * --------------------------------------------------------------------------------- */
 typedef struct ipp_chain_geom {
-    int32_t frame_w, frame_h;            /* decoded frame size (BGR, 3 bytes/px)      */
-    int32_t crop_l, crop_t, crop_w, crop_h; /* border crop rect (recadrages.py:46)    */
-    int32_t bg_w, bg_h;                  /* background size (RGB, 3 bytes/px)          */
+    int32_t frame_w, frame_h;               /* decoded frame (BGR, 3 bytes/px)           */
+    int32_t crop_l, crop_t, crop_w, crop_h; /* border crop rect (recadrages.py:46)        */
+    int32_t bg_w, bg_h;                     /* backgrounds (RGB, 3 bytes/px)              */
     int32_t n_ranges;
     ipp_hsv_range ranges[IPP_MAX_HSV_RANGES];
 } ipp_chain_geom;
 
-/* per-image record living in DEVICE memory, filled stage by stage (int32 fields) */
+/* one rotated sprite whose alpha bbox is wanted (stage B1); 16 x int32 */
+typedef struct ipp_chain_rot {
+    int32_t frame;                      /* source frame index                               */
+    int32_t cc_x, cc_y, cc_w, cc_h;     /* kept component's rect inside the cropped frame   */
+    int32_t kind;                       /* 0 affine, 1 copy, 2 rot180, 3 rot90, 4 rot270    */
+    int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (kind 0)           */
+    int32_t canvas_w, canvas_h;
+    int32_t tile_start;                 /* first 32x32 tile of this canvas in the flat grid */
+    int32_t _pad;
+} ipp_chain_rot;
+
+/* one output image (stages B2 and C); 40 x int32 + 3 x int64 */
 typedef struct ipp_chain_item {
-    /* stage A out: component bbox inside the cropped frame + area */
-    int32_t cc_x, cc_y, cc_w, cc_h, cc_area, n_fg, _pad0, _pad1;
-    /* stage B1 in (host): rotation kind (0 affine,1 copy,2 rot180,3 rot90,4 rot270),
-       fixed-point coefficients, canvas size */
-    int32_t rot_kind, a0, a1, a2, a3, a4, a5, canvas_w, canvas_h;
-    /* stage B1 out: alpha bbox on the canvas {x0,y0,x1,y1} (INT_MAX,INT_MAX,0,0 if empty) */
-    int32_t rb_x0, rb_y0, rb_x1, rb_y1;
-    /* stage B2/C in (host): flips, resized sprite size, paste position, final crop */
-    int32_t flip_h, flip_v, spr_w, spr_h, new_w, new_h, pos_x, pos_y, sq_x0, sq_y0, sq_size;
-    /* offsets (in int32 elements) of this image's coefficient tables in the tables buffer */
-    int32_t h_bounds_off, h_kk_off, h_ksize, v_bounds_off, v_kk_off, v_ksize;
-    /* offsets (bytes) of this image's scratch in the sprite workspace */
-    int64_t rot_off, tmp_off, spr_off;
+    int32_t frame, bg;
+    int32_t cc_x, cc_y, cc_w, cc_h;
+    int32_t kind, a0, a1, a2, a3, a4, a5;
+    int32_t fit_x0, fit_y0, spr_w, spr_h;   /* getbbox crop inside the canvas, sprite size     */
+    int32_t flip_h, flip_v;
+    int32_t new_w, new_h, pos_x, pos_y;     /* resized sprite and paste position (overlays.py) */
+    int32_t sq_x0, sq_y0, sq_size;          /* final square crop (crop_square.py)              */
+    int32_t h_ksize, v_ksize;               /* 0 = pass skipped (size unchanged)               */
+    int32_t hb_off, hk_off, vb_off, vk_off; /* int32 offsets of this item's tables             */
+    int32_t gather_tile_start, h_tile_start, v_tile_start;
+    int32_t _pad[5];
+    int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace            */
 } ipp_chain_item;
 
-int64_t ipp_chain_workspace_bytes(const ipp_chain_geom* geom_host, int n);
-/* stage A: frames (n x frame_h x frame_w x 3, BGR) -> keep bitmask + items[i].cc_* */
+int64_t ipp_chain_mask_workspace_bytes(const ipp_chain_geom* geom_host, int n_frames);
+/* stage A: frames (n x frame_h x frame_w x 3, BGR) -> keep-mask (inside workspace) and
+ * info_out int32[n][8] = {x, y, w, h of the kept component (cropped-frame coords), area,
+ * n_fg, 0, 0} (all zero when the key removed everything). */
 int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
-                      const ipp_chain_geom* geom_host, ipp_chain_item* items,
-                      void* workspace, int64_t workspace_bytes, int n, void* stream);
-/* stage B1: alpha bbox of every rotated sprite canvas -> items[i].rb_* */
-int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, ipp_chain_item* items,
-                       void* workspace, int64_t workspace_bytes, int n, int max_canvas_w, int max_canvas_h,
-                       void* stream);
-/* stage B2: rotate∘fit∘flip gather + premultiply -> LANCZOS h/v passes -> sprites */
+                      const ipp_chain_geom* geom_host, int32_t* info_out,
+                      void* workspace, int64_t workspace_bytes, int n_frames, void* stream);
+/* stage B1: alpha bbox of every rotated sprite -> bbox_out int32[n_rot][4]
+ * {x0,y0,x1,y1}; empty <=> x1 == 0.  total_tiles = sum over sprites of 32x32 canvas tiles. */
+int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rots, int n_rot, int total_tiles,
+                       const void* workspace, int32_t* bbox_out, void* stream);
+/* stage B2: rotate∘fit∘flip gather (premultiplied) -> LANCZOS h pass -> v pass ->
+ * straight-alpha sprites in sprite_ws at items[i].spr_off. */
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
-                       const ipp_chain_geom* geom_host, ipp_chain_item* items, const int32_t* tables,
-                       void* workspace, int64_t workspace_bytes,
-                       uint8_t* sprite_ws, int n, int max_spr_w, int max_spr_h, int max_new_w, int max_new_h,
-                       void* stream);
-/* stage C: background crop + alpha paste -> out (n x sq x sq x 3, RGB) */
+                       const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
+                       int gather_tiles, int h_tiles, int v_tiles,
+                       const int32_t* tables, const void* workspace, uint8_t* sprite_ws, void* stream);
+/* stage C: out[i] (sq x sq x 3, RGB) = crop(paste(background[bg], sprite_i, pos), square) */
 int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
-                      const ipp_chain_geom* geom_host, const ipp_chain_item* items,
+                      const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
                       const uint8_t* sprite_ws,
-                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int n, void* stream);
+                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_size, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,84 @@
+"""Parity of the fused device chain against the oracle chain (the reference's steps
+run one after the other with the reference's own cv2 / Pillow calls).  All integer:
+images bit-exact, label files string-identical, same draw order from ``random``."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chain as OC
+
+pytestmark = pytest.mark.gpu
+
+chain = pytest.importorskip("image_processor_pipeline_b200.chain")
+from image_processor_pipeline_b200 import synth  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _run_both(frames, bgs, seed, **kw):
+    random.seed(seed)
+    ref_imgs, ref_labels, ref_recs = OC.run_chain(frames, bgs, **kw)
+    state_after_ref = random.getstate()
+    random.seed(seed)
+    res = chain.run_chain(torch.from_numpy(np.stack(frames)).to(DEV), torch.from_numpy(np.stack(bgs)).to(DEV),
+                          chain.ChainParams(**kw))
+    assert random.getstate() == state_after_ref, "the chain must consume the RNG exactly like the reference"
+    return res, ref_imgs, ref_labels, ref_recs
+
+
+def _compare(res, ref_imgs, ref_labels, ref_recs):
+    assert len(res.labels) == len(ref_labels) == res.images.shape[0]
+    out = res.images.cpu().numpy()
+    for i, (img, lab, rec) in enumerate(zip(ref_imgs, ref_labels, ref_recs)):
+        mine = res.records[i]
+        assert (mine["frame"], mine["rot_index"], mine["sym"], mine["bg"]) == (rec["frame"], rec["rot_index"], rec["sym"], rec["bg"])
+        assert tuple(mine["new"]) == tuple(rec["new"]) and tuple(mine["pos"]) == tuple(rec["pos"]) and tuple(mine["sq"]) == tuple(rec["sq"])
+        assert res.labels[i] == lab
+        assert np.array_equal(out[i], img), f"image {i} differs ({(out[i] != img).sum()} bytes)"
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(num_rotations=2, include_original=True, pool=["o", "h", "v", "hv"], choose_random=2),
+    dict(num_rotations=1, include_original=False, pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False),
+    dict(num_rotations=3, include_original=False, angle_min=80.0, angle_max=100.0, pool=["hv"], sym_include_original=True,
+         scale_min=0.4, scale_max=0.8, yolo_class_id=3),
+])
+def test_chain_small(cfg):
+    H, W = 270, 480
+    frames = [synth.frame(5, i, H, W) for i in range(4)]
+    bgs = [synth.background(5, i, H, W) for i in range(3)]
+    kw = dict(crop_margins=(0.05, 4, 0.02, 6), color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **cfg)
+    _compare(*_run_both(frames, bgs, 3, **kw))
+
+
+def test_chain_zones_gimp_and_portrait_background():
+    H, W = 200, 320
+    frames = [synth.frame(9, i, H, W, speck_density=0.03) for i in range(3)]
+    bgs = [synth.background(9, i, 300, 220) for i in range(2)]          # portrait: square crop is 220 wide
+    kw = dict(crop_margins=(0, 0, 0, 0), color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS,
+              zones=[(0, 0, 0, 0), (3, 4, 5, 6), None, (10, 0, 0, 20)], num_rotations=2, include_original=False,
+              pool=["h", "v"], choose_random=1, sym_include_original=False)
+    _compare(*_run_both(frames, bgs, 11, **kw))
+
+
+def test_chain_dropped_items_and_noise_frames():
+    # frame 1 is keyed out entirely (no component) and disappears; frame 2 is pure noise (worst-case CCL)
+    H, W = 160, 200
+    frames = [synth.frame(13, 0, H, W), np.zeros((H, W, 3), np.uint8), synth.noise(13, 2, (H, W, 3)), synth.frame(13, 3, H, W)]
+    bgs = [synth.background(13, i, 240, 260) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=True,
+              pool=["o", "hv"], choose_random=1, sym_include_original=False)
+    res, ref_imgs, ref_labels, ref_recs = _run_both(frames, bgs, 17, **kw)
+    assert all(r["frame"] != 1 for r in res.records)
+    _compare(res, ref_imgs, ref_labels, ref_recs)
+
+
+def test_chain_1080p():
+    H, W = 1080, 1920
+    frames = [synth.frame(21, i, H, W) for i in range(2)]
+    bgs = [synth.background(21, i, H, W) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    _compare(*_run_both(frames, bgs, 23, **kw))
