@@ -49,6 +49,9 @@ PROTOTYPES = {
     "ipp_version": (_int, []),
     "ipp_last_error_string": (C.c_char_p, []),
     "ipp_sm_count": (_int, [C.POINTER(C.c_int)]),
+    "ipp_launch_count": (C.c_longlong, []),
+    "ipp_timing_enable": (_int, [_int]),
+    "ipp_timing_report": (_int, [C.c_char_p, _int]),
     "ipp_remap_u8": (_int, [_u8p, _i64, _int, _int, _int, _int, _int, _int, _int, _int, _int,
                             _u8p, _i64, _int, _i64, _i64, _vp]),
     "ipp_symmetries_u8": (_int, [_u8p, _i64, _int, _int, _int, _u8p, _u8p, _u8p, _u8p, _i64, _int, _i64, _i64, _vp]),
@@ -107,3 +110,23 @@ def check(code: int, what: str = ""):
     if code < 0:
         raise EXCEPTION_FOR_CODE.get(code, RuntimeError)(msg or what)
     raise IppError(f"{what}: CUDA error {code}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().ipp_launch_count())
+
+
+def timing_enable(on: bool):
+    check(load().ipp_timing_enable(int(on)), "ipp_timing_enable")
+
+
+def timing_report() -> dict:
+    """{kernel: (launches, total_ms)} since the previous report (synchronises)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().ipp_timing_report(buf, len(buf)), "ipp_timing_report")
+    out = {}
+    for part in buf.value.decode().split(";"):
+        if part:
+            name, cnt, ms = part.rsplit(":", 2)
+            out[name] = (int(cnt), float(ms))
+    return out

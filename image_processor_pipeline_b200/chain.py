@@ -312,3 +312,22 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     records = [dict(frame=it["frame"], rot_index=it["rot_index"], angle=it["angle"], sym=it["sym"], bg=it["bg"],
                     ratio=it["ratio"], new=it["new"], pos=it["pos"], sq=it["sq"], fit=it["fit"], cc=it["cc"]) for it in finals]
     return ChainResult(out, [it["label"] for it in finals], records)
+
+
+def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
+                   out_host: Optional[torch.Tensor] = None, rng=_random) -> ChainResult:
+    """End-to-end entry for HOST buffers (the call a pipeline step makes after decoding):
+    pinned host frames / backgrounds -> H2D -> run_chain -> D2H of the output images.
+    ``out_host`` (pinned, [>=K, cs, cs, 3]) receives the images; ChainResult.images is that
+    host tensor (first K rows)."""
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        f = frames_host.to(dev, non_blocking=True)
+        b = backgrounds_host.to(dev, non_blocking=True)
+        res = run_chain(f, b, params, rng)
+        k = res.images.shape[0]
+        if out_host is None:
+            out_host = torch.empty(res.images.shape, dtype=torch.uint8).pin_memory()
+        out_host[:k].copy_(res.images, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return ChainResult(out_host[:k], res.labels, res.records)

@@ -66,8 +66,8 @@ int ipp_boxes_square_crop_f32(const double* boxes_in, const int32_t* box_offsets
                 "ipp_boxes_square_crop_f32: NULL pointer");
     IPP_REQUIRE(n_images >= 0, IPP_ERR_BAD_ARG, "ipp_boxes_square_crop_f32: n_images=%d", n_images);
     if (n_images == 0) return IPP_OK;
-    boxes_square_crop_kernel<<<ceil_div((int64_t)n_images * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-        boxes_in, box_offsets, params, boxes_out, valid_out, n_images);
+    { ipp::LaunchTimer _lt("boxes_square_crop_kernel", (cudaStream_t)stream); boxes_square_crop_kernel<<<ceil_div((int64_t)n_images * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+        boxes_in, box_offsets, params, boxes_out, valid_out, n_images); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -77,7 +77,7 @@ int ipp_boxes_xyxy2xywhn_f32(const int32_t* xyxy, const int32_t* img_wh, float* 
     IPP_REQUIRE(xyxy && img_wh && xywhn_out, IPP_ERR_BAD_ARG, "ipp_boxes_xyxy2xywhn_f32: NULL pointer");
     IPP_REQUIRE(n_boxes >= 0, IPP_ERR_BAD_ARG, "ipp_boxes_xyxy2xywhn_f32: n_boxes=%d", n_boxes);
     if (n_boxes == 0) return IPP_OK;
-    boxes_xyxy2xywhn_kernel<<<ceil_div(n_boxes, 128), 128, 0, (cudaStream_t)stream>>>(xyxy, img_wh, xywhn_out, n_boxes);
+    { ipp::LaunchTimer _lt("boxes_xyxy2xywhn_kernel", (cudaStream_t)stream); boxes_xyxy2xywhn_kernel<<<ceil_div(n_boxes, 128), 128, 0, (cudaStream_t)stream>>>(xyxy, img_wh, xywhn_out, n_boxes); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

@@ -277,16 +277,16 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
 int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
     const int64_t groups = (int64_t)g.bh * g.bww * n;
     const int gb = ceil_div(groups, 256);
-    ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    { ipp::LaunchTimer _lt("ccl_init_kernel", st); ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    ccl_merge_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    { ipp::LaunchTimer _lt("ccl_merge_kernel", st); ccl_merge_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    ccl_area_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    { ipp::LaunchTimer _lt("ccl_area_kernel", st); ccl_area_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    ccl_best_kernel<<<gb, 256, 0, st>>>(g, b, n);
+    { ipp::LaunchTimer _lt("ccl_best_kernel", st); ccl_best_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
     const int64_t words = (int64_t)g.h * g.wpr * n;
-    ccl_keep_kernel<<<ceil_div(words, 256), 256, 0, st>>>(g, b, n);
+    { ipp::LaunchTimer _lt("ccl_keep_kernel", st); ccl_keep_kernel<<<ceil_div(words, 256), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -395,17 +395,17 @@ int ipp_keep_largest_cc_u8(uint8_t* bgra, int64_t pitch, int w, int h,
     {
         const int wpr32 = (g.wpr + 31) / 32;
         const int64_t warps = (int64_t)g.h * wpr32 * n;
-        alpha_to_bits_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b.bits, n);
+        { ipp::LaunchTimer _lt("alpha_to_bits_kernel", st); alpha_to_bits_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b.bits, n); }
         IPP_LAUNCH_CHECK();
     }
     const int rc = ccl_run(g, b, n, st);
     if (rc != IPP_OK) return rc;
     {
         const int64_t warps = (int64_t)g.h * g.wpr * n;
-        apply_keep_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b, n);
+        { ipp::LaunchTimer _lt("apply_keep_kernel", st); apply_keep_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(bgra, pitch, image_stride, g, b, n); }
         IPP_LAUNCH_CHECK();
     }
-    ccl_info_kernel<<<ceil_div(n, 128), 128, 0, st>>>(b, info_out, n);
+    { ipp::LaunchTimer _lt("ccl_info_kernel", st); ccl_info_kernel<<<ceil_div(n, 128), 128, 0, st>>>(b, info_out, n); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

@@ -410,11 +410,11 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     if (smem > 40 * 1024)
         IPP_CUDA(cudaFuncSetAttribute(chain_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g->crop_h, rows), n_frames);
-    chain_mask_kernel<<<grid, kMaskThreads, smem, st>>>(p);
+    { ipp::LaunchTimer _lt("chain_mask_kernel", st); chain_mask_kernel<<<grid, kMaskThreads, smem, st>>>(p); }
     IPP_LAUNCH_CHECK();
     rc = ccl_run(cg, b, n_frames, st);
     if (rc != IPP_OK) return rc;
-    ccl_info_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(b, info_out, n_frames);
+    { ipp::LaunchTimer _lt("ccl_info_kernel", st); ccl_info_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(b, info_out, n_frames); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -428,10 +428,10 @@ int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n
     IPP_REQUIRE(rots && workspace && bbox_out && n_rot >= 0 && total_tiles >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b1: bad arguments");
     if (n_rot == 0) return IPP_OK;
     const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
-    bbox_reset_kernel<<<ceil_div(n_rot, 256), 256, 0, st>>>(bbox_out, n_rot);
+    { ipp::LaunchTimer _lt("bbox_reset_kernel", st); bbox_reset_kernel<<<ceil_div(n_rot, 256), 256, 0, st>>>(bbox_out, n_rot); }
     IPP_LAUNCH_CHECK();
     if (total_tiles == 0) return IPP_OK;
-    chain_rot_bbox_kernel<<<total_tiles, 256, 0, st>>>(rots, n_rot, (const uint32_t*)workspace, cg.bits_stride, cg.wpr, bbox_out);
+    { ipp::LaunchTimer _lt("chain_rot_bbox_kernel", st); chain_rot_bbox_kernel<<<total_tiles, 256, 0, st>>>(rots, n_rot, (const uint32_t*)workspace, cg.bits_stride, cg.wpr, bbox_out); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -454,15 +454,15 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
     c.bits = (const uint32_t*)workspace; c.bits_stride = cg.bits_stride; c.wpr = cg.wpr;
     c.items = items; c.n_items = n_items; c.tables = tables; c.sprite_ws = sprite_ws;
     if (gather_tiles > 0) {
-        chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c);
+        { ipp::LaunchTimer _lt("chain_gather_kernel", st); chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }
     if (h_tiles > 0) {
-        chain_hpass_kernel<<<h_tiles, 256, 0, st>>>(c);
+        { ipp::LaunchTimer _lt("chain_hpass_kernel", st); chain_hpass_kernel<<<h_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }
     if (v_tiles > 0) {
-        chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c);
+        { ipp::LaunchTimer _lt("chain_vpass_kernel", st); chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }
     return IPP_OK;
@@ -494,7 +494,7 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
     if (smem > 48 * 1024)
         IPP_CUDA(cudaFuncSetAttribute(chain_paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(out_size, rows), n_items);
-    chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c);
+    { ipp::LaunchTimer _lt("chain_paste_kernel", st); chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

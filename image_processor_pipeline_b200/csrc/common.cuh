@@ -40,6 +40,17 @@ int sm_count();
         }                                                                           \
     } while (0)
 
+// RAII hook around every kernel launch of the library: counts launches and, when
+// ipp_timing_enable(1) was called, brackets the launch with CUDA events on the launching
+// stream so that ipp_timing_report() can give per-kernel device time.
+struct LaunchTimer {
+    LaunchTimer(const char* name, cudaStream_t st);
+    ~LaunchTimer();
+    const char* name_;
+    cudaStream_t st_;
+    int slot_;
+};
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- device helpers

@@ -146,7 +146,7 @@ extern "C" int ipp_hsv_ranges_to_alpha_u8(const uint8_t* bgr, int64_t src_pitch,
     if (smem > 40 * 1024)
         IPP_CUDA(cudaFuncSetAttribute(hsv_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(h, rows), n);
-    hsv_alpha_kernel<<<grid, kHsvThreads, smem, (cudaStream_t)stream>>>(p);
+    { ipp::LaunchTimer _lt("hsv_alpha_kernel", (cudaStream_t)stream); hsv_alpha_kernel<<<grid, kHsvThreads, smem, (cudaStream_t)stream>>>(p); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

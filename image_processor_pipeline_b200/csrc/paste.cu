@@ -168,7 +168,7 @@ extern "C" int ipp_paste_rgba_on_rgb_u8(const uint8_t* bg, int64_t bg_pitch, int
     const size_t smem = (size_t)rows * p.smem_row_stride;
     if (smem > 48 * 1024)
         IPP_CUDA(cudaFuncSetAttribute(paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    paste_kernel<<<ceil_div(crop_h, rows), kPasteThreads, smem, (cudaStream_t)stream>>>(p);
+    { ipp::LaunchTimer _lt("paste_kernel", (cudaStream_t)stream); paste_kernel<<<ceil_div(crop_h, rows), kPasteThreads, smem, (cudaStream_t)stream>>>(p); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

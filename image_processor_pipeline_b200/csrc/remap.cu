@@ -149,7 +149,7 @@ static int launch_rows(RowsParams& p, int n, cudaStream_t st) {
         IPP_CUDA(cudaFuncSetAttribute(rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 grid(ceil_div(p.out_h, rows), n);
-    rows_kernel<<<grid, kRowsThreads, smem, st>>>(p);
+    { ipp::LaunchTimer _lt("rows_kernel", st); rows_kernel<<<grid, kRowsThreads, smem, st>>>(p); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -226,7 +226,7 @@ int ipp_rot90_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int c
     IPP_REQUIRE(((src_pitch | dst_pitch) & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 3) == 0, IPP_ERR_BAD_ARG,
                 "ipp_rot90_rgba_u8: RGBA images must be 4-byte aligned");
     dim3 grid(ceil_div(h, 32), ceil_div(w, 32));
-    rot90_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, dst, dst_pitch, counter_clockwise);
+    { ipp::LaunchTimer _lt("rot90_rgba_kernel", (cudaStream_t)stream); rot90_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, dst, dst_pitch, counter_clockwise); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -281,7 +281,7 @@ int ipp_to_rgba_u8(const uint8_t* src, int64_t src_pitch, int w, int h, int src_
                 IPP_ERR_BAD_SHAPE, "ipp_to_rgba_u8: bad size/pitch");
     if (w == 0 || h == 0) return IPP_OK;
     dim3 grid(ceil_div(w, 256), h);
-    to_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, src_channels, swap_rb, dst, dst_pitch);
+    { ipp::LaunchTimer _lt("to_rgba_kernel", (cudaStream_t)stream); to_rgba_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_pitch, w, h, src_channels, swap_rb, dst, dst_pitch); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

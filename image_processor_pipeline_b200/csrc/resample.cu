@@ -180,18 +180,18 @@ extern "C" int ipp_resample_rgba_u8(const uint8_t* src, int64_t src_pitch, int s
         IPP_REQUIRE(tmp && (((uintptr_t)tmp) & 3) == 0, IPP_ERR_WORKSPACE, "ipp_resample_rgba_u8: tmp scratch missing");
         const int64_t tpitch = (int64_t)dst_w * 4;
         dim3 g1(ceil_div(dst_w, 32), ceil_div(src_h, 8));
-        resample_h_kernel<true, false><<<g1, 256, 0, st>>>(src, src_pitch, src_h, tmp, tpitch, dst_w, h_bounds, h_kk, h_ksize);
+        { ipp::LaunchTimer _lt("resample_h_kernel", st); resample_h_kernel<true, false><<<g1, 256, 0, st>>>(src, src_pitch, src_h, tmp, tpitch, dst_w, h_bounds, h_kk, h_ksize); }
         IPP_LAUNCH_CHECK();
         dim3 g2(ceil_div(dst_w, 32), ceil_div(dst_h, 8));
-        resample_v_kernel<false, true><<<g2, 256, 0, st>>>(tmp, tpitch, dst_w, dst, dst_pitch, dst_h, v_bounds, v_kk, v_ksize);
+        { ipp::LaunchTimer _lt("resample_v_kernel", st); resample_v_kernel<false, true><<<g2, 256, 0, st>>>(tmp, tpitch, dst_w, dst, dst_pitch, dst_h, v_bounds, v_kk, v_ksize); }
         IPP_LAUNCH_CHECK();
     } else if (do_h) {
         dim3 g1(ceil_div(dst_w, 32), ceil_div(src_h, 8));
-        resample_h_kernel<true, true><<<g1, 256, 0, st>>>(src, src_pitch, src_h, dst, dst_pitch, dst_w, h_bounds, h_kk, h_ksize);
+        { ipp::LaunchTimer _lt("resample_h_kernel", st); resample_h_kernel<true, true><<<g1, 256, 0, st>>>(src, src_pitch, src_h, dst, dst_pitch, dst_w, h_bounds, h_kk, h_ksize); }
         IPP_LAUNCH_CHECK();
     } else {
         dim3 g2(ceil_div(dst_w, 32), ceil_div(dst_h, 8));
-        resample_v_kernel<true, true><<<g2, 256, 0, st>>>(src, src_pitch, dst_w, dst, dst_pitch, dst_h, v_bounds, v_kk, v_ksize);
+        { ipp::LaunchTimer _lt("resample_v_kernel", st); resample_v_kernel<true, true><<<g2, 256, 0, st>>>(src, src_pitch, dst_w, dst, dst_pitch, dst_h, v_bounds, v_kk, v_ksize); }
         IPP_LAUNCH_CHECK();
     }
     return IPP_OK;

@@ -223,7 +223,7 @@ extern "C" {
 int ipp_bbox_reset(int32_t* bbox, int n, void* stream) {
     using namespace ipp;
     IPP_REQUIRE(bbox && n >= 1, IPP_ERR_BAD_ARG, "ipp_bbox_reset: bad arguments");
-    bbox_reset_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(bbox, n);
+    { ipp::LaunchTimer _lt("bbox_reset_kernel", (cudaStream_t)stream); bbox_reset_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(bbox, n); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -235,12 +235,12 @@ int ipp_alpha_bbox_u8(const uint8_t* img, int64_t pitch, int w, int h, int chann
     IPP_REQUIRE(channels >= 1 && channels <= 4 && w >= 0 && h >= 0 && pitch >= (int64_t)w * channels,
                 IPP_ERR_BAD_SHAPE, "ipp_alpha_bbox_u8: bad geometry");
     cudaStream_t st = (cudaStream_t)stream;
-    bbox_reset_kernel<<<1, 32, 0, st>>>(bbox_out, 1);
+    { ipp::LaunchTimer _lt("bbox_reset_kernel", st); bbox_reset_kernel<<<1, 32, 0, st>>>(bbox_out, 1); }
     IPP_LAUNCH_CHECK();
     if (w == 0 || h == 0) return IPP_OK;
     const int rowbytes = w * channels;
     dim3 grid(min(8, ceil_div(rowbytes, 256 * 16)), h);
-    alpha_bbox_kernel<<<grid, 256, 0, st>>>(img, pitch, w, h, channels, alpha_only, bbox_out);
+    { ipp::LaunchTimer _lt("alpha_bbox_kernel", st); alpha_bbox_kernel<<<grid, 256, 0, st>>>(img, pitch, w, h, channels, alpha_only, bbox_out); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
@@ -266,10 +266,10 @@ int ipp_rotate_rgba_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src
     if (mode == 0) {
         p.a0 = coef_fixed_host[0]; p.a1 = coef_fixed_host[1]; p.a2 = coef_fixed_host[2];
         p.a3 = coef_fixed_host[3]; p.a4 = coef_fixed_host[4]; p.a5 = coef_fixed_host[5];
-        rotate_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        { ipp::LaunchTimer _lt("rotate_nearest_kernel", (cudaStream_t)stream); rotate_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p); }
     } else {
         for (int i = 0; i < 6; ++i) p.m[i] = coef_f64_host[i];
-        rotate_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        { ipp::LaunchTimer _lt("rotate_bilinear_kernel", (cudaStream_t)stream); rotate_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p); }
     }
     IPP_LAUNCH_CHECK();
     return IPP_OK;

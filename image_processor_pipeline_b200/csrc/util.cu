@@ -1,6 +1,12 @@
 // util.cu — error plumbing, version, device queries of libippgpu.
 #include "common.cuh"
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace ipp {
 
 static thread_local char g_err[512] = "";
@@ -24,9 +30,79 @@ int sm_count() {
     return cached[dev];
 }
 
+// ---------------------------------------------------------------- launch accounting
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_timing{0};
+struct TimedLaunch {
+    const char* name;
+    cudaEvent_t a, b;
+};
+static std::mutex g_tmu;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_event_pool;
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(st), slot_(-1) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_tmu);
+    TimedLaunch t;
+    t.name = name;
+    if (!g_event_pool.empty()) {
+        t.a = g_event_pool.back().first;
+        t.b = g_event_pool.back().second;
+        g_event_pool.pop_back();
+    } else {
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+    }
+    cudaEventRecord(t.a, st);
+    g_timed.push_back(t);
+    slot_ = (int)g_timed.size() - 1;
+}
+
+LaunchTimer::~LaunchTimer() {
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lock(g_tmu);
+    if (slot_ < (int)g_timed.size()) cudaEventRecord(g_timed[slot_].b, st_);
+}
+
 }  // namespace ipp
 
 extern "C" {
+
+long long ipp_launch_count(void) { return ipp::g_launches.load(); }
+
+int ipp_timing_enable(int on) {
+    ipp::g_timing.store(on ? 1 : 0);
+    return IPP_OK;
+}
+
+// "name:launches:total_ms;..." for every kernel launched since the last report; synchronises.
+int ipp_timing_report(char* buf_host, int buflen) {
+    using namespace ipp;
+    IPP_REQUIRE(buf_host && buflen > 0, IPP_ERR_BAD_ARG, "ipp_timing_report: bad buffer");
+    std::lock_guard<std::mutex> lock(g_tmu);
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto& t : g_timed) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            auto& e = acc[t.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        g_event_pool.push_back({t.a, t.b});
+    }
+    g_timed.clear();
+    std::string out;
+    for (auto& kv : acc) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s:%d:%.6f;", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    snprintf(buf_host, buflen, "%s", out.c_str());
+    return IPP_OK;
+}
+
 
 int ipp_version(void) { return IPP_VERSION; }
 

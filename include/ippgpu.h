@@ -46,6 +46,13 @@ int ipp_version(void);
 const char* ipp_last_error_string(void);
 /* number of SMs of the current device (grid sizing on the host side) */
 int ipp_sm_count(int* out_host);
+/* launch accounting: total kernels launched by this library in the process; optional
+ * per-kernel device timing (CUDA events on the launching stream around every launch).
+ * ipp_timing_report writes "kernel:launches:total_ms;..." for the launches since the
+ * previous report into buf_host and synchronises on them. */
+long long ipp_launch_count(void);
+int ipp_timing_enable(int on);
+int ipp_timing_report(char* buf_host, int buflen);
 
 /* ---------------------------------------------------------------------------------
  * 1. flip x crop x copy as one load-address remap.
