@@ -129,8 +129,92 @@ def _rot_records(rots: List[dict]):
     return arr, tile
 
 
-def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random) -> ChainResult:
-    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB."""
+def plan_items(rots: List[dict], bbox: np.ndarray, params: ChainParams, rng, m: int, BW: int, BH: int) -> List[dict]:
+    """Host bookkeeping + draws of the steps after the rotation: getbbox fit
+    (rotations.py:99-110), symmetry selection (symmetry.py:97-126), overlay size / position /
+    label (overlays.py:104-149), square crop offset + label (crop_square.py:163-217).
+    Pure host code (no device access): ``bbox`` holds stage B1's result per rotated sprite.
+    Items are processed step-major in file-name order, drawing from ``rng`` exactly as the
+    reference's steps would."""
+    sprites = []
+    for r, bb in zip(rots, bbox):
+        cw, ch = r["plan"].size
+        if r["original"] or bb[2] <= 0:          # original is saved un-cropped; empty bbox => un-cropped canvas
+            fit = (0, 0, cw, ch)
+        else:
+            fit = (int(bb[0]), int(bb[1]), int(bb[2] - bb[0]), int(bb[3] - bb[1]))
+        sprites.append(dict(r, fit=fit))
+
+    pool = params.pool if params.pool else ["o", "h", "v", "hv"]
+    if any(s not in SYM_ORDER for s in pool):
+        raise ValueError(f"`pool` contient des éléments invalides : {[s for s in pool if s not in SYM_ORDER]}")
+    choose = len(pool) if params.choose_random is None else params.choose_random
+    if choose < 0:
+        raise ValueError("`choose_random` doit être >= 0")
+    variants = []
+    for s in sprites:
+        filt = rng.sample(pool, choose)
+        if params.sym_include_original and "o" not in set(filt):
+            filt.append("o")
+        for sym in sorted(set(filt), key=SYM_ORDER.get):       # next step lists the directory sorted by name
+            variants.append(dict(s, sym=sym))
+
+    planned = []
+    for k, v in enumerate(variants):
+        bg = k % m
+        ratio = rng.uniform(params.scale_min, params.scale_max)
+        sw, sh = v["fit"][2], v["fit"][3]
+        try:
+            nw, nh = hostmath.overlay_size(sw, sh, BW, BH, ratio)
+            if nw <= 0 or nh <= 0:
+                raise ValueError("height and width must be > 0")
+            pos_x = rng.randint(0, BW - nw)
+            pos_y = rng.randint(0, BH - nh)
+        except ValueError:
+            continue                                            # overlays.py:151-153: print + return None
+        box = np.array([pos_x, pos_y, pos_x + nw, pos_y + nh]).reshape(1, 4)
+        y = np.empty_like(box, dtype=np.float32)               # xyxy2xywhn, float32 store (overlays.py:146)
+        y[..., 0] = ((box[..., 0] + box[..., 2]) / 2) / BW
+        y[..., 1] = ((box[..., 1] + box[..., 3]) / 2) / BH
+        y[..., 2] = (box[..., 2] - box[..., 0]) / BW
+        y[..., 3] = (box[..., 3] - box[..., 1]) / BH
+        cx, cy, wn, hn = y[0]
+        label1 = f"{params.yolo_class_id} {cx:.6f} {cy:.6f} {wn:.6f} {hn:.6f}"
+        planned.append(dict(v, bg=bg, ratio=ratio, new=(nw, nh), pos=(pos_x, pos_y), label1=label1))
+
+    finals = []
+    for it in planned:
+        data = np.loadtxt([it["label1"]], ndmin=2)             # crop_square.py:62-65
+        cls, boxes = data[:, 0].astype(int), data[:, 1:5].astype(float)
+        try:
+            crop_size, (lbx, ubx), (lby, uby) = hostmath.square_crop_bounds(boxes, BW, BH)
+        except RuntimeError:
+            continue
+        x0 = rng.randint(lbx, ubx)
+        y0 = rng.randint(lby, uby)
+        absolute = hostmath.xywhn2xyxy_f32(boxes, BW, BH)
+        shifted = absolute - np.array([[x0, y0, x0, y0]])
+        clipped = np.clip(shifted, 0, crop_size)
+        valid = (clipped[:, 0] < clipped[:, 2]) & (clipped[:, 1] < clipped[:, 3])
+        if not valid.any():
+            continue
+        kept = clipped[valid]
+        nb = np.empty_like(kept, dtype=np.float32)
+        nb[..., 0] = ((kept[..., 0] + kept[..., 2]) / 2) / crop_size
+        nb[..., 1] = ((kept[..., 1] + kept[..., 3]) / 2) / crop_size
+        nb[..., 2] = (kept[..., 2] - kept[..., 0]) / crop_size
+        nb[..., 3] = (kept[..., 3] - kept[..., 1]) / crop_size
+        finals.append(dict(it, sq=(x0, y0, crop_size), label=hostmath.format_label_rows(cls[valid], nb)))
+
+    return finals
+
+
+def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None):
+    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB.
+    ``_shard`` (set by sharding.run_chain_sharded): this call holds frames [lo, hi) of a larger
+    job; stage-A / B1 metadata is gathered across ranks, the plan is made for ALL items with
+    the shared ``rng`` and only the items of the local frames are executed.  Returns then
+    (ChainResult, global item indices)."""
     if not (frames.is_cuda and backgrounds.is_cuda):
         raise RuntimeError("run_chain needs CUDA tensors (there is no CPU fallback)")
     if frames.dtype != torch.uint8 or backgrounds.dtype != torch.uint8 or frames.dim() != 4 or backgrounds.dim() != 4:
@@ -154,93 +238,39 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                             ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
         info = info_d.cpu().numpy()                                   # sync #1
+        lo = 0
+        if _shard is not None:
+            lo = _shard["lo"]
+            info = _shard["gather"](info)                             # 32 bytes of metadata per frame
 
         # ------------------------------------------------------------------ rotation step (host) + stage B1
         rots = plan_rotations(info, params, rng)
-        if not rots:
+        if not rots and _shard is None:
             return ChainResult(torch.empty((0, cs, cs, 3), dtype=torch.uint8, device=dev), [], [])
+        all_rots = rots
+        if _shard is not None:                                        # execute only the sprites of local frames
+            rots = [dict(r, frame=r["frame"] - lo) for r in all_rots if lo <= r["frame"] < _shard["hi"]]
         rot_arr, rot_tiles = _rot_records(rots)
         rot_d = torch.from_numpy(rot_arr.view(np.uint8)).to(dev)
         bbox_d = torch.empty((len(rots), 4), dtype=torch.int32, device=dev)
-        _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots), rot_tiles, ws.data_ptr(),
-                                             bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
+        if len(rots):
+            _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots), rot_tiles, ws.data_ptr(),
+                                                 bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
         bbox = bbox_d.cpu().numpy()                                   # sync #2
+        if _shard is not None:
+            bbox = _shard["gather"](bbox)                             # 16 bytes per sprite, rank order == item order
+            rots = all_rots
 
-        # ------------------------------------------------------------------ host: fit, symmetry, overlay, square-crop plans
-        sprites = []
-        for r, bb in zip(rots, bbox):
-            cw, ch = r["plan"].size
-            if r["original"] or bb[2] <= 0:          # original is saved un-cropped; empty bbox => un-cropped canvas
-                fit = (0, 0, cw, ch)
-            else:
-                fit = (int(bb[0]), int(bb[1]), int(bb[2] - bb[0]), int(bb[3] - bb[1]))
-            sprites.append(dict(r, fit=fit))
+        finals = plan_items(rots, bbox, params, rng, m, BW, BH)
 
-        pool = params.pool if params.pool else ["o", "h", "v", "hv"]
-        if any(s not in SYM_ORDER for s in pool):
-            raise ValueError(f"`pool` contient des éléments invalides : {[s for s in pool if s not in SYM_ORDER]}")
-        choose = len(pool) if params.choose_random is None else params.choose_random
-        if choose < 0:
-            raise ValueError("`choose_random` doit être >= 0")
-        variants = []
-        for s in sprites:
-            filt = rng.sample(pool, choose)
-            if params.sym_include_original and "o" not in set(filt):
-                filt.append("o")
-            for sym in sorted(set(filt), key=SYM_ORDER.get):       # next step lists the directory sorted by name
-                variants.append(dict(s, sym=sym))
-
-        planned = []
-        for k, v in enumerate(variants):
-            bg = k % m
-            ratio = rng.uniform(params.scale_min, params.scale_max)
-            sw, sh = v["fit"][2], v["fit"][3]
-            try:
-                nw, nh = hostmath.overlay_size(sw, sh, BW, BH, ratio)
-                if nw <= 0 or nh <= 0:
-                    raise ValueError("height and width must be > 0")
-                pos_x = rng.randint(0, BW - nw)
-                pos_y = rng.randint(0, BH - nh)
-            except ValueError:
-                continue                                            # overlays.py:151-153: print + return None
-            box = np.array([pos_x, pos_y, pos_x + nw, pos_y + nh]).reshape(1, 4)
-            y = np.empty_like(box, dtype=np.float32)               # xyxy2xywhn, float32 store (overlays.py:146)
-            y[..., 0] = ((box[..., 0] + box[..., 2]) / 2) / BW
-            y[..., 1] = ((box[..., 1] + box[..., 3]) / 2) / BH
-            y[..., 2] = (box[..., 2] - box[..., 0]) / BW
-            y[..., 3] = (box[..., 3] - box[..., 1]) / BH
-            cx, cy, wn, hn = y[0]
-            label1 = f"{params.yolo_class_id} {cx:.6f} {cy:.6f} {wn:.6f} {hn:.6f}"
-            planned.append(dict(v, bg=bg, ratio=ratio, new=(nw, nh), pos=(pos_x, pos_y), label1=label1))
-
-        finals = []
-        for it in planned:
-            data = np.loadtxt([it["label1"]], ndmin=2)             # crop_square.py:62-65
-            cls, boxes = data[:, 0].astype(int), data[:, 1:5].astype(float)
-            try:
-                crop_size, (lbx, ubx), (lby, uby) = hostmath.square_crop_bounds(boxes, BW, BH)
-            except RuntimeError:
-                continue
-            x0 = rng.randint(lbx, ubx)
-            y0 = rng.randint(lby, uby)
-            absolute = hostmath.xywhn2xyxy_f32(boxes, BW, BH)
-            shifted = absolute - np.array([[x0, y0, x0, y0]])
-            clipped = np.clip(shifted, 0, crop_size)
-            valid = (clipped[:, 0] < clipped[:, 2]) & (clipped[:, 1] < clipped[:, 3])
-            if not valid.any():
-                continue
-            kept = clipped[valid]
-            nb = np.empty_like(kept, dtype=np.float32)
-            nb[..., 0] = ((kept[..., 0] + kept[..., 2]) / 2) / crop_size
-            nb[..., 1] = ((kept[..., 1] + kept[..., 3]) / 2) / crop_size
-            nb[..., 2] = (kept[..., 2] - kept[..., 0]) / crop_size
-            nb[..., 3] = (kept[..., 3] - kept[..., 1]) / crop_size
-            finals.append(dict(it, sq=(x0, y0, crop_size), label=hostmath.format_label_rows(cls[valid], nb)))
-
+        own = list(range(len(finals)))
+        if _shard is not None:
+            own = [i for i, f in enumerate(finals) if lo <= f["frame"] < _shard["hi"]]
+            finals = [dict(finals[i], frame=finals[i]["frame"] - lo) for i in own]
         K = len(finals)
         out = torch.empty((K, cs, cs, 3), dtype=torch.uint8, device=dev)
         if K == 0:
-            return ChainResult(out, [], [])
+            return ChainResult(out, [], []) if _shard is None else (ChainResult(out, [], []), own)
 
         # ------------------------------------------------------------------ item records, tables, sprite workspace
         items = np.zeros(K, dtype=ITEM_DTYPE)
@@ -311,7 +341,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
 
     records = [dict(frame=it["frame"], rot_index=it["rot_index"], angle=it["angle"], sym=it["sym"], bg=it["bg"],
                     ratio=it["ratio"], new=it["new"], pos=it["pos"], sq=it["sq"], fit=it["fit"], cc=it["cc"]) for it in finals]
-    return ChainResult(out, [it["label"] for it in finals], records)
+    res = ChainResult(out, [it["label"] for it in finals], records)
+    return res if _shard is None else (res, own)
 
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
