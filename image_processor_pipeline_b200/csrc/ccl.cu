@@ -160,61 +160,109 @@ __device__ __forceinline__ int segment_end(uint32_t C, int i) {
     return above ? (__ffs(above) - 1) : 32;
 }
 
-// ---- phase 3: per-segment pixel counts onto the root, compress run-start entries
+// ---- phase 3: per-segment pixel counts onto the root, compress run-start entries.
+// Lanes of a warp cover neighbouring block groups, so most of their segments belong to the
+// same component: counts are combined per root inside the warp (match.any + redux) and a
+// single atomicAdd per distinct root and round reaches L2 — a big blob costs ~1 atomic per
+// warp instead of one per run segment (same-address atomics serialise in L2).
 __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const CclBuffers b, int n) {
     const GroupIdx t = group_index(g, n);
-    if (!t.ok) return;
-    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
-    const uint32_t F = b.fbits[cf + t.k];
-    if (F == 0u) return;
-    const uint32_t C = b.cbits[cf + t.k];
-    const uint32_t* crow = b.cbits + cf;
-    const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
-    const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
-    const uint64_t p0 = load_px64(r0, t.k, g.wpr);
-    const uint64_t p1 = ((2 * t.by + 1) < g.h) ? load_px64(r0 + g.wpr, t.k, g.wpr) : 0ull;
-    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
-    int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
-    const int rowbase = t.by * g.bw, gb0 = t.k << 5;
-    uint32_t starts = F & (~C | 1u);
-    int nfg = 0;
-    while (starts) {
-        const int i = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const int e = segment_end(C, i);
-        const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
-        const int cnt = __popcll(p0 & pm) + __popcll(p1 & pm);
-        const bool own = ((C >> i) & 1u) == 0u;
-        const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
-        const int root = find_root(L, rowbase + s);
-        atomicAdd(&A[root], cnt);
-        if (own) L[rowbase + gb0 + i] = root;
-        nfg += cnt;
-    }
-    if (nfg) atomicAdd(&b.acc[8 * t.img + 4], nfg);
-}
-
-// ---- phase 4: argmax over roots of (area, smallest block index)
-__global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
-    if (!t.ok) return;
-    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
-    uint32_t S = b.fbits[cf] & ~b.cbits[cf];
-    if (S == 0u) return;
-    const int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
-    const int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
-    const int base = t.by * g.bw + (t.k << 5);
-    unsigned long long best = 0ull;
-    while (S) {
-        const int i = __ffs(S) - 1;
-        S &= S - 1;
-        const int bi = base + i;
-        if (L[bi] == bi) {
-            const unsigned long long key = ((unsigned long long)(uint32_t)A[bi] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
-            best = key > best ? key : best;
+    uint32_t starts = 0, C = 0;
+    uint64_t p0 = 0, p1 = 0;
+    const uint32_t* crow = nullptr;
+    int32_t* L = nullptr;
+    int32_t* A = nullptr;
+    int rowbase = 0, gb0 = 0;
+    if (t.ok) {
+        const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
+        const uint32_t F = b.fbits[cf + t.k];
+        if (F) {
+            C = b.cbits[cf + t.k];
+            crow = b.cbits + cf;
+            const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+            const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+            p0 = load_px64(r0, t.k, g.wpr);
+            p1 = ((2 * t.by + 1) < g.h) ? load_px64(r0 + g.wpr, t.k, g.wpr) : 0ull;
+            L = b.label + (int64_t)t.img * g.lab_stride;
+            A = b.area + (int64_t)t.img * g.lab_stride;
+            rowbase = t.by * g.bw;
+            gb0 = t.k << 5;
+            starts = F & (~C | 1u);
         }
     }
-    if (best) atomicMax(&b.best[t.img], best);
+    int nfg = 0;
+    const int lane = threadIdx.x & 31;
+    while (__any_sync(0xffffffffu, starts != 0u)) {
+        long long key = -1 - (long long)lane;          // unique per lane when it has nothing to add
+        int cnt = 0;
+        int32_t* slot = nullptr;
+        if (starts) {
+            const int i = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int e = segment_end(C, i);
+            const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
+            cnt = __popcll(p0 & pm) + __popcll(p1 & pm);
+            const bool own = ((C >> i) & 1u) == 0u;
+            const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
+            const int root = find_root(L, rowbase + s);
+            if (own) L[rowbase + gb0 + i] = root;
+            slot = A + root;
+            key = (long long)(uintptr_t)slot;
+            nfg += cnt;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const int sum = __reduce_add_sync(peers, cnt);
+        if (slot && lane == __ffs(peers) - 1) atomicAdd(slot, sum);
+    }
+    // foreground pixel count per image: one atomic per warp when the warp sits in one image
+    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
+    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
+        const int tot = __reduce_add_sync(0xffffffffu, nfg);
+        if (lane == 0 && tot) atomicAdd(&b.acc[8 * img0 + 4], tot);
+    } else if (nfg) {
+        atomicAdd(&b.acc[8 * t.img + 4], nfg);
+    }
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// ---- phase 4: argmax over roots of (area, smallest block index); one atomic per warp
+__global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const CclBuffers b, int n) {
+    const GroupIdx t = group_index(g, n);
+    unsigned long long best = 0ull;
+    if (t.ok) {
+        const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
+        uint32_t S = b.fbits[cf] & ~b.cbits[cf];
+        if (S) {
+            const int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+            const int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+            const int base = t.by * g.bw + (t.k << 5);
+            while (S) {
+                const int i = __ffs(S) - 1;
+                S &= S - 1;
+                const int bi = base + i;
+                if (L[bi] == bi) {
+                    const unsigned long long key =
+                        ((unsigned long long)(uint32_t)A[bi] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
+                    best = key > best ? key : best;
+                }
+            }
+        }
+    }
+    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
+    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
+        const unsigned long long m = warp_max_u64(best);
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(&b.best[img0], m);
+    } else if (best) {
+        atomicMax(&b.best[t.img], best);
+    }
 }
 
 // ---- phase 5: keep-mask (in place) + bounding box of the kept pixels
