@@ -38,6 +38,21 @@ class ChainGeom(C.Structure):
                 ("ranges", HsvRange * IPP_MAX_HSV_RANGES)]
 
 
+class PlanParams(C.Structure):
+    _fields_ = [("num_rotations", C.c_int32), ("include_original", C.c_int32),
+                ("angle_min", C.c_double), ("angle_max", C.c_double),
+                ("pool", C.c_int32 * 4), ("pool_len", C.c_int32),
+                ("choose_random", C.c_int32), ("sym_include_original", C.c_int32),
+                ("yolo_class_id", C.c_int32),
+                ("scale_min", C.c_double), ("scale_max", C.c_double),
+                ("bg_w", C.c_int32), ("bg_h", C.c_int32), ("n_bgs", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PlanTotals(C.Structure):
+    _fields_ = [("table_ints", C.c_int64), ("table_rows", C.c_int64), ("sprite_ws_bytes", C.c_int64),
+                ("gather_tiles", C.c_int32), ("h_tiles", C.c_int32), ("v_tiles", C.c_int32), ("labels_bytes", C.c_int32)]
+
+
 _u8p = C.c_void_p      # device pointers travel as integers
 _i32p = C.c_void_p
 _vp = C.c_void_p
@@ -73,6 +88,11 @@ PROTOTYPES = {
     "ipp_keep_largest_cc_u8": (_int, [_u8p, _i64, _int, _int, _i32p, _vp, _i64, _int, _i64, _vp]),
     "ipp_boxes_square_crop_f32": (_int, [_vp, _i32p, _i32p, _vp, _i32p, _int, _vp]),
     "ipp_boxes_xyxy2xywhn_f32": (_int, [_i32p, _i32p, _vp, _int, _vp]),
+    "ipp_plan_rotations_host": (_int, [_vp, _int, C.POINTER(PlanParams), _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "ipp_plan_items_host": (_int, [_vp, _vp, _int, _vp, C.POINTER(PlanParams), _vp, _vp, _vp, _vp, _int, _vp,
+                                   _vp, _int, C.POINTER(PlanTotals)]),
+    "ipp_lanczos_row_host": (_int, [_int, _int, _int, _vp, _vp]),
+    "ipp_chain_tables": (_int, [_vp, _int, _int, _i32p, _i32p, _int, C.c_double, _vp]),
     "ipp_chain_mask_workspace_bytes": (_i64, [C.POINTER(ChainGeom), _int]),
     "ipp_chain_stage_a": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _i32p, _vp, _i64, _int, _vp]),
     "ipp_chain_stage_b1": (_int, [C.POINTER(ChainGeom), _vp, _int, _int, _vp, _i32p, _vp]),

@@ -20,12 +20,16 @@ Semantics kept from the reference:
 Device work is three stages separated only where a data-dependent size has to reach
 the host RNG (randint bounds depend on the sprite size): stage A (mask + largest
 component), stage B1 (rotated bbox), stage B2 + C (sprite gather, LANCZOS, paste + crop).
+
+Two interchangeable host planners do the bookkeeping + draws between the stages:
+``planner="native"`` (default; C++ in libippgpu, planner.cu — it advances the very state
+of the Python generator it is given) and ``planner="python"`` (the readable twin below).
 """
 from __future__ import annotations
 
 import ctypes as C
 import random as _random
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -34,7 +38,11 @@ import torch
 from . import _native, hostmath
 
 SYM_ORDER = {"h": 0, "hv": 1, "o": 2, "v": 3}        # file-name order of `<stem>_<sym>.png`
+SYM_CODE = {"o": 0, "h": 1, "v": 2, "hv": 3}
+SYM_NAME = ["o", "h", "v", "hv"]
 KIND = {"affine": 0, "copy": 1, "rot180": 2, "rot90": 3, "rot270": 4}
+AMBIGUITY_EPS = 2e-7          # device LANCZOS tables: re-derive rows this close to a rounding boundary
+AMB_CAPACITY = 4096
 
 ROT_DTYPE = np.dtype([(n, "<i4") for n in
                       ("frame", "cc_x", "cc_y", "cc_w", "cc_h", "kind", "a0", "a1", "a2", "a3", "a4", "a5",
@@ -43,10 +51,11 @@ ITEM_DTYPE = np.dtype([(n, "<i4") for n in
                        ("frame", "bg", "cc_x", "cc_y", "cc_w", "cc_h", "kind", "a0", "a1", "a2", "a3", "a4", "a5",
                         "fit_x0", "fit_y0", "spr_w", "spr_h", "flip_h", "flip_v", "new_w", "new_h", "pos_x", "pos_y",
                         "sq_x0", "sq_y0", "sq_size", "h_ksize", "v_ksize", "hb_off", "hk_off", "vb_off", "vk_off",
-                        "gather_tile_start", "h_tile_start", "v_tile_start",
-                        "_p0", "_p1", "_p2", "_p3", "_p4")] +
+                        "gather_tile_start", "h_tile_start", "v_tile_start", "tab_row_start", "out_slot",
+                        "_p0", "_p1", "_p2")] +
                       [("rot_off", "<i8"), ("tmp_off", "<i8"), ("spr_off", "<i8")])
-assert ROT_DTYPE.itemsize == 64 and ITEM_DTYPE.itemsize == 184
+AUX_DTYPE = np.dtype([("ratio", "<f8"), ("rot", "<i4"), ("sym", "<i4")])
+assert ROT_DTYPE.itemsize == 64 and ITEM_DTYPE.itemsize == 184 and AUX_DTYPE.itemsize == 16
 
 
 @dataclass
@@ -71,12 +80,46 @@ class ChainParams:
     scale_min: float = 0.15
     scale_max: float = 0.30
 
+    def resolved_pool(self):
+        pool = self.pool if self.pool else ["o", "h", "v", "hv"]
+        bad = [s for s in pool if s not in SYM_ORDER]
+        if bad:
+            raise ValueError(f"`pool` contient des éléments invalides : {bad}")
+        choose = len(pool) if self.choose_random is None else self.choose_random
+        if choose < 0:
+            raise ValueError(f"`choose_random` ({choose}) doit être >= 0.")
+        if choose > len(pool):
+            raise ValueError("Sample larger than population or is negative")     # what random.sample raises
+        return pool, choose
 
-@dataclass
+
 class ChainResult:
-    images: torch.Tensor                 # [K, cs, cs, 3] uint8 RGB on the device
-    labels: List[str]                    # YOLO label file content per image (crop_square.py:98-101)
-    records: List[dict] = field(default_factory=list)   # provenance / parameters per image
+    """images: [K, cs, cs, 3] uint8 RGB (device, or host for run_chain_host); labels: YOLO label
+    file content per image (crop_square.py:98-101); records: provenance per image (built lazily)."""
+
+    def __init__(self, images, labels, records=None, record_arrays=None):
+        self.images = images
+        self.labels = labels
+        self._records = records
+        self._arrays = record_arrays
+
+    @property
+    def records(self) -> List[dict]:
+        if self._records is None:
+            items, aux, rot_index, angles = self._arrays
+            recs = []
+            for i in range(len(items)):
+                it, ax = items[i], aux[i]
+                r = int(ax["rot"])
+                ang = float(angles[r])
+                recs.append(dict(frame=int(it["frame"]), rot_index=int(rot_index[r]), angle=None if ang != ang else ang,
+                                 sym=SYM_NAME[int(ax["sym"])], bg=int(it["bg"]), ratio=float(ax["ratio"]),
+                                 new=(int(it["new_w"]), int(it["new_h"])), pos=(int(it["pos_x"]), int(it["pos_y"])),
+                                 sq=(int(it["sq_x0"]), int(it["sq_y0"]), int(it["sq_size"])),
+                                 fit=(int(it["fit_x0"]), int(it["fit_y0"]), int(it["spr_w"]), int(it["spr_h"])),
+                                 cc=(int(it["cc_x"]), int(it["cc_y"]), int(it["cc_w"]), int(it["cc_h"]))))
+            self._records = recs
+        return self._records
 
 
 def _geom_struct(frame_w, frame_h, rect, bg_w, bg_h, ranges):
@@ -94,10 +137,7 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-class ChainPlanError(RuntimeError):
-    pass
-
-
+# =========================================================================== python planner
 def plan_rotations(info: np.ndarray, p: ChainParams, rng) -> List[dict]:
     """Rotation step bookkeeping + draws (rotations.py:77-119).  info = stage-A rows."""
     rots = []
@@ -209,16 +249,179 @@ def plan_items(rots: List[dict], bbox: np.ndarray, params: ChainParams, rng, m: 
     return finals
 
 
-def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None):
+def _python_plan_to_arrays(rots: List[dict], finals: List[dict]):
+    """The python planner's dict records -> the arrays the native planner produces."""
+    rot_id = {id(r["plan"]): i for i, r in enumerate(rots)}
+    items = np.zeros(len(finals), dtype=ITEM_DTYPE)
+    aux = np.zeros(len(finals), dtype=AUX_DTYPE)
+    for i, it in enumerate(finals):
+        plan = it["plan"]
+        a = plan.fixed if plan.kind == "affine" else (0,) * 6
+        rec = items[i]
+        rec["frame"], rec["bg"] = it["frame"], it["bg"]
+        rec["cc_x"], rec["cc_y"], rec["cc_w"], rec["cc_h"] = it["cc"]
+        rec["kind"] = KIND[plan.kind]
+        for j in range(6):
+            rec[f"a{j}"] = a[j]
+        rec["fit_x0"], rec["fit_y0"], rec["spr_w"], rec["spr_h"] = it["fit"]
+        rec["flip_h"] = int(it["sym"] in ("h", "hv"))
+        rec["flip_v"] = int(it["sym"] in ("v", "hv"))
+        rec["new_w"], rec["new_h"] = it["new"]
+        rec["pos_x"], rec["pos_y"] = it["pos"]
+        rec["sq_x0"], rec["sq_y0"], rec["sq_size"] = it["sq"]
+        aux[i] = (it["ratio"], rot_id[id(plan)], SYM_CODE[it["sym"]])
+    return items, aux
+
+
+# =========================================================================== native planner
+def _plan_params(p: ChainParams, BW: int, BH: int, m: int) -> _native.PlanParams:
+    pool, choose = p.resolved_pool()
+    if len(pool) > 4 or len(set(pool)) != len(pool):
+        raise NotImplementedError("symmetry pool must hold at most four distinct entries")
+    pp = _native.PlanParams()
+    pp.num_rotations, pp.include_original = int(p.num_rotations), int(bool(p.include_original))
+    pp.angle_min, pp.angle_max = float(p.angle_min), float(p.angle_max)
+    for i, s in enumerate(pool):
+        pp.pool[i] = SYM_CODE[s]
+    pp.pool_len, pp.choose_random = len(pool), choose
+    pp.sym_include_original = int(bool(p.sym_include_original))
+    pp.yolo_class_id = int(p.yolo_class_id)
+    pp.scale_min, pp.scale_max = float(p.scale_min), float(p.scale_max)
+    pp.bg_w, pp.bg_h, pp.n_bgs = BW, BH, m
+    return pp
+
+
+class _RngBridge:
+    """Lends the state of a Python ``random`` generator (module or Random instance) to the C++
+    planner and writes the advanced state back."""
+
+    def __init__(self, rng):
+        self.rng = rng
+        st = rng.getstate()
+        self.version, self.gauss = st[0], st[2]
+        self.mt = np.array(st[1][:624], dtype=np.uint32)
+        self.idx = np.array([st[1][624]], dtype=np.int32)
+
+    def commit(self):
+        self.rng.setstate((self.version, tuple(self.mt.tolist()) + (int(self.idx[0]),), self.gauss))
+
+
+def native_plan_rotations(info: np.ndarray, pp: _native.PlanParams, bridge: _RngBridge):
+    lib = _native.load()
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    cap = max(1, info.shape[0] * (pp.num_rotations + pp.include_original))
+    rots = np.zeros(cap, dtype=ROT_DTYPE)
+    angles = np.zeros(cap, dtype=np.float64)
+    rot_index = np.zeros(cap, dtype=np.int32)
+    n_rot = C.c_int32(0)
+    tiles = C.c_int32(0)
+    _native.check(lib.ipp_plan_rotations_host(info.ctypes.data, info.shape[0], C.byref(pp), bridge.mt.ctypes.data,
+                                              bridge.idx.ctypes.data, rots.ctypes.data, angles.ctypes.data,
+                                              rot_index.ctypes.data, cap, C.addressof(n_rot), C.addressof(tiles)),
+                  "ipp_plan_rotations_host")
+    n = n_rot.value
+    return rots[:n], angles[:n], rot_index[:n]
+
+
+def native_plan_items(rots: np.ndarray, rot_index: np.ndarray, bbox: np.ndarray, pp: _native.PlanParams, bridge: _RngBridge):
+    lib = _native.load()
+    n_rot = len(rots)
+    cap = max(1, n_rot * 4)
+    items = np.zeros(cap, dtype=ITEM_DTYPE)
+    aux = np.zeros(cap, dtype=AUX_DTYPE)
+    labels = np.zeros(cap * 64, dtype=np.uint8)
+    is_orig = np.ascontiguousarray(rot_index == 0, dtype=np.int32)
+    bbox = np.ascontiguousarray(bbox, dtype=np.int32).reshape(-1, 4)
+    rots = np.ascontiguousarray(rots)
+    n_items = C.c_int32(0)
+    totals = _native.PlanTotals()
+    _native.check(lib.ipp_plan_items_host(rots.ctypes.data, is_orig.ctypes.data, n_rot, bbox.ctypes.data, C.byref(pp),
+                                          bridge.mt.ctypes.data, bridge.idx.ctypes.data, items.ctypes.data, aux.ctypes.data,
+                                          cap, C.addressof(n_items), labels.ctypes.data, labels.size, C.byref(totals)),
+                  "ipp_plan_items_host")
+    k = n_items.value
+    text = labels[:totals.labels_bytes].tobytes().decode("ascii")
+    lab = text.split("\0")[:k] if k else []
+    return items[:k].copy(), aux[:k].copy(), lab
+
+
+def _excl(a):
+    return np.concatenate([[0], np.cumsum(a)[:-1]]) if len(a) else np.zeros(0, np.int64)
+
+
+def lanczos_ksize(n_in, n_out):
+    """libImaging precompute_coeffs: ksize = ceil(3 * max(in/out, 1)) * 2 + 1 (vectorised)."""
+    scale = np.asarray(n_in, dtype=np.float64) / np.asarray(n_out, dtype=np.float64)
+    return (np.ceil(3.0 * np.maximum(scale, 1.0)).astype(np.int64) * 2 + 1)
+
+
+def _layout(items: np.ndarray):
+    """Tile starts, table offsets and workspace offsets of an item array (numpy, vectorised) —
+    the device-side schedule of the variable-sized sprites."""
+    k = len(items)
+    sw, sh, nw, nh = (items[n].astype(np.int64) for n in ("spr_w", "spr_h", "new_w", "new_h"))
+    hk = np.where(sw != nw, lanczos_ksize(sw, nw), 0)
+    vk = np.where(sh != nh, lanczos_ksize(sh, nh), 0)
+    items["h_ksize"], items["v_ksize"] = hk, vk
+    hsz = np.where(hk > 0, 2 * nw + nw * hk, 0)
+    vsz = np.where(vk > 0, 2 * nh + nh * vk, 0)
+    start = _excl(hsz + vsz)
+    items["hb_off"] = np.where(hk > 0, start, 0)
+    items["hk_off"] = np.where(hk > 0, start + 2 * nw, 0)
+    items["vb_off"] = np.where(vk > 0, start + hsz, 0)
+    items["vk_off"] = np.where(vk > 0, start + hsz + 2 * nh, 0)
+    rows = np.where(hk > 0, nw, 0) + np.where(vk > 0, nh, 0)
+    items["tab_row_start"] = _excl(rows)
+    gt = ((sw + 31) // 32) * ((sh + 31) // 32)
+    ht = ((nw + 31) // 32) * ((sh + 7) // 8)
+    vt = ((nw + 31) // 32) * ((nh + 7) // 8)
+    items["gather_tile_start"], items["h_tile_start"], items["v_tile_start"] = _excl(gt), _excl(ht), _excl(vt)
+    a256 = lambda v: (v + 255) // 256 * 256
+    s0, s1, s2 = a256(sw * sh * 4), a256(nw * sh * 4), a256(nw * nh * 4)
+    base = _excl(s0 + s1 + s2)
+    items["rot_off"], items["tmp_off"], items["spr_off"] = base, base + s0, base + s0 + s1
+    items["out_slot"] = np.arange(k)
+    if int((hsz + vsz).sum()) >= 2 ** 31:
+        raise NotImplementedError("coefficient tables exceed 2^31 entries; use a smaller batch")
+    return dict(table_ints=int((hsz + vsz).sum()), max_rows=int(rows.max()) if k else 0,
+                ws=int((s0 + s1 + s2).sum()), gt=int(gt.sum()), ht=int(ht.sum()), vt=int(vt.sum()))
+
+
+def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
+    """Exact LANCZOS tables on the host (C library sin) for every item."""
+    tab = np.zeros(max(1, n_ints), dtype=np.int32)
+    for it in items:
+        for axis in (0, 1):
+            ks = int(it["v_ksize" if axis else "h_ksize"])
+            if not ks:
+                continue
+            n_in, n_out = (int(it["spr_h"]), int(it["new_h"])) if axis else (int(it["spr_w"]), int(it["new_w"]))
+            bo, ko = (int(it["vb_off"]), int(it["vk_off"])) if axis else (int(it["hb_off"]), int(it["hk_off"]))
+            b = np.empty((n_out, 2), np.int32)
+            kk = np.empty((n_out, ks), np.int32)
+            _native.check(lib.ipp_lanczos_coeffs_host(n_in, n_out, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_coeffs_host")
+            tab[bo:bo + 2 * n_out] = b.ravel()
+            tab[ko:ko + n_out * ks] = kk.ravel()
+    return tab
+
+
+# =========================================================================== the chain
+def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
+              planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS):
     """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB.
-    ``_shard`` (set by sharding.run_chain_sharded): this call holds frames [lo, hi) of a larger
-    job; stage-A / B1 metadata is gathered across ranks, the plan is made for ALL items with
-    the shared ``rng`` and only the items of the local frames are executed.  Returns then
-    (ChainResult, global item indices)."""
+    Returns a ChainResult.  ``planner``: "native" (C++) or "python"; ``device_tables``: compute the
+    LANCZOS tables on the GPU (default with the native planner) with exact host fix-up of ambiguous
+    rows.  ``_shard`` (set by sharding.run_chain_sharded): this call holds frames [lo, hi) of a larger
+    job; stage-A / B1 metadata is gathered across ranks, the plan is made for ALL items with the shared
+    ``rng`` and only the items of the local frames are executed; returns (ChainResult, global indices)."""
     if not (frames.is_cuda and backgrounds.is_cuda):
         raise RuntimeError("run_chain needs CUDA tensors (there is no CPU fallback)")
     if frames.dtype != torch.uint8 or backgrounds.dtype != torch.uint8 or frames.dim() != 4 or backgrounds.dim() != 4:
         raise TypeError("frames / backgrounds must be uint8 [N, H, W, 3]")
+    if planner not in ("native", "python"):
+        raise ValueError("planner must be 'native' or 'python'")
+    if device_tables is None:
+        device_tables = planner == "native"
     lib = _native.load()
     dev = frames.device
     frames = frames.contiguous()
@@ -229,6 +432,14 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
     geom = _geom_struct(FW, FH, rect, BW, BH, ranges)
     cs = min(BH, BW)
+    pp = _plan_params(params, BW, BH, m)
+    bridge = _RngBridge(rng) if planner == "native" else None
+    lo, hi = (0, n) if _shard is None else (_shard["lo"], _shard["hi"])
+
+    def finish(res, own):
+        if bridge is not None:
+            bridge.commit()
+        return res if _shard is None else (res, own)
 
     with torch.cuda.device(dev):
         # ------------------------------------------------------------------ stage A
@@ -238,115 +449,128 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                             ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
         info = info_d.cpu().numpy()                                   # sync #1
-        lo = 0
         if _shard is not None:
-            lo = _shard["lo"]
             info = _shard["gather"](info)                             # 32 bytes of metadata per frame
 
         # ------------------------------------------------------------------ rotation step (host) + stage B1
-        rots = plan_rotations(info, params, rng)
-        if not rots and _shard is None:
-            return ChainResult(torch.empty((0, cs, cs, 3), dtype=torch.uint8, device=dev), [], [])
-        all_rots = rots
-        if _shard is not None:                                        # execute only the sprites of local frames
-            rots = [dict(r, frame=r["frame"] - lo) for r in all_rots if lo <= r["frame"] < _shard["hi"]]
-        rot_arr, rot_tiles = _rot_records(rots)
-        rot_d = torch.from_numpy(rot_arr.view(np.uint8)).to(dev)
-        bbox_d = torch.empty((len(rots), 4), dtype=torch.int32, device=dev)
-        if len(rots):
-            _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots), rot_tiles, ws.data_ptr(),
+        if planner == "native":
+            rots_all, angles, rot_index = native_plan_rotations(info, pp, bridge)
+            py_rots = None
+        else:
+            py_rots = plan_rotations(info, params, rng)
+            rots_all, _ = _rot_records(py_rots)
+            angles = np.array([np.nan if r["angle"] is None else r["angle"] for r in py_rots], dtype=np.float64)
+            rot_index = np.array([r["rot_index"] for r in py_rots], dtype=np.int32)
+        local = (rots_all["frame"] >= lo) & (rots_all["frame"] < hi)
+        rots_loc = rots_all[local].copy()
+        rots_loc["frame"] -= lo
+        tiles = ((rots_loc["canvas_w"].astype(np.int64) + 31) // 32) * ((rots_loc["canvas_h"].astype(np.int64) + 31) // 32)
+        rots_loc["tile_start"] = _excl(tiles)
+        bbox_d = torch.empty((max(1, len(rots_loc)), 4), dtype=torch.int32, device=dev)
+        rot_d = None
+        if len(rots_loc):
+            rot_d = torch.from_numpy(rots_loc.view(np.uint8)).to(dev)
+            _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots_loc), int(tiles.sum()), ws.data_ptr(),
                                                  bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
-        bbox = bbox_d.cpu().numpy()                                   # sync #2
+        bbox = bbox_d.cpu().numpy()[:len(rots_loc)]                   # sync #2
         if _shard is not None:
             bbox = _shard["gather"](bbox)                             # 16 bytes per sprite, rank order == item order
-            rots = all_rots
 
-        finals = plan_items(rots, bbox, params, rng, m, BW, BH)
-
-        own = list(range(len(finals)))
+        # ------------------------------------------------------------------ host: fit, symmetry, overlay, square-crop plans
+        if planner == "native":
+            items, aux, labels = native_plan_items(rots_all, rot_index, bbox, pp, bridge)
+        else:
+            finals = plan_items(py_rots, bbox, params, rng, m, BW, BH)
+            items, aux = _python_plan_to_arrays(py_rots, finals)
+            labels = [f["label"] for f in finals]
+        own = np.flatnonzero((items["frame"] >= lo) & (items["frame"] < hi))
         if _shard is not None:
-            own = [i for i, f in enumerate(finals) if lo <= f["frame"] < _shard["hi"]]
-            finals = [dict(finals[i], frame=finals[i]["frame"] - lo) for i in own]
-        K = len(finals)
+            items, aux = items[own].copy(), aux[own].copy()
+            labels = [labels[i] for i in own]
+            items["frame"] -= lo
+        tot = _layout(items)
+        K = len(items)
         out = torch.empty((K, cs, cs, 3), dtype=torch.uint8, device=dev)
+        rec_arrays = (items, aux, rot_index, angles)
         if K == 0:
-            return ChainResult(out, [], []) if _shard is None else (ChainResult(out, [], []), own)
+            return finish(ChainResult(out, [], record_arrays=rec_arrays), own.tolist())
 
-        # ------------------------------------------------------------------ item records, tables, sprite workspace
-        items = np.zeros(K, dtype=ITEM_DTYPE)
-        tables: List[np.ndarray] = []
-        toff = 0
-        woff = 0
-        gt = ht = vt = 0
-
-        def align(v, a=256):
-            return (v + a - 1) // a * a
-
-        for i, it in enumerate(finals):
-            plan = it["plan"]
-            a = plan.fixed if plan.kind == "affine" else (0,) * 6
-            fx, fy, sw, sh = it["fit"]
-            nw, nh = it["new"]
-            rec = items[i]
-            rec["frame"], rec["bg"] = it["frame"], it["bg"]
-            rec["cc_x"], rec["cc_y"], rec["cc_w"], rec["cc_h"] = it["cc"]
-            rec["kind"] = KIND[plan.kind]
-            for j in range(6):
-                rec[f"a{j}"] = a[j]
-            rec["fit_x0"], rec["fit_y0"], rec["spr_w"], rec["spr_h"] = fx, fy, sw, sh
-            rec["flip_h"] = int(it["sym"] in ("h", "hv"))
-            rec["flip_v"] = int(it["sym"] in ("v", "hv"))
-            rec["new_w"], rec["new_h"] = nw, nh
-            rec["pos_x"], rec["pos_y"] = it["pos"]
-            rec["sq_x0"], rec["sq_y0"], rec["sq_size"] = it["sq"]
-            if nw != sw:
-                ks = lib.ipp_lanczos_ksize(sw, nw)
-                b = np.empty((nw, 2), dtype=np.int32)
-                kk = np.empty((nw, ks), dtype=np.int32)
-                _native.check(lib.ipp_lanczos_coeffs_host(sw, nw, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_coeffs_host")
-                rec["h_ksize"], rec["hb_off"], rec["hk_off"] = ks, toff, toff + b.size
-                tables += [b.ravel(), kk.ravel()]
-                toff += b.size + kk.size
-            if nh != sh:
-                ks = lib.ipp_lanczos_ksize(sh, nh)
-                b = np.empty((nh, 2), dtype=np.int32)
-                kk = np.empty((nh, ks), dtype=np.int32)
-                _native.check(lib.ipp_lanczos_coeffs_host(sh, nh, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_coeffs_host")
-                rec["v_ksize"], rec["vb_off"], rec["vk_off"] = ks, toff, toff + b.size
-                tables += [b.ravel(), kk.ravel()]
-                toff += b.size + kk.size
-            rec["gather_tile_start"], rec["h_tile_start"], rec["v_tile_start"] = gt, ht, vt
-            gt += ((sw + 31) // 32) * ((sh + 31) // 32)
-            ht += ((nw + 31) // 32) * ((sh + 7) // 8)
-            vt += ((nw + 31) // 32) * ((nh + 7) // 8)
-            rec["rot_off"] = woff; woff = align(woff + sw * sh * 4)
-            rec["tmp_off"] = woff; woff = align(woff + nw * sh * 4)
-            rec["spr_off"] = woff; woff = align(woff + nw * nh * 4)
-
+        # ------------------------------------------------------------------ tables, sprite workspace
         items_d = torch.from_numpy(items.view(np.uint8)).to(dev)
-        tab = np.concatenate(tables) if tables else np.zeros(1, dtype=np.int32)
-        tab_d = torch.from_numpy(tab).to(dev)
-        spr_ws = torch.empty(max(woff, 256), dtype=torch.uint8, device=dev)
+        spr_ws = torch.empty(max(tot["ws"], 256), dtype=torch.uint8, device=dev)
+        amb_d = None
+        if device_tables:
+            tab_d = torch.empty(max(1, tot["table_ints"]), dtype=torch.int32, device=dev)
+            amb_d = torch.empty(1 + 3 * AMB_CAPACITY, dtype=torch.int32, device=dev)
+            _native.check(lib.ipp_chain_tables(items_d.data_ptr(), K, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
+                                               AMB_CAPACITY, float(ambiguity_eps), _stream()), "ipp_chain_tables")
+        else:
+            tab_d = torch.from_numpy(_host_tables(items, lib, tot["table_ints"])).to(dev)
 
         # ------------------------------------------------------------------ stage B2 + C
-        _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_d.data_ptr(), K,
-                                             gt, ht, vt, tab_d.data_ptr(), ws.data_ptr(), spr_ws.data_ptr(), _stream()),
-                      "ipp_chain_stage_b2")
-        _native.check(lib.ipp_chain_stage_c(backgrounds.data_ptr(), BW * 3, BH * BW * 3, C.byref(geom), items_d.data_ptr(), K,
-                                            spr_ws.data_ptr(), out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
-                      "ipp_chain_stage_c")
-        # keep the scratch alive until the stream has consumed it
-        for t in (ws, rot_d, items_d, tab_d, spr_ws):
-            t.record_stream(torch.cuda.current_stream())
+        def run_b2_c(items_dev, k, gt, ht, vt):
+            _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
+                                                 gt, ht, vt, tab_d.data_ptr(), ws.data_ptr(), spr_ws.data_ptr(), _stream()),
+                          "ipp_chain_stage_b2")
+            _native.check(lib.ipp_chain_stage_c(backgrounds.data_ptr(), BW * 3, BH * BW * 3, C.byref(geom), items_dev.data_ptr(), k,
+                                                spr_ws.data_ptr(), out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
+                          "ipp_chain_stage_c")
 
-    records = [dict(frame=it["frame"], rot_index=it["rot_index"], angle=it["angle"], sym=it["sym"], bg=it["bg"],
-                    ratio=it["ratio"], new=it["new"], pos=it["pos"], sq=it["sq"], fit=it["fit"], cc=it["cc"]) for it in finals]
-    res = ChainResult(out, [it["label"] for it in finals], records)
-    return res if _shard is None else (res, own)
+        run_b2_c(items_d, K, tot["gt"], tot["ht"], tot["vt"])
+
+        # ------------------------------------------------------------------ exactness fix-up of device tables (rare)
+        n_fixed = 0
+        if device_tables:
+            n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
+            if n_amb:
+                n_fixed = _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev)
+        for t in (ws, rot_d, items_d, tab_d, spr_ws, amb_d):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+
+    res = ChainResult(out, labels, record_arrays=rec_arrays)
+    res.tables_flagged_rows = n_amb if device_tables else 0
+    res.tables_fixed_items = n_fixed
+    return finish(res, own.tolist())
+
+
+def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
+    """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C
+    library's sin() (ipp_lanczos_row_host).  If a row really differs it is patched on the device and
+    the h/v passes + paste of the affected items are re-run (their gathered sprites are still valid).
+    Returns the number of items that had to be redone."""
+    if n_amb > AMB_CAPACITY:          # far too many flags: check every row
+        triples = [(i, a, r) for i in range(len(items)) for a in (0, 1) if items[i]["v_ksize" if a else "h_ksize"]
+                   for r in range(int(items[i]["new_h" if a else "new_w"]))]
+    else:
+        triples = amb_d[1:1 + 3 * n_amb].cpu().numpy().reshape(-1, 3).tolist()
+    dirty = set()
+    for item, axis, row in triples:
+        it = items[item]
+        ks = int(it["v_ksize" if axis else "h_ksize"])
+        n_in, n_out = (int(it["spr_h"]), int(it["new_h"])) if axis else (int(it["spr_w"]), int(it["new_w"]))
+        bo, ko = (int(it["vb_off"]), int(it["vk_off"])) if axis else (int(it["hb_off"]), int(it["hk_off"]))
+        b = np.empty(2, np.int32)
+        kk = np.empty(ks, np.int32)
+        _native.check(lib.ipp_lanczos_row_host(n_in, n_out, row, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_row_host")
+        dev_row = tab_d[ko + row * ks: ko + (row + 1) * ks].cpu().numpy()
+        if not np.array_equal(dev_row, kk):
+            tab_d[ko + row * ks: ko + (row + 1) * ks] = torch.from_numpy(kk).to(dev)
+            tab_d[bo + 2 * row: bo + 2 * row + 2] = torch.from_numpy(b).to(dev)
+            dirty.add(item)
+    if dirty:
+        sub = items[sorted(dirty)].copy()
+        ht = ((sub["new_w"].astype(np.int64) + 31) // 32) * ((sub["spr_h"].astype(np.int64) + 7) // 8)
+        vt = ((sub["new_w"].astype(np.int64) + 31) // 32) * ((sub["new_h"].astype(np.int64) + 7) // 8)
+        sub["h_tile_start"], sub["v_tile_start"] = _excl(ht), _excl(vt)
+        sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
+        run_b2_c(sub_d, len(sub), 0, int(ht.sum()), int(vt.sum()))
+        torch.cuda.current_stream().synchronize()
+    return len(dirty)
 
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
-                   out_host: Optional[torch.Tensor] = None, rng=_random) -> ChainResult:
+                   out_host: Optional[torch.Tensor] = None, rng=_random, **kw) -> ChainResult:
     """End-to-end entry for HOST buffers (the call a pipeline step makes after decoding):
     pinned host frames / backgrounds -> H2D -> run_chain -> D2H of the output images.
     ``out_host`` (pinned, [>=K, cs, cs, 3]) receives the images; ChainResult.images is that
@@ -355,10 +579,10 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
     with torch.cuda.device(dev):
         f = frames_host.to(dev, non_blocking=True)
         b = backgrounds_host.to(dev, non_blocking=True)
-        res = run_chain(f, b, params, rng)
+        res = run_chain(f, b, params, rng, **kw)
         k = res.images.shape[0]
         if out_host is None:
             out_host = torch.empty(res.images.shape, dtype=torch.uint8).pin_memory()
         out_host[:k].copy_(res.images, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    return ChainResult(out_host[:k], res.labels, res.records)
+    return ChainResult(out_host[:k], res.labels, res._records, res._arrays)

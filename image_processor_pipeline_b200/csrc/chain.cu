@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
     p.sprite_pitch = (int64_t)it.new_w * 4;
     p.sprite_w = it.new_w; p.sprite_h = it.new_h; p.pos_x = it.pos_x; p.pos_y = it.pos_y;
     p.crop_x0 = it.sq_x0; p.crop_y0 = it.sq_y0; p.crop_w = it.sq_size; p.crop_h = it.sq_size;
-    p.dst = c.out + (int64_t)blockIdx.y * c.out_stride;
+    p.dst = c.out + (int64_t)it.out_slot * c.out_stride;
     p.dst_pitch = c.out_pitch;
     const int row0 = blockIdx.x * c.rows_per_cta;
     if (row0 >= p.crop_h) return;
@@ -356,6 +356,75 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
     }
     mbar_wait(&bar, 0);
     paste_rows_from_smem(p, smem, c.smem_row_stride, row0, nrows, tid);
+}
+
+// ===================================================================== device LANCZOS tables
+struct TabParams {
+    const ipp_chain_item* items;
+    int32_t* tables;
+    int32_t* amb;      // [0] = count, then triples
+    int amb_cap;
+    double eps;
+};
+
+__device__ __forceinline__ double d_sinc(double x) {
+    if (x == 0.0) return 1.0;
+    x = __dmul_rn(x, 3.14159265358979323846);
+    return __ddiv_rn(sin(x), x);
+}
+__device__ __forceinline__ double d_lanczos(double x) {
+    if (-3.0 <= x && x < 3.0) return __dmul_rn(d_sinc(x), d_sinc(__ddiv_rn(x, 3.0)));
+    return 0.0;
+}
+
+// one thread = one output row (its bounds pair and ksize coefficients)
+__global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
+    const ipp_chain_item& it = p.items[blockIdx.y];
+    const int hrows = it.h_ksize ? it.new_w : 0, vrows = it.v_ksize ? it.new_h : 0;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hrows + vrows) return;
+    const int axis = idx >= hrows;
+    const int xx = axis ? idx - hrows : idx;
+    const int in_size = axis ? it.spr_h : it.spr_w, out_size = axis ? it.new_h : it.new_w;
+    const int ksize = axis ? it.v_ksize : it.h_ksize;
+    int32_t* bounds = p.tables + (axis ? it.vb_off : it.hb_off) + 2 * xx;
+    int32_t* k = p.tables + (axis ? it.vk_off : it.hk_off) + (int64_t)xx * ksize;
+    const double scale = __ddiv_rn((double)in_size, (double)out_size);
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = __dmul_rn(3.0, filterscale);
+    const double ss = __ddiv_rn(1.0, filterscale);
+    const double center = __dmul_rn((double)xx + 0.5, scale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x)
+        ww = __dadd_rn(ww, d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss)));
+    bool amb = false;
+    for (int x = 0; x < ksize; ++x) {
+        int c = 0;
+        if (x < xmax) {
+            double w = d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+            if (ww != 0.0) w = __ddiv_rn(w, ww);
+            const double v = __dmul_rn(w, 4194304.0);
+            const double t = (w < 0) ? __dadd_rn(-0.5, v) : __dadd_rn(0.5, v);
+            c = (int)t;
+            if (fabs(t - rint(t)) < p.eps) amb = true;
+        }
+        k[x] = c;
+    }
+    bounds[0] = xmin;
+    bounds[1] = xmax;
+    if (amb) {
+        const int slot = atomicAdd(&p.amb[0], 1);
+        if (slot < p.amb_cap) {
+            p.amb[1 + 3 * slot] = (int)blockIdx.y;
+            p.amb[2 + 3 * slot] = axis;
+            p.amb[3 + 3 * slot] = xx;
+        }
+    }
 }
 
 }  // namespace ipp
@@ -465,6 +534,21 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
         { ipp::LaunchTimer _lt("chain_vpass_kernel", st); chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }
+    return IPP_OK;
+}
+
+int ipp_chain_tables(const ipp_chain_item* items, int n_items, int max_rows_per_item, int32_t* tables,
+                     int32_t* amb_out, int amb_capacity, double eps, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(items && tables && amb_out && n_items >= 0 && amb_capacity >= 0 && eps >= 0.0, IPP_ERR_BAD_ARG,
+                "ipp_chain_tables: bad arguments");
+    IPP_CUDA(cudaMemsetAsync(amb_out, 0, sizeof(int32_t), st));
+    if (n_items == 0 || max_rows_per_item <= 0) return IPP_OK;
+    TabParams p{items, tables, amb_out, amb_capacity, eps};
+    dim3 grid(ceil_div(max_rows_per_item, 128), n_items);
+    { ipp::LaunchTimer _lt("chain_tables_kernel", st); chain_tables_kernel<<<grid, 128, 0, st>>>(p); }
+    IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
 

@@ -9,3 +9,4 @@
 #include "ccl.cu"
 #include "boxes.cu"
 #include "chain.cu"
+#include "planner.cu"

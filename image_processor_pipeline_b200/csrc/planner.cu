@@ -1,0 +1,410 @@
+// planner.cu — the chain's HOST planner in C++ (no device code): the reference's per-step
+// bookkeeping and random draws between the device stages, at native speed.
+//
+// What it restates (file:line of the reference, or of the Python runtime the reference
+// runs on — the draws come from Python's `random`, a Mersenne Twister):
+//   * Python random: MT19937 genrand_uint32 / random() (53-bit) / uniform / getrandbits /
+//     _randbelow_with_getrandbits / randint / sample (pool branch, n <= 21)
+//   * rotation step: transforms/rotations.py:77-119 + Pillow Image.rotate parameter math
+//     (PIL/Image.py:2509-2585) + libImaging affine_fixed coefficients (Geometry.c)
+//   * symmetry step: transforms/symmetry.py:97-126 (+ sorted file-name order of the
+//     next step's directory listing, pipeline.py:137)
+//   * overlay step: transforms/overlays.py:104-149 (size math, randint position,
+//     xyxy2xywhn float32, "%.6f" label)
+//   * square-crop step: transforms/crop_square.py:62-65,163-217 (label parse, float32
+//     xywhn2xyxy, bounds, randint offset, shift/clip/valid, xyxy2xywhn, label rows)
+// The Python planner in chain.py is the readable twin; tests require both to agree
+// (records, labels and the RNG state afterwards).
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(ipp_chain_rot) == 64, "ipp_chain_rot layout (chain.py ROT_DTYPE)");
+static_assert(sizeof(ipp_chain_item) == 184, "ipp_chain_item layout (chain.py ITEM_DTYPE)");
+static_assert(sizeof(ipp_plan_params) == 88 && sizeof(ipp_plan_aux) == 16 && sizeof(ipp_plan_totals) == 40, "planner struct layout");
+
+namespace ipp {
+namespace plan {
+
+// ------------------------------------------------------------------ Python's random.Random
+struct PyRandom {
+    uint32_t* mt;     // 624 words
+    int32_t* idx;     // state index (0..624)
+
+    uint32_t genrand_uint32() {
+        static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
+        if (*idx >= 624) {
+            int kk;
+            uint32_t y;
+            for (kk = 0; kk < 624 - 397; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < 623; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+            *idx = 0;
+        }
+        uint32_t y = mt[(*idx)++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double random() {   // genrand_res53
+        const uint32_t a = genrand_uint32() >> 5, b = genrand_uint32() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    double uniform(double a, double b) { return a + (b - a) * random(); }
+    uint32_t randbelow(uint32_t n) {   // n > 0, n < 2^32
+        int k = 0;
+        for (uint32_t t = n; t; t >>= 1) ++k;
+        uint32_t r = genrand_uint32() >> (32 - k);
+        while (r >= n) r = genrand_uint32() >> (32 - k);
+        return r;
+    }
+    // randint(a, b); ok=false when the range is empty (Python raises ValueError)
+    long long randint(long long a, long long b, bool* ok) {
+        const long long width = b + 1 - a;
+        if (width <= 0) {
+            *ok = false;
+            return 0;
+        }
+        *ok = true;
+        return a + (long long)randbelow((uint32_t)width);
+    }
+};
+
+// round(x, 15) of Python: exact decimal rounding (half-even on the exact binary value), then back
+static double round15(double x) {
+    char buf[400];
+    snprintf(buf, sizeof(buf), "%.15f", x);
+    return strtod(buf, nullptr);
+}
+static double py_fmod360(double a) {
+    double m = std::fmod(a, 360.0);
+    if (m != 0.0) {
+        if (m < 0.0) m += 360.0;
+    } else {
+        m = std::copysign(0.0, 360.0);
+    }
+    return m;
+}
+static int fix16(double v) {
+    const double t = v * 65536.0 + 0.5;
+    return t >= 0.0 ? (int)t : (int)std::floor(t);
+}
+
+// Pillow Image.rotate(angle, expand=True) parameter math for a w x h image
+static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r) {
+    angle = py_fmod360(angle);
+    r->a0 = r->a1 = r->a2 = r->a3 = r->a4 = r->a5 = 0;
+    if (angle == 0.0) { r->kind = 1; r->canvas_w = w; r->canvas_h = h; return 0; }
+    if (angle == 180.0) { r->kind = 2; r->canvas_w = w; r->canvas_h = h; return 0; }
+    if (angle == 90.0 || angle == 270.0) { r->kind = angle == 90.0 ? 3 : 4; r->canvas_w = h; r->canvas_h = w; return 0; }
+    const double cx = w / 2.0, cy = h / 2.0;
+    const double a = -(angle * (M_PI / 180.0));
+    double m[6] = {round15(std::cos(a)), round15(std::sin(a)), 0.0, round15(-std::sin(a)), round15(std::cos(a)), 0.0};
+    auto tfx = [&](double x, double y) { return m[0] * x + m[1] * y + m[2]; };
+    auto tfy = [&](double x, double y) { return m[3] * x + m[4] * y + m[5]; };
+    {
+        const double nx = tfx(-cx, -cy), ny = tfy(-cx, -cy);
+        m[2] = nx;
+        m[5] = ny;
+    }
+    m[2] += cx;
+    m[5] += cy;
+    const double xs[4] = {0.0, (double)w, (double)w, 0.0}, ys[4] = {0.0, 0.0, (double)h, (double)h};
+    double minx = 0, maxx = 0, miny = 0, maxy = 0;
+    for (int i = 0; i < 4; ++i) {
+        const double tx = tfx(xs[i], ys[i]), ty = tfy(xs[i], ys[i]);
+        if (i == 0) { minx = maxx = tx; miny = maxy = ty; }
+        else { minx = std::fmin(minx, tx); maxx = std::fmax(maxx, tx); miny = std::fmin(miny, ty); maxy = std::fmax(maxy, ty); }
+    }
+    const int nw = (int)std::ceil(maxx) - (int)std::floor(minx);
+    const int nh = (int)std::ceil(maxy) - (int)std::floor(miny);
+    {
+        const double nx = tfx(-(nw - w) / 2.0, -(nh - h) / 2.0), ny = tfy(-(nw - w) / 2.0, -(nh - h) / 2.0);
+        m[2] = nx;
+        m[5] = ny;
+    }
+    auto in_range = [&](double x, double y) {
+        return std::fabs(x * m[0] + y * m[1] + m[2]) < 32768.0 && std::fabs(x * m[3] + y * m[4] + m[5]) < 32768.0;
+    };
+    if (!(in_range(0, 0) && in_range(nw, nh) && in_range(0, nh) && in_range(nw, 0)) || (m[1] == 0.0 && m[3] == 0.0))
+        return IPP_ERR_UNSUPPORTED;      // outside libImaging's affine_fixed path
+    r->kind = 0;
+    r->a0 = fix16(m[0]); r->a1 = fix16(m[1]); r->a2 = fix16(m[2] + m[0] * 0.5 + m[1] * 0.5);
+    r->a3 = fix16(m[3]); r->a4 = fix16(m[4]); r->a5 = fix16(m[5] + m[3] * 0.5 + m[4] * 0.5);
+    r->canvas_w = nw; r->canvas_h = nh;
+    return 0;
+}
+
+// reference transforms/overlays.py:106-126; false when PIL's resize would raise (size <= 0)
+static bool overlay_size(int ow, int oh, int bw, int bh, double ratio, int* nw, int* nh) {
+    if (oh == 0) return false;
+    const double bg_diag = std::hypot((double)bw, (double)bh);
+    const double target = bg_diag * ratio;
+    const double ar = (double)ow / (double)oh;
+    const double h_max = std::fmin((double)bw / ar, (double)bh);
+    const double max_diag = std::hypot(ar * h_max, h_max);
+    const double d = std::fmin(target, max_diag);
+    const double hh = std::sqrt(std::pow(d, 2.0) / (std::pow(ar, 2.0) + 1.0));
+    if (!(hh == hh)) return false;
+    *nh = (int)hh;
+    *nw = (int)(ar * (double)*nh);
+    return *nw > 0 && *nh > 0;
+}
+
+static int lanczos_ksize(int in_size, int out_size) {
+    double fs = (double)((float)in_size - 0.0f) / out_size;
+    if (fs < 1.0) fs = 1.0;
+    return (int)std::ceil(3.0 * fs) * 2 + 1;
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace plan
+}  // namespace ipp
+
+extern "C" {
+
+// Rotation step.  info: stage-A rows int32[n_frames][8] (first_frame = global index of row 0,
+// for sharded runs pass the gathered rows and 0).  Outputs one ipp_chain_rot per sprite
+// (original first when include_original, then the rotations), angle (NaN for the original)
+// and rot_index (0 = original).  Returns IPP_ERR_WORKSPACE when capacity is too small.
+int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
+                            ipp_chain_rot* rots_out, double* angles_out, int32_t* rot_index_out, int capacity,
+                            int32_t* n_rot_out, int32_t* total_tiles_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE(info && p && rng_mt624 && rng_index && rots_out && angles_out && rot_index_out && n_rot_out && total_tiles_out,
+                IPP_ERR_BAD_ARG, "ipp_plan_rotations_host: NULL pointer");
+    PyRandom rng{rng_mt624, rng_index};
+    int n = 0;
+    long long tiles = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const int32_t* row = info + 8 * f;
+        const int w = row[2], h = row[3];
+        if (w <= 0 || h <= 0) continue;
+        for (int i = (p->include_original ? 0 : 1); i <= p->num_rotations; ++i) {
+            IPP_REQUIRE(n < capacity, IPP_ERR_WORKSPACE, "ipp_plan_rotations_host: capacity %d too small", capacity);
+            ipp_chain_rot* r = rots_out + n;
+            memset(r, 0, sizeof(*r));
+            r->frame = f; r->cc_x = row[0]; r->cc_y = row[1]; r->cc_w = w; r->cc_h = h;
+            if (i == 0) {
+                r->kind = 1; r->canvas_w = w; r->canvas_h = h;
+                angles_out[n] = NAN;
+            } else {
+                const double angle = rng.uniform(p->angle_min, p->angle_max);
+                const int rc = rotation_plan(w, h, angle, r);
+                IPP_REQUIRE(rc == 0, rc, "ipp_plan_rotations_host: rotation outside libImaging's 16.16 fixed-point range");
+                angles_out[n] = angle;
+            }
+            rot_index_out[n] = i;
+            r->tile_start = (int32_t)tiles;
+            tiles += (long long)((r->canvas_w + 31) / 32) * ((r->canvas_h + 31) / 32);
+            IPP_REQUIRE(tiles < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_rotations_host: too many tiles");
+            ++n;
+        }
+    }
+    *n_rot_out = n;
+    *total_tiles_out = (int32_t)tiles;
+    return IPP_OK;
+}
+
+// Steps after the rotation: fit, symmetry, overlay, square crop.  bbox: stage-B1 rows
+// int32[n_rot][4].  Fills item records (frame, bg, geometry, flips, sizes, positions, crop,
+// table offsets, tile starts, workspace offsets), aux rows {rot (index into rots), sym
+// (0 o,1 h,2 v,3 hv), ratio} and the label text of every item (labels_out, '\0'-separated).
+int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_original, int n_rot, const int32_t* bbox,
+                        const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
+                        ipp_chain_item* items_out, ipp_plan_aux* aux_out, int capacity, int32_t* n_items_out,
+                        char* labels_out, int labels_capacity, ipp_plan_totals* totals_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE(rots && rot_is_original && bbox && p && rng_mt624 && rng_index && items_out && aux_out && n_items_out &&
+                    labels_out && totals_out,
+                IPP_ERR_BAD_ARG, "ipp_plan_items_host: NULL pointer");
+    IPP_REQUIRE(p->pool_len >= 1 && p->pool_len <= 4 && p->choose_random >= 0 && p->choose_random <= p->pool_len && p->n_bgs >= 1,
+                IPP_ERR_BAD_ARG, "ipp_plan_items_host: bad symmetry pool / choose_random / background count");
+    PyRandom rng{rng_mt624, rng_index};
+    const int BW = p->bg_w, BH = p->bg_h;
+    static const int sym_file_order[4] = {2, 0, 3, 1};   // o, h, v, hv -> rank of "_o" < ... in file-name order: h < hv < o < v
+
+    struct Var { int rot, sym, fx, fy, sw, sh; };
+    std::vector<Var> variants;
+    variants.reserve((size_t)n_rot * 2);
+    // ---- symmetry step: one sample per sprite (symmetry.py:122-126), then sorted by file name
+    for (int r = 0; r < n_rot; ++r) {
+        const ipp_chain_rot& R = rots[r];
+        const int32_t* bb = bbox + 4 * r;
+        int fx = 0, fy = 0, sw = R.canvas_w, sh = R.canvas_h;
+        if (!rot_is_original[r] && bb[2] > 0) { fx = bb[0]; fy = bb[1]; sw = bb[2] - bb[0]; sh = bb[3] - bb[1]; }
+        int pool[4], n = p->pool_len, chosen[5], nc = 0;
+        for (int i = 0; i < n; ++i) pool[i] = p->pool[i];
+        for (int i = 0; i < p->choose_random; ++i) {
+            const int j = (int)rng.randbelow((uint32_t)(n - i));
+            chosen[nc++] = pool[j];
+            pool[j] = pool[n - i - 1];
+        }
+        bool has_o = false;
+        for (int i = 0; i < nc; ++i) has_o |= (chosen[i] == 0);
+        if (p->sym_include_original && !has_o) chosen[nc++] = 0;
+        bool present[4] = {false, false, false, false};
+        for (int i = 0; i < nc; ++i) present[chosen[i]] = true;
+        static const int by_name[4] = {1, 3, 0, 2};      // h, hv, o, v
+        (void)sym_file_order;
+        for (int k = 0; k < 4; ++k)
+            if (present[by_name[k]]) variants.push_back({r, by_name[k], fx, fy, sw, sh});
+    }
+    // ---- overlay step (overlays.py:104-149)
+    struct Ov { Var v; int bg, nw, nh, px, py; double ratio; char label[96]; };
+    std::vector<Ov> overlays;
+    overlays.reserve(variants.size());
+    for (size_t k = 0; k < variants.size(); ++k) {
+        const Var& v = variants[k];
+        Ov o;
+        o.v = v;
+        o.bg = (int)(k % (size_t)p->n_bgs);
+        o.ratio = rng.uniform(p->scale_min, p->scale_max);
+        if (!overlay_size(v.sw, v.sh, BW, BH, o.ratio, &o.nw, &o.nh)) continue;   // ValueError -> print, None
+        bool ok;
+        o.px = (int)rng.randint(0, BW - o.nw, &ok);
+        if (!ok) continue;
+        o.py = (int)rng.randint(0, BH - o.nh, &ok);
+        if (!ok) continue;
+        const long long x1 = o.px, y1 = o.py, x2 = o.px + o.nw, y2 = o.py + o.nh;
+        const float cx = (float)(((double)(x1 + x2) / 2.0) / (double)BW), cy = (float)(((double)(y1 + y2) / 2.0) / (double)BH);
+        const float wn = (float)((double)(x2 - x1) / (double)BW), hn = (float)((double)(y2 - y1) / (double)BH);
+        snprintf(o.label, sizeof(o.label), "%d %.6f %.6f %.6f %.6f", p->yolo_class_id, (double)cx, (double)cy, (double)wn, (double)hn);
+        overlays.push_back(o);
+    }
+    // ---- square-crop step (crop_square.py:62-65,163-217) + records
+    int n = 0;
+    int64_t toff = 0, woff = 0, tab_rows = 0;
+    long long gt = 0, ht = 0, vt = 0;
+    size_t lpos = 0;
+    const int cs = BW < BH ? BW : BH;
+    for (const Ov& o : overlays) {
+        // np.loadtxt: class id and the four 6-decimal numbers back to float64
+        int cls = 0;
+        double b[4];
+        {
+            const char* s = o.label;
+            char* end;
+            cls = (int)strtod(s, &end);       // data[:, 0].astype(int)
+            for (int i = 0; i < 4; ++i) { s = end; b[i] = strtod(s, &end); }
+        }
+        // xywhn2xyxy: float64 expression, float32 store
+        const float ax1 = (float)((double)BW * (b[0] - b[2] / 2.0)), ay1 = (float)((double)BH * (b[1] - b[3] / 2.0));
+        const float ax2 = (float)((double)BW * (b[0] + b[2] / 2.0)), ay2 = (float)((double)BH * (b[1] + b[3] / 2.0));
+        const int lbx = std::max(0, (int)(ax2 - (float)cs)), ubx = std::min((int)ax1, BW - cs);
+        const int lby = std::max(0, (int)(ay2 - (float)cs)), uby = std::min((int)ay1, BH - cs);
+        if (lbx > ubx || lby > uby) continue;                     // RuntimeError in the reference -> item logged as Error
+        bool ok;
+        const int x0 = (int)rng.randint(lbx, ubx, &ok);
+        const int y0 = (int)rng.randint(lby, uby, &ok);
+        auto clip = [&](double v) { return std::fmin(std::fmax(v, 0.0), (double)cs); };
+        const double x1 = clip((double)ax1 - (double)x0), y1 = clip((double)ay1 - (double)y0);
+        const double x2 = clip((double)ax2 - (double)x0), y2 = clip((double)ay2 - (double)y0);
+        if (!(x1 < x2 && y1 < y2)) continue;                       // "Aucune bbox résiduelle après le crop."
+        const float ncx = (float)(((x1 + x2) / 2.0) / (double)cs), ncy = (float)(((y1 + y2) / 2.0) / (double)cs);
+        const float nwn = (float)((x2 - x1) / (double)cs), nhn = (float)((y2 - y1) / (double)cs);
+
+        IPP_REQUIRE(n < capacity, IPP_ERR_WORKSPACE, "ipp_plan_items_host: capacity %d too small", capacity);
+        char row[160];
+        const int len = snprintf(row, sizeof(row), "%d %.6f %.6f %.6f %.6f\n", cls, (double)ncx, (double)ncy, (double)nwn, (double)nhn);
+        IPP_REQUIRE(lpos + (size_t)len + 1 <= (size_t)labels_capacity, IPP_ERR_WORKSPACE, "ipp_plan_items_host: label buffer too small");
+        memcpy(labels_out + lpos, row, (size_t)len + 1);
+        lpos += (size_t)len + 1;
+
+        const ipp_chain_rot& R = rots[o.v.rot];
+        ipp_chain_item* it = items_out + n;
+        memset(it, 0, sizeof(*it));
+        it->frame = R.frame; it->bg = o.bg;
+        it->cc_x = R.cc_x; it->cc_y = R.cc_y; it->cc_w = R.cc_w; it->cc_h = R.cc_h;
+        it->kind = R.kind; it->a0 = R.a0; it->a1 = R.a1; it->a2 = R.a2; it->a3 = R.a3; it->a4 = R.a4; it->a5 = R.a5;
+        it->fit_x0 = o.v.fx; it->fit_y0 = o.v.fy; it->spr_w = o.v.sw; it->spr_h = o.v.sh;
+        it->flip_h = (o.v.sym == 1 || o.v.sym == 3); it->flip_v = (o.v.sym == 2 || o.v.sym == 3);
+        it->new_w = o.nw; it->new_h = o.nh; it->pos_x = o.px; it->pos_y = o.py;
+        it->sq_x0 = x0; it->sq_y0 = y0; it->sq_size = cs;
+        it->tab_row_start = (int32_t)tab_rows;
+        if (o.nw != o.v.sw) {
+            it->h_ksize = lanczos_ksize(o.v.sw, o.nw);
+            it->hb_off = (int32_t)toff; it->hk_off = (int32_t)(toff + 2 * (int64_t)o.nw);
+            toff += 2 * (int64_t)o.nw + (int64_t)o.nw * it->h_ksize;
+            tab_rows += o.nw;
+        }
+        if (o.nh != o.v.sh) {
+            it->v_ksize = lanczos_ksize(o.v.sh, o.nh);
+            it->vb_off = (int32_t)toff; it->vk_off = (int32_t)(toff + 2 * (int64_t)o.nh);
+            toff += 2 * (int64_t)o.nh + (int64_t)o.nh * it->v_ksize;
+            tab_rows += o.nh;
+        }
+        IPP_REQUIRE(toff < (1LL << 31) && tab_rows < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_items_host: coefficient tables exceed 2^31 entries");
+        it->gather_tile_start = (int32_t)gt; it->h_tile_start = (int32_t)ht; it->v_tile_start = (int32_t)vt;
+        gt += (long long)((o.v.sw + 31) / 32) * ((o.v.sh + 31) / 32);
+        ht += (long long)((o.nw + 31) / 32) * ((o.v.sh + 7) / 8);
+        vt += (long long)((o.nw + 31) / 32) * ((o.nh + 7) / 8);
+        IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_items_host: too many tiles");
+        it->rot_off = woff; woff = align_up(woff + (int64_t)o.v.sw * o.v.sh * 4, 256);
+        it->tmp_off = woff; woff = align_up(woff + (int64_t)o.nw * o.v.sh * 4, 256);
+        it->spr_off = woff; woff = align_up(woff + (int64_t)o.nw * o.nh * 4, 256);
+        aux_out[n].ratio = o.ratio;
+        aux_out[n].rot = o.v.rot;
+        aux_out[n].sym = o.v.sym;
+        ++n;
+    }
+    *n_items_out = n;
+    totals_out->table_ints = toff;
+    totals_out->table_rows = tab_rows;
+    totals_out->sprite_ws_bytes = woff;
+    totals_out->gather_tiles = (int32_t)gt;
+    totals_out->h_tiles = (int32_t)ht;
+    totals_out->v_tiles = (int32_t)vt;
+    totals_out->labels_bytes = (int32_t)lpos;
+    return IPP_OK;
+}
+
+// one exact table row (libm sin) for the rare fix-up of rows the device flagged as ambiguous
+int ipp_lanczos_row_host(int in_size, int out_size, int xx, int32_t* bounds2_host, int32_t* kk_row_host) {
+    using namespace ipp;
+    IPP_REQUIRE(in_size > 0 && out_size > 0 && xx >= 0 && xx < out_size && bounds2_host && kk_row_host, IPP_ERR_BAD_ARG,
+                "ipp_lanczos_row_host: bad arguments");
+    double scale, filterscale, support;
+    int ksize;
+    lanczos_scale(in_size, out_size, &scale, &filterscale, &support, &ksize);
+    const double ss = 1.0 / filterscale;
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    std::vector<double> w((size_t)ksize, 0.0);
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+        w[x] = lanczos_filter((x + xmin - center + 0.5) * ss);
+        ww += w[x];
+    }
+    for (int x = 0; x < ksize; ++x) {
+        double v = x < xmax ? w[x] : 0.0;
+        if (x < xmax && ww != 0.0) v /= ww;
+        kk_row_host[x] = (v < 0) ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
+    }
+    bounds2_host[0] = xmin;
+    bounds2_host[1] = xmax;
+    return IPP_OK;
+}
+
+}  // extern "C"

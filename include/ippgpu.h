@@ -247,9 +247,54 @@ typedef struct ipp_chain_item {
     int32_t h_ksize, v_ksize;               /* 0 = pass skipped (size unchanged)               */
     int32_t hb_off, hk_off, vb_off, vk_off; /* int32 offsets of this item's tables             */
     int32_t gather_tile_start, h_tile_start, v_tile_start;
-    int32_t _pad[5];
+    int32_t tab_row_start;                  /* first coefficient-table row of this item (h rows, then v rows) */
+    int32_t out_slot;                       /* index of the output image this item writes            */
+    int32_t _pad[3];
     int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace            */
 } ipp_chain_item;
+
+/* ---- host planner (C++ twin of chain.py's planner; no device work) ------------------
+ * The reference draws its random parameters from Python's `random` (MT19937), step-major;
+ * rng_mt624 / rng_index are random.getstate()[1][:624] / [624] and are advanced in place. */
+typedef struct ipp_plan_params {
+    int32_t num_rotations, include_original;      /* rotations.py:9-10                         */
+    double angle_min, angle_max;                  /* rotations.py:11-12                        */
+    int32_t pool[4], pool_len;                    /* symmetry codes 0 o, 1 h, 2 v, 3 hv        */
+    int32_t choose_random, sym_include_original;  /* symmetry.py:17-18 (choose_random resolved) */
+    int32_t yolo_class_id;                        /* overlays.py:30                            */
+    double scale_min, scale_max;                  /* overlays.py:31-32                         */
+    int32_t bg_w, bg_h, n_bgs;
+    int32_t _pad;
+} ipp_plan_params;
+
+typedef struct ipp_plan_aux {
+    double ratio;        /* overlay target ratio drawn for this item          */
+    int32_t rot;         /* index of the sprite in the rots array             */
+    int32_t sym;         /* 0 o, 1 h, 2 v, 3 hv                               */
+} ipp_plan_aux;
+
+typedef struct ipp_plan_totals {
+    int64_t table_ints, table_rows, sprite_ws_bytes;
+    int32_t gather_tiles, h_tiles, v_tiles, labels_bytes;
+} ipp_plan_totals;
+
+int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
+                            ipp_chain_rot* rots_out, double* angles_out, int32_t* rot_index_out, int capacity,
+                            int32_t* n_rot_out, int32_t* total_tiles_out);
+int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_original, int n_rot, const int32_t* bbox,
+                        const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
+                        ipp_chain_item* items_out, ipp_plan_aux* aux_out, int capacity, int32_t* n_items_out,
+                        char* labels_out, int labels_capacity, ipp_plan_totals* totals_out);
+int ipp_lanczos_row_host(int in_size, int out_size, int xx, int32_t* bounds2_host, int32_t* kk_row_host);
+
+/* LANCZOS coefficient tables of all items computed ON THE DEVICE (double precision, the
+ * libImaging operation order).  The C library's sin() cannot be reproduced bit for bit on the
+ * GPU, so every coefficient whose rounding decision lies within `eps` (in units of 2^-22) of
+ * a boundary is reported: amb_out[0] = count, then {item, axis, row} triples (capacity
+ * amb_capacity).  The caller re-derives those rows with ipp_lanczos_row_host and re-runs
+ * the affected items if a row really differs — results stay bit-exact. */
+int ipp_chain_tables(const ipp_chain_item* items, int n_items, int max_rows_per_item, int32_t* tables,
+                     int32_t* amb_out, int amb_capacity, double eps, void* stream);
 
 int64_t ipp_chain_mask_workspace_bytes(const ipp_chain_geom* geom_host, int n_frames);
 /* stage A: frames (n x frame_h x frame_w x 3, BGR) -> keep-mask (inside workspace) and

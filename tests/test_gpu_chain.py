@@ -17,13 +17,13 @@ from image_processor_pipeline_b200 import synth  # noqa: E402
 DEV = "cuda:0"
 
 
-def _run_both(frames, bgs, seed, **kw):
+def _run_both(frames, bgs, seed, run_kw=None, **kw):
     random.seed(seed)
     ref_imgs, ref_labels, ref_recs = OC.run_chain(frames, bgs, **kw)
     state_after_ref = random.getstate()
     random.seed(seed)
     res = chain.run_chain(torch.from_numpy(np.stack(frames)).to(DEV), torch.from_numpy(np.stack(bgs)).to(DEV),
-                          chain.ChainParams(**kw))
+                          chain.ChainParams(**kw), **(run_kw or {}))
     assert random.getstate() == state_after_ref, "the chain must consume the RNG exactly like the reference"
     return res, ref_imgs, ref_labels, ref_recs
 
@@ -45,12 +45,17 @@ def _compare(res, ref_imgs, ref_labels, ref_recs):
     dict(num_rotations=3, include_original=False, angle_min=80.0, angle_max=100.0, pool=["hv"], sym_include_original=True,
          scale_min=0.4, scale_max=0.8, yolo_class_id=3),
 ])
-def test_chain_small(cfg):
+@pytest.mark.parametrize("run_kw", [dict(planner="native"), dict(planner="python"), dict(planner="native", device_tables=False),
+                                    dict(planner="native", ambiguity_eps=0.2)])
+def test_chain_small(cfg, run_kw):
     H, W = 270, 480
     frames = [synth.frame(5, i, H, W) for i in range(4)]
     bgs = [synth.background(5, i, H, W) for i in range(3)]
     kw = dict(crop_margins=(0.05, 4, 0.02, 6), color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **cfg)
-    _compare(*_run_both(frames, bgs, 3, **kw))
+    res, *ref = _run_both(frames, bgs, 3, run_kw=run_kw, **kw)
+    _compare(res, *ref)
+    if run_kw.get("ambiguity_eps"):
+        assert res.tables_flagged_rows > 0          # the exact-row verification path really ran
 
 
 def test_chain_zones_gimp_and_portrait_background():
@@ -82,3 +87,40 @@ def test_chain_1080p():
     kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
               pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
     _compare(*_run_both(frames, bgs, 23, **kw))
+
+
+def test_device_lanczos_tables_equal_host_tables():
+    """Device-computed coefficient tables (CUDA sin) vs libm tables for many size pairs; every row that
+    differs must have been flagged as ambiguous (then the host fixes it) — in practice none differs."""
+    import ctypes as C
+    from image_processor_pipeline_b200 import _native
+    lib = _native.load()
+    r = np.random.default_rng(5)
+    k = 200
+    items = np.zeros(k, dtype=chain.ITEM_DTYPE)
+    items["spr_w"] = r.integers(2, 900, k); items["spr_h"] = r.integers(2, 900, k)
+    items["new_w"] = r.integers(1, 700, k); items["new_h"] = r.integers(1, 700, k)
+    items["new_w"][:5] = items["spr_w"][:5]                       # some skipped passes
+    tot = chain._layout(items)
+    host = chain._host_tables(items, lib, tot["table_ints"])
+    items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)
+    tab_d = torch.zeros(tot["table_ints"], dtype=torch.int32, device=DEV)
+    amb_d = torch.zeros(1 + 3 * chain.AMB_CAPACITY, dtype=torch.int32, device=DEV)
+    _native.check(lib.ipp_chain_tables(items_d.data_ptr(), k, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
+                                       chain.AMB_CAPACITY, chain.AMBIGUITY_EPS, torch.cuda.current_stream().cuda_stream), "tables")
+    dev_tab = tab_d.cpu().numpy()
+    n_amb = int(amb_d[0].item())
+    flagged = set(map(tuple, amb_d[1:1 + 3 * n_amb].cpu().numpy().reshape(-1, 3).tolist()))
+    bad = np.flatnonzero(dev_tab != host)
+    for idx in bad:                                               # map the flat index back to (item, axis, row)
+        i = int(np.searchsorted(items["hb_off"] + (items["h_ksize"] == 0) * 0, idx, side="right") - 1)
+        found = False
+        for it_i in range(k):
+            it = items[it_i]
+            for axis, (ko, ks, n_out) in enumerate(((int(it["hk_off"]), int(it["h_ksize"]), int(it["new_w"])),
+                                                    (int(it["vk_off"]), int(it["v_ksize"]), int(it["new_h"])))):
+                if ks and ko <= idx < ko + ks * n_out:
+                    assert (it_i, axis, (idx - ko) // ks) in flagged, "a differing row was not flagged"
+                    found = True
+        assert found, "bounds differ: they involve no transcendental and must be identical"
+    assert len(bad) <= 2 and n_amb < 200, (len(bad), n_amb)
