@@ -260,7 +260,8 @@ def main():
     torch.cuda.synchronize()
     rep = _native.timing_report()
     _native.timing_enable(False)
-    alg = {"chain_mask_kernel": B * 3 * FW * FH,                       # frame read once
+    alg = {"chain_mask_kernel": B * 3 * FW * FH,                       # frame read once (generic mask kernel)
+           "chain_mask_fast_kernel": B * 3 * FW * FH,                  # frame read once (table-driven mask kernel)
            "chain_paste_kernel": B * 2 * 3 * 1080 * 1080}              # background crop read + output write
     peak, peak_src = measured_peak()
     kern = {k: {"launches": c, "total_ms": round(t, 4), "avg_ms": round(t / c, 5)} for k, (c, t) in rep.items()}

@@ -13,6 +13,9 @@
 #include "hsv.cuh"
 #include "staging.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace ipp {
 
 // ===================================================================== stage A: mask
@@ -94,6 +97,218 @@ __global__ void __launch_bounds__(kMaskThreads) chain_mask_kernel(const MaskPara
         v |= __shfl_xor_sync(0xffffffffu, v, 2);
         v |= __shfl_xor_sync(0xffffffffu, v, 4);
         if (it < items && (gi & 7) == 0) out_img[(int64_t)(row0 + r) * p.wpr + (gi >> 3)] = v;
+    }
+}
+
+// ===================================================================== stage A: mask, fast path
+// Persistent LUT variant used when every filter covers the whole image (no zones) and there
+// are at most 8 filters — the reference's own use (filtres_liste.py:186-199).
+//
+//  * V and S of OpenCV's HSV depend only on (v = max, d = max - min), so "which filters accept
+//    this pixel's V and S" is one byte of a 64 KB table T[v][d] living in shared memory for the
+//    whole kernel (built once per call by hsv_lut_kernel; exact, same sdiv table).  A filter
+//    whose H range is [0, >=180] needs nothing else: the pixel is keyed out by one table hit.
+//    Hue is computed only for pixels that pass V/S of a filter with a real H range.
+//  * max/min of (b, g, r) for TWO pixels per instruction with the DPX 16x2 three-input
+//    min/max (VIMNMX3), after byte->halfword unpacking with PRMT.
+//  * one CTA per SM, 1024 threads, loops over (frame, row group) work units; a 3-stage ring
+//    of bulk-copy (UBLKCP) row windows completes on mbarriers while the previous unit is
+//    being converted, so HBM reads never wait for the ALU work.
+struct HsvFast {
+    int n_hue;                       // filters with a real hue range (<= 7), table bits 0..6
+    int h_lo[7], h_hi[7];
+};
+
+// table byte: bit 7 = V,S accepted by a filter that accepts every hue (pixel keyed out at once);
+// bits 0..6 = V,S accepted by hue filter j (hue test still to do)
+__global__ void hsv_lut_kernel(const HsvFilterSet f, uint8_t* __restrict__ lut) {
+    const int v = blockIdx.x, d = threadIdx.x;
+    uint32_t m = 0;
+    if (d <= v) {
+        const int s = (d * g_hsv_sdiv[v] + (1 << 11)) >> 12;
+        const uint32_t X = ((uint32_t)s << 10) | ((uint32_t)v << 20);
+        constexpr uint32_t kGuardSV = (1u << 19) | (1u << 29);
+        int j = 0;
+        for (int k = 0; k < f.n; ++k) {
+            const bool sv = (((X + (f.clo[k] & ~0x3ffu)) & ((f.chi[k] & ~0x3ffu) - X)) & kGuardSV) == kGuardSV;
+            const int lo = 512 - (int)(f.clo[k] & 0x3ffu), hi = (int)(f.chi[k] & 0x3ffu) - 512;
+            const bool any_hue = lo <= 0 && hi >= 180;
+            if (any_hue) {
+                if (sv) m |= 0x80u;
+            } else {
+                if (sv) m |= 1u << j;
+                ++j;
+            }
+        }
+    }
+    lut[v * 256 + d] = (uint8_t)m;
+}
+
+struct MaskFastParams {
+    const uint8_t* frames;
+    int64_t pitch, stride;
+    int crop_l, crop_t, w, h;
+    int wpr;
+    uint32_t* bits;
+    int64_t bits_stride;
+    int rows_per_unit, units_per_frame, n_units;
+    uint32_t smem_row_stride;
+    const uint8_t* lut;
+    HsvFast f;
+};
+
+constexpr int kFastThreads = 1024;
+constexpr int kFastStages = 3;
+
+__device__ __forceinline__ int hue_of(int b, int g, int r, int v, int d, const int* hdiv) {
+    int hn;
+    if (v == r) hn = g - b;
+    else if (v == g) hn = b - r + 2 * d;
+    else hn = r - g + 4 * d;
+    int h = (hn * hdiv[d] + (1 << 11)) >> 12;
+    if (h < 0) h += 180;
+    return h;
+}
+
+// rare path: some pixel of the group passed V/S of a filter with a real hue range
+__device__ __noinline__ uint32_t hue_tests(uint32_t M, uint32_t B01, uint32_t G01, uint32_t R01, uint32_t B23, uint32_t G23,
+                                           uint32_t R23, uint32_t V01, uint32_t V23, uint32_t D01, uint32_t D23,
+                                           const HsvFast& f, const int* hdiv) {
+    uint32_t ex = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t cand = (M >> (8 * k)) & 0x7fu;
+        if (!cand) continue;
+        const uint32_t Bp = k < 2 ? B01 : B23, Gp = k < 2 ? G01 : G23, Rp = k < 2 ? R01 : R23;
+        const uint32_t Vp = k < 2 ? V01 : V23, Dp = k < 2 ? D01 : D23;
+        const int sh = (k & 1) * 16;
+        const int h = hue_of((Bp >> sh) & 0xffff, (Gp >> sh) & 0xffff, (Rp >> sh) & 0xffff, (Vp >> sh) & 0xffff,
+                             (Dp >> sh) & 0xffff, hdiv);
+        while (cand) {
+            const int q = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (h >= f.h_lo[q] && h <= f.h_hi[q]) ex |= 1u << k;
+        }
+    }
+    return ex;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warp 31 = producer (one lane issues the bulk copies of the next units as soon
+// as the 31 consumer warps have released a ring stage), warps 0..30 = consumers.  No block-wide
+// barrier inside the unit loop.
+constexpr int kFastConsumers = kFastThreads / 32 - 1;
+
+__global__ void __launch_bounds__(kFastThreads, 1) chain_mask_fast_kernel(const MaskFastParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[kFastStages], empty[kFastStages];
+    __shared__ int hdiv[256];
+    uint8_t* lut = smem;                                  // 64 KB
+    uint8_t* ring = smem + 65536;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rowbytes = (uint32_t)p.w * 3u;
+    const uint32_t stage_bytes = (uint32_t)p.rows_per_unit * p.smem_row_stride;
+
+    if (tid == 0) {
+        for (int s = 0; s < kFastStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFastConsumers);
+        }
+    }
+    // the table: 64 KB, L2 resident, coalesced 16-byte copies
+    for (int i = tid; i < 65536 / 16; i += kFastThreads)
+        reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(p.lut) + i);
+    for (int i = tid; i < 256; i += kFastThreads) hdiv[i] = g_hsv_hdiv[i];
+    __syncthreads();
+
+    if (warp == kFastConsumers) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int it = 0;
+            for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
+                const int stage = it % kFastStages, use = it / kFastStages;
+                if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
+                const int img = unit / p.units_per_frame;
+                const int row0 = (unit - img * p.units_per_frame) * p.rows_per_unit;
+                const int nrows = min(p.rows_per_unit, p.h - row0);
+                const uint8_t* src = p.frames + (int64_t)img * p.stride + (int64_t)(p.crop_t + row0) * p.pitch + (int64_t)p.crop_l * 3;
+                uint32_t total = 0;
+                for (int r = 0; r < nrows; ++r) total += make_window(src + (int64_t)r * p.pitch, rowbytes).bytes;
+                mbar_expect_tx(&full[stage], total);
+                for (int r = 0; r < nrows; ++r) {
+                    const Window w = make_window(src + (int64_t)r * p.pitch, rowbytes);
+                    bulk_g2s(ring + (size_t)stage * stage_bytes + (size_t)r * p.smem_row_stride, w.base, w.bytes, &full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int cpr = (p.wpr + 3) >> 2;                     // warp chunks (32 groups = 128 px = 4 mask words) per row
+    const int last_x = p.w & ~3;                          // first pixel of a partial last group (== w when w % 4 == 0)
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
+        const int stage = it % kFastStages;
+        mbar_wait(&full[stage], (uint32_t)(it / kFastStages) & 1u);
+        const int img = unit / p.units_per_frame;
+        const int row0 = (unit - img * p.units_per_frame) * p.rows_per_unit;
+        const int nrows = min(p.rows_per_unit, p.h - row0);
+        const uint8_t* src = p.frames + (int64_t)img * p.stride + (int64_t)(p.crop_t + row0) * p.pitch + (int64_t)p.crop_l * 3;
+        const uint8_t* tile = ring + (size_t)stage * stage_bytes;
+        uint32_t* out_unit = p.bits + (int64_t)img * p.bits_stride + (int64_t)row0 * p.wpr;
+        // chunk list of this warp: ch = warp, warp + 31, ... mapped to (row, chunk-in-row) without a division per chunk
+        int r = warp / cpr, c = warp - r * cpr;
+        while (r < nrows) {
+            const uint32_t shift = (uint32_t)((uintptr_t)(src + (int64_t)r * p.pitch) & 15);
+            const uint32_t bs = (shift & 3u) * 8u;
+            const uint32_t* row32 = reinterpret_cast<const uint32_t*>(tile + (size_t)r * p.smem_row_stride);
+            uint32_t* out_row = out_unit + (int64_t)r * p.wpr;
+            const int x = (c * 32 + lane) * 4;
+            uint32_t nib = 0;
+            if (x < p.w) {
+                const uint32_t* w32 = row32 + ((shift + (uint32_t)x * 3u) >> 2);
+                uint32_t rx, ry, rz;                                        // 12 bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                if (bs == 0) {
+                    rx = w32[0]; ry = w32[1]; rz = w32[2];
+                } else {
+                    const uint32_t a0 = w32[0], a1 = w32[1], a2 = w32[2], a3 = w32[3];
+                    rx = __funnelshift_r(a0, a1, bs); ry = __funnelshift_r(a1, a2, bs); rz = __funnelshift_r(a2, a3, bs);
+                }
+                const uint32_t B01 = __byte_perm(rx, 0u, 0x4340), G01 = __byte_perm(rx, ry, 0x0401) & 0x00ff00ffu;
+                const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
+                const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
+                const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
+                const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
+                const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
+                const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
+                const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
+                                   ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
+                // bit 7 of every byte -> 4 adjacent bits (the multiply gathers them at bits 21..24)
+                const uint32_t hit = (M & 0x80808080u) >> 7;
+                uint32_t ex = ((hit * 0x00204081u) >> 21) & 15u;
+                if (M & 0x7f7f7f7fu & ~(hit * 0x7fu))
+                    ex |= hue_tests(M, B01, G01, R01, B23, G23, R23, V01, V23, D01, D23, p.f, hdiv);
+                nib = ~ex & 15u;
+                if (x >= last_x) nib &= (1u << (p.w - x)) - 1u;             // partial last group of the row
+            }
+            uint32_t v = nib << (4 * (lane & 7));
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            const int word = c * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && word < p.wpr) out_row[word] = v;
+            c += kFastConsumers;
+            while (c >= cpr) {
+                c -= cpr;
+                ++r;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
     }
 }
 
@@ -463,14 +678,59 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     const int te = ensure_hsv_tables();
     IPP_REQUIRE(te == 0, te, "ipp_chain_stage_a: table upload failed (%d)", te);
     const CclBuffers b = carve_ccl(workspace, cg, n_frames);
+    const HsvFilterSet fs = pack_filters(g->ranges, g->n_ranges, g->crop_w, g->crop_h);
+    const uint32_t rowbytes = (uint32_t)g->crop_w * 3u;
+    const uint32_t row_stride = staged_row_stride(rowbytes);
+    IPP_REQUIRE(row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_a: row too long");
+    int fast_rows = (int)((200 * 1024 - 65536) / kFastStages / row_stride);
+    if (fast_rows > 8) fast_rows = 8;
+    // the 64 KB V/S table borrows the head of the area[] scratch: ccl_init (which runs after the
+    // mask kernel) only ever writes run-start entries there before anything reads them
+    const bool lut_fits = (int64_t)cg.lab_stride * 4 * n_frames >= 65536;
+    int n_hue_filters = 0;
+    for (int k = 0; k < fs.n; ++k) {
+        const int lo = 512 - (int)(fs.clo[k] & 0x3ffu), hi = (int)(fs.chi[k] & 0x3ffu) - 512;
+        n_hue_filters += !(lo <= 0 && hi >= 180);
+    }
+    const bool fast = fs.all_zones_full && n_hue_filters <= 7 && fast_rows >= 1 && lut_fits && getenv("IPP_MASK_GENERIC") == nullptr;
+    if (fast) {
+        uint8_t* lut = (uint8_t*)b.area;
+        { ipp::LaunchTimer _lt("hsv_lut_kernel", st); hsv_lut_kernel<<<256, 256, 0, st>>>(fs, lut); }
+        IPP_LAUNCH_CHECK();
+        MaskFastParams p{};
+        p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
+        p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
+        p.wpr = cg.wpr; p.bits = b.bits; p.bits_stride = cg.bits_stride;
+        p.rows_per_unit = fast_rows;
+        p.units_per_frame = ceil_div(g->crop_h, fast_rows);
+        p.n_units = p.units_per_frame * n_frames;
+        p.smem_row_stride = row_stride;
+        p.lut = lut;
+        for (int k = 0; k < fs.n; ++k) {
+            const int lo = 512 - (int)(fs.clo[k] & 0x3ffu), hi = (int)(fs.chi[k] & 0x3ffu) - 512;
+            if (!(lo <= 0 && hi >= 180)) {
+                p.f.h_lo[p.f.n_hue] = lo;
+                p.f.h_hi[p.f.n_hue] = hi;
+                ++p.f.n_hue;
+            }
+        }
+        const size_t smem = 65536 + (size_t)kFastStages * fast_rows * row_stride;
+        static size_t smem_set = 0;     // the attribute only ever grows; setting it is not free
+        if (smem > smem_set) {
+            IPP_CUDA(cudaFuncSetAttribute(chain_mask_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        const int grid = std::min(sm_count(), p.n_units);
+        { ipp::LaunchTimer _lt("chain_mask_fast_kernel", st); chain_mask_fast_kernel<<<grid, kFastThreads, smem, st>>>(p); }
+        IPP_LAUNCH_CHECK();
+    }
+    if (!fast) {
     MaskParams p{};
     p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
     p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
     p.wpr = cg.wpr; p.bits = b.bits; p.bits_stride = cg.bits_stride;
-    p.f = pack_filters(g->ranges, g->n_ranges, g->crop_w, g->crop_h);
-    const uint32_t rowbytes = (uint32_t)g->crop_w * 3u;
-    p.smem_row_stride = staged_row_stride(rowbytes);
-    IPP_REQUIRE(p.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_a: row too long");
+    p.f = fs;
+    p.smem_row_stride = row_stride;
     int rows = (int)(24576 / p.smem_row_stride);
     if (rows < 1) rows = 1;
     if (rows > g->crop_h) rows = g->crop_h;
@@ -481,6 +741,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     dim3 grid(ceil_div(g->crop_h, rows), n_frames);
     { ipp::LaunchTimer _lt("chain_mask_kernel", st); chain_mask_kernel<<<grid, kMaskThreads, smem, st>>>(p); }
     IPP_LAUNCH_CHECK();
+    }
     rc = ccl_run(cg, b, n_frames, st);
     if (rc != IPP_OK) return rc;
     { ipp::LaunchTimer _lt("ccl_info_kernel", st); ccl_info_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(b, info_out, n_frames); }

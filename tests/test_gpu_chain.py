@@ -124,3 +124,40 @@ def test_device_lanczos_tables_equal_host_tables():
                     found = True
         assert found, "bounds differ: they involve no transcendental and must be identical"
     assert len(bad) <= 2 and n_amb < 200, (len(bad), n_amb)
+
+
+def test_chain_generic_mask_kernel_still_matches(monkeypatch):
+    """Stage A has two mask kernels: the persistent table-driven one (no zones, <= 8 filters) and the
+    generic one.  Force the generic one on a configuration the fast one would take."""
+    monkeypatch.setenv("IPP_MASK_GENERIC", "1")
+    H, W = 270, 480
+    frames = [synth.frame(31, i, H, W) for i in range(3)] + [synth.noise(31, 9, (H, W, 3))]
+    bgs = [synth.background(31, i, H, W) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    _compare(*_run_both(frames, bgs, 5, **kw))
+
+
+def test_chain_mask_fast_path_on_all_colours_and_hue_filters():
+    """Every BGR colour through the table-driven mask kernel, with filters that need the hue test
+    (real H ranges incl. the wrap-free red band) — against cv2 via the oracle chain's first stage."""
+    from oracle import libcalls as L
+    c = np.arange(1 << 24, dtype=np.uint32)
+    bgr = np.stack([c & 255, (c >> 8) & 255, (c >> 16) & 255], -1).astype(np.uint8).reshape(16, 1024, 1024, 3)
+    filters = [(0, 0, 0, 180, 255, 40), (15, 60, 200, 35, 255, 255), (100, 30, 30, 130, 255, 255), (0, 200, 100, 8, 255, 255),
+               (170, 100, 100, 180, 255, 255), (40, 0, 240, 90, 20, 255)]
+    from image_processor_pipeline_b200 import _native, hostmath
+    import ctypes as C
+    lib = _native.load()
+    geom = chain._geom_struct(1024, 1024, (0, 0, 1024, 1024), 1024, 1024, hostmath.pack_hsv_ranges(filters))
+    n = 16
+    ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    info = torch.empty((n, 8), dtype=torch.int32, device=DEV)
+    fr = torch.from_numpy(bgr).to(DEV)
+    _native.check(lib.ipp_chain_stage_a(fr.data_ptr(), 1024 * 3, 1024 * 1024 * 3, C.byref(geom), info.data_ptr(), ws.data_ptr(),
+                                        ws_bytes, n, torch.cuda.current_stream().cuda_stream), "stage_a")
+    n_fg = info.cpu().numpy()[:, 5]
+    for i in range(n):
+        keyed = L.color_masks_to_alpha(bgr[i], filters)
+        assert n_fg[i] == int((keyed[..., 3] > 1).sum()), i
