@@ -137,6 +137,29 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Grow-only scratch buffers per device: the chain's workspaces change size from batch to batch
+# (sprite sizes are data dependent); asking the caching allocator for a new size every call
+# costs a cudaMalloc (and a device synchronisation) each time.
+_SCRATCH = {}
+
+
+def _scratch(name: str, nbytes: int, dev: torch.device, dtype=torch.uint8) -> torch.Tensor:
+    key = (name, dev.index if dev.index is not None else torch.cuda.current_device())
+    item = torch.empty(0, dtype=dtype).element_size()
+    n = max(1, (int(nbytes) + item - 1) // item)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < n or buf.dtype != dtype:
+        grow = int(n * 1.25) + 1024
+        buf = torch.empty(grow, dtype=dtype, device=dev)
+        _SCRATCH[key] = buf
+    return buf[:n]
+
+
+def release_scratch():
+    """Drop the cached workspaces (they are re-created on demand)."""
+    _SCRATCH.clear()
+
+
 # =========================================================================== python planner
 def plan_rotations(info: np.ndarray, p: ChainParams, rng) -> List[dict]:
     """Rotation step bookkeeping + draws (rotations.py:77-119).  info = stage-A rows."""
@@ -401,7 +424,8 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
             kk = np.empty((n_out, ks), np.int32)
             _native.check(lib.ipp_lanczos_coeffs_host(n_in, n_out, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_coeffs_host")
             tab[bo:bo + 2 * n_out] = b.ravel()
-            tab[ko:ko + n_out * ks] = kk.ravel()
+            # device layout: vertical tables [row][tap], horizontal tables transposed [tap][row]
+            tab[ko:ko + n_out * ks] = kk.ravel() if axis else kk.T.ravel()
     return tab
 
 
@@ -444,8 +468,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     with torch.cuda.device(dev):
         # ------------------------------------------------------------------ stage A
         ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        info_d = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        ws = _scratch("mask", ws_bytes, dev)
+        info_d = _scratch("info", n * 32, dev, torch.int32).view(n, 8)
         _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                             ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
         info = info_d.cpu().numpy()                                   # sync #1
@@ -466,7 +490,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         rots_loc["frame"] -= lo
         tiles = ((rots_loc["canvas_w"].astype(np.int64) + 31) // 32) * ((rots_loc["canvas_h"].astype(np.int64) + 31) // 32)
         rots_loc["tile_start"] = _excl(tiles)
-        bbox_d = torch.empty((max(1, len(rots_loc)), 4), dtype=torch.int32, device=dev)
+        bbox_d = _scratch("bbox", max(1, len(rots_loc)) * 16, dev, torch.int32).view(-1, 4)
         rot_d = None
         if len(rots_loc):
             rot_d = torch.from_numpy(rots_loc.view(np.uint8)).to(dev)
@@ -497,11 +521,11 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
 
         # ------------------------------------------------------------------ tables, sprite workspace
         items_d = torch.from_numpy(items.view(np.uint8)).to(dev)
-        spr_ws = torch.empty(max(tot["ws"], 256), dtype=torch.uint8, device=dev)
+        spr_ws = _scratch("sprites", max(tot["ws"], 256), dev)
         amb_d = None
         if device_tables:
-            tab_d = torch.empty(max(1, tot["table_ints"]), dtype=torch.int32, device=dev)
-            amb_d = torch.empty(1 + 3 * AMB_CAPACITY, dtype=torch.int32, device=dev)
+            tab_d = _scratch("tables", max(1, tot["table_ints"]) * 4, dev, torch.int32)
+            amb_d = _scratch("amb", (1 + 3 * AMB_CAPACITY) * 4, dev, torch.int32)
             _native.check(lib.ipp_chain_tables(items_d.data_ptr(), K, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
                                                AMB_CAPACITY, float(ambiguity_eps), _stream()), "ipp_chain_tables")
         else:
@@ -524,7 +548,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
             if n_amb:
                 n_fixed = _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev)
-        for t in (ws, rot_d, items_d, tab_d, spr_ws, amb_d):
+        for t in (rot_d, items_d):
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
 
@@ -553,9 +577,10 @@ def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
         b = np.empty(2, np.int32)
         kk = np.empty(ks, np.int32)
         _native.check(lib.ipp_lanczos_row_host(n_in, n_out, row, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_row_host")
-        dev_row = tab_d[ko + row * ks: ko + (row + 1) * ks].cpu().numpy()
-        if not np.array_equal(dev_row, kk):
-            tab_d[ko + row * ks: ko + (row + 1) * ks] = torch.from_numpy(kk).to(dev)
+        # vertical tables are [row][tap]; horizontal ones are transposed, [tap][row]
+        view = tab_d[ko + row * ks: ko + (row + 1) * ks] if axis else tab_d[ko + row: ko + row + n_out * ks: n_out]
+        if not np.array_equal(view.cpu().numpy(), kk):
+            view.copy_(torch.from_numpy(kk).to(dev))
             tab_d[bo + 2 * row: bo + 2 * row + 2] = torch.from_numpy(b).to(dev)
             dirty.add(item)
     if dirty:

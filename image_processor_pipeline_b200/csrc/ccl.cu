@@ -34,23 +34,23 @@ __device__ __forceinline__ int run_start(const uint32_t* crow, int gbx) {
     return (k << 5) + 31 - __clz(m);
 }
 
-__device__ __forceinline__ int find_root(const int32_t* L, int x) {
+__device__ __forceinline__ int find_root(const int2* L, int x) {
     int p;
-    while ((p = __ldcg(L + x)) != x) x = p;
+    while ((p = __ldcg(&L[x].x)) != x) x = p;
     return x;
 }
 
-__device__ __forceinline__ void unite(int32_t* L, int a, int b) {
+__device__ __forceinline__ void unite(int2* L, int a, int b) {
     bool done;
     do {
         a = find_root(L, a);
         b = find_root(L, b);
         if (a < b) {
-            const int old = atomicMin(&L[b], a);
+            const int old = atomicMin(&L[b].x, a);
             done = (old == b);
             b = old;
         } else if (b < a) {
-            const int old = atomicMin(&L[a], b);
+            const int old = atomicMin(&L[a].x, b);
             done = (old == a);
             a = old;
         } else {
@@ -93,14 +93,12 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const Cc
     b.cbits[cf] = C;
     b.fbits[cf] = F;
     uint32_t S = F & ~C;
-    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
-    int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+    int2* L = b.la + (int64_t)t.img * g.lab_stride;
     const int base = t.by * g.bw + (t.k << 5);
     while (S) {
         const int i = __ffs(S) - 1;
         S &= S - 1;
-        L[base + i] = base + i;
-        A[base + i] = 0;
+        L[base + i] = make_int2(base + i, 0);
     }
     if (t.by == 0 && t.k == 0) {
         b.best[t.img] = 0ull;
@@ -135,7 +133,7 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const CclGeom g, const C
     uint32_t nU = cU & ~(C & ((cUR << 1) | (Cu & (cU << 1))));
     uint32_t nUL = cUL & ~(cU & Cu) & ~(C & (cU << 1));
     uint32_t nUR = cUR & ~(cU & Cush);
-    int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
+    int2* L = b.la + (int64_t)t.img * g.lab_stride;
     const int rowbase = t.by * g.bw, rowbaseU = rowbase - g.bw, gb0 = t.k << 5;
     while (nU) {
         const int i = __ffs(nU) - 1;
@@ -170,8 +168,7 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
     uint32_t starts = 0, C = 0;
     uint64_t p0 = 0, p1 = 0;
     const uint32_t* crow = nullptr;
-    int32_t* L = nullptr;
-    int32_t* A = nullptr;
+    int2* L = nullptr;
     int rowbase = 0, gb0 = 0;
     if (t.ok) {
         const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
@@ -183,8 +180,7 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
             const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
             p0 = load_px64(r0, t.k, g.wpr);
             p1 = ((2 * t.by + 1) < g.h) ? load_px64(r0 + g.wpr, t.k, g.wpr) : 0ull;
-            L = b.label + (int64_t)t.img * g.lab_stride;
-            A = b.area + (int64_t)t.img * g.lab_stride;
+            L = b.la + (int64_t)t.img * g.lab_stride;
             rowbase = t.by * g.bw;
             gb0 = t.k << 5;
             starts = F & (~C | 1u);
@@ -205,8 +201,8 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
             const bool own = ((C >> i) & 1u) == 0u;
             const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
             const int root = find_root(L, rowbase + s);
-            if (own) L[rowbase + gb0 + i] = root;
-            slot = A + root;
+            if (own) L[rowbase + gb0 + i].x = root;
+            slot = &L[root].y;
             key = (long long)(uintptr_t)slot;
             nfg += cnt;
         }
@@ -241,16 +237,16 @@ __global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const Cc
         const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
         uint32_t S = b.fbits[cf] & ~b.cbits[cf];
         if (S) {
-            const int32_t* L = b.label + (int64_t)t.img * g.lab_stride;
-            const int32_t* A = b.area + (int64_t)t.img * g.lab_stride;
+            const int2* L = b.la + (int64_t)t.img * g.lab_stride;
             const int base = t.by * g.bw + (t.k << 5);
             while (S) {
                 const int i = __ffs(S) - 1;
                 S &= S - 1;
                 const int bi = base + i;
-                if (L[bi] == bi) {
+                const int2 la = L[bi];
+                if (la.x == bi) {
                     const unsigned long long key =
-                        ((unsigned long long)(uint32_t)A[bi] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
+                        ((unsigned long long)(uint32_t)la.y << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
                     best = key > best ? key : best;
                 }
             }
@@ -284,7 +280,7 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
             const int by = y >> 1, k = kx >> 1, half = (kx & 1) * 16;
             const uint32_t* crow = b.cbits + (int64_t)img * g.cf_stride + (int64_t)by * g.bww;
             const uint32_t C = crow[k];
-            const int32_t* L = b.label + (int64_t)img * g.lab_stride;
+            const int2* L = b.la + (int64_t)img * g.lab_stride;
             const int rowbase = by * g.bw;
             uint32_t rem_bits = bits, keep = 0;
             while (rem_bits) {
@@ -295,7 +291,7 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
                 const int hi = min(32, 2 * (e - half));
                 const uint32_t pm = ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
                 const int s = run_start(crow, (k << 5) + i);
-                if (L[rowbase + s] == best_root) keep |= bits & pm;
+                if (L[rowbase + s].x == best_root) keep |= bits & pm;
                 rem_bits &= ~pm;
             }
             if (keep != bits) *pw = keep;

@@ -40,8 +40,8 @@ struct CclBuffers {
     uint32_t* bits;      // [n][h][wpr]       pixel mask in, keep-mask out
     uint32_t* cbits;     // [n][bh][bww]
     uint32_t* fbits;     // [n][bh][bww]
-    int32_t* label;      // [n][bh*bw]
-    int32_t* area;       // [n][bh*bw]
+    int2* la;            // [n][bh*bw]  .x = union-find parent (label), .y = area (valid on roots);
+                         //              interleaved: a run start costs one 32-byte sector, not two
     unsigned long long* best;   // [n]  (area << 32) | (0xffffffff - root)
     int32_t* acc;        // [n][8]  minx, miny, maxx1, maxy1, n_fg, -, -, -
 };
@@ -78,8 +78,7 @@ static inline CclBuffers carve_ccl(void* ws, const CclGeom& g, int n) {
     b.bits = (uint32_t*)p;   p += align256(g.bits_stride * 4 * n);
     b.cbits = (uint32_t*)p;  p += align256(g.cf_stride * 4 * n);
     b.fbits = (uint32_t*)p;  p += align256(g.cf_stride * 4 * n);
-    b.label = (int32_t*)p;   p += align256(g.lab_stride * 4 * n);
-    b.area = (int32_t*)p;    p += align256(g.lab_stride * 4 * n);
+    b.la = (int2*)p;         p += 2 * align256(g.lab_stride * 4 * n);
     b.best = (unsigned long long*)p; p += align256((int64_t)8 * n);
     b.acc = (int32_t*)p;
     return b;

@@ -457,7 +457,20 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
     return c0 | (c1 << 8) | (c2 << 16) | (a << 24);
 }
 
-// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles)
+// One tap group: 4 independent loads are issued before any of them is used, so a warp keeps
+// 4 memory requests in flight instead of walking a dependent chain (the passes are latency
+// bound on small, L2-resident sprites, not bandwidth bound).
+#define IPP_ACC4(px, w)                                                                \
+    {                                                                                  \
+        s0 += (int)((px) & 255u) * (w);                                                \
+        s1 += (int)(((px) >> 8) & 255u) * (w);                                         \
+        s2 += (int)(((px) >> 16) & 255u) * (w);                                        \
+        s3 += (int)((px) >> 24) * (w);                                                 \
+    }
+
+// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles).
+// Horizontal coefficients are stored TRANSPOSED ([tap][X]) so that the 32 lanes of a warp
+// (32 consecutive X) read consecutive words.
 __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -465,28 +478,34 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int tile = (int)blockIdx.x - it.h_tile_start;
-    const int tiles_x = (it.new_w + 31) >> 5;
+    const int new_w = it.new_w;
+    const int tiles_x = (new_w + 31) >> 5;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int X = tx * 32 + (threadIdx.x & 31);
     const int y = ty * 8 + (threadIdx.x >> 5);
-    if (X >= it.new_w || y >= it.spr_h) return;
+    if (X >= new_w || y >= it.spr_h) return;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.rot_off) + (int64_t)y * it.spr_w;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.tmp_off) + (int64_t)y * it.new_w;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.tmp_off) + (int64_t)y * new_w;
     if (it.h_ksize == 0) {          // width unchanged: Pillow skips the horizontal pass
         dst[X] = src[X];
         return;
     }
     const int32_t* bounds = c.tables + it.hb_off;
     const int xmin = bounds[2 * X], n = bounds[2 * X + 1];
-    const int32_t* k = c.tables + it.hk_off + (int64_t)X * it.h_ksize;
+    const int32_t* k = c.tables + it.hk_off + X;          // [tap][X]
+    src += xmin;
     int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t v = src[xmin + i];
-        const int w = __ldg(k + i);
-        s0 += (int)(v & 255u) * w;
-        s1 += (int)((v >> 8) & 255u) * w;
-        s2 += (int)((v >> 16) & 255u) * w;
-        s3 += (int)(v >> 24) * w;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t v0 = src[i], v1 = src[i + 1], v2 = src[i + 2], v3 = src[i + 3];
+        const int w0 = __ldg(k + (int64_t)i * new_w), w1 = __ldg(k + (int64_t)(i + 1) * new_w);
+        const int w2 = __ldg(k + (int64_t)(i + 2) * new_w), w3 = __ldg(k + (int64_t)(i + 3) * new_w);
+        IPP_ACC4(v0, w0) IPP_ACC4(v1, w1) IPP_ACC4(v2, w2) IPP_ACC4(v3, w3)
+    }
+    for (; i < n; ++i) {
+        const uint32_t v = src[i];
+        const int w = __ldg(k + (int64_t)i * new_w);
+        IPP_ACC4(v, w)
     }
     dst[X] = c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24);
 }
@@ -499,28 +518,34 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int tile = (int)blockIdx.x - it.v_tile_start;
-    const int tiles_x = (it.new_w + 31) >> 5;
+    const int new_w = it.new_w;
+    const int tiles_x = (new_w + 31) >> 5;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int x = tx * 32 + (threadIdx.x & 31);
     const int Y = ty * 8 + (threadIdx.x >> 5);
-    if (x >= it.new_w || Y >= it.new_h) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.tmp_off);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off) + (int64_t)Y * it.new_w;
+    if (x >= new_w || Y >= it.new_h) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.tmp_off) + x;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off) + (int64_t)Y * new_w;
     if (it.v_ksize == 0) {
-        dst[x] = c_unpremultiply(src[(int64_t)Y * it.new_w + x]);
+        dst[x] = c_unpremultiply(src[(int64_t)Y * new_w]);
         return;
     }
     const int32_t* bounds = c.tables + it.vb_off;
     const int ymin = bounds[2 * Y], n = bounds[2 * Y + 1];
-    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;
+    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;    // [Y][tap]: uniform per warp
+    src += (int64_t)ymin * new_w;
     int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t v = src[(int64_t)(ymin + i) * it.new_w + x];
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t v0 = src[(int64_t)i * new_w], v1 = src[(int64_t)(i + 1) * new_w];
+        const uint32_t v2 = src[(int64_t)(i + 2) * new_w], v3 = src[(int64_t)(i + 3) * new_w];
+        const int w0 = __ldg(k + i), w1 = __ldg(k + i + 1), w2 = __ldg(k + i + 2), w3 = __ldg(k + i + 3);
+        IPP_ACC4(v0, w0) IPP_ACC4(v1, w1) IPP_ACC4(v2, w2) IPP_ACC4(v3, w3)
+    }
+    for (; i < n; ++i) {
+        const uint32_t v = src[(int64_t)i * new_w];
         const int w = __ldg(k + i);
-        s0 += (int)(v & 255u) * w;
-        s1 += (int)((v >> 8) & 255u) * w;
-        s2 += (int)((v >> 16) & 255u) * w;
-        s3 += (int)(v >> 24) * w;
+        IPP_ACC4(v, w)
     }
     dst[x] = c_unpremultiply(c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24));
 }
@@ -603,7 +628,9 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
     const int in_size = axis ? it.spr_h : it.spr_w, out_size = axis ? it.new_h : it.new_w;
     const int ksize = axis ? it.v_ksize : it.h_ksize;
     int32_t* bounds = p.tables + (axis ? it.vb_off : it.hb_off) + 2 * xx;
-    int32_t* k = p.tables + (axis ? it.vk_off : it.hk_off) + (int64_t)xx * ksize;
+    // vertical tables are [row][tap]; horizontal tables are stored transposed, [tap][row]
+    int32_t* k = p.tables + (axis ? it.vk_off + (int64_t)xx * ksize : it.hk_off + (int64_t)xx);
+    const int64_t kstep = axis ? 1 : out_size;
     const double scale = __ddiv_rn((double)in_size, (double)out_size);
     const double filterscale = scale < 1.0 ? 1.0 : scale;
     const double support = __dmul_rn(3.0, filterscale);
@@ -628,7 +655,7 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
             c = (int)t;
             if (fabs(t - rint(t)) < p.eps) amb = true;
         }
-        k[x] = c;
+        k[(int64_t)x * kstep] = c;
     }
     bounds[0] = xmin;
     bounds[1] = xmax;
@@ -684,8 +711,8 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     IPP_REQUIRE(row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_a: row too long");
     int fast_rows = (int)((200 * 1024 - 65536) / kFastStages / row_stride);
     if (fast_rows > 8) fast_rows = 8;
-    // the 64 KB V/S table borrows the head of the area[] scratch: ccl_init (which runs after the
-    // mask kernel) only ever writes run-start entries there before anything reads them
+    // the 64 KB V/S table borrows the head of the label/area scratch: ccl_init (which runs after
+    // the mask kernel) writes the run-start entries there before anything reads them
     const bool lut_fits = (int64_t)cg.lab_stride * 4 * n_frames >= 65536;
     int n_hue_filters = 0;
     for (int k = 0; k < fs.n; ++k) {
@@ -694,7 +721,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     }
     const bool fast = fs.all_zones_full && n_hue_filters <= 7 && fast_rows >= 1 && lut_fits && getenv("IPP_MASK_GENERIC") == nullptr;
     if (fast) {
-        uint8_t* lut = (uint8_t*)b.area;
+        uint8_t* lut = (uint8_t*)b.la;
         { ipp::LaunchTimer _lt("hsv_lut_kernel", st); hsv_lut_kernel<<<256, 256, 0, st>>>(fs, lut); }
         IPP_LAUNCH_CHECK();
         MaskFastParams p{};

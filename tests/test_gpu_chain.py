@@ -120,7 +120,8 @@ def test_device_lanczos_tables_equal_host_tables():
             for axis, (ko, ks, n_out) in enumerate(((int(it["hk_off"]), int(it["h_ksize"]), int(it["new_w"])),
                                                     (int(it["vk_off"]), int(it["v_ksize"]), int(it["new_h"])))):
                 if ks and ko <= idx < ko + ks * n_out:
-                    assert (it_i, axis, (idx - ko) // ks) in flagged, "a differing row was not flagged"
+                    row = (idx - ko) // ks if axis else (idx - ko) % n_out      # h tables are stored [tap][row]
+                    assert (it_i, axis, row) in flagged, "a differing row was not flagged"
                     found = True
         assert found, "bounds differ: they involve no transcendental and must be identical"
     assert len(bad) <= 2 and n_amb < 200, (len(bad), n_amb)
