@@ -123,55 +123,66 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def _cpu_worker(args):
-    seed, first, count = args
+_WORKER = {}
+
+
+def _cpu_worker_init(seed, count):
+    """Per-process set-up, outside any timed region: imports, single-threaded cv2, and this
+    worker's own `count` synthetic frames/backgrounds."""
     import cv2
     cv2.setNumThreads(1)
     from image_processor_pipeline_b200 import synth
     from oracle import chain as OC
+    first = (os.getpid() * 7919) % 100_000
     frames, bgs = make_inputs(count, seed, first, base=min(4, count))
-    random.seed(seed + first)
+    _WORKER.update(frames=list(frames), bgs=list(bgs), OC=OC, filters=synth.REFERENCE_FILTERS, seed=seed + first)
+
+
+def _cpu_worker_run(step):
+    """One pass of the oracle chain (the reference's cv2/Pillow call sequence, in memory) over the
+    worker's frames.  Returns (images produced, seconds of chain work)."""
+    w = _WORKER
+    random.seed(w["seed"] + step)
     t0 = time.perf_counter()
-    imgs, labels, _ = OC.run_chain(list(frames), list(bgs), color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
+    imgs, labels, _ = w["OC"].run_chain(w["frames"], w["bgs"], color_ranges_to_exclude_hsv=w["filters"], **CHAIN_KW)
     return len(imgs), time.perf_counter() - t0
 
 
-def cpu_chain_rate(n_images: int, workers: int, seed: int = 1):
-    """images/s of the oracle chain with `workers` processes (1 = in-process, cv2 single-threaded)."""
-    if workers <= 1:
-        done, dt = _cpu_worker((seed, 0, n_images))
-        return done / dt, dt
-    from concurrent.futures import ProcessPoolExecutor
-    per = max(1, n_images // workers)
-    jobs = [(seed, w * per, per) for w in range(workers)]
-    with ProcessPoolExecutor(max_workers=workers) as ex:
-        list(ex.map(_cpu_worker, [(seed, 0, 1)] * workers))       # spin the pool up (imports) outside the clock
-        t0 = time.perf_counter()
-        res = list(ex.map(_cpu_worker, jobs))
-        dt = time.perf_counter() - t0
-    return sum(r[0] for r in res) / dt, dt
+def cpu_chain_rate_single(n_images: int, seed: int = 1):
+    """images/s of the oracle chain in this process, cv2 single-threaded."""
+    _cpu_worker_init(seed, n_images)
+    _cpu_worker_run(0) if n_images <= 4 else None            # warm the libraries on tiny samples only
+    done, dt = _cpu_worker_run(1)
+    return done / dt, dt
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's CPU path on all host cores.  ProcessPoolExecutor(cpu_count)
+    is the reference's own workers=-1 mode (pipeline.py:88-90, :372); every worker owns
+    `per_worker` frames and one step = every worker running the oracle chain over its frames."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from concurrent.futures import ProcessPoolExecutor
     cores = os.cpu_count() or 1
-    per_step = max(cores, 8)
-    rates = []
-    for s in range(args.warmup + args.steps):
-        rate, dt = cpu_chain_rate(per_step, cores, seed=100 + s)
-        if s >= args.warmup:
-            rates.append((per_step, dt))
-    total = sum(r[0] for r in rates)
-    t = sum(r[1] for r in rates)
-    value = total / t
+    per_worker = 4
+    per_step = per_worker * cores
+    elapsed, produced = 0.0, 0
+    with ProcessPoolExecutor(max_workers=cores, initializer=_cpu_worker_init, initargs=(100, per_worker)) as ex:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = list(ex.map(_cpu_worker_run, [s] * cores, chunksize=1))
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                elapsed += dt
+                produced += sum(r[0] for r in res)
+    value = produced / elapsed
     line = {"impl": "reference", "metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} frames per step over a ProcessPoolExecutor({cores}), oracle chain = the reference's cv2/Pillow call sequence in memory (no file I/O)"},
+                             "sample": f"{per_step} frames per step ({per_worker} per worker) over a ProcessPoolExecutor({cores}); oracle chain = the reference's cv2/Pillow call sequence in memory (no file I/O), inputs generated outside the timed region"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -187,6 +198,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -282,17 +294,17 @@ def main():
 
         def step_e2e(s):
             random.seed(1000 * rank + s)
-            return chain.run_chain_host(frames_pin, bgs_pin, params, dev, out_pin)
+            return chain.run_chain_host(frames_pin, bgs_pin, params, dev, out_pin, chunk=args.e2e_chunk)
 
         ems, en, _ = timed(step_e2e, max(2, args.steps // 2), 1)
-        e2e = {"value": en / (ems * 1e-3), "unit": "images/s",
+        e2e = {"value": en / (ems * 1e-3), "unit": "images/s", "pipelined_slice_frames": args.e2e_chunk,
                "h2d_bytes_per_step": int(frames_pin.numel() + bgs_pin.numel()),
                "d2h_bytes_per_step": int(out_pin.numel())}
 
     if rank == 0:
         cpu = None
         if world == 1:
-            rate, dt = cpu_chain_rate(args.cpu_sample, 1)
+            rate, dt = cpu_chain_rate_single(args.cpu_sample)
             cpu = {"value": rate, "unit": "images/s", "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_sample} frames of the same workload, oracle chain (the reference's cv2/Pillow call sequence in memory, cv2.setNumThreads(1)), {dt:.1f} s",
                    "host_cores_available": os.cpu_count()}
@@ -301,7 +313,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B,
                            "l2": f"inputs per step {2 * B * 3 * FW * FH / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
-                           "host_work_in_step": "python planner + 2 device->host size read-backs per batch (RNG bounds depend on sprite sizes)"},
+                           "host_work_in_step": "C++ planner (Python-compatible MT19937 draws) + 3 small device->host read-backs per batch (RNG bounds depend on sprite sizes; table-ambiguity count)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "chain_algorithmic_gbs": chain_gbs, "chain_frac_of_peak": chain_gbs / peak,
                 "kernels": kern, "cpu_baseline": cpu}

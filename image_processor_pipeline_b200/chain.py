@@ -424,8 +424,7 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
             kk = np.empty((n_out, ks), np.int32)
             _native.check(lib.ipp_lanczos_coeffs_host(n_in, n_out, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_coeffs_host")
             tab[bo:bo + 2 * n_out] = b.ravel()
-            # device layout: vertical tables [row][tap], horizontal tables transposed [tap][row]
-            tab[ko:ko + n_out * ks] = kk.ravel() if axis else kk.T.ravel()
+            tab[ko:ko + n_out * ks] = kk.ravel()
     return tab
 
 
@@ -577,8 +576,7 @@ def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
         b = np.empty(2, np.int32)
         kk = np.empty(ks, np.int32)
         _native.check(lib.ipp_lanczos_row_host(n_in, n_out, row, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_row_host")
-        # vertical tables are [row][tap]; horizontal ones are transposed, [tap][row]
-        view = tab_d[ko + row * ks: ko + (row + 1) * ks] if axis else tab_d[ko + row: ko + row + n_out * ks: n_out]
+        view = tab_d[ko + row * ks: ko + (row + 1) * ks]
         if not np.array_equal(view.cpu().numpy(), kk):
             view.copy_(torch.from_numpy(kk).to(dev))
             tab_d[bo + 2 * row: bo + 2 * row + 2] = torch.from_numpy(b).to(dev)
@@ -595,19 +593,109 @@ def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
 
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
-                   out_host: Optional[torch.Tensor] = None, rng=_random, **kw) -> ChainResult:
-    """End-to-end entry for HOST buffers (the call a pipeline step makes after decoding):
-    pinned host frames / backgrounds -> H2D -> run_chain -> D2H of the output images.
-    ``out_host`` (pinned, [>=K, cs, cs, 3]) receives the images; ChainResult.images is that
-    host tensor (first K rows)."""
+                   out_host: Optional[torch.Tensor] = None, rng=_random, chunk: Optional[int] = None, **kw) -> ChainResult:
+    """End-to-end entry for HOST buffers (what a pipeline step does after decoding): pinned host
+    frames / backgrounds -> H2D -> chain -> D2H of the output images.
+
+    ``chunk=None``: one chain over the whole batch (draw order identical to ``run_chain``).
+    ``chunk=k``: the batch is cut into slices of k frames that flow through a three-stream pipeline
+    — H2D of slice c+1 and D2H of slice c-1 overlap the chain of slice c (PCIe is full duplex and
+    is the bound of this entry point).  Every slice is a complete chain of its own, so the random
+    draws are step-major inside a slice and slice after slice (like running the reference's
+    pipeline once per sub-folder); slice c pairs its items with backgrounds[c*k : (c+1)*k].
+    ``out_host`` (pinned, [>= K, cs, cs, 3]) receives the images; ChainResult.images is that host
+    tensor (first K rows)."""
     dev = torch.device(device)
+    n = frames_host.shape[0]
+    m = backgrounds_host.shape[0]
+    cs = min(backgrounds_host.shape[1], backgrounds_host.shape[2])
     with torch.cuda.device(dev):
-        f = frames_host.to(dev, non_blocking=True)
-        b = backgrounds_host.to(dev, non_blocking=True)
-        res = run_chain(f, b, params, rng, **kw)
-        k = res.images.shape[0]
+        if chunk is None or chunk >= n:
+            f = frames_host.to(dev, non_blocking=True)
+            b = backgrounds_host.to(dev, non_blocking=True)
+            res = run_chain(f, b, params, rng, **kw)
+            k = res.images.shape[0]
+            if out_host is None:
+                out_host = torch.empty(res.images.shape, dtype=torch.uint8).pin_memory()
+            out_host[:k].copy_(res.images, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return ChainResult(out_host[:k], res.labels, res._records, res._arrays)
+
+        if m != n:
+            raise ValueError("chunked run_chain_host pairs slice c with backgrounds[c*chunk:(c+1)*chunk]: pass one background per frame")
+        compute = torch.cuda.current_stream()
+        up, down = _side_streams(dev)
+        slots = [dict(f=_scratch(f"h2d_f{i}", chunk * frames_host[0].numel(), dev).view((chunk,) + tuple(frames_host.shape[1:])),
+                      b=_scratch(f"h2d_b{i}", chunk * backgrounds_host[0].numel(), dev).view((chunk,) + tuple(backgrounds_host.shape[1:])),
+                      ready=torch.cuda.Event(), free=torch.cuda.Event()) for i in range(2)]
+        bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+
+        def upload(c):
+            lo, hi = bounds[c]
+            s = slots[c % 2]
+            up.wait_event(s["free"])                      # the chain that last used this slot has finished
+            with torch.cuda.stream(up):
+                s["f"][:hi - lo].copy_(frames_host[lo:hi], non_blocking=True)
+                s["b"][:hi - lo].copy_(backgrounds_host[lo:hi], non_blocking=True)
+                s["ready"].record(up)
+
+        for s in slots:
+            s["free"].record(compute)
+        upload(0)
+        labels: List[str] = []
+        arrays = []
+        k_total = 0
+        pending = []
         if out_host is None:
-            out_host = torch.empty(res.images.shape, dtype=torch.uint8).pin_memory()
-        out_host[:k].copy_(res.images, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    return ChainResult(out_host[:k], res.labels, res._records, res._arrays)
+            out_host = torch.empty((n * 4, cs, cs, 3), dtype=torch.uint8).pin_memory()
+        for c, (lo, hi) in enumerate(bounds):
+            if c + 1 < len(bounds):
+                upload(c + 1)
+            s = slots[c % 2]
+            compute.wait_event(s["ready"])
+            res = run_chain(s["f"][:hi - lo], s["b"][:hi - lo], params, rng, **kw)
+            s["free"].record(compute)
+            k = res.images.shape[0]
+            done = torch.cuda.Event()
+            done.record(compute)
+            down.wait_event(done)
+            with torch.cuda.stream(down):
+                out_host[k_total:k_total + k].copy_(res.images, non_blocking=True)
+            res.images.record_stream(down)
+            pending.append(res.images)
+            labels += res.labels
+            items, aux, rot_index, angles = res._arrays
+            arrays.append((items, aux, rot_index, angles, lo))
+            k_total += k
+        down.synchronize()
+        compute.synchronize()
+    merged = ChainResult(out_host[:k_total], labels, records=None, record_arrays=None)
+    merged._chunks = arrays
+    merged._records = None
+    merged.__class__ = _ChunkedResult
+    return merged
+
+
+class _ChunkedResult(ChainResult):
+    @property
+    def records(self) -> List[dict]:
+        if self._records is None:
+            recs = []
+            for items, aux, rot_index, angles, lo in self._chunks:
+                part = ChainResult(None, None, record_arrays=(items, aux, rot_index, angles)).records
+                for r in part:
+                    r["frame"] += lo
+                    r["bg"] += lo
+                recs += part
+            self._records = recs
+        return self._records
+
+
+_SIDE = {}
+
+
+def _side_streams(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE[key]

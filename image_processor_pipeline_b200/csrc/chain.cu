@@ -457,9 +457,11 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
     return c0 | (c1 << 8) | (c2 << 16) | (a << 24);
 }
 
-// One tap group: 4 independent loads are issued before any of them is used, so a warp keeps
-// 4 memory requests in flight instead of walking a dependent chain (the passes are latency
-// bound on small, L2-resident sprites, not bandwidth bound).
+// The two LANCZOS passes are instruction-issue bound (ncu: ~70 % issue slots busy, L1 hit rate
+// 75-90 %): every tap costs four 8-bit x 23-bit integer multiply-adds that must stay exact, so
+// neither packed DP4A on byte planes (IDP.4A issues slower than IMAD here; measured slower) nor
+// floating point helps.  What the loops do instead: 4 taps per iteration so loads are issued
+// ahead of their use, and coefficient rows laid out so that a warp reads them contiguously.
 #define IPP_ACC4(px, w)                                                                \
     {                                                                                  \
         s0 += (int)((px) & 255u) * (w);                                                \
@@ -468,9 +470,7 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
         s3 += (int)((px) >> 24) * (w);                                                 \
     }
 
-// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles).
-// Horizontal coefficients are stored TRANSPOSED ([tap][X]) so that the 32 lanes of a warp
-// (32 consecutive X) read consecutive words.
+// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles); coefficients [X][tap]
 __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -492,25 +492,19 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     }
     const int32_t* bounds = c.tables + it.hb_off;
     const int xmin = bounds[2 * X], n = bounds[2 * X + 1];
-    const int32_t* k = c.tables + it.hk_off + X;          // [tap][X]
+    const int32_t* k = c.tables + it.hk_off + (int64_t)X * it.h_ksize;
     src += xmin;
     int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t v0 = src[i], v1 = src[i + 1], v2 = src[i + 2], v3 = src[i + 3];
-        const int w0 = __ldg(k + (int64_t)i * new_w), w1 = __ldg(k + (int64_t)(i + 1) * new_w);
-        const int w2 = __ldg(k + (int64_t)(i + 2) * new_w), w3 = __ldg(k + (int64_t)(i + 3) * new_w);
-        IPP_ACC4(v0, w0) IPP_ACC4(v1, w1) IPP_ACC4(v2, w2) IPP_ACC4(v3, w3)
-    }
-    for (; i < n; ++i) {
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
         const uint32_t v = src[i];
-        const int w = __ldg(k + (int64_t)i * new_w);
+        const int w = __ldg(k + i);
         IPP_ACC4(v, w)
     }
     dst[X] = c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24);
 }
 
-// vertical pass + un-premultiply: spr[Y][x], Y < new_h, x < new_w   (32 x 8 tiles)
+// vertical pass + un-premultiply: spr[Y][x], Y < new_h, x < new_w   (32 x 8 tiles); coefficients [Y][tap]
 __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -532,18 +526,19 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     }
     const int32_t* bounds = c.tables + it.vb_off;
     const int ymin = bounds[2 * Y], n = bounds[2 * Y + 1];
-    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;    // [Y][tap]: uniform per warp
+    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;    // uniform per warp
     src += (int64_t)ymin * new_w;
     int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
     int i = 0;
     for (; i + 4 <= n; i += 4) {
-        const uint32_t v0 = src[(int64_t)i * new_w], v1 = src[(int64_t)(i + 1) * new_w];
-        const uint32_t v2 = src[(int64_t)(i + 2) * new_w], v3 = src[(int64_t)(i + 3) * new_w];
+        const uint32_t v0 = src[0], v1 = src[new_w], v2 = src[2 * new_w], v3 = src[3 * new_w];
         const int w0 = __ldg(k + i), w1 = __ldg(k + i + 1), w2 = __ldg(k + i + 2), w3 = __ldg(k + i + 3);
+        src += 4 * new_w;
         IPP_ACC4(v0, w0) IPP_ACC4(v1, w1) IPP_ACC4(v2, w2) IPP_ACC4(v3, w3)
     }
     for (; i < n; ++i) {
-        const uint32_t v = src[(int64_t)i * new_w];
+        const uint32_t v = src[0];
+        src += new_w;
         const int w = __ldg(k + i);
         IPP_ACC4(v, w)
     }
@@ -628,9 +623,7 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
     const int in_size = axis ? it.spr_h : it.spr_w, out_size = axis ? it.new_h : it.new_w;
     const int ksize = axis ? it.v_ksize : it.h_ksize;
     int32_t* bounds = p.tables + (axis ? it.vb_off : it.hb_off) + 2 * xx;
-    // vertical tables are [row][tap]; horizontal tables are stored transposed, [tap][row]
-    int32_t* k = p.tables + (axis ? it.vk_off + (int64_t)xx * ksize : it.hk_off + (int64_t)xx);
-    const int64_t kstep = axis ? 1 : out_size;
+    int32_t* k = p.tables + (axis ? it.vk_off : it.hk_off) + (int64_t)xx * ksize;
     const double scale = __ddiv_rn((double)in_size, (double)out_size);
     const double filterscale = scale < 1.0 ? 1.0 : scale;
     const double support = __dmul_rn(3.0, filterscale);
@@ -655,7 +648,7 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
             c = (int)t;
             if (fabs(t - rint(t)) < p.eps) amb = true;
         }
-        k[(int64_t)x * kstep] = c;
+        k[x] = c;
     }
     bounds[0] = xmin;
     bounds[1] = xmax;

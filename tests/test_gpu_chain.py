@@ -120,8 +120,7 @@ def test_device_lanczos_tables_equal_host_tables():
             for axis, (ko, ks, n_out) in enumerate(((int(it["hk_off"]), int(it["h_ksize"]), int(it["new_w"])),
                                                     (int(it["vk_off"]), int(it["v_ksize"]), int(it["new_h"])))):
                 if ks and ko <= idx < ko + ks * n_out:
-                    row = (idx - ko) // ks if axis else (idx - ko) % n_out      # h tables are stored [tap][row]
-                    assert (it_i, axis, row) in flagged, "a differing row was not flagged"
+                    assert (it_i, axis, (idx - ko) // ks) in flagged, "a differing row was not flagged"
                     found = True
         assert found, "bounds differ: they involve no transcendental and must be identical"
     assert len(bad) <= 2 and n_amb < 200, (len(bad), n_amb)
@@ -162,3 +161,29 @@ def test_chain_mask_fast_path_on_all_colours_and_hue_filters():
     for i in range(n):
         keyed = L.color_masks_to_alpha(bgr[i], filters)
         assert n_fg[i] == int((keyed[..., 3] > 1).sum()), i
+
+
+def test_run_chain_host_whole_and_chunked():
+    """Host-buffer entry point: one chain over the batch == run_chain; the pipelined (chunked) mode ==
+    the oracle run slice after slice with the same generator."""
+    H, W = 200, 320
+    frames = [synth.frame(41, i, H, W) for i in range(6)]
+    bgs = [synth.background(41, i, 240, 300) for i in range(6)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    fh = torch.from_numpy(np.stack(frames)).pin_memory()
+    bh = torch.from_numpy(np.stack(bgs)).pin_memory()
+    random.seed(9)
+    ref_imgs, ref_labels, _ = OC.run_chain(frames, bgs, **kw)
+    random.seed(9)
+    res = chain.run_chain_host(fh, bh, chain.ChainParams(**kw), DEV)
+    assert res.labels == ref_labels and all(np.array_equal(a, b) for a, b in zip(res.images.numpy(), ref_imgs))
+    random.seed(9)
+    ref_imgs, ref_labels, ref_frames = [], [], []
+    for lo in range(0, 6, 4):
+        i, l, r = OC.run_chain(frames[lo:lo + 4], bgs[lo:lo + 4], **kw)
+        ref_imgs += i; ref_labels += l; ref_frames += [x["frame"] + lo for x in r]
+    random.seed(9)
+    res = chain.run_chain_host(fh, bh, chain.ChainParams(**kw), DEV, chunk=4)
+    assert res.labels == ref_labels and [r["frame"] for r in res.records] == ref_frames
+    assert all(np.array_equal(a, b) for a, b in zip(res.images.numpy(), ref_imgs))
