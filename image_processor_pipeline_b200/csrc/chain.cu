@@ -248,8 +248,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) chain_mask_fast_kernel(const 
     }
 
     // ---------------------------------------------------------------------- consumers
-    const int cpr = (p.wpr + 3) >> 2;                     // warp chunks (32 groups = 128 px = 4 mask words) per row
-    const int last_x = p.w & ~3;                          // first pixel of a partial last group (== w when w % 4 == 0)
+    // A lane converts 8 pixels (24 staged bytes = two groups of four) per step, a warp 256 pixels =
+    // 8 mask words; four lanes are OR-combined into one word by two shuffles.
+    const int cpr = (p.wpr + 7) >> 3;                     // warp chunks per row
     int it = 0;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
         const int stage = it % kFastStages;
@@ -260,47 +261,50 @@ __global__ void __launch_bounds__(kFastThreads, 1) chain_mask_fast_kernel(const 
         const uint8_t* src = p.frames + (int64_t)img * p.stride + (int64_t)(p.crop_t + row0) * p.pitch + (int64_t)p.crop_l * 3;
         const uint8_t* tile = ring + (size_t)stage * stage_bytes;
         uint32_t* out_unit = p.bits + (int64_t)img * p.bits_stride + (int64_t)row0 * p.wpr;
-        // chunk list of this warp: ch = warp, warp + 31, ... mapped to (row, chunk-in-row) without a division per chunk
+        // chunk list of this warp: warp, warp + 31, ... mapped to (row, chunk-in-row) without a division per chunk
         int r = warp / cpr, c = warp - r * cpr;
         while (r < nrows) {
             const uint32_t shift = (uint32_t)((uintptr_t)(src + (int64_t)r * p.pitch) & 15);
             const uint32_t bs = (shift & 3u) * 8u;
             const uint32_t* row32 = reinterpret_cast<const uint32_t*>(tile + (size_t)r * p.smem_row_stride);
-            uint32_t* out_row = out_unit + (int64_t)r * p.wpr;
-            const int x = (c * 32 + lane) * 4;
-            uint32_t nib = 0;
+            const int x = (c * 32 + lane) * 8;
+            uint32_t byte = 0;                                              // keep bits of this lane's 8 pixels
             if (x < p.w) {
                 const uint32_t* w32 = row32 + ((shift + (uint32_t)x * 3u) >> 2);
-                uint32_t rx, ry, rz;                                        // 12 bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-                if (bs == 0) {
-                    rx = w32[0]; ry = w32[1]; rz = w32[2];
-                } else {
-                    const uint32_t a0 = w32[0], a1 = w32[1], a2 = w32[2], a3 = w32[3];
-                    rx = __funnelshift_r(a0, a1, bs); ry = __funnelshift_r(a1, a2, bs); rz = __funnelshift_r(a2, a3, bs);
+                uint32_t q[7];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) q[j] = w32[j];
+                if (bs) {
+                    q[6] = w32[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) q[j] = __funnelshift_r(q[j], q[j + 1], bs);
                 }
-                const uint32_t B01 = __byte_perm(rx, 0u, 0x4340), G01 = __byte_perm(rx, ry, 0x0401) & 0x00ff00ffu;
-                const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
-                const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
-                const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
-                const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
-                const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
-                const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
-                const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
-                                   ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
-                // bit 7 of every byte -> 4 adjacent bits (the multiply gathers them at bits 21..24)
-                const uint32_t hit = (M & 0x80808080u) >> 7;
-                uint32_t ex = ((hit * 0x00204081u) >> 21) & 15u;
-                if (M & 0x7f7f7f7fu & ~(hit * 0x7fu))
-                    ex |= hue_tests(M, B01, G01, R01, B23, G23, R23, V01, V23, D01, D23, p.f, hdiv);
-                nib = ~ex & 15u;
-                if (x >= last_x) nib &= (1u << (p.w - x)) - 1u;             // partial last group of the row
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t rx = q[3 * g], ry = q[3 * g + 1], rz = q[3 * g + 2];   // b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                    const uint32_t B01 = __byte_perm(rx, 0u, 0x4340), G01 = __byte_perm(rx, ry, 0x0401) & 0x00ff00ffu;
+                    const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
+                    const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
+                    const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
+                    const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
+                    const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
+                    const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
+                    const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
+                                       ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
+                    // bit 7 of every byte -> 4 adjacent bits (the multiply gathers them at bits 21..24)
+                    const uint32_t hit = (M & 0x80808080u) >> 7;
+                    uint32_t ex = ((hit * 0x00204081u) >> 21) & 15u;
+                    if (M & 0x7f7f7f7fu & ~(hit * 0x7fu))
+                        ex |= hue_tests(M, B01, G01, R01, B23, G23, R23, V01, V23, D01, D23, p.f, hdiv);
+                    byte |= (~ex & 15u) << (4 * g);
+                }
+                if (x + 8 > p.w) byte &= (1u << (p.w - x)) - 1u;            // partial last group of the row
             }
-            uint32_t v = nib << (4 * (lane & 7));
+            uint32_t v = byte << (8 * (lane & 3));
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
             v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            const int word = c * 4 + (lane >> 3);
-            if ((lane & 7) == 0 && word < p.wpr) out_row[word] = v;
+            const int word = c * 8 + (lane >> 2);
+            if ((lane & 3) == 0 && word < p.wpr) out_unit[(int64_t)r * p.wpr + word] = v;
             c += kFastConsumers;
             while (c >= cpr) {
                 c -= cpr;
