@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -237,6 +238,20 @@ def main():
         random.seed(1000 * rank + s)
         return chain.run_chain(frames_d, bgs_d, params)
 
+    pipe = chain.ChainStream(params)
+
+    def run_pipelined(first, count):
+        """`count` steps, software-pipelined: stage A of step s+1 is in flight while step s is planned
+        and finished (ChainStream).  Exactly `count` stage-A launches, `count` finishes."""
+        n_out = 0
+        ticket = pipe.submit(frames_d, bgs_d)
+        for s in range(count):
+            nxt = pipe.submit(frames_d, bgs_d) if s + 1 < count else None
+            random.seed(1000 * rank + first + s)
+            n_out += pipe.finish(ticket).images.shape[0]
+            ticket = nxt
+        return n_out
+
     def timed(fn, steps, warmup):
         for s in range(warmup):
             fn(s)
@@ -260,8 +275,31 @@ def main():
             n_out = int(c.item())
         return ms, n_out, launches
 
+    def timed_pipelined(steps, warmup):
+        run_pipelined(0, warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _native.launch_count()
+        e0.record()
+        n_out = run_pipelined(warmup, steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _native.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            c = torch.tensor([n_out], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            n_out = int(c.item())
+        return ms, n_out, launches
+
     with ClockSampler(local) as clk:
-        ms, n_out, launches = timed(step_resident, args.steps, args.warmup)
+        if args.no_pipeline:
+            ms, n_out, launches = timed(step_resident, args.steps, args.warmup)
+        else:
+            ms, n_out, launches = timed_pipelined(args.steps, args.warmup)
     clocks = clk.summary()
     value = n_out / (ms * 1e-3)
 
@@ -311,7 +349,7 @@ def main():
         line = {"metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B,
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline,
                            "l2": f"inputs per step {2 * B * 3 * FW * FH / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                            "host_work_in_step": "C++ planner (Python-compatible MT19937 draws) + 3 small device->host read-backs per batch (RNG bounds depend on sprite sizes; table-ambiguity count)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -429,8 +429,55 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
 
 
 # =========================================================================== the chain
+def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, slot: int = 0) -> dict:
+    """Launch stage A (frame -> keep-mask + largest component; no random draws) of a batch on a side
+    stream, into the scratch of ``slot`` (0 or 1), and return a ticket for ``run_chain(..., _ticket=)``.
+    Lets the HBM-bound pass of batch k+1 run while the host plans / the GPU finishes batch k."""
+    if not frames.is_cuda:
+        raise RuntimeError("prefetch_stage_a needs CUDA tensors (there is no CPU fallback)")
+    lib = _native.load()
+    dev = frames.device
+    frames = frames.contiguous()
+    n, FH, FW, _ = frames.shape
+    m, BH, BW, _ = backgrounds.shape
+    rect = hostmath.border_crop_rect(FW, FH, params.crop_margins)
+    ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
+    geom = _geom_struct(FW, FH, rect, BW, BH, ranges)
+    with torch.cuda.device(dev):
+        side = _side_streams(dev)[0]
+        ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
+        ws = _scratch(f"mask_s{slot}", ws_bytes, dev)
+        info_d = _scratch(f"info_s{slot}", n * 32, dev, torch.int32).view(n, 8)
+        side.wait_stream(torch.cuda.current_stream())            # inputs / previous users of this slot
+        _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, n, side.cuda_stream), "ipp_chain_stage_a")
+        done = torch.cuda.Event()
+        done.record(side)
+    return dict(frames=frames, ws=ws, ws_bytes=ws_bytes, info_d=info_d, done=done, geom=geom, n=n)
+
+
+class ChainStream:
+    """Software pipeline over consecutive batches: ``submit`` launches stage A of a batch on a side
+    stream right away; ``finish`` does the rest (host planning, stages B1/B2/C).  Submitting batch
+    k+1 before finishing batch k keeps the GPU busy during batch k's host work.  Random draws still
+    happen batch after batch, step-major inside a batch (no draw is made by ``submit``)."""
+
+    def __init__(self, params: ChainParams, **run_kw):
+        self.params, self.run_kw, self._n = params, run_kw, 0
+
+    def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor):
+        ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=self._n % 2)
+        ticket["backgrounds"] = backgrounds
+        self._n += 1
+        return ticket
+
+    def finish(self, ticket, rng=_random) -> "ChainResult":
+        return run_chain(ticket["frames"], ticket["backgrounds"], self.params, rng, _ticket=ticket, **self.run_kw)
+
+
 def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
-              planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS):
+              planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
+              _ticket: Optional[dict] = None):
     """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB.
     Returns a ChainResult.  ``planner``: "native" (C++) or "python"; ``device_tables``: compute the
     LANCZOS tables on the GPU (default with the native planner) with exact host fix-up of ambiguous
@@ -466,11 +513,15 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
 
     with torch.cuda.device(dev):
         # ------------------------------------------------------------------ stage A
-        ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-        ws = _scratch("mask", ws_bytes, dev)
-        info_d = _scratch("info", n * 32, dev, torch.int32).view(n, 8)
-        _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
-                                            ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
+        if _ticket is not None:                                       # stage A was launched ahead on a side stream
+            ws, ws_bytes, info_d = _ticket["ws"], _ticket["ws_bytes"], _ticket["info_d"]
+            torch.cuda.current_stream().wait_event(_ticket["done"])
+        else:
+            ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
+            ws = _scratch("mask", ws_bytes, dev)
+            info_d = _scratch("info", n * 32, dev, torch.int32).view(n, 8)
+            _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
+                                                ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
         info = info_d.cpu().numpy()                                   # sync #1
         if _shard is not None:
             info = _shard["gather"](info)                             # 32 bytes of metadata per frame

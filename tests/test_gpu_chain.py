@@ -187,3 +187,29 @@ def test_run_chain_host_whole_and_chunked():
     res = chain.run_chain_host(fh, bh, chain.ChainParams(**kw), DEV, chunk=4)
     assert res.labels == ref_labels and [r["frame"] for r in res.records] == ref_frames
     assert all(np.array_equal(a, b) for a, b in zip(res.images.numpy(), ref_imgs))
+
+
+def test_chain_stream_pipelining_is_transparent():
+    """ChainStream (stage A of batch k+1 launched before batch k is finished) gives the same images,
+    labels and generator state as plain run_chain calls."""
+    H, W = 200, 320
+    batches = [([synth.frame(50 + b, i, H, W) for i in range(3)], [synth.background(50 + b, i, 240, 300) for i in range(2)]) for b in range(3)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    dev_batches = [(torch.from_numpy(np.stack(f)).to(DEV), torch.from_numpy(np.stack(b)).to(DEV)) for f, b in batches]
+    random.seed(77)
+    plain = [chain.run_chain(f, b, chain.ChainParams(**kw)) for f, b in dev_batches]
+    plain = [(r.images.cpu().numpy(), r.labels) for r in plain]
+    state = random.getstate()
+    random.seed(77)
+    pipe = chain.ChainStream(chain.ChainParams(**kw))
+    ticket = pipe.submit(*dev_batches[0])
+    got = []
+    for k in range(3):
+        nxt = pipe.submit(*dev_batches[k + 1]) if k + 1 < 3 else None
+        r = pipe.finish(ticket)
+        got.append((r.images.cpu().numpy(), r.labels))
+        ticket = nxt
+    assert random.getstate() == state
+    for (a, la), (b, lb) in zip(plain, got):
+        assert la == lb and np.array_equal(a, b)
