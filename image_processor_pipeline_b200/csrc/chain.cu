@@ -364,19 +364,32 @@ __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = tx * 32 + lane;
     const SrcMap m{rec.kind, rec.a0, rec.a1, rec.a2, rec.a3, rec.a4, rec.a5, rec.cc_w, rec.cc_h};
-    const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride;
+    const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride + (int64_t)rec.cc_y * wpr;
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
+    const int y0 = ty * 32 + warp * 4;
+    // affine case: the fixed-point source coordinates advance by (a1, a4) per canvas row
+    int xx = rec.a2 + y0 * rec.a1 + x * rec.a0, yy = rec.a5 + y0 * rec.a4 + x * rec.a3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int y = ty * 32 + warp * 4 + j;
+        const int y = y0 + j;
         bool on = false;
         if (x < rec.canvas_w && y < rec.canvas_h) {
             int xin, yin;
-            if (map_canvas(m, x, y, xin, yin)) {
-                const int fx = rec.cc_x + xin, fy = rec.cc_y + yin;
-                on = (fb[(int64_t)fy * wpr + (fx >> 5)] >> (fx & 31)) & 1u;
+            bool inside;
+            if (rec.kind == 0) {
+                xin = xx >> 16;
+                yin = yy >> 16;
+                inside = (unsigned)xin < (unsigned)rec.cc_w && (unsigned)yin < (unsigned)rec.cc_h;
+            } else {
+                inside = map_canvas(m, x, y, xin, yin);
+            }
+            if (inside) {
+                const int fx = rec.cc_x + xin;
+                on = (fb[yin * wpr + (fx >> 5)] >> (fx & 31)) & 1u;
             }
         }
+        xx += rec.a1;
+        yy += rec.a4;
         const uint32_t mask = __ballot_sync(0xffffffffu, on);
         if (mask) {
             minx = min(minx, tx * 32 + __ffs(mask) - 1);
@@ -425,21 +438,37 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     const int X = tx * 32 + lane;
     if (X >= spr_w) return;
     const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, it.cc_w, it.cc_h};
-    const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride;
-    const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride;
+    const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride + (int64_t)it.cc_y * c.wpr;
+    const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride + (int64_t)(c.crop_t + it.cc_y) * c.pitch +
+                           (int64_t)(c.crop_l + it.cc_x) * 3;
     uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.rot_off);
     const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
+    const int Y0 = ty * 32 + warp * 4;
+    // affine case: canvas row cy = fit_y0 + (flip_v ? spr_h-1-Y : Y) moves by +-1 per sprite row
+    const int cy0 = (it.flip_v ? (spr_h - 1 - Y0) : Y0) + it.fit_y0;
+    const int dy = it.flip_v ? -1 : 1;
+    int xx = it.a2 + cy0 * it.a1 + cx * it.a0, yy = it.a5 + cy0 * it.a4 + cx * it.a3;
+    const int sx = dy * it.a1, sy = dy * it.a4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int Y = ty * 32 + warp * 4 + j;
+        const int Y = Y0 + j;
         if (Y >= spr_h) break;
-        const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
         uint32_t px = 0;
         int xin, yin;
-        if (map_canvas(m, cx, cy, xin, yin)) {
-            const int fx = it.cc_x + xin, fy = it.cc_y + yin;
-            if ((fb[(int64_t)fy * c.wpr + (fx >> 5)] >> (fx & 31)) & 1u) {
-                const uint8_t* s = frame + (int64_t)(c.crop_t + fy) * c.pitch + (int64_t)(c.crop_l + fx) * 3;
+        bool inside;
+        if (it.kind == 0) {
+            xin = xx >> 16;
+            yin = yy >> 16;
+            inside = (unsigned)xin < (unsigned)it.cc_w && (unsigned)yin < (unsigned)it.cc_h;
+        } else {
+            inside = map_canvas(m, cx, cy0 + dy * j, xin, yin);
+        }
+        xx += sx;
+        yy += sy;
+        if (inside) {
+            const int fx = it.cc_x + xin;
+            if ((fb[yin * c.wpr + (fx >> 5)] >> (fx & 31)) & 1u) {
+                const uint8_t* s = frame + (int64_t)yin * c.pitch + xin * 3;
                 px = (uint32_t)s[2] | ((uint32_t)s[1] << 8) | ((uint32_t)s[0] << 16) | 0xff000000u;   // BGR -> RGBA
             }
         }
@@ -855,7 +884,8 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
     const uint32_t rowbytes = (uint32_t)out_size * 3u;
     c.smem_row_stride = staged_row_stride(rowbytes);
     IPP_REQUIRE(c.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
-    int rows = (int)(24576 / c.smem_row_stride);
+    int rows = (int)(32768 / c.smem_row_stride);            // one warp per row: 8 rows when they fit
+    if (rows > kPasteThreads / 32) rows = kPasteThreads / 32;
     if (rows < 1) rows = 1;
     if (rows > out_size) rows = out_size;
     c.rows_per_cta = rows;

@@ -58,39 +58,73 @@ __device__ __forceinline__ void blend_bytes(const PasteParams& p, uint8_t* bytes
     }
 }
 
-// emit rows [row0, row0+nrows) of the cropped composite from staged background windows
+// 16 output bytes cut from two aligned vectors of the staged window; WS = word shift (0..3),
+// bs = byte shift inside the word in bits — both uniform for a whole row.
+template <int WS>
+__device__ __forceinline__ uint4 cut16(const uint4& lo, const uint4& hi, uint32_t bs) {
+    uint32_t v0, v1, v2, v3, v4;
+    if (WS == 0) { v0 = lo.x; v1 = lo.y; v2 = lo.z; v3 = lo.w; v4 = hi.x; }
+    else if (WS == 1) { v0 = lo.y; v1 = lo.z; v2 = lo.w; v3 = hi.x; v4 = hi.y; }
+    else if (WS == 2) { v0 = lo.z; v1 = lo.w; v2 = hi.x; v3 = hi.y; v4 = hi.z; }
+    else { v0 = lo.w; v1 = hi.x; v2 = hi.y; v3 = hi.z; v4 = hi.w; }
+    return make_uint4(__funnelshift_r(v0, v1, bs), __funnelshift_r(v1, v2, bs), __funnelshift_r(v2, v3, bs),
+                      __funnelshift_r(v3, v4, bs));
+}
+
+// aligned 16-byte body of one output row, lanes striding over the chunks
+template <int WS>
+__device__ __forceinline__ void paste_row_body(const PasteParams& p, const uint8_t* win, uint32_t off0, uint8_t* d,
+                                               uint32_t head, uint32_t nb, bool row_hit, int hit_b0, int hit_b1, int sy, int lane) {
+    const uint32_t bs = (off0 & 3u) * 8u;
+    const uint8_t* src = win + (off0 & ~15u);
+    const bool aligned = (off0 & 15u) == 0u;
+    for (uint32_t c = lane; c < nb; c += 32) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(src + (c << 4));
+        uint4 val = lo;
+        if (!aligned) {
+            const uint4 hi = *reinterpret_cast<const uint4*>(src + (c << 4) + 16);
+            val = cut16<WS>(lo, hi, bs);
+        }
+        const uint32_t ob = head + (c << 4);
+        if (row_hit && (int)(ob + 15u) >= hit_b0 && (int)ob < hit_b1) {
+            __align__(16) uint8_t bytes[16];
+            *reinterpret_cast<uint4*>(bytes) = val;
+            blend_bytes(p, bytes, ob, 16, sy);
+            val = *reinterpret_cast<uint4*>(bytes);
+        }
+        stg_stream16(d + ob, val);
+    }
+}
+
+// emit rows [row0, row0+nrows) of the cropped composite from staged background windows.
+// One warp per row (row-uniform alignment, sprite-hit range and pointers live in uniform
+// registers); lanes stride over the aligned 16-byte output vectors of the row.
 __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const uint8_t* smem, uint32_t smem_row_stride,
                                                      int row0, int nrows, int tid) {
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
+    const int lane = tid & 31, warp = tid >> 5;
     // output byte range of a row that can intersect the sprite
-    const int spr_q0 = max(p.pos_x - p.crop_x0, 0);
-    const int spr_q1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w);   // exclusive
-    const uint32_t cpr = (rowbytes >> 4) + 2;
-    const uint32_t items = (uint32_t)nrows * cpr;
-    for (uint32_t it = tid; it < items; it += kPasteThreads) {
-        const uint32_t r = it / cpr;
-        const uint32_t c = it - r * cpr;
-        const int y = row0 + (int)r;
+    const int hit_b0 = max(p.pos_x - p.crop_x0, 0) * 3;
+    const int hit_b1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w) * 3;   // exclusive
+    for (int r = warp; r < nrows; r += kPasteThreads / 32) {
+        const int y = row0 + r;
         uint8_t* d = p.dst + (int64_t)y * p.dst_pitch;
         const uint8_t* win = smem + (size_t)r * smem_row_stride;
         const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + y) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
         const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
         const RowSplit sp = split_row(d, rowbytes);
         const int sy = p.crop_y0 + y - p.pos_y;
-        const bool row_hit = (sy >= 0 && sy < p.sprite_h && spr_q1 > spr_q0);
-        if (c < sp.nb) {
-            const uint32_t ob = sp.head + (c << 4);
-            uint4 val = window_load16(win, shift + ob);
-            if (row_hit && (int)(ob + 15u) >= spr_q0 * 3 && (int)ob < spr_q1 * 3) {
-                __align__(16) uint8_t bytes[16];
-                *reinterpret_cast<uint4*>(bytes) = val;
-                blend_bytes(p, bytes, ob, 16, sy);
-                val = *reinterpret_cast<uint4*>(bytes);
-            }
-            stg_stream16(d + ob, val);
-        } else if (c >= cpr - 2) {
-            const uint32_t b0 = (c == cpr - 2) ? 0u : sp.head + (sp.nb << 4);
-            const int cnt = (int)((c == cpr - 2) ? sp.head : sp.tail);
+        const bool row_hit = (sy >= 0 && sy < p.sprite_h && hit_b1 > hit_b0);
+        const uint32_t off0 = shift + sp.head;            // window offset of the first aligned output vector
+        switch ((off0 & 15u) >> 2) {
+            case 0: paste_row_body<0>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
+            case 1: paste_row_body<1>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
+            case 2: paste_row_body<2>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
+            default: paste_row_body<3>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
+        }
+        if (lane < 2) {                                   // lane 0: unaligned head bytes, lane 1: tail bytes
+            const uint32_t b0 = lane == 0 ? 0u : sp.head + (sp.nb << 4);
+            const int cnt = (int)(lane == 0 ? sp.head : sp.tail);
             if (cnt > 0) {
                 uint8_t bytes[16];
                 for (int k = 0; k < cnt; ++k) bytes[k] = win[shift + b0 + k];
