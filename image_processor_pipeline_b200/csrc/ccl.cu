@@ -40,11 +40,26 @@ __device__ __forceinline__ int find_root(const int2* L, int x) {
     return x;
 }
 
+// find with path halving (used while unions are in flight): every visited node is re-pointed to
+// its grandparent with atomicMin — parents only ever decrease, so concurrent unions stay valid —
+// which keeps the chains short for the later passes (area / keep), whose time is the length of
+// the longest pointer chase.
+__device__ __forceinline__ int find_root_halving(int2* L, int x) {
+    int p = __ldcg(&L[x].x);
+    while (p != x) {
+        const int gp = __ldcg(&L[p].x);
+        if (gp != p) atomicMin(&L[x].x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
 __device__ __forceinline__ void unite(int2* L, int a, int b) {
     bool done;
     do {
-        a = find_root(L, a);
-        b = find_root(L, b);
+        a = find_root_halving(L, a);
+        b = find_root_halving(L, b);
         if (a < b) {
             const int old = atomicMin(&L[b].x, a);
             done = (old == b);
