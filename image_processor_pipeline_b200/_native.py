@@ -99,6 +99,7 @@ PROTOTYPES = {
     "ipp_chain_stage_b2": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _int, _int, _int,
                                   _i32p, _vp, _u8p, _vp]),
     "ipp_chain_stage_c": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _u8p, _u8p, _i64, _i64, _int, _vp]),
+    "ipp_chain_upload_windows": (_int, [_vp, _i64, _i64, _int, _int, _int, _vp, _int, _int, _u8p, _vp]),
 }
 
 EXCEPTION_FOR_CODE = {-1: ValueError, -2: ValueError, -3: MemoryError, -4: NotImplementedError}

@@ -477,15 +477,21 @@ class ChainStream:
 
 def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
               planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
-              _ticket: Optional[dict] = None):
-    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB.
+              _ticket: Optional[dict] = None, _upload_stream=None):
+    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB,
+    either on the same device or in PINNED HOST memory.  Host backgrounds are never uploaded whole:
+    once the square-crop offsets are planned, only each item's crop window crosses PCIe
+    (ipp_chain_upload_windows, on a side stream, overlapping stage B2).
     Returns a ChainResult.  ``planner``: "native" (C++) or "python"; ``device_tables``: compute the
     LANCZOS tables on the GPU (default with the native planner) with exact host fix-up of ambiguous
     rows.  ``_shard`` (set by sharding.run_chain_sharded): this call holds frames [lo, hi) of a larger
     job; stage-A / B1 metadata is gathered across ranks, the plan is made for ALL items with the shared
     ``rng`` and only the items of the local frames are executed; returns (ChainResult, global indices)."""
-    if not (frames.is_cuda and backgrounds.is_cuda):
-        raise RuntimeError("run_chain needs CUDA tensors (there is no CPU fallback)")
+    if not frames.is_cuda:
+        raise RuntimeError("run_chain needs CUDA frames (there is no CPU fallback)")
+    host_bgs = not backgrounds.is_cuda
+    if host_bgs and not backgrounds.is_pinned():
+        raise RuntimeError("host backgrounds must live in pinned memory (tensor.pin_memory())")
     if frames.dtype != torch.uint8 or backgrounds.dtype != torch.uint8 or frames.dim() != 4 or backgrounds.dim() != 4:
         raise TypeError("frames / backgrounds must be uint8 [N, H, W, 3]")
     if planner not in ("native", "python"):
@@ -495,6 +501,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     lib = _native.load()
     dev = frames.device
     frames = frames.contiguous()
+    if host_bgs and not backgrounds.is_contiguous():
+        raise ValueError("host backgrounds must be contiguous")
     backgrounds = backgrounds.contiguous()
     n, FH, FW, _ = frames.shape
     m, BH, BW, _ = backgrounds.shape
@@ -581,34 +589,66 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         else:
             tab_d = torch.from_numpy(_host_tables(items, lib, tot["table_ints"])).to(dev)
 
+        # ------------------------------------------------------------------ stage C input: device backgrounds or host windows
+        h2d_bytes = 0
+        bg_ready = None
+        if host_bgs and K * cs * cs >= m * BH * BW:                   # many items per background: whole images are fewer bytes
+            backgrounds = backgrounds.to(dev, non_blocking=True)
+            h2d_bytes = int(backgrounds.numel())
+            host_bgs = False
+        if host_bgs:
+            items_c = items.copy()                                     # stage C sees window i as "background i", crop origin (0, 0)
+            items_c["bg"] = np.arange(K)
+            items_c["pos_x"] -= items["sq_x0"]
+            items_c["pos_y"] -= items["sq_y0"]
+            items_c["sq_x0"] = 0
+            items_c["sq_y0"] = 0
+            items_c_d = torch.from_numpy(items_c.view(np.uint8)).to(dev)
+            bg_dev = _scratch("bg_windows", K * cs * cs * 3, dev)
+            geom_c = _geom_struct(FW, FH, rect, cs, cs, ranges)
+            bg_pitch, bg_stride = cs * 3, cs * cs * 3
+            up = _upload_stream if _upload_stream is not None else _side_streams(dev)[0]
+            up.wait_stream(torch.cuda.current_stream())                # previous readers of the window buffer
+            _native.check(lib.ipp_chain_upload_windows(backgrounds.data_ptr(), BW * 3, BH * BW * 3, BW, BH, m, items.ctypes.data, K, cs,
+                                                       bg_dev.data_ptr(), up.cuda_stream), "ipp_chain_upload_windows")
+            bg_ready = torch.cuda.Event()
+            bg_ready.record(up)
+            h2d_bytes = K * cs * cs * 3
+        else:
+            items_c, items_c_d, bg_dev, geom_c = items, items_d, backgrounds, geom
+            bg_pitch, bg_stride = BW * 3, BH * BW * 3
+
         # ------------------------------------------------------------------ stage B2 + C
-        def run_b2_c(items_dev, k, gt, ht, vt):
+        def run_b2_c(items_dev, items_c_dev, k, gt, ht, vt):
             _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
                                                  gt, ht, vt, tab_d.data_ptr(), ws.data_ptr(), spr_ws.data_ptr(), _stream()),
                           "ipp_chain_stage_b2")
-            _native.check(lib.ipp_chain_stage_c(backgrounds.data_ptr(), BW * 3, BH * BW * 3, C.byref(geom), items_dev.data_ptr(), k,
+            if bg_ready is not None:
+                torch.cuda.current_stream().wait_event(bg_ready)       # the windows have landed (copied while B2 ran)
+            _native.check(lib.ipp_chain_stage_c(bg_dev.data_ptr(), bg_pitch, bg_stride, C.byref(geom_c), items_c_dev.data_ptr(), k,
                                                 spr_ws.data_ptr(), out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
                           "ipp_chain_stage_c")
 
-        run_b2_c(items_d, K, tot["gt"], tot["ht"], tot["vt"])
+        run_b2_c(items_d, items_c_d, K, tot["gt"], tot["ht"], tot["vt"])
 
         # ------------------------------------------------------------------ exactness fix-up of device tables (rare)
         n_fixed = 0
         if device_tables:
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
             if n_amb:
-                n_fixed = _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev)
-        for t in (rot_d, items_d):
+                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev)
+        for t in (rot_d, items_d, items_c_d):
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
 
     res = ChainResult(out, labels, record_arrays=rec_arrays)
     res.tables_flagged_rows = n_amb if device_tables else 0
     res.tables_fixed_items = n_fixed
+    res.h2d_background_bytes = h2d_bytes
     return finish(res, own.tolist())
 
 
-def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
+def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
     """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C
     library's sin() (ipp_lanczos_row_host).  If a row really differs it is patched on the device and
     the h/v passes + paste of the affected items are re-run (their gathered sprites are still valid).
@@ -638,13 +678,18 @@ def _fix_ambiguous_rows(lib, items, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
         vt = ((sub["new_w"].astype(np.int64) + 31) // 32) * ((sub["new_h"].astype(np.int64) + 7) // 8)
         sub["h_tile_start"], sub["v_tile_start"] = _excl(ht), _excl(vt)
         sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
-        run_b2_c(sub_d, len(sub), 0, int(ht.sum()), int(vt.sum()))
+        sub_c = items_c[sorted(dirty)].copy()                  # stage C's view of the same items (host-window mode: shifted copies)
+        for name in ("h_tile_start", "v_tile_start"):
+            sub_c[name] = sub[name]
+        sub_c_d = torch.from_numpy(sub_c.view(np.uint8)).to(dev)
+        run_b2_c(sub_d, sub_c_d, len(sub), 0, int(ht.sum()), int(vt.sum()))
         torch.cuda.current_stream().synchronize()
     return len(dirty)
 
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
-                   out_host: Optional[torch.Tensor] = None, rng=_random, chunk: Optional[int] = None, **kw) -> ChainResult:
+                   out_host: Optional[torch.Tensor] = None, rng=_random, chunk: Optional[int] = None,
+                   background_windows: bool = True, **kw) -> ChainResult:
     """End-to-end entry for HOST buffers (what a pipeline step does after decoding): pinned host
     frames / backgrounds -> H2D -> chain -> D2H of the output images.
 
@@ -654,32 +699,40 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
     is the bound of this entry point).  Every slice is a complete chain of its own, so the random
     draws are step-major inside a slice and slice after slice (like running the reference's
     pipeline once per sub-folder); slice c pairs its items with backgrounds[c*k : (c+1)*k].
+    ``background_windows``: backgrounds stay on the host until their square-crop offsets are planned;
+    then only the crop windows are copied (22 % fewer H2D bytes per 1080p image).  False: whole
+    backgrounds are uploaded up front.
     ``out_host`` (pinned, [>= K, cs, cs, 3]) receives the images; ChainResult.images is that host
-    tensor (first K rows)."""
+    tensor (first K rows).  ChainResult.h2d_bytes = bytes that crossed PCIe host->device."""
     dev = torch.device(device)
     n = frames_host.shape[0]
     m = backgrounds_host.shape[0]
     cs = min(backgrounds_host.shape[1], backgrounds_host.shape[2])
+    windows = bool(background_windows) and backgrounds_host.is_pinned() and backgrounds_host.is_contiguous()
     with torch.cuda.device(dev):
         if chunk is None or chunk >= n:
             f = frames_host.to(dev, non_blocking=True)
-            b = backgrounds_host.to(dev, non_blocking=True)
+            b = backgrounds_host if windows else backgrounds_host.to(dev, non_blocking=True)
             res = run_chain(f, b, params, rng, **kw)
             k = res.images.shape[0]
             if out_host is None:
                 out_host = torch.empty(res.images.shape, dtype=torch.uint8).pin_memory()
             out_host[:k].copy_(res.images, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return ChainResult(out_host[:k], res.labels, res._records, res._arrays)
+            merged = ChainResult(out_host[:k], res.labels, res._records, res._arrays)
+            merged.h2d_bytes = int(frames_host.numel()) + (res.h2d_background_bytes if windows else int(backgrounds_host.numel()))
+            return merged
 
         if m != n:
             raise ValueError("chunked run_chain_host pairs slice c with backgrounds[c*chunk:(c+1)*chunk]: pass one background per frame")
         compute = torch.cuda.current_stream()
         up, down = _side_streams(dev)
         slots = [dict(f=_scratch(f"h2d_f{i}", chunk * frames_host[0].numel(), dev).view((chunk,) + tuple(frames_host.shape[1:])),
-                      b=_scratch(f"h2d_b{i}", chunk * backgrounds_host[0].numel(), dev).view((chunk,) + tuple(backgrounds_host.shape[1:])),
+                      b=None if windows else
+                      _scratch(f"h2d_b{i}", chunk * backgrounds_host[0].numel(), dev).view((chunk,) + tuple(backgrounds_host.shape[1:])),
                       ready=torch.cuda.Event(), free=torch.cuda.Event()) for i in range(2)]
         bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        h2d_bytes = 0
 
         def upload(c):
             lo, hi = bounds[c]
@@ -687,7 +740,8 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
             up.wait_event(s["free"])                      # the chain that last used this slot has finished
             with torch.cuda.stream(up):
                 s["f"][:hi - lo].copy_(frames_host[lo:hi], non_blocking=True)
-                s["b"][:hi - lo].copy_(backgrounds_host[lo:hi], non_blocking=True)
+                if not windows:
+                    s["b"][:hi - lo].copy_(backgrounds_host[lo:hi], non_blocking=True)
                 s["ready"].record(up)
 
         for s in slots:
@@ -701,11 +755,14 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
             out_host = torch.empty((n * 4, cs, cs, 3), dtype=torch.uint8).pin_memory()
         for c, (lo, hi) in enumerate(bounds):
             if c + 1 < len(bounds):
-                upload(c + 1)
+                upload(c + 1)                             # frames of the next slice go first; this slice's windows queue behind them
             s = slots[c % 2]
             compute.wait_event(s["ready"])
-            res = run_chain(s["f"][:hi - lo], s["b"][:hi - lo], params, rng, **kw)
+            bgs = backgrounds_host[lo:hi] if windows else s["b"][:hi - lo]
+            res = run_chain(s["f"][:hi - lo], bgs, params, rng, _upload_stream=up, **kw)
             s["free"].record(compute)
+            h2d_bytes += (hi - lo) * int(frames_host[0].numel())
+            h2d_bytes += res.h2d_background_bytes if windows else (hi - lo) * int(backgrounds_host[0].numel())
             k = res.images.shape[0]
             done = torch.cuda.Event()
             done.record(compute)
@@ -723,6 +780,7 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
     merged = ChainResult(out_host[:k_total], labels, records=None, record_arrays=None)
     merged._chunks = arrays
     merged._records = None
+    merged.h2d_bytes = h2d_bytes
     merged.__class__ = _ChunkedResult
     return merged
 

@@ -595,12 +595,14 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
 // neither packed DP4A on byte planes (IDP.4A issues slower than IMAD here; measured slower) nor
 // floating point helps.  What the loops do instead: 4 taps per iteration so loads are issued
 // ahead of their use, and coefficient rows laid out so that a warp reads them contiguously.
+// byte k of a word, zero-extended, in ONE alu-pipe instruction (PRMT) instead of shift + mask
+#define IPP_BYTE(px, k) ((int)__byte_perm((px), 0u, 0x4440 + (k)))
 #define IPP_ACC4(px, w)                                                                \
     {                                                                                  \
-        s0 += (int)((px) & 255u) * (w);                                                \
-        s1 += (int)(((px) >> 8) & 255u) * (w);                                         \
-        s2 += (int)(((px) >> 16) & 255u) * (w);                                        \
-        s3 += (int)((px) >> 24) * (w);                                                 \
+        s0 += IPP_BYTE(px, 0) * (w);                                                   \
+        s1 += IPP_BYTE(px, 1) * (w);                                                   \
+        s2 += IPP_BYTE(px, 2) * (w);                                                   \
+        s3 += IPP_BYTE(px, 3) * (w);                                                   \
     }
 
 // horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles); coefficients [X][tap]
@@ -1021,6 +1023,28 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
     dim3 grid(ceil_div(out_size, rows), n_items);
     { ipp::LaunchTimer _lt("chain_paste_kernel", st); chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c); }
     IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h, int n_bgs,
+                             const ipp_chain_item* items_host, int n_items, int out_size,
+                             uint8_t* windows_dev, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(bgs_host && items_host && windows_dev && n_items >= 0 && n_bgs >= 1, IPP_ERR_BAD_ARG,
+                "ipp_chain_upload_windows: bad arguments");
+    IPP_REQUIRE(out_size > 0 && out_size <= bg_w && out_size <= bg_h && bg_pitch >= (int64_t)bg_w * 3, IPP_ERR_BAD_SHAPE,
+                "ipp_chain_upload_windows: bad geometry");
+    const size_t row = (size_t)out_size * 3;
+    for (int i = 0; i < n_items; ++i) {
+        const ipp_chain_item& it = items_host[i];
+        IPP_REQUIRE(it.bg >= 0 && it.bg < n_bgs && it.sq_size == out_size && it.sq_x0 >= 0 && it.sq_y0 >= 0 &&
+                        it.sq_x0 + out_size <= bg_w && it.sq_y0 + out_size <= bg_h,
+                    IPP_ERR_BAD_ARG, "ipp_chain_upload_windows: item %d has a window outside its background", i);
+        const uint8_t* src = bgs_host + (int64_t)it.bg * bg_stride + (int64_t)it.sq_y0 * bg_pitch + (int64_t)it.sq_x0 * 3;
+        IPP_CUDA(cudaMemcpy2DAsync(windows_dev + (size_t)i * row * out_size, row, src, (size_t)bg_pitch, row, (size_t)out_size,
+                                   cudaMemcpyHostToDevice, st));
+    }
     return IPP_OK;
 }
 

@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(256) resample_h_kernel(const uint8_t* __restri
         uint32_t v = __ldg(row + i);
         if (PREMUL) v = premultiply_px(v);
         const int c = __ldg(k + i);
-        s0 += (int)(v & 255u) * c;
-        s1 += (int)((v >> 8) & 255u) * c;
-        s2 += (int)((v >> 16) & 255u) * c;
-        s3 += (int)(v >> 24) * c;
+        s0 += (int)__byte_perm(v, 0u, 0x4440) * c;      // PRMT: one alu op per byte instead of shift + mask
+        s1 += (int)__byte_perm(v, 0u, 0x4441) * c;
+        s2 += (int)__byte_perm(v, 0u, 0x4442) * c;
+        s3 += (int)__byte_perm(v, 0u, 0x4443) * c;
     }
     uint32_t o = clip8(s0) | (clip8(s1) << 8) | (clip8(s2) << 16) | (clip8(s3) << 24);
     if (UNPREMUL) o = unpremultiply_px(o);
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(256) resample_v_kernel(const uint8_t* __restri
         uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)(ymin + i) * src_pitch) + x);
         if (PREMUL) v = premultiply_px(v);
         const int c = __ldg(k + i);
-        s0 += (int)(v & 255u) * c;
-        s1 += (int)((v >> 8) & 255u) * c;
-        s2 += (int)((v >> 16) & 255u) * c;
-        s3 += (int)(v >> 24) * c;
+        s0 += (int)__byte_perm(v, 0u, 0x4440) * c;      // PRMT: one alu op per byte instead of shift + mask
+        s1 += (int)__byte_perm(v, 0u, 0x4441) * c;
+        s2 += (int)__byte_perm(v, 0u, 0x4442) * c;
+        s3 += (int)__byte_perm(v, 0u, 0x4443) * c;
     }
     uint32_t o = clip8(s0) | (clip8(s1) << 8) | (clip8(s2) << 16) | (clip8(s3) << 24);
     if (UNPREMUL) o = unpremultiply_px(o);

@@ -319,6 +319,17 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
                       const uint8_t* sprite_ws,
                       uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_size, void* stream);
 
+/* Host-background variant of stage C's input: copies, for every item, ONLY the square-crop window
+ * [sq_y0, sq_y0+out_size) x [sq_x0, sq_x0+out_size) of its background from (pinned) host memory to
+ * windows_dev[i] (out_size x out_size x 3, dense) with one cudaMemcpy2DAsync per item on `stream`
+ * — the final square crop (crop_square.py:196) folded into the host->device copy, so the
+ * columns/rows the crop throws away never cross PCIe.  Stage C is then called on windows_dev with
+ * items whose bg = i, sq_x0 = sq_y0 = 0 and pos_x/pos_y shifted by the window origin.
+ * items_host is a HOST array. */
+int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h, int n_bgs,
+                             const ipp_chain_item* items_host, int n_items, int out_size,
+                             uint8_t* windows_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

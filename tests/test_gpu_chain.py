@@ -184,9 +184,47 @@ def test_run_chain_host_whole_and_chunked():
         i, l, r = OC.run_chain(frames[lo:lo + 4], bgs[lo:lo + 4], **kw)
         ref_imgs += i; ref_labels += l; ref_frames += [x["frame"] + lo for x in r]
     random.seed(9)
-    res = chain.run_chain_host(fh, bh, chain.ChainParams(**kw), DEV, chunk=4)
-    assert res.labels == ref_labels and [r["frame"] for r in res.records] == ref_frames
-    assert all(np.array_equal(a, b) for a, b in zip(res.images.numpy(), ref_imgs))
+    for windows in (True, False):
+        random.seed(9)
+        res = chain.run_chain_host(fh, bh, chain.ChainParams(**kw), DEV, chunk=4, background_windows=windows)
+        assert res.labels == ref_labels and [r["frame"] for r in res.records] == ref_frames
+        assert all(np.array_equal(a, b) for a, b in zip(res.images.numpy(), ref_imgs))
+        whole = fh.numel() + bh.numel()
+        assert res.h2d_bytes == (fh.numel() + len(ref_imgs) * 240 * 240 * 3 if windows else whole)
+
+
+@pytest.mark.parametrize("bg_shape", [(240, 300), (300, 220), (256, 256)])
+@pytest.mark.parametrize("run_kw", [dict(), dict(ambiguity_eps=0.2)])
+def test_host_backgrounds_upload_only_crop_windows(bg_shape, run_kw):
+    """Backgrounds left in pinned host memory: only each item's square-crop window is copied to the
+    device (ipp_chain_upload_windows) — same images / labels / generator state as device backgrounds,
+    and fewer bytes than the whole images."""
+    H, W = 200, 320
+    frames = [synth.frame(61, i, H, W) for i in range(5)]
+    bgs = [synth.background(61, i, *bg_shape) for i in range(5)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    fd = torch.from_numpy(np.stack(frames)).to(DEV)
+    bh = torch.from_numpy(np.stack(bgs)).pin_memory()
+    random.seed(5)
+    ref = chain.run_chain(fd, bh.to(DEV), chain.ChainParams(**kw), **run_kw)
+    state = random.getstate()
+    random.seed(5)
+    res = chain.run_chain(fd, bh, chain.ChainParams(**kw), **run_kw)
+    assert random.getstate() == state and res.labels == ref.labels
+    assert torch.equal(res.images, ref.images)
+    cs = min(bg_shape)
+    assert res.h2d_background_bytes == res.images.shape[0] * cs * cs * 3
+    # many items per background: whole backgrounds are fewer bytes than one window per item
+    kw2 = dict(kw, num_rotations=3, choose_random=2)
+    random.seed(6)
+    ref = chain.run_chain(fd, bh[:1].to(DEV), chain.ChainParams(**kw2))
+    random.seed(6)
+    res = chain.run_chain(fd, bh[:1].contiguous().pin_memory(), chain.ChainParams(**kw2))
+    assert res.labels == ref.labels and torch.equal(res.images, ref.images)
+    assert res.h2d_background_bytes == bh[:1].numel()
+    with pytest.raises(RuntimeError):
+        chain.run_chain(fd, torch.from_numpy(np.stack(bgs)), chain.ChainParams(**kw))      # pageable host memory
 
 
 def test_chain_stream_pipelining_is_transparent():
