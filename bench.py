@@ -312,7 +312,8 @@ def main():
     rep = _native.timing_report()
     _native.timing_enable(False)
     alg = {"chain_mask_kernel": B * 3 * FW * FH,                       # frame read once (generic mask kernel)
-           "chain_mask_fast_kernel": B * 3 * FW * FH,                  # frame read once (table-driven mask kernel)
+           "chain_mask_fast_kernel": B * 3 * FW * FH,                  # frame read once (table-driven ring kernel)
+           "chain_mask_seg_kernel": B * 3 * FW * FH,                   # frame read once (table-driven per-warp segment kernel)
            "chain_paste_kernel": B * 2 * 3 * 1080 * 1080}              # background crop read + output write
     peak, peak_src = measured_peak()
     kern = {k: {"launches": c, "total_ms": round(t, 4), "avg_ms": round(t / c, 5)} for k, (c, t) in rep.items()}
@@ -320,8 +321,15 @@ def main():
     dom = max(alg, key=lambda k: rep.get(k, (1, 0.0))[1])
     dcnt, dms = rep.get(dom, (1, float("nan")))
     achieved = alg[dom] / (dms / dcnt * 1e-3) / 1e9
+    traffic, traffic_src = None, None                                  # dram bytes per launch from the committed ncu --set full capture
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.is_file():
+        rec = json.loads(tp.read_text()).get(dom)
+        if rec:
+            traffic = rec["dram_bytes_per_frame"] * B
+            traffic_src = rec["source"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dms / dcnt,
                 "share_of_kernel_time": dms / total_kernel_ms if total_kernel_ms else None}
     chain_gbs = ALG_BYTES_PER_IMAGE * (n_out / world / args.steps) / (ms / args.steps * 1e-3) / 1e9

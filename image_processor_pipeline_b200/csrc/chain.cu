@@ -122,6 +122,9 @@ struct HsvFast {
     // 2: T >= 128 (byte > T <=> bit7 & carry(low7 + 255 - T)).  dark_add = the per-byte addend.
     int dark_mode;
     uint32_t dark_add;
+    // byte s (0 = max channel is R, 1 = G, 2 = B): hue filters whose range meets the hues that sector can produce
+    // (R: [150,180) u [0,30], G: [30,90], B: [90,150])
+    uint32_t sector_mask;
 };
 
 // table byte: bit 7 = V,S accepted by a filter that accepts every hue (pixel keyed out at once);
@@ -413,6 +416,256 @@ __global__ void __launch_bounds__(kFastThreads, 1) chain_mask_fast_kernel(const 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+}
+
+// ===================================================================== stage A: mask, segment kernel
+// Same table-driven classification as chain_mask_fast_kernel, but every WARP runs its own pipeline:
+//
+//  * work unit = a SEGMENT: up to 512 pixels of one row (1536 bytes, 16 mask words).  Warps draw
+//    batches of 16 consecutive segments from a global counter (dynamic balance: segments that cross
+//    the object cost several times more than backdrop segments).
+//  * each warp owns a private 3-stage ring in shared memory; lane 0 keeps two bulk copies (UBLKCP)
+//    in flight while the warp converts the third — 32 warps x 2 x 1.5 KB = 96 KB in flight per SM,
+//    no CTA-wide barrier anywhere, no producer warp.
+//  * pass 1 (whole warp, 16 pixels per lane): conservative "any byte above the dark threshold" test
+//    on the four aligned 16-byte vectors covering the lane's two 8-pixel groups.  With a threshold
+//    T >= 128 the first cut is just the OR of the vectors' bit 7 (0.5 op per word); only when many
+//    groups are flagged is the exact SWAR compare run to thin them out.
+//  * pass 2 (flagged groups only): a task = HALF a group (4 pixels, two 16x2 DPX min/max pairs), so a
+//    segment with a dozen bright specks still fills most of the warp's lanes in one round.  V/S
+//    classification is one byte of the 64 KB table per pixel; the hue is computed only for pixels
+//    the table marks as candidates of a filter with a real hue range.
+//  * mask nibbles are assembled in a per-warp 128-byte scratch and leave as 16 coalesced words.
+struct MaskSegParams {
+    const uint8_t* frames;
+    int64_t pitch, stride;
+    int crop_l, crop_t, w, h;
+    int wpr;
+    uint32_t* bits;
+    int64_t bits_stride;             // words per image
+    int segs_per_row, segs_per_frame;
+    uint32_t n_segs;
+    unsigned int* counter;           // zeroed before the launch
+    const uint8_t* lut;
+    HsvFast f;
+};
+
+constexpr int kSegPx = 512;
+constexpr int kSegThreads = 1024;
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kSegStages = 3;
+constexpr uint32_t kSegStageBytes = 1552;          // 1536 + 15 bytes of misalignment, rounded up to 16 (covers every whole-vector / whole-word read)
+constexpr int kSegBatch = 16;
+constexpr int kSegRefine = 20;                      // more cheaply-flagged groups than this: run the exact dark test
+constexpr size_t kSegSmem = 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192;
+
+__global__ void __launch_bounds__(kSegThreads, 1) chain_mask_seg_kernel(const MaskSegParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[kSegWarps][kSegStages];
+    __shared__ int hdiv[256];
+    __shared__ uint8_t h2f[192];                 // hue (0..179) -> bit j set when hue filter j accepts it
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 192) {
+        uint32_t mk = 0;
+        for (int j = 0; j < p.f.n_hue; ++j) mk |= (uint32_t)(tid >= p.f.h_lo[j] && tid <= p.f.h_hi[j]) << j;
+        h2f[tid] = (uint8_t)mk;
+    }
+    uint8_t* lut = smem;
+    uint8_t* ring = smem + 65536 + (size_t)warp * kSegStages * kSegStageBytes;
+    uint8_t* wq = smem + 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)warp * 192;   // 64 queue bytes
+    uint8_t* nib = wq + 64;                                                                              // 128 nibble bytes
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kSegStages; ++s) mbar_init(&full[warp][s], 1);
+    }
+    for (int i = tid; i < 65536 / 16; i += kSegThreads)
+        reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(p.lut) + i);
+    for (int i = tid; i < 256; i += kSegThreads) hdiv[i] = g_hsv_hdiv[i];
+    __syncthreads();
+
+    // ---- issue side: position of the next segment to request (warp-uniform registers)
+    uint32_t is_left = 0;                        // segments left in the drawn batch
+    int is_row = 0, is_sx = 0;
+    const uint8_t* is_rowptr = nullptr;          // first wanted byte of the current row
+    uint32_t is_outrow = 0;                      // word index of the current row's first mask word
+    bool is_done = false;
+    // per stage: word index of the segment's first mask word, and npx | shift << 16 (npx == 0: no segment)
+    uint32_t d_out[kSegStages], d_geo[kSegStages];
+
+    auto issue = [&](int s) {
+        if (!is_done && is_left == 0) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(p.counter, (unsigned)kSegBatch);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= p.n_segs) {
+                is_done = true;
+            } else {
+                is_left = min((uint32_t)kSegBatch, p.n_segs - b);
+                const int frame = (int)(b / (uint32_t)p.segs_per_frame);
+                const int rem = (int)(b - (uint32_t)frame * (uint32_t)p.segs_per_frame);
+                is_row = rem / p.segs_per_row;
+                is_sx = rem - is_row * p.segs_per_row;
+                is_rowptr = p.frames + (int64_t)frame * p.stride + (int64_t)(p.crop_t + is_row) * p.pitch + (int64_t)p.crop_l * 3;
+                is_outrow = (uint32_t)((int64_t)frame * p.bits_stride + (int64_t)is_row * p.wpr);
+            }
+        }
+        if (is_done) {
+            d_geo[s] = 0;
+            return;
+        }
+        const int x0 = is_sx * kSegPx;
+        const int npx = min(kSegPx, p.w - x0);
+        const uint8_t* src = is_rowptr + x0 * 3;
+        const uint32_t shift = (uint32_t)((uintptr_t)src & 15u);
+        d_out[s] = is_outrow + (uint32_t)is_sx * (kSegPx / 32);
+        d_geo[s] = (uint32_t)npx | (shift << 16);
+        if (lane == 0) {
+            const uint32_t bytes = (shift + (uint32_t)npx * 3u + 15u) & ~15u;
+            mbar_expect_tx(&full[warp][s], bytes);
+            bulk_g2s(ring + (size_t)s * kSegStageBytes, src - shift, bytes, &full[warp][s]);
+        }
+        --is_left;
+        if (++is_sx == p.segs_per_row) {
+            is_sx = 0;
+            is_outrow += (uint32_t)p.wpr;
+            if (++is_row == p.h) {               // next frame: rows are not contiguous across frames in general
+                is_row = 0;
+                is_rowptr += p.stride - (int64_t)(p.h - 1) * p.pitch;
+                is_outrow += (uint32_t)(p.bits_stride - (int64_t)p.h * p.wpr);
+            } else {
+                is_rowptr += p.pitch;
+            }
+        }
+    };
+
+    const int dark_mode = p.f.dark_mode;
+    const uint32_t dark_add = p.f.dark_add;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t sm_r = p.f.sector_mask & 0x7fu, sm_g = (p.f.sector_mask >> 8) & 0x7fu, sm_b = (p.f.sector_mask >> 16) & 0x7fu;
+
+#pragma unroll
+    for (int s = 0; s < kSegStages - 1; ++s) issue(s);
+
+    for (uint32_t round = 0;; ++round) {
+        bool finished = false;
+#pragma unroll
+        for (int s = 0; s < kSegStages; ++s) {
+            if (finished) break;
+            // refill the stage consumed one step ago (all lanes are past it: __syncwarp at the end of the step)
+            if (s == 0) issue(kSegStages - 1); else issue(s - 1);
+            const uint32_t geo = d_geo[s];
+            const int npx = (int)(geo & 0xffffu);
+            if (npx == 0) { finished = true; break; }
+            const uint32_t shift = geo >> 16;
+            // stage s is refilled once per round (stage kSegStages-1 first in the prologue's absence: see parity below)
+            mbar_wait(&full[warp][s], round & 1u);
+            const uint8_t* tile = ring + (size_t)s * kSegStageBytes;
+            const int ngroups = (npx + 7) >> 3;
+
+            // ---------------------------------------------------------------- pass 1
+            const int g0 = 2 * lane;
+            const bool inA = g0 < ngroups, inB = g0 + 1 < ngroups;
+            bool needA = inA, needB = inB;
+            if (dark_mode != 0) {
+                const uint4* vec = reinterpret_cast<const uint4*>(tile + 48 * lane);
+                const uint4 q0 = vec[0], q1 = vec[1], q2 = vec[2], q3 = vec[3];
+                const uint32_t mA2 = shift > 8u ? 0xffffffffu : 0u, mB1 = shift < 8u ? 0xffffffffu : 0u, mB3 = shift > 0u ? 0xffffffffu : 0u;
+                uint32_t f0, f1, f2, f3;
+                if (dark_mode == 2) {                 // T >= 128: a byte above T has bit 7 set (conservative first cut)
+                    f0 = q0.x | q0.y | q0.z | q0.w; f1 = q1.x | q1.y | q1.z | q1.w;
+                    f2 = q2.x | q2.y | q2.z | q2.w; f3 = q3.x | q3.y | q3.z | q3.w;
+                } else {                              // T < 128: exact, bit 7 or carry out of the low 7 bits
+#define IPP_DARK1(q) (((q.x & 0x7f7f7f7fu) + dark_add) | q.x | ((q.y & 0x7f7f7f7fu) + dark_add) | q.y | \
+                      ((q.z & 0x7f7f7f7fu) + dark_add) | q.z | ((q.w & 0x7f7f7f7fu) + dark_add) | q.w)
+                    f0 = IPP_DARK1(q0); f1 = IPP_DARK1(q1); f2 = IPP_DARK1(q2); f3 = IPP_DARK1(q3);
+#undef IPP_DARK1
+                }
+                needA = inA && (((f0 | f1 | (f2 & mA2)) & 0x80808080u) != 0u);
+                needB = inB && ((((f1 & mB1) | f2 | (f3 & mB3)) & 0x80808080u) != 0u);
+                if (dark_mode == 2) {
+                    const int cheap = __popc(__ballot_sync(0xffffffffu, needA)) + __popc(__ballot_sync(0xffffffffu, needB));
+                    if (cheap > kSegRefine) {         // busy segment: exact compare (bit 7 AND carry of low7 + 255 - T)
+#define IPP_DARK2(q) ((((q.x & 0x7f7f7f7fu) + dark_add) & q.x) | (((q.y & 0x7f7f7f7fu) + dark_add) & q.y) | \
+                      (((q.z & 0x7f7f7f7fu) + dark_add) & q.z) | (((q.w & 0x7f7f7f7fu) + dark_add) & q.w))
+                        f0 = IPP_DARK2(q0); f1 = IPP_DARK2(q1); f2 = IPP_DARK2(q2); f3 = IPP_DARK2(q3);
+#undef IPP_DARK2
+                        needA = inA && (((f0 | f1 | (f2 & mA2)) & 0x80808080u) != 0u);
+                        needB = inB && ((((f1 & mB1) | f2 | (f3 & mB3)) & 0x80808080u) != 0u);
+                    }
+                }
+            }
+            reinterpret_cast<uint32_t*>(nib)[lane] = 0u;                    // 16 pixels keyed out unless pass 2 says otherwise
+            const uint32_t balA = __ballot_sync(0xffffffffu, needA), balB = __ballot_sync(0xffffffffu, needB);
+            const int nA = __popc(balA);
+            const int ntasks = 2 * (nA + __popc(balB));
+            if (needA) wq[__popc(balA & lt_mask)] = (uint8_t)g0;
+            if (needB) wq[nA + __popc(balB & lt_mask)] = (uint8_t)(g0 + 1);
+            __syncwarp();
+
+            // ---------------------------------------------------------------- pass 2: half-group tasks
+            for (int t0 = 0; t0 < ntasks; t0 += 32) {
+                const int t = t0 + lane;
+                if (t < ntasks) {
+                    const int hg = 2 * (int)wq[t >> 1] + (t & 1);           // half-group index: pixels 4*hg .. 4*hg+3
+                    const uint32_t boff = shift + 12u * (uint32_t)hg;
+                    const uint32_t bs = (boff & 3u) * 8u;
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(tile + (boff & ~3u));
+                    uint32_t rx = w32[0], ry = w32[1], rz = w32[2];
+                    if (bs) {
+                        const uint32_t r3 = w32[3];
+                        rx = __funnelshift_r(rx, ry, bs);
+                        ry = __funnelshift_r(ry, rz, bs);
+                        rz = __funnelshift_r(rz, r3, bs);
+                    }
+                    // rx ry rz = b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                    const uint32_t B01 = __byte_perm(rx, 0u, 0x4340), G01 = __byte_perm(rx, ry, 0x0401) & 0x00ff00ffu;
+                    const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
+                    const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
+                    const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
+                    const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
+                    const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
+                    const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
+                    const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
+                                       ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
+                    const uint32_t hit = (M & 0x80808080u) >> 7;
+                    uint32_t ex = ((hit * 0x00204081u) >> 21) & 15u;        // bit 7 of every byte -> 4 adjacent bits
+                    const uint32_t M2 = M & 0x7f7f7f7fu & ~(hit * 0x7fu);   // hue-filter candidates of pixels not keyed out yet
+                    // hue test of the candidates, one pixel per iteration and lane (bytes re-read from the tile): a lane
+                    // with a single bright speck loops once, a lane inside the object four times
+                    uint32_t m = M2;
+                    while (m) {
+                        const int k = (__ffs(m) - 1) >> 3;
+                        const uint32_t cand = (m >> (8 * k)) & 0x7fu;
+                        m &= ~(0xffu << (8 * k));
+                        const uint8_t* t = tile + boff + 3 * k;
+                        const int b = t[0], g = t[1], r = t[2];
+                        const int v = max(max(b, g), r), d = v - min(min(b, g), r);
+                        // hue sector of the pixel (max channel) -> filters whose hue range can contain it at all
+                        const uint32_t sm = (v == r) ? sm_r : (v == g) ? sm_g : sm_b;
+                        if (cand & sm) {
+                            const int hh = hue_of(b, g, r, v, d, hdiv);
+                            if (h2f[hh] & cand) ex |= 1u << k;
+                        }
+                    }
+                    uint32_t nb = ~ex & 15u;
+                    const int left = npx - 4 * hg;                          // partial last group of the row
+                    if (left < 4) nb &= (1u << max(left, 0)) - 1u;
+                    nib[hg] = (uint8_t)nb;
+                }
+            }
+            __syncwarp();
+
+            // ---------------------------------------------------------------- nibbles -> mask words
+            uint32_t x = reinterpret_cast<const uint32_t*>(nib)[lane];      // four nibbles: pixels 16*lane .. 16*lane+15
+            x = (x | (x >> 4)) & 0x00ff00ffu;
+            x = (x | (x >> 8)) & 0xffffu;
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, x, 1);
+            if ((lane & 1) == 0 && 16 * lane < npx) p.bits[(size_t)d_out[s] + (lane >> 1)] = x | (hi << 16);
+            __syncwarp();                                                   // everyone is done with this stage, the queue and the nibbles
+        }
+        if (finished) break;
     }
 }
 
@@ -861,9 +1114,58 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     }
     const bool fast = fs.all_zones_full && n_hue_filters <= 7 && fast_rows >= 1 && lut_fits && getenv("IPP_MASK_GENERIC") == nullptr;
     if (fast) {
+        HsvFast hf{};
+        int dark_t = -1;
+        for (int k = 0; k < fs.n; ++k) {
+            const int lo = 512 - (int)(fs.clo[k] & 0x3ffu), hi = (int)(fs.chi[k] & 0x3ffu) - 512;
+            if (!(lo <= 0 && hi >= 180)) {
+                hf.h_lo[hf.n_hue] = lo <= hi ? lo : (1 << 20);       // empty range: nothing passes the unsigned window test
+                hf.h_hi[hf.n_hue] = lo <= hi ? hi : (1 << 20);
+                ++hf.n_hue;
+            } else {
+                // any hue: is it also "any S, V in [0, T]" ?
+                const int s_lo = 512 - (int)((fs.clo[k] >> 10) & 0x3ffu), s_hi = (int)((fs.chi[k] >> 10) & 0x3ffu) - 512;
+                const int v_lo = 512 - (int)((fs.clo[k] >> 20) & 0x3ffu), v_hi = (int)((fs.chi[k] >> 20) & 0x3ffu) - 512;
+                if (s_lo <= 0 && s_hi >= 255 && v_lo <= 0 && v_hi >= 0) dark_t = std::max(dark_t, std::min(v_hi, 255));
+            }
+        }
+        if (dark_t >= 0 && dark_t < 255) {
+            hf.dark_mode = dark_t >= 128 ? 2 : 1;
+            hf.dark_add = 0x01010101u * (uint32_t)(dark_t >= 128 ? 255 - dark_t : 127 - dark_t);
+        }
+        for (int j = 0; j < hf.n_hue; ++j) {
+            const int lo = hf.h_lo[j], hi = hf.h_hi[j];
+            auto meets = [&](int a, int z) { return lo <= z && hi >= a; };
+            if (meets(0, 30) || meets(150, 179)) hf.sector_mask |= 1u << j;
+            if (meets(30, 90)) hf.sector_mask |= 1u << (8 + j);
+            if (meets(90, 150)) hf.sector_mask |= 1u << (16 + j);
+        }
         uint8_t* lut = (uint8_t*)b.la;
         { ipp::LaunchTimer _lt("hsv_lut_kernel", st); hsv_lut_kernel<<<256, 256, 0, st>>>(fs, lut); }
         IPP_LAUNCH_CHECK();
+        const int64_t n_segs = (int64_t)ceil_div(g->crop_w, kSegPx) * g->crop_h * n_frames;
+        const bool seg_ok = n_segs < (1LL << 31) && cg.bits_stride * n_frames < (1LL << 32) && getenv("IPP_MASK_RING") == nullptr;
+        if (seg_ok) {
+            MaskSegParams p{};
+            p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
+            p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
+            p.wpr = cg.wpr; p.bits = b.bits; p.bits_stride = cg.bits_stride;
+            p.segs_per_row = ceil_div(g->crop_w, kSegPx);
+            p.segs_per_frame = p.segs_per_row * g->crop_h;
+            p.n_segs = (uint32_t)n_segs;
+            p.counter = (unsigned int*)b.acc;          // ccl_init re-initialises acc afterwards
+            p.lut = lut;
+            p.f = hf;
+            IPP_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+            static bool attr_set = false;
+            if (!attr_set) {
+                IPP_CUDA(cudaFuncSetAttribute(chain_mask_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem));
+                attr_set = true;
+            }
+            const int grid = (int)std::min<int64_t>(sm_count(), ceil_div(n_segs, kSegWarps));
+            { ipp::LaunchTimer _lt("chain_mask_seg_kernel", st); chain_mask_seg_kernel<<<grid, kSegThreads, kSegSmem, st>>>(p); }
+            IPP_LAUNCH_CHECK();
+        } else {
         MaskFastParams p{};
         p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
         p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
@@ -876,24 +1178,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
                         getenv("IPP_MASK_ROWCOPIES") == nullptr) ? 1 : 0;
         p.stage_bytes = p.contiguous ? (((uint32_t)fast_rows * rowbytes + 30u) & ~15u) + 64u : (uint32_t)fast_rows * row_stride;
         p.lut = lut;
-        int dark_t = -1;
-        for (int k = 0; k < fs.n; ++k) {
-            const int lo = 512 - (int)(fs.clo[k] & 0x3ffu), hi = (int)(fs.chi[k] & 0x3ffu) - 512;
-            if (!(lo <= 0 && hi >= 180)) {
-                p.f.h_lo[p.f.n_hue] = lo;
-                p.f.h_hi[p.f.n_hue] = hi;
-                ++p.f.n_hue;
-            } else {
-                // any hue: is it also "any S, V in [0, T]" ?
-                const int s_lo = 512 - (int)((fs.clo[k] >> 10) & 0x3ffu), s_hi = (int)((fs.chi[k] >> 10) & 0x3ffu) - 512;
-                const int v_lo = 512 - (int)((fs.clo[k] >> 20) & 0x3ffu), v_hi = (int)((fs.chi[k] >> 20) & 0x3ffu) - 512;
-                if (s_lo <= 0 && s_hi >= 255 && v_lo <= 0 && v_hi >= 0) dark_t = std::max(dark_t, std::min(v_hi, 255));
-            }
-        }
-        if (dark_t >= 0 && dark_t < 255) {
-            p.f.dark_mode = dark_t >= 128 ? 2 : 1;
-            p.f.dark_add = 0x01010101u * (uint32_t)(dark_t >= 128 ? 255 - dark_t : 127 - dark_t);
-        }
+        p.f = hf;
         // LUT + ring (+128: pass 1 reads whole aligned vectors past a row's end) + three queue slots of uint16
         const size_t smem = 65536 + (size_t)kFastStages * p.stage_bytes + 128 + (size_t)3 * fast_rows * cg.wpr * 4 * sizeof(uint16_t);
         static size_t smem_set = 0;     // the attribute only ever grows; setting it is not free
@@ -904,6 +1189,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
         const int grid = std::min(sm_count(), p.n_units);
         { ipp::LaunchTimer _lt("chain_mask_fast_kernel", st); chain_mask_fast_kernel<<<grid, kFastThreads, smem, st>>>(p); }
         IPP_LAUNCH_CHECK();
+            }
     }
     if (!fast) {
     MaskParams p{};
