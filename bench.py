@@ -21,6 +21,7 @@ reference's workers=-1 mode, pipeline.py:88-90,372).
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import random
@@ -199,6 +200,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
+    ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
     args = ap.parse_args()
@@ -239,18 +241,21 @@ def main():
         random.seed(1000 * rank + s)
         return chain.run_chain(frames_d, bgs_d, params)
 
-    pipe = chain.ChainStream(params)
+    pipe = chain.ChainStream(params, inputs_ready=True, slots=args.ahead + 1)   # frames_d / bgs_d are resident and complete
 
     def run_pipelined(first, count):
-        """`count` steps, software-pipelined: stage A of step s+1 is in flight while step s is planned
-        and finished (ChainStream).  Exactly `count` stage-A launches, `count` finishes."""
+        """`count` steps, software-pipelined: stage A of the next `--ahead` steps is in flight while step s is
+        planned and its stages B2/C are queued (ChainStream).  Exactly `count` stage-A launches, `count` finishes."""
         n_out = 0
-        ticket = pipe.submit(frames_d, bgs_d)
+        tickets = collections.deque(pipe.submit(frames_d, bgs_d) for _ in range(min(args.ahead, count)))
+        submitted = len(tickets)
         for s in range(count):
-            nxt = pipe.submit(frames_d, bgs_d) if s + 1 < count else None
+            if submitted < count:
+                tickets.append(pipe.submit(frames_d, bgs_d))
+                submitted += 1
             random.seed(1000 * rank + first + s)
-            n_out += pipe.finish(ticket).images.shape[0]
-            ticket = nxt
+            n_out += pipe.finish(tickets.popleft()).images.shape[0]
+        pipe.flush()                                           # deferred table verification of the last batch
         return n_out
 
     def timed(fn, steps, warmup):
@@ -364,7 +369,7 @@ def main():
         line = {"metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline,
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline, "stage_a_steps_ahead": args.ahead,
                            "l2": f"inputs per step {2 * B * 3 * FW * FH / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                            "host_work_in_step": "C++ planner (Python-compatible MT19937 draws) + 3 small device->host read-backs per batch (RNG bounds depend on sprite sizes; table-ambiguity count)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -27,6 +27,7 @@ of the Python generator it is given) and ``planner="python"`` (the readable twin
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import random as _random
 from dataclasses import dataclass
@@ -137,6 +138,16 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional host-side phase trace (profiles/prof_chain_phases.py): TRACE = [] collects (phase, perf_counter()).
+TRACE = None
+
+
+def _mark(name: str):
+    if TRACE is not None:
+        import time
+        TRACE.append((name, time.perf_counter()))
+
+
 # Grow-only scratch buffers per device: the chain's workspaces change size from batch to batch
 # (sprite sizes are data dependent); asking the caching allocator for a new size every call
 # costs a cudaMalloc (and a device synchronisation) each time.
@@ -158,6 +169,37 @@ def _scratch(name: str, nbytes: int, dev: torch.device, dtype=torch.uint8) -> to
 def release_scratch():
     """Drop the cached workspaces (they are re-created on demand)."""
     _SCRATCH.clear()
+    _PINNED.clear()
+
+
+# Small host->device uploads (plan records) go through rotating PINNED staging buffers: a copy from
+# pageable memory can block the host until the stream reaches it, which would stall the planner of
+# batch k+1 behind the kernels of batch k.
+_PINNED = {}
+_PIN_RING = 4
+
+
+def _upload(name: str, arr: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """uint8 device copy of ``arr`` (any dtype, C-contiguous), issued on the current stream."""
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    n = raw.size
+    key = (name, dev.index if dev.index is not None else torch.cuda.current_device())
+    ring = _PINNED.setdefault(key, dict(bufs=[None] * _PIN_RING, events=[None] * _PIN_RING, i=0))
+    i = ring["i"]
+    ring["i"] = (i + 1) % _PIN_RING
+    buf = ring["bufs"][i]
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(int(n * 1.5) + 4096, dtype=torch.uint8).pin_memory()
+        ring["bufs"][i] = buf
+    elif ring["events"][i] is not None:
+        ring["events"][i].synchronize()                  # the copy that last read this staging buffer has finished
+    buf.numpy()[:n] = raw
+    out = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    out[:n].copy_(buf[:n], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    ring["events"][i] = ev
+    return out
 
 
 # =========================================================================== python planner
@@ -188,7 +230,8 @@ def _rot_records(rots: List[dict]):
         a = plan.fixed if plan.kind == "affine" else (0,) * 6
         cw, ch = plan.size
         arr[i] = (r["frame"], *r["cc"], KIND[plan.kind], *a, cw, ch, tile, 0)
-        tile += ((cw + 31) // 32) * ((ch + 31) // 32)
+        x, _, w, h = r["cc"]
+        tile += ((((x + w + 31) >> 5) - (x >> 5)) * h + 255) // 256
     return arr, tile
 
 
@@ -368,6 +411,13 @@ def native_plan_items(rots: np.ndarray, rot_index: np.ndarray, bbox: np.ndarray,
     return items[:k].copy(), aux[:k].copy(), lab
 
 
+def _b1_tiles(rots: np.ndarray) -> np.ndarray:
+    """Stage B1 work list: one tile = 256 mask words of a sprite's component rect (chain_rot_bbox_kernel)."""
+    x, w, h = (rots[n].astype(np.int64) for n in ("cc_x", "cc_w", "cc_h"))
+    nw = ((x + w + 31) >> 5) - (x >> 5)
+    return (nw * h + 255) // 256
+
+
 def _excl(a):
     return np.concatenate([[0], np.cumsum(a)[:-1]]) if len(a) else np.zeros(0, np.int64)
 
@@ -429,10 +479,13 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
 
 
 # =========================================================================== the chain
-def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, slot: int = 0) -> dict:
+def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, slot: int = 0,
+                     wait_events: Sequence = (), wait_current: bool = True) -> dict:
     """Launch stage A (frame -> keep-mask + largest component; no random draws) of a batch on a side
     stream, into the scratch of ``slot`` (0 or 1), and return a ticket for ``run_chain(..., _ticket=)``.
-    Lets the HBM-bound pass of batch k+1 run while the host plans / the GPU finishes batch k."""
+    Lets the HBM-bound pass of batch k+1 run while the host plans / the GPU finishes batch k.
+    The launch waits for ``wait_events`` (previous readers of the slot) and, when ``wait_current``, for
+    everything queued so far on the current stream (the producer of ``frames``)."""
     if not frames.is_cuda:
         raise RuntimeError("prefetch_stage_a needs CUDA tensors (there is no CPU fallback)")
     lib = _native.load()
@@ -448,36 +501,94 @@ def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: Ch
         ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
         ws = _scratch(f"mask_s{slot}", ws_bytes, dev)
         info_d = _scratch(f"info_s{slot}", n * 32, dev, torch.int32).view(n, 8)
-        side.wait_stream(torch.cuda.current_stream())            # inputs / previous users of this slot
+        if wait_current:
+            side.wait_stream(torch.cuda.current_stream())        # inputs / previous users of this slot
+        for ev in wait_events:
+            side.wait_event(ev)
         _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                             ws.data_ptr(), ws_bytes, n, side.cuda_stream), "ipp_chain_stage_a")
         done = torch.cuda.Event()
         done.record(side)
-    return dict(frames=frames, ws=ws, ws_bytes=ws_bytes, info_d=info_d, done=done, geom=geom, n=n)
+    return dict(frames=frames, ws=ws, ws_bytes=ws_bytes, info_d=info_d, done=done, geom=geom, n=n, slot=slot)
 
 
 class ChainStream:
-    """Software pipeline over consecutive batches: ``submit`` launches stage A of a batch on a side
-    stream right away; ``finish`` does the rest (host planning, stages B1/B2/C).  Submitting batch
-    k+1 before finishing batch k keeps the GPU busy during batch k's host work.  Random draws still
-    happen batch after batch, step-major inside a batch (no draw is made by ``submit``)."""
+    """Software pipeline over consecutive batches.  ``submit`` launches stage A of a batch on a side
+    stream right away; ``finish`` does the rest: host planning, stage B1 on a third stream, stages
+    B2 + C queued on the current stream — and returns WITHOUT waiting for them (the images are ordinary
+    stream-ordered CUDA tensors).  With batch k+1 submitted before batch k is finished, the GPU always
+    has a stage A and a stage B2/C to run while the host plans: no device idle time between batches.
 
-    def __init__(self, params: ChainParams, **run_kw):
+    The one read-back stages B2/C need (the count of LANCZOS table rows flagged for exact host
+    verification) is copied to pinned memory asynchronously and looked at during the NEXT ``finish``
+    (before anything overwrites the shared workspaces), or by ``flush()``.  Random draws still happen
+    batch after batch, step-major inside a batch (no draw is made by ``submit``).
+
+    ``slots``: number of keep-mask workspaces = how many batches may be submitted ahead of the one being
+    finished, plus one (2: one batch ahead; 3: two ahead — stage A of batch k+2 is already done when
+    batch k+1 is planned, so the host never waits for it).
+
+    ``inputs_ready=True``: the caller guarantees that the tensors passed to ``submit`` are complete
+    (resident batches, or the caller synchronised) — stage A then does not wait for the work queued
+    on the current stream.  Default False: it waits (safe, but serialises behind stages B2/C)."""
+
+    def __init__(self, params: ChainParams, inputs_ready: bool = False, slots: int = 2, **run_kw):
+        if slots < 2:
+            raise ValueError("ChainStream needs at least two keep-mask slots")
         self.params, self.run_kw, self._n = params, run_kw, 0
+        self.inputs_ready = bool(inputs_ready)
+        self.slots = int(slots)                 # batches that may be between submit() and the end of their stage B2
+        self._slot_free = [None] * self.slots   # event: stages B2/C of the batch that last used the slot are done
+        self._pending = None                    # deferred table verification of the previous batch
+        self._b1 = {}
+        self._amb_host = None
 
     def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor):
-        ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=self._n % 2)
+        slot = self._n % self.slots
+        waits = [self._slot_free[slot]] if self._slot_free[slot] is not None else []
+        ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=slot, wait_events=waits,
+                                  wait_current=not self.inputs_ready)
         ticket["backgrounds"] = backgrounds
         self._n += 1
         return ticket
 
     def finish(self, ticket, rng=_random) -> "ChainResult":
-        return run_chain(ticket["frames"], ticket["backgrounds"], self.params, rng, _ticket=ticket, **self.run_kw)
+        return run_chain(ticket["frames"], ticket["backgrounds"], self.params, rng, _ticket=ticket, _pipe=self, **self.run_kw)
+
+    def flush(self):
+        """Resolve the deferred verification of the last finished batch (synchronises with it)."""
+        self._resolve_pending()
+
+    # ---- used by run_chain
+    def _b1_stream(self, dev):
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in self._b1:
+            self._b1[key] = torch.cuda.Stream(dev)
+        return self._b1[key]
+
+    def _resolve_pending(self):
+        pend, self._pending = self._pending, None
+        if pend is None:
+            return
+        pend["event"].synchronize()
+        n_amb = int(pend["host"][0])
+        res = pend["res"]
+        res.tables_flagged_rows = n_amb
+        res.tables_fixed_items = pend["fix"](n_amb) if n_amb else 0
+
+    def _defer(self, amb_d, res, fix):
+        if self._amb_host is None:
+            self._amb_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+        host = self._amb_host[self._n % 2]
+        host.copy_(amb_d[:1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._pending = dict(event=ev, host=host, res=res, fix=fix)
 
 
 def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
               planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
-              _ticket: Optional[dict] = None, _upload_stream=None):
+              _ticket: Optional[dict] = None, _upload_stream=None, _pipe: Optional["ChainStream"] = None):
     """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB,
     either on the same device or in PINNED HOST memory.  Host backgrounds are never uploaded whole:
     once the square-crop offsets are planned, only each item's crop window crosses PCIe
@@ -530,7 +641,9 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             info_d = _scratch("info", n * 32, dev, torch.int32).view(n, 8)
             _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                                 ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
+        _mark("stage_a_issued")
         info = info_d.cpu().numpy()                                   # sync #1
+        _mark("sync1_info")
         if _shard is not None:
             info = _shard["gather"](info)                             # 32 bytes of metadata per frame
 
@@ -546,15 +659,21 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         local = (rots_all["frame"] >= lo) & (rots_all["frame"] < hi)
         rots_loc = rots_all[local].copy()
         rots_loc["frame"] -= lo
-        tiles = ((rots_loc["canvas_w"].astype(np.int64) + 31) // 32) * ((rots_loc["canvas_h"].astype(np.int64) + 31) // 32)
+        tiles = _b1_tiles(rots_loc)
         rots_loc["tile_start"] = _excl(tiles)
         bbox_d = _scratch("bbox", max(1, len(rots_loc)) * 16, dev, torch.int32).view(-1, 4)
         rot_d = None
-        if len(rots_loc):
-            rot_d = torch.from_numpy(rots_loc.view(np.uint8)).to(dev)
-            _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots_loc), int(tiles.sum()), ws.data_ptr(),
-                                                 bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
-        bbox = bbox_d.cpu().numpy()[:len(rots_loc)]                   # sync #2
+        # pipelined: B1 runs on its own stream (stage A of this batch is complete — its info was read back),
+        # so it does not queue behind stages B2/C of the previous batch on the current stream
+        b1_ctx = torch.cuda.stream(_pipe._b1_stream(dev)) if _pipe is not None else contextlib.nullcontext()
+        with b1_ctx:
+            if len(rots_loc):
+                rot_d = _upload("rots", rots_loc, dev)
+                _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots_loc), int(tiles.sum()), ws.data_ptr(),
+                                                     bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
+            _mark("plan_rot+b1_issued")
+            bbox = bbox_d.cpu().numpy()[:len(rots_loc)]               # sync #2
+        _mark("sync2_bbox")
         if _shard is not None:
             bbox = _shard["gather"](bbox)                             # 16 bytes per sprite, rank order == item order
 
@@ -570,15 +689,19 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             items, aux = items[own].copy(), aux[own].copy()
             labels = [labels[i] for i in own]
             items["frame"] -= lo
+        _mark("plan_items")
         tot = _layout(items)
         K = len(items)
+        _mark("layout")
         out = torch.empty((K, cs, cs, 3), dtype=torch.uint8, device=dev)
         rec_arrays = (items, aux, rot_index, angles)
         if K == 0:
             return finish(ChainResult(out, [], record_arrays=rec_arrays), own.tolist())
 
         # ------------------------------------------------------------------ tables, sprite workspace
-        items_d = torch.from_numpy(items.view(np.uint8)).to(dev)
+        if _pipe is not None:
+            _pipe._resolve_pending()          # previous batch's table check, before its workspaces are overwritten
+        items_d = _upload("items", items, dev)
         spr_ws = _scratch("sprites", max(tot["ws"], 256), dev)
         amb_d = None
         if device_tables:
@@ -603,7 +726,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             items_c["pos_y"] -= items["sq_y0"]
             items_c["sq_x0"] = 0
             items_c["sq_y0"] = 0
-            items_c_d = torch.from_numpy(items_c.view(np.uint8)).to(dev)
+            items_c_d = _upload("items_c", items_c, dev)
             bg_dev = _scratch("bg_windows", K * cs * cs * 3, dev)
             geom_c = _geom_struct(FW, FH, rect, cs, cs, ranges)
             bg_pitch, bg_stride = cs * 3, cs * cs * 3
@@ -630,20 +753,31 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
                           "ipp_chain_stage_c")
 
         run_b2_c(items_d, items_c_d, K, tot["gt"], tot["ht"], tot["vt"])
+        _mark("tables+b2+c_issued")
+
+        if _ticket is not None and _pipe is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            _pipe._slot_free[_ticket["slot"]] = ev                    # the keep-mask of this slot may be overwritten after this
 
         # ------------------------------------------------------------------ exactness fix-up of device tables (rare)
-        n_fixed = 0
-        if device_tables:
+        n_fixed, n_amb = 0, 0
+        res = ChainResult(out, labels, record_arrays=rec_arrays)
+        if device_tables and _pipe is not None:
+            res.tables_flagged_rows = res.tables_fixed_items = None   # known once the next finish() / flush() has looked
+            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev))
+        elif device_tables:
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
+            _mark("sync3_amb")
             if n_amb:
                 n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev)
         for t in (rot_d, items_d, items_c_d):
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
 
-    res = ChainResult(out, labels, record_arrays=rec_arrays)
-    res.tables_flagged_rows = n_amb if device_tables else 0
-    res.tables_fixed_items = n_fixed
+    if not (device_tables and _pipe is not None):
+        res.tables_flagged_rows = n_amb
+        res.tables_fixed_items = n_fixed
     res.h2d_background_bytes = h2d_bytes
     return finish(res, own.tolist())
 

@@ -90,35 +90,104 @@ __device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n) {
     return r;
 }
 
-// ---- phase 1: block bits, horizontal connectivity, initialise run-start entries
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// pixels of `row` dilated by one to the left and right (8-neighbourhood seen from the row above/below),
+// for the 64 pixels of group k; 0 when the row does not exist
+__device__ __forceinline__ uint64_t dilated_px64(const uint32_t* row, int k, int wpr) {
+    const uint64_t v = load_px64(row, k, wpr);
+    const uint64_t prev = (k > 0) ? (uint64_t)(row[2 * k - 1] >> 31) : 0ull;
+    const uint64_t next = (2 * k + 2 < wpr) ? (uint64_t)(row[2 * k + 2] & 1u) : 0ull;
+    return v | (v << 1) | (v >> 1) | prev | (next << 63);
+}
+
+// ---- phase 0: per-image reduction state
+__global__ void ccl_reset_kernel(const CclBuffers b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    b.best[i] = 0ull;
+    int32_t* acc = b.acc + 8 * i;
+    acc[0] = INT_MAX; acc[1] = INT_MAX; acc[2] = 0; acc[3] = 0; acc[4] = 0; acc[5] = 0; acc[6] = 0; acc[7] = 0;
+}
+
+// ---- phase 1: block bits, horizontal connectivity, initialise run-start entries.
+// ISOLATED RUNS — runs that lie inside one 32-block group and touch no foreground pixel of the pixel
+// rows above and below — are complete components (a keyed frame has thousands of them: specks).
+// They are finished right here: area = popcount, straight into the per-image argmax; their blocks are
+// cleared from F so that no later phase spends a label entry, a pointer chase or an atomic on them.
+// (F then means "block of a run that needs union-find"; a set pixel whose F bit is clear belongs to an
+// isolated run, whose identity is its first block.)
 __global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const CclBuffers b, int n) {
     const GroupIdx t = group_index(g, n);
-    if (!t.ok) return;
-    const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
-    const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
-    const bool has1 = (2 * t.by + 1) < g.h;
-    const uint32_t* r1 = r0 + g.wpr;
-    const uint64_t any = load_px64(r0, t.k, g.wpr) | (has1 ? load_px64(r1, t.k, g.wpr) : 0ull);
-    const uint32_t Lc = compress_even(any), Rc = compress_even(any >> 1);
-    const uint32_t F = Lc | Rc;
-    uint32_t carry = 0;
-    if (t.k > 0) carry = (r0[2 * t.k - 1] | (has1 ? r1[2 * t.k - 1] : 0u)) >> 31;
-    const uint32_t C = ((Rc << 1) | carry) & Lc;
-    const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
-    b.cbits[cf] = C;
-    b.fbits[cf] = F;
-    uint32_t S = F & ~C;
-    int2* L = b.la + (int64_t)t.img * g.lab_stride;
-    const int base = t.by * g.bw + (t.k << 5);
-    while (S) {
-        const int i = __ffs(S) - 1;
-        S &= S - 1;
-        L[base + i] = make_int2(base + i, 0);
+    unsigned long long cand = 0ull;
+    int nfg_iso = 0;
+    if (t.ok) {
+        const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+        const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+        const bool has1 = (2 * t.by + 1) < g.h;
+        const uint32_t* r1 = r0 + g.wpr;
+        const uint64_t p0 = load_px64(r0, t.k, g.wpr), p1 = has1 ? load_px64(r1, t.k, g.wpr) : 0ull;
+        const uint64_t any = p0 | p1;
+        const uint32_t Lc = compress_even(any), Rc = compress_even(any >> 1);
+        uint32_t F = Lc | Rc;
+        uint32_t carry = 0;
+        if (t.k > 0) carry = (r0[2 * t.k - 1] | (has1 ? r1[2 * t.k - 1] : 0u)) >> 31;
+        const uint32_t C = ((Rc << 1) | carry) & Lc;
+        const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
+        if (F) {
+            // blocks with a pixel that touches the row above / below
+            uint64_t touch = 0ull;
+            if (t.by > 0) touch |= p0 & dilated_px64(r0 - g.wpr, t.k, g.wpr);
+            if (2 * t.by + 2 < g.h) touch |= p1 & dilated_px64(r1 + g.wpr, t.k, g.wpr);
+            const uint32_t X = compress_even(touch | (touch >> 1));
+            // does the run that reaches block 31 continue in the next group ?
+            uint32_t next_c0 = 0;
+            if ((Rc >> 31) && 2 * t.k + 2 < g.wpr) next_c0 = (r0[2 * t.k + 2] | (has1 ? r1[2 * t.k + 2] : 0u)) & 1u;
+            int2* L = b.la + (int64_t)t.img * g.lab_stride;
+            const int base = t.by * g.bw + (t.k << 5);
+            uint32_t S = F & ~C, iso = 0;
+            while (S) {
+                const int i = __ffs(S) - 1;
+                S &= S - 1;
+                const uint32_t above = (i == 31) ? 0u : (~C & (0xffffffffu << (i + 1)));
+                const int e = above ? (__ffs(above) - 1) : 32;                 // end (exclusive) of the run inside the group
+                const uint32_t rm = ((e == 32) ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << i) - 1u);
+                if ((X & rm) == 0u && !(e == 32 && next_c0)) {
+                    const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
+                    const int area = __popcll(p0 & pm) + __popcll(p1 & pm);
+                    const unsigned long long key =
+                        ((unsigned long long)(uint32_t)area << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(base + i));
+                    cand = key > cand ? key : cand;
+                    nfg_iso += area;
+                    iso |= rm;
+                } else {
+                    L[base + i] = make_int2(base + i, 0);
+                }
+            }
+            F &= ~iso;
+        }
+        b.cbits[cf] = C;
+        b.fbits[cf] = F;
     }
-    if (t.by == 0 && t.k == 0) {
-        b.best[t.img] = 0ull;
-        int32_t* acc = b.acc + 8 * t.img;
-        acc[0] = INT_MAX; acc[1] = INT_MAX; acc[2] = 0; acc[3] = 0; acc[4] = 0; acc[5] = 0; acc[6] = 0; acc[7] = 0;
+    // isolated runs: one argmax / pixel-count atomic per warp (warps straddle images only at image boundaries)
+    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
+    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
+        const unsigned long long m = warp_max_u64(cand);
+        const int tot = __reduce_add_sync(0xffffffffu, nfg_iso);
+        if ((threadIdx.x & 31) == 0 && tot) {
+            if (m > __ldcg(&b.best[img0])) atomicMax(&b.best[img0], m);   // best only grows: a stale read can only cause a redundant atomic
+            atomicAdd(&b.acc[8 * img0 + 4], tot);
+        }
+    } else if (nfg_iso) {
+        atomicMax(&b.best[t.img], cand);
+        atomicAdd(&b.acc[8 * t.img + 4], nfg_iso);
     }
 }
 
@@ -235,15 +304,6 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
     }
 }
 
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w > v ? w : v;
-    }
-    return v;
-}
-
 // ---- phase 4: argmax over roots of (area, smallest block index); one atomic per warp
 __global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const CclBuffers b, int n) {
     const GroupIdx t = group_index(g, n);
@@ -276,59 +336,84 @@ __global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const Cc
     }
 }
 
-// ---- phase 5: keep-mask (in place) + bounding box of the kept pixels
+// each of the 32 low bits doubled: block bit i -> pixel bits 2i, 2i+1
+__device__ __forceinline__ uint64_t spread_pairs(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & kEven;
+    return x | (x << 1);
+}
+
+// ---- phase 5: keep-mask (in place) + bounding box of the kept pixels; one thread per 32-block group
+// (64 pixels x 2 rows).  Run segments are classified once for both pixel rows; isolated runs (pixels
+// whose F bit is clear) need no label lookup at all.
 __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = (int64_t)g.h * g.wpr;
+    const GroupIdx t = group_index(g, n);
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
-    int img = 0;
-    const bool ok = tt < per * n;
-    if (ok) {
-        img = (int)(tt / per);
-        const int rem = (int)(tt - (int64_t)img * per);
-        const int y = rem / g.wpr, kx = rem - y * g.wpr;
-        uint32_t* pw = b.bits + (int64_t)img * g.bits_stride + (int64_t)y * g.wpr + kx;
-        const uint32_t bits = *pw;
-        if (bits) {
-            const unsigned long long bk = b.best[img];
+    if (t.ok) {
+        uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+        uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+        uint32_t* r1 = r0 + g.wpr;
+        const bool has1 = (2 * t.by + 1) < g.h;
+        const uint64_t p0 = load_px64(r0, t.k, g.wpr), p1 = has1 ? load_px64(r1, t.k, g.wpr) : 0ull;
+        const uint64_t any = p0 | p1;
+        if (any) {
+            const unsigned long long bk = b.best[t.img];
             const int best_root = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
-            const int by = y >> 1, k = kx >> 1, half = (kx & 1) * 16;
-            const uint32_t* crow = b.cbits + (int64_t)img * g.cf_stride + (int64_t)by * g.bww;
-            const uint32_t C = crow[k];
-            const int2* L = b.la + (int64_t)img * g.lab_stride;
-            const int rowbase = by * g.bw;
-            uint32_t rem_bits = bits, keep = 0;
-            while (rem_bits) {
-                const int px = __ffs(rem_bits) - 1;
-                const int i = half + (px >> 1);
+            const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
+            const uint32_t* crow = b.cbits + cf;
+            const uint32_t C = crow[t.k], F = b.fbits[cf + t.k];
+            const uint32_t Fall = compress_even(any) | compress_even(any >> 1);
+            const int2* L = b.la + (int64_t)t.img * g.lab_stride;
+            const int rowbase = t.by * g.bw, gb0 = t.k << 5;
+            uint32_t starts = Fall & (~C | 1u), keep = 0;
+            while (starts) {
+                const int i = __ffs(starts) - 1;
+                starts &= starts - 1;
                 const int e = segment_end(C, i);
-                const int lo = 2 * (i - half);
-                const int hi = min(32, 2 * (e - half));
-                const uint32_t pm = ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                const int s = run_start(crow, (k << 5) + i);
-                if (L[rowbase + s].x == best_root) keep |= bits & pm;
-                rem_bits &= ~pm;
+                const uint32_t sm = ((e == 32) ? 0xffffffffu : ((1u << e) - 1u)) & ~((1u << i) - 1u);
+                bool kept;
+                if (((F >> i) & 1u) == 0u) {
+                    kept = (rowbase + gb0 + i) == best_root;                  // isolated run: its first block is its identity
+                } else {
+                    const int s0 = (((C >> i) & 1u) == 0u) ? (gb0 + i) : run_start(crow, gb0 + i);
+                    kept = L[rowbase + s0].x == best_root;
+                }
+                if (kept) keep |= sm;
             }
-            if (keep != bits) *pw = keep;
-            if (keep) {
-                minx = 32 * kx + __ffs(keep) - 1;
-                maxx1 = 32 * kx + 32 - __clz(keep);
-                miny = y;
-                maxy1 = y + 1;
+            const uint64_t km = spread_pairs(keep);
+            const uint64_t k0 = p0 & km, k1 = p1 & km;
+            if (k0 != p0) {
+                r0[2 * t.k] = (uint32_t)k0;
+                if (2 * t.k + 1 < g.wpr) r0[2 * t.k + 1] = (uint32_t)(k0 >> 32);
+            }
+            if (k1 != p1) {
+                r1[2 * t.k] = (uint32_t)k1;
+                if (2 * t.k + 1 < g.wpr) r1[2 * t.k + 1] = (uint32_t)(k1 >> 32);
+            }
+            const uint64_t ka = k0 | k1;
+            if (ka) {
+                minx = 64 * t.k + __ffsll((long long)ka) - 1;
+                maxx1 = 64 * t.k + 64 - __clzll((long long)ka);
+                miny = k0 ? 2 * t.by : 2 * t.by + 1;
+                maxy1 = k1 ? 2 * t.by + 2 : 2 * t.by + 1;
             }
         }
     }
-    // a CTA may straddle two images only at image boundaries; reduce per warp, then atomics
-    const int wimg = __shfl_sync(0xffffffffu, img, 0);
-    const bool uniform = __all_sync(0xffffffffu, img == wimg || !ok);
+    // a warp may straddle two images only at image boundaries; reduce per warp, then atomics
+    const int wimg = __shfl_sync(0xffffffffu, t.img, 0);
+    const bool uniform = __all_sync(0xffffffffu, t.img == wimg || !t.ok);
     if (uniform) {
         minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
         if ((threadIdx.x & 31) == 0 && maxx1 > 0) {
             int32_t* acc = b.acc + 8 * wimg;
             atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
         }
-    } else if (ok && maxx1 > 0) {
-        int32_t* acc = b.acc + 8 * img;
+    } else if (t.ok && maxx1 > 0) {
+        int32_t* acc = b.acc + 8 * t.img;
         atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
     }
 }
@@ -336,6 +421,8 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
 int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
     const int64_t groups = (int64_t)g.bh * g.bww * n;
     const int gb = ceil_div(groups, 256);
+    { ipp::LaunchTimer _lt("ccl_reset_kernel", st); ccl_reset_kernel<<<ceil_div(n, 256), 256, 0, st>>>(b, n); }
+    IPP_LAUNCH_CHECK();
     { ipp::LaunchTimer _lt("ccl_init_kernel", st); ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
     { ipp::LaunchTimer _lt("ccl_merge_kernel", st); ccl_merge_kernel<<<gb, 256, 0, st>>>(g, b, n); }
@@ -344,8 +431,7 @@ int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
     IPP_LAUNCH_CHECK();
     { ipp::LaunchTimer _lt("ccl_best_kernel", st); ccl_best_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    const int64_t words = (int64_t)g.h * g.wpr * n;
-    { ipp::LaunchTimer _lt("ccl_keep_kernel", st); ccl_keep_kernel<<<ceil_div(words, 256), 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_keep_kernel", st); ccl_keep_kernel<<<gb, 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

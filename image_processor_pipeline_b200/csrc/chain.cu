@@ -700,64 +700,121 @@ __device__ __forceinline__ int find_record(const Rec* recs, int n, int tile, Get
 }
 
 // ===================================================================== stage B1: rotated bbox
+// PIL's getbbox of the rotated sprite WITHOUT touching the canvas pixel by pixel.
+//
+// A canvas pixel P is set iff its source S = map(P) (16.16 fixed point, nearest) is a kept pixel.
+// If P is extreme (say the left-most set pixel), its neighbour P' = P - (1, 0) is not set; the
+// fixed-point steps |a0|, |a3| (and |a1|, |a4| for vertical moves) are <= 1.0, so map(P') lies in the
+// 8-neighbourhood of S (or is S itself) — hence S has an unset 8-neighbour (or lies on the rect's
+// border): S is a BOUNDARY pixel of the kept component.  Conversely every canvas pixel that maps
+// to a given S lies within +-1 of round(forward(S)): the pre-image of a unit square under a rotation
+// is a unit square around forward(centre of S), per-axis half extent <= 0.7072, plus <= 0.5 of rounding.
+// So: scan the component rect's mask words (bits only), peel the 8-boundary with shifts and ANDs,
+// forward-map each boundary pixel in float, and test the 3x3 canvas pixels around it with the EXACT
+// integer inverse map.  Work ~ perimeter instead of canvas area; the result is identical.
+// One thread = one mask word; a CTA = 256 consecutive words of one sprite's rect (flat tile list).
 __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot* __restrict__ rots, int n_rot,
                                                              const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
-                                                             int32_t* bbox_out) {
+                                                             int frame_h, int32_t* bbox_out) {
     __shared__ int s_rec;
-    __shared__ int s_box[4];
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0)
         s_rec = find_record(rots, n_rot, (int)blockIdx.x, [](const ipp_chain_rot& r) { return r.tile_start; });
-        s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = 0; s_box[3] = 0;
-    }
     __syncthreads();
     const ipp_chain_rot rec = rots[s_rec];
-    const int tile = (int)blockIdx.x - rec.tile_start;
-    const int tiles_x = (rec.canvas_w + 31) >> 5;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int chunk = (int)blockIdx.x - rec.tile_start;
+    int32_t* out = bbox_out + 4 * s_rec;
+    if (rec.kind != 0) {
+        // copy / rot90 / rot180 / rot270 are exact permutations and the rect is the component's tight box
+        if (chunk == 0 && threadIdx.x == 0) { out[0] = 0; out[1] = 0; out[2] = rec.canvas_w; out[3] = rec.canvas_h; }
+        return;
+    }
+    const int w0 = rec.cc_x >> 5;
+    const int nw = ((rec.cc_x + rec.cc_w + 31) >> 5) - w0;
+    const int q = chunk * 256 + (int)threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = tx * 32 + lane;
-    const SrcMap m{rec.kind, rec.a0, rec.a1, rec.a2, rec.a3, rec.a4, rec.a5, rec.cc_w, rec.cc_h};
-    const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride + (int64_t)rec.cc_y * wpr;
+    const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride;
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
-    const int y0 = ty * 32 + warp * 4;
-    // affine case: the fixed-point source coordinates advance by (a1, a4) per canvas row
-    int xx = rec.a2 + y0 * rec.a1 + x * rec.a0, yy = rec.a5 + y0 * rec.a4 + x * rec.a3;
+    // ---- phase 1: boundary pixels of this thread's word
+    uint32_t bnd = 0;
+    int row = 0, wi = 0;
+    if (q < nw * rec.cc_h) {
+        row = q / nw;
+        wi = w0 + (q - row * nw);
+        const int fy = rec.cc_y + row;
+        const uint32_t* pr = fb + (int64_t)fy * wpr + wi;
+        const uint32_t m = pr[0];
+        if (m) {
+            const bool hasl = wi > 0, hasr = wi + 1 < wpr;
+            // pixels whose left, own and right neighbours are all set, for one row (zero row when it does not exist)
+            auto hcore = [&](const uint32_t* r, bool exists) -> uint32_t {
+                if (!exists) return 0u;
+                const uint32_t x = r[0];
+                const uint32_t l = (x << 1) | (hasl ? (r[-1] >> 31) : 0u);
+                const uint32_t rr = (x >> 1) | (hasr ? (r[1] << 31) : 0u);
+                return x & l & rr;
+            };
+            const uint32_t interior = hcore(pr, true) & hcore(pr - wpr, fy > 0) & hcore(pr + wpr, fy + 1 < frame_h);
+            bnd = m & ~interior;
+        }
+    }
+    // ---- phase 2: the warp's boundary pixels, compacted (a flat edge puts 32 of them in one lane's word)
+    __shared__ uint32_t s_q[8][1024];
+    const int cnt = __popc(bnd);
+    int incl = cnt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int y = y0 + j;
-        bool on = false;
-        if (x < rec.canvas_w && y < rec.canvas_h) {
-            int xin, yin;
-            bool inside;
-            if (rec.kind == 0) {
-                xin = xx >> 16;
-                yin = yy >> 16;
-                inside = (unsigned)xin < (unsigned)rec.cc_w && (unsigned)yin < (unsigned)rec.cc_h;
-            } else {
-                inside = map_canvas(m, x, y, xin, yin);
-            }
-            if (inside) {
-                const int fx = rec.cc_x + xin;
-                on = (fb[yin * wpr + (fx >> 5)] >> (fx & 31)) & 1u;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+        int off = incl - cnt;
+        const uint32_t hi = (uint32_t)row << 16;
+        const int xbase = wi * 32 - rec.cc_x;
+        while (bnd) {
+            const int bit = __ffs(bnd) - 1;
+            bnd &= bnd - 1;
+            s_q[warp][off++] = (uint32_t)(xbase + bit) | hi;
+        }
+        __syncwarp();
+        // forward map (float): canvas = A^-1 * (65536 * (S + 0.5) - (a2, a5))
+        const double det = (double)rec.a0 * (double)rec.a4 - (double)rec.a1 * (double)rec.a3;
+        const float i00 = (float)((double)rec.a4 / det), i01 = (float)(-(double)rec.a1 / det);
+        const float i10 = (float)(-(double)rec.a3 / det), i11 = (float)((double)rec.a0 / det);
+        for (int i = lane; i < total; i += 32) {
+            const uint32_t e = s_q[warp][i];
+            const int xin = (int)(e & 0xffffu), yin = (int)(e >> 16);
+            const float u = (float)((xin << 16) + 32768 - rec.a2), v = (float)((yin << 16) + 32768 - rec.a5);
+            const int cx0 = (int)rintf(i00 * u + i01 * v) - 1, cy0 = (int)rintf(i10 * u + i11 * v) - 1;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int cy = cy0 + dy;
+                if (cy < 0 || cy >= rec.canvas_h) continue;
+                int xx = rec.a2 + cy * rec.a1 + cx0 * rec.a0, yy = rec.a5 + cy * rec.a4 + cx0 * rec.a3;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int cx = cx0 + dx;
+                    const int xi = xx >> 16, yi = yy >> 16;
+                    xx += rec.a0;
+                    yy += rec.a3;
+                    if (cx < 0 || cx >= rec.canvas_w) continue;
+                    if (cx >= minx && cx < maxx1 && cy >= miny && cy < maxy1) continue;      // cannot extend this lane's box
+                    if ((unsigned)xi >= (unsigned)rec.cc_w || (unsigned)yi >= (unsigned)rec.cc_h) continue;
+                    const int fx = rec.cc_x + xi;
+                    if ((fb[(int64_t)(rec.cc_y + yi) * wpr + (fx >> 5)] >> (fx & 31)) & 1u) {
+                        minx = min(minx, cx); maxx1 = max(maxx1, cx + 1);
+                        miny = min(miny, cy); maxy1 = max(maxy1, cy + 1);
+                    }
+                }
             }
         }
-        xx += rec.a1;
-        yy += rec.a4;
-        const uint32_t mask = __ballot_sync(0xffffffffu, on);
-        if (mask) {
-            minx = min(minx, tx * 32 + __ffs(mask) - 1);
-            maxx1 = max(maxx1, tx * 32 + 32 - __clz(mask));
-            miny = min(miny, y);
-            maxy1 = max(maxy1, y + 1);
-        }
     }
-    if (lane == 0 && maxx1 > 0) {
-        atomicMin(&s_box[0], minx); atomicMin(&s_box[1], miny); atomicMax(&s_box[2], maxx1); atomicMax(&s_box[3], maxy1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_box[2] > 0) {
-        int32_t* o = bbox_out + 4 * s_rec;
-        atomicMin(&o[0], s_box[0]); atomicMin(&o[1], s_box[1]); atomicMax(&o[2], s_box[2]); atomicMax(&o[3], s_box[3]);
+    minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
+    if ((threadIdx.x & 31) == 0 && maxx1 > 0) {
+        if (minx < __ldcg(&out[0])) atomicMin(&out[0], minx);
+        if (miny < __ldcg(&out[1])) atomicMin(&out[1], miny);
+        if (maxx1 > __ldcg(&out[2])) atomicMax(&out[2], maxx1);
+        if (maxy1 > __ldcg(&out[3])) atomicMax(&out[3], maxy1);
     }
 }
 
@@ -1228,7 +1285,7 @@ int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n
     { ipp::LaunchTimer _lt("bbox_reset_kernel", st); bbox_reset_kernel<<<ceil_div(n_rot, 256), 256, 0, st>>>(bbox_out, n_rot); }
     IPP_LAUNCH_CHECK();
     if (total_tiles == 0) return IPP_OK;
-    { ipp::LaunchTimer _lt("chain_rot_bbox_kernel", st); chain_rot_bbox_kernel<<<total_tiles, 256, 0, st>>>(rots, n_rot, (const uint32_t*)workspace, cg.bits_stride, cg.wpr, bbox_out); }
+    { ipp::LaunchTimer _lt("chain_rot_bbox_kernel", st); chain_rot_bbox_kernel<<<total_tiles, 256, 0, st>>>(rots, n_rot, (const uint32_t*)workspace, cg.bits_stride, cg.wpr, cg.h, bbox_out); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }

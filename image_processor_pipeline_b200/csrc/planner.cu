@@ -212,7 +212,10 @@ int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_pa
             }
             rot_index_out[n] = i;
             r->tile_start = (int32_t)tiles;
-            tiles += (long long)((r->canvas_w + 31) / 32) * ((r->canvas_h + 31) / 32);
+            {   // stage B1 tile = 256 mask words of the component rect (chain_rot_bbox_kernel)
+                const long long nw = ((r->cc_x + r->cc_w + 31) >> 5) - (r->cc_x >> 5);
+                tiles += (nw * r->cc_h + 255) / 256;
+            }
             IPP_REQUIRE(tiles < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_rotations_host: too many tiles");
             ++n;
         }

@@ -231,7 +231,9 @@ typedef struct ipp_chain_rot {
     int32_t kind;                       /* 0 affine, 1 copy, 2 rot180, 3 rot90, 4 rot270    */
     int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (kind 0)           */
     int32_t canvas_w, canvas_h;
-    int32_t tile_start;                 /* first 32x32 tile of this canvas in the flat grid */
+    int32_t tile_start;                 /* first stage-B1 tile of this sprite in the flat grid; a tile =
+                                           256 mask words of the component rect, whose rows span
+                                           nw = ((cc_x+cc_w+31)>>5) - (cc_x>>5) words: ceil(nw*cc_h/256) tiles */
     int32_t _pad;
 } ipp_chain_rot;
 
@@ -304,7 +306,9 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
                       const ipp_chain_geom* geom_host, int32_t* info_out,
                       void* workspace, int64_t workspace_bytes, int n_frames, void* stream);
 /* stage B1: alpha bbox of every rotated sprite -> bbox_out int32[n_rot][4]
- * {x0,y0,x1,y1}; empty <=> x1 == 0.  total_tiles = sum over sprites of 32x32 canvas tiles. */
+ * {x0,y0,x1,y1}; empty <=> x1 == 0.  total_tiles = sum over sprites of their tiles (see tile_start).
+ * Only the 8-boundary pixels of the kept component are mapped (the extreme pixels of the rotated
+ * sprite are images of boundary pixels), each checked with the exact fixed-point inverse map. */
 int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rots, int n_rot, int total_tiles,
                        const void* workspace, int32_t* bbox_out, void* stream);
 /* stage B2: rotate∘fit∘flip gather (premultiplied) -> LANCZOS h pass -> v pass ->

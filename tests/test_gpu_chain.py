@@ -227,27 +227,36 @@ def test_host_backgrounds_upload_only_crop_windows(bg_shape, run_kw):
         chain.run_chain(fd, torch.from_numpy(np.stack(bgs)), chain.ChainParams(**kw))      # pageable host memory
 
 
-def test_chain_stream_pipelining_is_transparent():
-    """ChainStream (stage A of batch k+1 launched before batch k is finished) gives the same images,
-    labels and generator state as plain run_chain calls."""
+@pytest.mark.parametrize("inputs_ready", [False, True])
+@pytest.mark.parametrize("run_kw", [dict(), dict(ambiguity_eps=0.2)])
+def test_chain_stream_pipelining_is_transparent(inputs_ready, run_kw):
+    """ChainStream (stage A of batch k+1 launched before batch k is finished, B1 on its own stream,
+    table verification deferred to the next finish / flush) gives the same images, labels and
+    generator state as plain run_chain calls — also when rows ARE flagged and re-derived."""
     H, W = 200, 320
-    batches = [([synth.frame(50 + b, i, H, W) for i in range(3)], [synth.background(50 + b, i, 240, 300) for i in range(2)]) for b in range(3)]
+    batches = [([synth.frame(50 + b, i, H, W) for i in range(3)], [synth.background(50 + b, i, 240, 300) for i in range(2)]) for b in range(4)]
     kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
               pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
     dev_batches = [(torch.from_numpy(np.stack(f)).to(DEV), torch.from_numpy(np.stack(b)).to(DEV)) for f, b in batches]
+    torch.cuda.synchronize()
     random.seed(77)
-    plain = [chain.run_chain(f, b, chain.ChainParams(**kw)) for f, b in dev_batches]
+    plain = [chain.run_chain(f, b, chain.ChainParams(**kw), **run_kw) for f, b in dev_batches]
+    flagged = [r.tables_flagged_rows for r in plain]
     plain = [(r.images.cpu().numpy(), r.labels) for r in plain]
     state = random.getstate()
     random.seed(77)
-    pipe = chain.ChainStream(chain.ChainParams(**kw))
+    pipe = chain.ChainStream(chain.ChainParams(**kw), inputs_ready=inputs_ready, **run_kw)
     ticket = pipe.submit(*dev_batches[0])
-    got = []
-    for k in range(3):
-        nxt = pipe.submit(*dev_batches[k + 1]) if k + 1 < 3 else None
-        r = pipe.finish(ticket)
-        got.append((r.images.cpu().numpy(), r.labels))
+    results = []
+    for k in range(4):
+        nxt = pipe.submit(*dev_batches[k + 1]) if k + 1 < 4 else None
+        results.append(pipe.finish(ticket))
         ticket = nxt
+    assert results[-1].tables_flagged_rows is None          # not looked at yet
+    pipe.flush()
     assert random.getstate() == state
-    for (a, la), (b, lb) in zip(plain, got):
-        assert la == lb and np.array_equal(a, b)
+    assert [r.tables_flagged_rows for r in results] == flagged
+    if run_kw:
+        assert sum(flagged) > 0
+    for (a, la), r in zip(plain, results):
+        assert la == r.labels and np.array_equal(a, r.images.cpu().numpy())
