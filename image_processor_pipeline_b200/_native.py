@@ -50,7 +50,9 @@ class PlanParams(C.Structure):
 
 class PlanTotals(C.Structure):
     _fields_ = [("table_ints", C.c_int64), ("table_rows", C.c_int64), ("sprite_ws_bytes", C.c_int64),
-                ("gather_tiles", C.c_int32), ("h_tiles", C.c_int32), ("v_tiles", C.c_int32), ("labels_bytes", C.c_int32)]
+                ("band_units", C.c_int64),
+                ("gather_tiles", C.c_int32), ("h_tiles", C.c_int32), ("v_tiles", C.c_int32), ("labels_bytes", C.c_int32),
+                ("max_rows", C.c_int32), ("max_band_warps", C.c_int32)]
 
 
 _u8p = C.c_void_p      # device pointers travel as integers
@@ -97,7 +99,8 @@ PROTOTYPES = {
     "ipp_chain_stage_a": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _i32p, _vp, _i64, _int, _vp]),
     "ipp_chain_stage_b1": (_int, [C.POINTER(ChainGeom), _vp, _int, _int, _vp, _i32p, _vp]),
     "ipp_chain_stage_b2": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _int, _int, _int,
-                                  _i32p, _vp, _u8p, _vp]),
+                                  _i32p, _vp, _int, _vp, _u8p, _vp]),
+    "ipp_chain_layout_host": (_int, [_vp, _int, C.POINTER(PlanTotals)]),
     "ipp_chain_stage_c": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _u8p, _u8p, _i64, _i64, _int, _vp]),
     "ipp_chain_upload_windows": (_int, [_vp, _i64, _i64, _int, _int, _int, _vp, _int, _int, _u8p, _vp]),
 }

@@ -53,7 +53,7 @@ ITEM_DTYPE = np.dtype([(n, "<i4") for n in
                         "fit_x0", "fit_y0", "spr_w", "spr_h", "flip_h", "flip_v", "new_w", "new_h", "pos_x", "pos_y",
                         "sq_x0", "sq_y0", "sq_size", "h_ksize", "v_ksize", "hb_off", "hk_off", "vb_off", "vk_off",
                         "gather_tile_start", "h_tile_start", "v_tile_start", "tab_row_start", "out_slot",
-                        "_p0", "_p1", "_p2")] +
+                        "hband_off", "vband_off", "nkb")] +
                       [("rot_off", "<i8"), ("tmp_off", "<i8"), ("spr_off", "<i8")])
 AUX_DTYPE = np.dtype([("ratio", "<f8"), ("rot", "<i4"), ("sym", "<i4")])
 assert ROT_DTYPE.itemsize == 64 and ITEM_DTYPE.itemsize == 184 and AUX_DTYPE.itemsize == 16
@@ -429,35 +429,20 @@ def lanczos_ksize(n_in, n_out):
 
 
 def _layout(items: np.ndarray):
-    """Tile starts, table offsets and workspace offsets of an item array (numpy, vectorised) —
-    the device-side schedule of the variable-sized sprites."""
-    k = len(items)
-    sw, sh, nw, nh = (items[n].astype(np.int64) for n in ("spr_w", "spr_h", "new_w", "new_h"))
-    hk = np.where(sw != nw, lanczos_ksize(sw, nw), 0)
-    vk = np.where(sh != nh, lanczos_ksize(sh, nh), 0)
-    items["h_ksize"], items["v_ksize"] = hk, vk
-    hsz = np.where(hk > 0, 2 * nw + nw * hk, 0)
-    vsz = np.where(vk > 0, 2 * nh + nh * vk, 0)
-    start = _excl(hsz + vsz)
-    items["hb_off"] = np.where(hk > 0, start, 0)
-    items["hk_off"] = np.where(hk > 0, start + 2 * nw, 0)
-    items["vb_off"] = np.where(vk > 0, start + hsz, 0)
-    items["vk_off"] = np.where(vk > 0, start + hsz + 2 * nh, 0)
-    rows = np.where(hk > 0, nw, 0) + np.where(vk > 0, nh, 0)
-    items["tab_row_start"] = _excl(rows)
-    gt = ((sw + 31) // 32) * ((sh + 31) // 32)
-    ht = ((nw + 31) // 32) * ((sh + 7) // 8)
-    vt = ((nw + 31) // 32) * ((nh + 7) // 8)
-    items["gather_tile_start"], items["h_tile_start"], items["v_tile_start"] = _excl(gt), _excl(ht), _excl(vt)
-    a256 = lambda v: (v + 255) // 256 * 256
-    s0, s1, s2 = a256(sw * sh * 4), a256(nw * sh * 4), a256(nw * nh * 4)
-    base = _excl(s0 + s1 + s2)
-    items["rot_off"], items["tmp_off"], items["spr_off"] = base, base + s0, base + s0 + s1
-    items["out_slot"] = np.arange(k)
-    if int((hsz + vsz).sum()) >= 2 ** 31:
-        raise NotImplementedError("coefficient tables exceed 2^31 entries; use a smaller batch")
-    return dict(table_ints=int((hsz + vsz).sum()), max_rows=int(rows.max()) if k else 0,
-                ws=int((s0 + s1 + s2).sum()), gt=int(gt.sum()), ht=int(ht.sum()), vt=int(vt.sum()))
+    """Device-side schedule of an item array (ipp_chain_layout_host): coefficient-table and fragment-table
+    offsets, flat tile starts, sprite-workspace offsets — filled in place."""
+    lib = _native.load()
+    assert items.flags.c_contiguous
+    tot = _native.PlanTotals()
+    _native.check(lib.ipp_chain_layout_host(items.ctypes.data, len(items), C.byref(tot)), "ipp_chain_layout_host")
+    return dict(table_ints=int(tot.table_ints), max_rows=int(tot.max_rows), ws=int(tot.sprite_ws_bytes), gt=int(tot.gather_tiles),
+                ht=int(tot.h_tiles), vt=int(tot.v_tiles), band_bytes=int(tot.band_units) * 8, max_band_warps=int(tot.max_band_warps))
+
+
+def _pass_tiles(items: np.ndarray):
+    """Flat tile counts of the two LANCZOS passes per item (chain_hpass_kernel / chain_vpass_kernel grids)."""
+    nw, nh = items["new_w"].astype(np.int64), items["new_h"].astype(np.int64)
+    return ((nw + 63) // 64) * 4, ((nh + 63) // 64) * ((nw + 127) // 128)
 
 
 def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
@@ -703,6 +688,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             _pipe._resolve_pending()          # previous batch's table check, before its workspaces are overwritten
         items_d = _upload("items", items, dev)
         spr_ws = _scratch("sprites", max(tot["ws"], 256), dev)
+        band_d = _scratch("bands", max(tot["band_bytes"], 256), dev)
         amb_d = None
         if device_tables:
             tab_d = _scratch("tables", max(1, tot["table_ints"]) * 4, dev, torch.int32)
@@ -744,7 +730,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         # ------------------------------------------------------------------ stage B2 + C
         def run_b2_c(items_dev, items_c_dev, k, gt, ht, vt):
             _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
-                                                 gt, ht, vt, tab_d.data_ptr(), ws.data_ptr(), spr_ws.data_ptr(), _stream()),
+                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"],
+                                                 ws.data_ptr(), spr_ws.data_ptr(), _stream()),
                           "ipp_chain_stage_b2")
             if bg_ready is not None:
                 torch.cuda.current_stream().wait_event(bg_ready)       # the windows have landed (copied while B2 ran)
@@ -808,8 +795,7 @@ def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev)
             dirty.add(item)
     if dirty:
         sub = items[sorted(dirty)].copy()
-        ht = ((sub["new_w"].astype(np.int64) + 31) // 32) * ((sub["spr_h"].astype(np.int64) + 7) // 8)
-        vt = ((sub["new_w"].astype(np.int64) + 31) // 32) * ((sub["new_h"].astype(np.int64) + 7) // 8)
+        ht, vt = _pass_tiles(sub)
         sub["h_tile_start"], sub["v_tile_start"] = _excl(ht), _excl(vt)
         sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
         sub_c = items_c[sorted(dirty)].copy()                  # stage C's view of the same items (host-window mode: shifted copies)

@@ -829,11 +829,13 @@ struct B2Common {
     const ipp_chain_item* items;
     int n_items;
     const int32_t* tables;
+    uint2* band;                 // banded int8 fragment tables (chain_band_kernel)
     uint8_t* sprite_ws;
 };
 
 // gather: sprite pixel (X, Y) after flip <- canvas (X' + fit_x0, Y' + fit_y0) <- frame pixel.
-// Stored premultiplied (alpha is 0 or 255 here): RGB order, R in byte 0.
+// Stored premultiplied (alpha is 0 or 255 here) as FOUR BYTE PLANES [R, G, B, A][spr_h][Wp] (Wp = spr_w
+// rounded up to 4): the layout the tensor-core LANCZOS pass reads its A fragments from.
 __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -851,7 +853,9 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride + (int64_t)it.cc_y * c.wpr;
     const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride + (int64_t)(c.crop_t + it.cc_y) * c.pitch +
                            (int64_t)(c.crop_l + it.cc_x) * 3;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.rot_off);
+    const int64_t Wp = (spr_w + 3) & ~3;
+    const int64_t plane = (int64_t)spr_h * Wp;
+    uint8_t* dst = c.sprite_ws + it.rot_off + X;
     const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
     const int Y0 = ty * 32 + warp * 4;
     // affine case: canvas row cy = fit_y0 + (flip_v ? spr_h-1-Y : Y) moves by +-1 per sprite row
@@ -882,10 +886,31 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
                 px = (uint32_t)s[2] | ((uint32_t)s[1] << 8) | ((uint32_t)s[0] << 16) | 0xff000000u;   // BGR -> RGBA
             }
         }
-        dst[(int64_t)Y * spr_w + X] = px;
+        uint8_t* d = dst + (int64_t)Y * Wp;
+        d[0] = (uint8_t)px;
+        d[plane] = (uint8_t)(px >> 8);
+        d[2 * plane] = (uint8_t)(px >> 16);
+        d[3 * plane] = (uint8_t)(px >> 24);
     }
 }
 
+// --------------------------------------------------------------------- LANCZOS on the tensor cores
+// Pillow's 8bpc resample is an exact integer convolution: out = clip8((2^21 + sum px * k) >> 22), k a
+// signed 23-bit coefficient, ~15-40 taps per output and pass.  On the CUDA cores every tap costs four
+// multiply-adds plus unpacking (the scalar kernels ran at ~70 % issue utilisation and 0.9 TB/s); as a
+// banded integer GEMM the same sums are a handful of IMMA instructions:
+//     coefficient k = k2 * 65536 + k1 * 256 + k0   (k0, k1 unsigned bytes, k2 a signed byte)
+//     sum px * k   = (sum px * k2) << 16  +  (sum px * k1) << 8  +  sum px * k0
+// with three u8 x {u8, u8, s8} -> s32 accumulators (mma.sync.m16n8k32), exact in two's complement because
+// the full sum fits 32 bits (Pillow accumulates in int32 as well).
+//
+// A fragment (data): 16 rows x 32 consecutive source positions of one byte plane; B fragment
+// (coefficients): the 32 x 8 band that 8 consecutive outputs cut out of those positions, pre-arranged
+// in fragment order by chain_band_kernel.  A tile of 8 outputs touches a window of
+// ceil(7 * in / out) + ksize source positions: nkb blocks of 32 (typically 2), ~25 % of the multiplies
+// are useful — still >10x fewer issue slots than scalar code, and the passes become L2/HBM bound.
+// A skipped pass (size unchanged; Pillow skips it) uses the identity band k = 2^22, which reproduces
+// the input bytes exactly, so both kernels have a single code path.
 constexpr int kPrec = 32 - 8 - 2;
 __device__ __forceinline__ uint32_t c_clip8(int v) {
     v >>= kPrec;
@@ -900,94 +925,223 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
     return c0 | (c1 << 8) | (c2 << 16) | (a << 24);
 }
 
-// The two LANCZOS passes are instruction-issue bound (ncu: ~70 % issue slots busy, L1 hit rate
-// 75-90 %): every tap costs four 8-bit x 23-bit integer multiply-adds that must stay exact, so
-// neither packed DP4A on byte planes (IDP.4A issues slower than IMAD here; measured slower) nor
-// floating point helps.  What the loops do instead: 4 taps per iteration so loads are issued
-// ahead of their use, and coefficient rows laid out so that a warp reads them contiguously.
-// byte k of a word, zero-extended, in ONE alu-pipe instruction (PRMT) instead of shift + mask
-#define IPP_BYTE(px, k) ((int)__byte_perm((px), 0u, 0x4440 + (k)))
-#define IPP_ACC4(px, w)                                                                \
-    {                                                                                  \
-        s0 += IPP_BYTE(px, 0) * (w);                                                   \
-        s1 += IPP_BYTE(px, 1) * (w);                                                   \
-        s2 += IPP_BYTE(px, 2) * (w);                                                   \
-        s3 += IPP_BYTE(px, 3) * (w);                                                   \
-    }
+__device__ __forceinline__ void mma_u8u8(int (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
 
-// horizontal pass: tmp[y][X], y < spr_h, X < new_w   (32 x 8 tiles); coefficients [X][tap]
+// layout of one axis' band table at `base` (uint2 units): [ceil(ntiles / 2)] header words holding the
+// first source position xb of every tile (int32 each), then [ntiles][nkb][3 planes][32 lanes] uint2.
+struct BandAxis {
+    int in_size, out_size, ksize, nkb, ntiles;
+    const int32_t* bounds;       // [out][2] (xmin, n)   (unused when ksize == 0)
+    const int32_t* kk;           // [out][ksize]
+};
+__device__ __forceinline__ BandAxis band_axis(const ipp_chain_item& it, const int32_t* tables, int axis) {
+    BandAxis a;
+    a.in_size = axis ? it.spr_h : it.spr_w;
+    a.out_size = axis ? it.new_h : it.new_w;
+    a.ksize = axis ? it.v_ksize : it.h_ksize;
+    a.nkb = axis ? (it.nkb >> 16) : (it.nkb & 0xffff);
+    a.ntiles = (a.out_size + 7) >> 3;
+    a.bounds = tables + (axis ? it.vb_off : it.hb_off);
+    a.kk = tables + (axis ? it.vk_off : it.hk_off);
+    return a;
+}
+
+// one warp = one (item, axis, tile of 8 outputs, k-block): the 32 x 8 coefficient band in B-fragment order,
+// split into three byte planes.  B fragment of m16n8k32: lane (g = lane / 4, t = lane % 4) holds, for
+// output column g, source positions 4t..4t+3 (register 0) and 16+4t..16+4t+3 (register 1).
+__global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
+    const ipp_chain_item& it = c.items[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    int w = (int)blockIdx.x * 8 + (int)(threadIdx.x >> 5);
+    const BandAxis ah = band_axis(it, c.tables, 0), av = band_axis(it, c.tables, 1);
+    const int nh_warps = ah.ntiles * ah.nkb;
+    const int axis = w >= nh_warps;
+    if (axis) w -= nh_warps;
+    const BandAxis a = axis ? av : ah;
+    if (w >= a.ntiles * a.nkb) return;
+    const int tile = w / a.nkb, kb = w - tile * a.nkb;
+    uint2* base = c.band + (axis ? it.vband_off : it.hband_off);
+    const int X0 = tile * 8;
+    const int xb = (a.ksize ? a.bounds[2 * X0] : X0) & ~3;
+    if (kb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb;
+    const int g = lane >> 2, t = lane & 3;
+    const int X = X0 + g;
+    int xmin = 0, n = 0;
+    const int32_t* k = nullptr;
+    if (X < a.out_size) {
+        if (a.ksize) {
+            xmin = a.bounds[2 * X];
+            n = a.bounds[2 * X + 1];
+            k = a.kk + (int64_t)X * a.ksize;
+        } else {
+            xmin = X;               // identity: one tap of weight 1.0
+            n = 1;
+        }
+    }
+    uint32_t r[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = xb + 32 * kb + 16 * half + 4 * t + j - xmin;
+            int wgt = 0;
+            if (idx >= 0 && idx < n) wgt = k ? k[idx] : (1 << kPrec);
+            r[0][half] |= ((uint32_t)wgt & 255u) << (8 * j);
+            r[1][half] |= (((uint32_t)wgt >> 8) & 255u) << (8 * j);
+            r[2][half] |= (((uint32_t)wgt >> 16) & 255u) << (8 * j);      // signed byte: |wgt| < 2^23
+        }
+    }
+    uint2* frag = base + ((a.ntiles + 1) >> 1) + ((int64_t)(tile * a.nkb + kb) * 3) * 32 + lane;
+    frag[0] = make_uint2(r[0][0], r[0][1]);
+    frag[32] = make_uint2(r[1][0], r[1][1]);
+    frag[64] = make_uint2(r[2][0], r[2][1]);
+}
+
+// A fragment of m16n8k32 for rows r_lo (= tile row g) and r_hi (= g + 8) of a byte plane:
+// registers {row g, k 4t..}, {row g+8, k 4t..}, {row g, k 16+4t..}, {row g+8, k 16+4t..}
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const uint8_t* r_lo, const uint8_t* r_hi, int koff) {
+    a[0] = *reinterpret_cast<const uint32_t*>(r_lo + koff);
+    a[1] = *reinterpret_cast<const uint32_t*>(r_hi + koff);
+    a[2] = *reinterpret_cast<const uint32_t*>(r_lo + koff + 16);
+    a[3] = *reinterpret_cast<const uint32_t*>(r_hi + koff + 16);
+}
+
+// horizontal pass.  CTA = (item, byte plane, group of 64 outputs); warp = 8 outputs; loop over the rows,
+// 32 at a time.  Result is written TRANSPOSED, [plane][X][y] with pitch Hp, so that the vertical pass
+// finds its reduction index contiguous: a warp transposes its 32 x 8 byte tile through shared memory
+// and stores 32-byte runs.
 __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __shared__ int s_rec;
+    __shared__ __align__(16) uint8_t s_t[8][8 * 36];
     if (threadIdx.x == 0)
         s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.h_tile_start; });
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
-    const int tile = (int)blockIdx.x - it.h_tile_start;
-    const int new_w = it.new_w;
-    const int tiles_x = (new_w + 31) >> 5;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int X = tx * 32 + (threadIdx.x & 31);
-    const int y = ty * 8 + (threadIdx.x >> 5);
-    if (X >= new_w || y >= it.spr_h) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.rot_off) + (int64_t)y * it.spr_w;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.tmp_off) + (int64_t)y * new_w;
-    if (it.h_ksize == 0) {          // width unchanged: Pillow skips the horizontal pass
-        dst[X] = src[X];
-        return;
+    const int lt = (int)blockIdx.x - it.h_tile_start;
+    const int pl = lt & 3, xgroup = lt >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int new_w = it.new_w, spr_h = it.spr_h;
+    const int ntiles = (new_w + 7) >> 3, nkb = it.nkb & 0xffff;
+    const int tile = xgroup * 8 + warp;
+    if (tile >= ntiles) return;
+    const uint2* base = c.band + it.hband_off;
+    const int xb = reinterpret_cast<const int32_t*>(base)[tile];
+    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nkb * 96 + lane;
+    const int64_t Wp = (it.spr_w + 3) & ~3, Hp = (spr_h + 3) & ~3;
+    const uint8_t* src = c.sprite_ws + it.rot_off + (int64_t)pl * spr_h * Wp + xb + 4 * t;
+    uint8_t* dst = c.sprite_ws + it.tmp_off + (int64_t)pl * new_w * Hp;
+    uint8_t* st = s_t[warp];
+    for (int y0 = 0; y0 < spr_h; y0 += 32) {
+        int acc[2][3][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[m][p][i] = 0;
+        const uint8_t* r0 = src + (int64_t)min(y0 + g, spr_h - 1) * Wp;
+        const uint8_t* r1 = src + (int64_t)min(y0 + g + 8, spr_h - 1) * Wp;
+        const uint8_t* r2 = src + (int64_t)min(y0 + g + 16, spr_h - 1) * Wp;
+        const uint8_t* r3 = src + (int64_t)min(y0 + g + 24, spr_h - 1) * Wp;
+        for (int kb = 0; kb < nkb; ++kb) {
+            uint32_t a0[4], a1[4];
+            load_a_frag(a0, r0, r1, 32 * kb);
+            load_a_frag(a1, r2, r3, 32 * kb);
+            const uint2 b0 = __ldg(frag + kb * 96), b1 = __ldg(frag + kb * 96 + 32), b2 = __ldg(frag + kb * 96 + 64);
+            mma_u8u8(acc[0][0], a0, b0); mma_u8u8(acc[1][0], a1, b0);
+            mma_u8u8(acc[0][1], a0, b1); mma_u8u8(acc[1][1], a1, b1);
+            mma_u8s8(acc[0][2], a0, b2); mma_u8s8(acc[1][2], a1, b2);
+        }
+        // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1}
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int v = acc[m][0][i] + (acc[m][1][i] << 8) + (acc[m][2][i] << 16) + (1 << (kPrec - 1));
+                const int yl = 16 * m + g + 8 * (i >> 1), xl = 2 * t + (i & 1);
+                st[xl * 36 + yl] = (uint8_t)c_clip8(v);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int wi = lane + 32 * h;                       // 8 columns x 8 words
+            const int xl = wi >> 3, q = wi & 7;
+            const int X = tile * 8 + xl, y = y0 + 4 * q;
+            if (X < new_w && y < spr_h)
+                *reinterpret_cast<uint32_t*>(dst + (int64_t)X * Hp + y) = *reinterpret_cast<const uint32_t*>(st + xl * 36 + 4 * q);
+        }
+        __syncwarp();
     }
-    const int32_t* bounds = c.tables + it.hb_off;
-    const int xmin = bounds[2 * X], n = bounds[2 * X + 1];
-    const int32_t* k = c.tables + it.hk_off + (int64_t)X * it.h_ksize;
-    src += xmin;
-    int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-        const uint32_t v = src[i];
-        const int w = __ldg(k + i);
-        IPP_ACC4(v, w)
-    }
-    dst[X] = c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24);
 }
 
-// vertical pass + un-premultiply: spr[Y][x], Y < new_h, x < new_w   (32 x 8 tiles); coefficients [Y][tap]
+// vertical pass + un-premultiply.  CTA = (item, group of 64 output rows, chunk of 128 columns); warp = 8 output
+// rows; the reduction runs over y, contiguous in the transposed planar intermediate.  All four byte planes of a
+// tile are accumulated by the same warp, so un-premultiply and the interleaved RGBA store are lane-local:
+// C fragment element (row = column X of the sprite, col = output row Y).
 __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
         s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
-    const int tile = (int)blockIdx.x - it.v_tile_start;
-    const int new_w = it.new_w;
-    const int tiles_x = (new_w + 31) >> 5;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int x = tx * 32 + (threadIdx.x & 31);
-    const int Y = ty * 8 + (threadIdx.x >> 5);
-    if (x >= new_w || Y >= it.new_h) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sprite_ws + it.tmp_off) + x;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off) + (int64_t)Y * new_w;
-    if (it.v_ksize == 0) {
-        dst[x] = c_unpremultiply(src[(int64_t)Y * new_w]);
-        return;
+    const int lt = (int)blockIdx.x - it.v_tile_start;
+    const int new_w = it.new_w, new_h = it.new_h, spr_h = it.spr_h;
+    const int xchunks = (new_w + 127) >> 7;
+    const int ygroup = lt / xchunks, xchunk = lt - ygroup * xchunks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntiles = (new_h + 7) >> 3, nkb = it.nkb >> 16;
+    const int tile = ygroup * 8 + warp;
+    if (tile >= ntiles) return;
+    const uint2* base = c.band + it.vband_off;
+    const int yb = reinterpret_cast<const int32_t*>(base)[tile];
+    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nkb * 96 + lane;
+    const int64_t Hp = (spr_h + 3) & ~3;
+    const int64_t plane = (int64_t)new_w * Hp;
+    const uint8_t* src = c.sprite_ws + it.tmp_off + yb + 4 * t;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off);
+    const int x_end = min(new_w, (xchunk + 1) * 128);
+    for (int X0 = xchunk * 128; X0 < x_end; X0 += 16) {
+        const uint8_t* r0 = src + (int64_t)min(X0 + g, new_w - 1) * Hp;
+        const uint8_t* r1 = src + (int64_t)min(X0 + g + 8, new_w - 1) * Hp;
+        uint32_t px[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+            int acc[3][4];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[p][i] = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                uint32_t a[4];
+                load_a_frag(a, r0 + pl * plane, r1 + pl * plane, 32 * kb);
+                mma_u8u8(acc[0], a, __ldg(frag + kb * 96));
+                mma_u8u8(acc[1], a, __ldg(frag + kb * 96 + 32));
+                mma_u8s8(acc[2], a, __ldg(frag + kb * 96 + 64));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
+                px[i] |= c_clip8(v) << (8 * pl);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int X = X0 + g + 8 * (i >> 1), Y = tile * 8 + 2 * t + (i & 1);
+            if (X < x_end && Y < new_h) dst[(int64_t)Y * new_w + X] = c_unpremultiply(px[i]);
+        }
     }
-    const int32_t* bounds = c.tables + it.vb_off;
-    const int ymin = bounds[2 * Y], n = bounds[2 * Y + 1];
-    const int32_t* k = c.tables + it.vk_off + (int64_t)Y * it.v_ksize;    // uniform per warp
-    src += (int64_t)ymin * new_w;
-    int s0 = 1 << (kPrec - 1), s1 = s0, s2 = s0, s3 = s0;
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t v0 = src[0], v1 = src[new_w], v2 = src[2 * new_w], v3 = src[3 * new_w];
-        const int w0 = __ldg(k + i), w1 = __ldg(k + i + 1), w2 = __ldg(k + i + 2), w3 = __ldg(k + i + 3);
-        src += 4 * new_w;
-        IPP_ACC4(v0, w0) IPP_ACC4(v1, w1) IPP_ACC4(v2, w2) IPP_ACC4(v3, w3)
-    }
-    for (; i < n; ++i) {
-        const uint32_t v = src[0];
-        src += new_w;
-        const int w = __ldg(k + i);
-        IPP_ACC4(v, w)
-    }
-    dst[x] = c_unpremultiply(c_clip8(s0) | (c_clip8(s1) << 8) | (c_clip8(s2) << 16) | (c_clip8(s3) << 24));
 }
 
 // ===================================================================== stage C
@@ -1293,20 +1447,28 @@ int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, const void* workspace, uint8_t* sprite_ws, void* stream) {
+                       const int32_t* tables, void* band, int max_band_warps,
+                       const void* workspace, uint8_t* sprite_ws, void* stream) {
     using namespace ipp;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = chain_check_geom(g);
     if (rc != IPP_OK) return rc;
-    IPP_REQUIRE(frames && items && workspace && sprite_ws && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: bad arguments");
-    IPP_REQUIRE((((uintptr_t)sprite_ws) & 15) == 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: sprite workspace must be 16-byte aligned");
+    IPP_REQUIRE(frames && items && workspace && sprite_ws && tables && band && n_items >= 0 && max_band_warps >= 0, IPP_ERR_BAD_ARG,
+                "ipp_chain_stage_b2: bad arguments");
+    IPP_REQUIRE((((uintptr_t)sprite_ws) & 255) == 0 && (((uintptr_t)band) & 15) == 0, IPP_ERR_BAD_ARG,
+                "ipp_chain_stage_b2: sprite workspace must be 256-byte aligned, fragment tables 16-byte aligned");
     if (n_items == 0) return IPP_OK;
     const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
     B2Common c{};
     c.frames = frames; c.pitch = frame_pitch; c.stride = frame_stride;
     c.crop_l = g->crop_l; c.crop_t = g->crop_t;
     c.bits = (const uint32_t*)workspace; c.bits_stride = cg.bits_stride; c.wpr = cg.wpr;
-    c.items = items; c.n_items = n_items; c.tables = tables; c.sprite_ws = sprite_ws;
+    c.items = items; c.n_items = n_items; c.tables = tables; c.band = (uint2*)band; c.sprite_ws = sprite_ws;
+    if (max_band_warps > 0 && (h_tiles > 0 || v_tiles > 0)) {
+        dim3 grid(ceil_div(max_band_warps, 8), n_items);
+        { ipp::LaunchTimer _lt("chain_band_kernel", st); chain_band_kernel<<<grid, 256, 0, st>>>(c); }
+        IPP_LAUNCH_CHECK();
+    }
     if (gather_tiles > 0) {
         { ipp::LaunchTimer _lt("chain_gather_kernel", st); chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();

@@ -26,7 +26,7 @@
 
 static_assert(sizeof(ipp_chain_rot) == 64, "ipp_chain_rot layout (chain.py ROT_DTYPE)");
 static_assert(sizeof(ipp_chain_item) == 184, "ipp_chain_item layout (chain.py ITEM_DTYPE)");
-static_assert(sizeof(ipp_plan_params) == 88 && sizeof(ipp_plan_aux) == 16 && sizeof(ipp_plan_totals) == 40, "planner struct layout");
+static_assert(sizeof(ipp_plan_params) == 88 && sizeof(ipp_plan_aux) == 16 && sizeof(ipp_plan_totals) == 56, "planner struct layout");
 
 namespace ipp {
 namespace plan {
@@ -225,6 +225,73 @@ int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_pa
     return IPP_OK;
 }
 
+// Device-side schedule of an item array: coefficient-table offsets, banded int8 fragment tables for the
+// tensor-core LANCZOS passes, flat tile starts, sprite-workspace offsets.  Shared by the planner and by
+// callers that build item arrays themselves (tests).
+int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* totals_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE((items || n_items == 0) && n_items >= 0 && totals_out, IPP_ERR_BAD_ARG, "ipp_chain_layout_host: bad arguments");
+    int64_t toff = 0, tab_rows = 0, woff = 0, boff = 0;
+    long long gt = 0, ht = 0, vt = 0;
+    int max_rows = 0, max_band_warps = 0;
+    for (int i = 0; i < n_items; ++i) {
+        ipp_chain_item* it = items + i;
+        const int sw = it->spr_w, sh = it->spr_h, nw = it->new_w, nh = it->new_h;
+        IPP_REQUIRE(sw > 0 && sh > 0 && nw > 0 && nh > 0, IPP_ERR_BAD_SHAPE, "ipp_chain_layout_host: item %d has an empty sprite", i);
+        it->h_ksize = it->v_ksize = 0;
+        it->hb_off = it->hk_off = it->vb_off = it->vk_off = 0;
+        it->tab_row_start = (int32_t)tab_rows;
+        int rows = 0;
+        if (nw != sw) {
+            it->h_ksize = lanczos_ksize(sw, nw);
+            it->hb_off = (int32_t)toff; it->hk_off = (int32_t)(toff + 2 * (int64_t)nw);
+            toff += 2 * (int64_t)nw + (int64_t)nw * it->h_ksize;
+            rows += nw;
+        }
+        if (nh != sh) {
+            it->v_ksize = lanczos_ksize(sh, nh);
+            it->vb_off = (int32_t)toff; it->vk_off = (int32_t)(toff + 2 * (int64_t)nh);
+            toff += 2 * (int64_t)nh + (int64_t)nh * it->v_ksize;
+            rows += nh;
+        }
+        tab_rows += rows;
+        max_rows = std::max(max_rows, rows);
+        IPP_REQUIRE(toff < (1LL << 31) && tab_rows < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: coefficient tables exceed 2^31 entries");
+        // banded fragment tables: an 8-output tile reads at most ceil(7 * in / out) + ksize + 4 source positions
+        // (window drift over 7 outputs + one window + alignment of the first position to 4), in blocks of 32
+        auto kblocks = [](int in, int out, int ks) { return (int)(((7LL * in + out - 1) / out + std::max(ks, 1) + 4 + 31) / 32); };
+        const int nkb_h = kblocks(sw, nw, it->h_ksize), nkb_v = kblocks(sh, nh, it->v_ksize);
+        const int nt_h = (nw + 7) / 8, nt_v = (nh + 7) / 8;
+        it->nkb = nkb_h | (nkb_v << 16);
+        it->hband_off = (int32_t)boff; boff += (nt_h + 1) / 2 + (int64_t)nt_h * nkb_h * 96;
+        it->vband_off = (int32_t)boff; boff += (nt_v + 1) / 2 + (int64_t)nt_v * nkb_v * 96;
+        IPP_REQUIRE(boff < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: fragment tables exceed 16 GiB; use a smaller batch");
+        max_band_warps = std::max(max_band_warps, nt_h * nkb_h + nt_v * nkb_v);
+        it->gather_tile_start = (int32_t)gt; it->h_tile_start = (int32_t)ht; it->v_tile_start = (int32_t)vt;
+        gt += (long long)((sw + 31) / 32) * ((sh + 31) / 32);
+        ht += (long long)((nw + 63) / 64) * 4;
+        vt += (long long)((nh + 63) / 64) * ((nw + 127) / 128);
+        IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: too many tiles");
+        // planar premultiplied sprite [4][sh][Wp], transposed planar h-pass result [4][nw][Hp], final RGBA sprite
+        const int64_t Wp = (sw + 3) & ~3, Hp = (sh + 3) & ~3;
+        it->rot_off = woff; woff = align_up(woff + 4 * (int64_t)sh * Wp + 512, 256);
+        it->tmp_off = woff; woff = align_up(woff + 4 * (int64_t)nw * Hp + 512, 256);
+        it->spr_off = woff; woff = align_up(woff + (int64_t)nw * nh * 4, 256);
+        it->out_slot = i;
+    }
+    totals_out->table_ints = toff;
+    totals_out->table_rows = tab_rows;
+    totals_out->sprite_ws_bytes = woff;
+    totals_out->band_units = boff;
+    totals_out->gather_tiles = (int32_t)gt;
+    totals_out->h_tiles = (int32_t)ht;
+    totals_out->v_tiles = (int32_t)vt;
+    totals_out->max_rows = max_rows;
+    totals_out->max_band_warps = max_band_warps;
+    return IPP_OK;
+}
+
 // Steps after the rotation: fit, symmetry, overlay, square crop.  bbox: stage-B1 rows
 // int32[n_rot][4].  Fills item records (frame, bg, geometry, flips, sizes, positions, crop,
 // table offsets, tile starts, workspace offsets), aux rows {rot (index into rots), sym
@@ -294,8 +361,6 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
     }
     // ---- square-crop step (crop_square.py:62-65,163-217) + records
     int n = 0;
-    int64_t toff = 0, woff = 0, tab_rows = 0;
-    long long gt = 0, ht = 0, vt = 0;
     size_t lpos = 0;
     const int cs = BW < BH ? BW : BH;
     for (const Ov& o : overlays) {
@@ -341,40 +406,14 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
         it->flip_h = (o.v.sym == 1 || o.v.sym == 3); it->flip_v = (o.v.sym == 2 || o.v.sym == 3);
         it->new_w = o.nw; it->new_h = o.nh; it->pos_x = o.px; it->pos_y = o.py;
         it->sq_x0 = x0; it->sq_y0 = y0; it->sq_size = cs;
-        it->tab_row_start = (int32_t)tab_rows;
-        if (o.nw != o.v.sw) {
-            it->h_ksize = lanczos_ksize(o.v.sw, o.nw);
-            it->hb_off = (int32_t)toff; it->hk_off = (int32_t)(toff + 2 * (int64_t)o.nw);
-            toff += 2 * (int64_t)o.nw + (int64_t)o.nw * it->h_ksize;
-            tab_rows += o.nw;
-        }
-        if (o.nh != o.v.sh) {
-            it->v_ksize = lanczos_ksize(o.v.sh, o.nh);
-            it->vb_off = (int32_t)toff; it->vk_off = (int32_t)(toff + 2 * (int64_t)o.nh);
-            toff += 2 * (int64_t)o.nh + (int64_t)o.nh * it->v_ksize;
-            tab_rows += o.nh;
-        }
-        IPP_REQUIRE(toff < (1LL << 31) && tab_rows < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_items_host: coefficient tables exceed 2^31 entries");
-        it->gather_tile_start = (int32_t)gt; it->h_tile_start = (int32_t)ht; it->v_tile_start = (int32_t)vt;
-        gt += (long long)((o.v.sw + 31) / 32) * ((o.v.sh + 31) / 32);
-        ht += (long long)((o.nw + 31) / 32) * ((o.v.sh + 7) / 8);
-        vt += (long long)((o.nw + 31) / 32) * ((o.nh + 7) / 8);
-        IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_items_host: too many tiles");
-        it->rot_off = woff; woff = align_up(woff + (int64_t)o.v.sw * o.v.sh * 4, 256);
-        it->tmp_off = woff; woff = align_up(woff + (int64_t)o.nw * o.v.sh * 4, 256);
-        it->spr_off = woff; woff = align_up(woff + (int64_t)o.nw * o.nh * 4, 256);
         aux_out[n].ratio = o.ratio;
         aux_out[n].rot = o.v.rot;
         aux_out[n].sym = o.v.sym;
         ++n;
     }
     *n_items_out = n;
-    totals_out->table_ints = toff;
-    totals_out->table_rows = tab_rows;
-    totals_out->sprite_ws_bytes = woff;
-    totals_out->gather_tiles = (int32_t)gt;
-    totals_out->h_tiles = (int32_t)ht;
-    totals_out->v_tiles = (int32_t)vt;
+    const int lrc = ipp_chain_layout_host(items_out, n, totals_out);
+    if (lrc != IPP_OK) return lrc;
     totals_out->labels_bytes = (int32_t)lpos;
     return IPP_OK;
 }

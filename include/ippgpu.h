@@ -251,8 +251,11 @@ typedef struct ipp_chain_item {
     int32_t gather_tile_start, h_tile_start, v_tile_start;
     int32_t tab_row_start;                  /* first coefficient-table row of this item (h rows, then v rows) */
     int32_t out_slot;                       /* index of the output image this item writes            */
-    int32_t _pad[3];
-    int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace            */
+    int32_t hband_off, vband_off;           /* 8-byte offsets of this item's banded int8 fragment tables (h, v) */
+    int32_t nkb;                            /* 32-wide k-blocks per 8-output tile: h | v << 16       */
+    int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace: planar premultiplied sprite
+                                               [4][spr_h][Wp], transposed planar h-pass result [4][new_w][Hp],
+                                               final RGBA sprite [new_h][new_w][4]; Wp/Hp = spr_w/spr_h rounded up to 4 */
 } ipp_chain_item;
 
 /* ---- host planner (C++ twin of chain.py's planner; no device work) ------------------
@@ -277,7 +280,9 @@ typedef struct ipp_plan_aux {
 
 typedef struct ipp_plan_totals {
     int64_t table_ints, table_rows, sprite_ws_bytes;
+    int64_t band_units;                     /* size of the fragment-table buffer in 8-byte units      */
     int32_t gather_tiles, h_tiles, v_tiles, labels_bytes;
+    int32_t max_rows, max_band_warps;       /* per-item maxima: coefficient rows, fragment-table warps */
 } ipp_plan_totals;
 
 int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
@@ -288,6 +293,10 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
                         ipp_chain_item* items_out, ipp_plan_aux* aux_out, int capacity, int32_t* n_items_out,
                         char* labels_out, int labels_capacity, ipp_plan_totals* totals_out);
 int ipp_lanczos_row_host(int in_size, int out_size, int xx, int32_t* bounds2_host, int32_t* kk_row_host);
+/* Device-side schedule of an item array (sizes, kind, flips, positions already set): coefficient-table
+ * and fragment-table offsets, flat tile starts, sprite-workspace offsets, out_slot = index.  Called by
+ * ipp_plan_items_host; exported for callers that assemble item arrays themselves. */
+int ipp_chain_layout_host(ipp_chain_item* items_host, int n_items, ipp_plan_totals* totals_out);
 
 /* LANCZOS coefficient tables of all items computed ON THE DEVICE (double precision, the
  * libImaging operation order).  The C library's sin() cannot be reproduced bit for bit on the
@@ -311,12 +320,17 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
  * sprite are images of boundary pixels), each checked with the exact fixed-point inverse map. */
 int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rots, int n_rot, int total_tiles,
                        const void* workspace, int32_t* bbox_out, void* stream);
-/* stage B2: rotate∘fit∘flip gather (premultiplied) -> LANCZOS h pass -> v pass ->
- * straight-alpha sprites in sprite_ws at items[i].spr_off. */
+/* stage B2: rotate∘fit∘flip gather (premultiplied, four byte planes) -> LANCZOS h pass -> v pass +
+ * un-premultiply -> straight-alpha RGBA sprites in sprite_ws at items[i].spr_off.
+ * The two passes are exact integer banded GEMMs on the tensor cores (mma.sync m16n8k32, u8 data x
+ * coefficients split into three byte planes, int32 accumulation = Pillow's own arithmetic); `band`
+ * (totals.band_units * 8 bytes) receives the coefficient bands in fragment order, derived from
+ * `tables` by this call (max_band_warps = totals.max_band_warps). */
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, const void* workspace, uint8_t* sprite_ws, void* stream);
+                       const int32_t* tables, void* band, int max_band_warps,
+                       const void* workspace, uint8_t* sprite_ws, void* stream);
 /* stage C: out[i] (sq x sq x 3, RGB) = crop(paste(background[bg], sprite_i, pos), square) */
 int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
                       const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
