@@ -835,7 +835,7 @@ struct B2Common {
 
 // gather: sprite pixel (X, Y) after flip <- canvas (X' + fit_x0, Y' + fit_y0) <- frame pixel.
 // Stored premultiplied (alpha is 0 or 255 here) as FOUR BYTE PLANES [R, G, B, A][spr_h][Wp] (Wp = spr_w
-// rounded up to 4): the layout the tensor-core LANCZOS pass reads its A fragments from.
+// rounded up to 16): the layout the tensor-core LANCZOS pass reads its A fragments from.
 __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride + (int64_t)it.cc_y * c.wpr;
     const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride + (int64_t)(c.crop_t + it.cc_y) * c.pitch +
                            (int64_t)(c.crop_l + it.cc_x) * 3;
-    const int64_t Wp = (spr_w + 3) & ~3;
+    const int64_t Wp = (spr_w + 15) & ~15;
     const int64_t plane = (int64_t)spr_h * Wp;
     uint8_t* dst = c.sprite_ws + it.rot_off + X;
     const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
@@ -904,11 +904,14 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
 // with three u8 x {u8, u8, s8} -> s32 accumulators (mma.sync.m16n8k32), exact in two's complement because
 // the full sum fits 32 bits (Pillow accumulates in int32 as well).
 //
-// A fragment (data): 16 rows x 32 consecutive source positions of one byte plane; B fragment
-// (coefficients): the 32 x 8 band that 8 consecutive outputs cut out of those positions, pre-arranged
-// in fragment order by chain_band_kernel.  A tile of 8 outputs touches a window of
-// ceil(7 * in / out) + ksize source positions: nkb blocks of 32 (typically 2), ~25 % of the multiplies
-// are useful — still >10x fewer issue slots than scalar code, and the passes become L2/HBM bound.
+// The reduction index of an MMA may be permuted freely as long as A and B agree, so the window a tile of
+// 8 outputs reads is cut into SUPER-BLOCKS of 64 source positions = two k-blocks, ordered such that one
+// aligned 16-byte load per lane and row IS the lane's share of both A fragments: lane (g, t) reads bytes
+// [16t, 16t+16) of row g; its four words are {k-block 0: a0, a2; k-block 1: a0, a2}.  (Fetching fragments in
+// their natural order costs four 4-byte loads per row group with 16 useful bytes per 128-byte line — the L1
+// tag stage then bounds the kernel.)  chain_band_kernel lays the coefficient bands out in the same order.
+// A tile touches ceil(7 * in / out) + ksize + 16 source positions (window drift over 7 outputs + one window
+// + alignment of the first position to 16): one super-block for scale factors up to ~3.5.
 // A skipped pass (size unchanged; Pillow skips it) uses the identity band k = 2^22, which reproduces
 // the input bytes exactly, so both kernels have a single code path.
 constexpr int kPrec = 32 - 8 - 2;
@@ -926,20 +929,21 @@ __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
 }
 
 __device__ __forceinline__ void mma_u8u8(int (&d)[4], const uint32_t (&a)[4], const uint2 b) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 __device__ __forceinline__ void mma_u8s8(int (&d)[4], const uint32_t (&a)[4], const uint2 b) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
 // layout of one axis' band table at `base` (uint2 units): [ceil(ntiles / 2)] header words holding the
-// first source position xb of every tile (int32 each), then [ntiles][nkb][3 planes][32 lanes] uint2.
+// first source position xb of every tile (int32 each, multiple of 16), then
+// [ntiles][nsb super-blocks][2 k-blocks][3 byte planes][32 lanes] uint2.
 struct BandAxis {
-    int in_size, out_size, ksize, nkb, ntiles;
+    int in_size, out_size, ksize, nsb, ntiles;
     const int32_t* bounds;       // [out][2] (xmin, n)   (unused when ksize == 0)
     const int32_t* kk;           // [out][ksize]
 };
@@ -948,31 +952,32 @@ __device__ __forceinline__ BandAxis band_axis(const ipp_chain_item& it, const in
     a.in_size = axis ? it.spr_h : it.spr_w;
     a.out_size = axis ? it.new_h : it.new_w;
     a.ksize = axis ? it.v_ksize : it.h_ksize;
-    a.nkb = axis ? (it.nkb >> 16) : (it.nkb & 0xffff);
+    a.nsb = axis ? (it.nkb >> 16) : (it.nkb & 0xffff);
     a.ntiles = (a.out_size + 7) >> 3;
     a.bounds = tables + (axis ? it.vb_off : it.hb_off);
     a.kk = tables + (axis ? it.vk_off : it.hk_off);
     return a;
 }
 
-// one warp = one (item, axis, tile of 8 outputs, k-block): the 32 x 8 coefficient band in B-fragment order,
-// split into three byte planes.  B fragment of m16n8k32: lane (g = lane / 4, t = lane % 4) holds, for
-// output column g, source positions 4t..4t+3 (register 0) and 16+4t..16+4t+3 (register 1).
+// one warp = one (item, axis, tile of 8 outputs, super-block): the 64 x 8 coefficient band in B-fragment order,
+// split into three byte planes.  B fragment of m16n8k32: lane (g = lane / 4, t = lane % 4) holds, for output
+// column g, reduction indices 4t..4t+3 (register 0) and 16+4t.. (register 1) of a k-block; with the permuted
+// order of the A side, index (k-block kbl, register h, byte j) is source position 16t + 4(2 kbl + h) + j.
 __global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
     const ipp_chain_item& it = c.items[blockIdx.y];
     const int lane = threadIdx.x & 31;
     int w = (int)blockIdx.x * 8 + (int)(threadIdx.x >> 5);
     const BandAxis ah = band_axis(it, c.tables, 0), av = band_axis(it, c.tables, 1);
-    const int nh_warps = ah.ntiles * ah.nkb;
+    const int nh_warps = ah.ntiles * ah.nsb;
     const int axis = w >= nh_warps;
     if (axis) w -= nh_warps;
     const BandAxis a = axis ? av : ah;
-    if (w >= a.ntiles * a.nkb) return;
-    const int tile = w / a.nkb, kb = w - tile * a.nkb;
+    if (w >= a.ntiles * a.nsb) return;
+    const int tile = w / a.nsb, sb = w - tile * a.nsb;
     uint2* base = c.band + (axis ? it.vband_off : it.hband_off);
     const int X0 = tile * 8;
-    const int xb = (a.ksize ? a.bounds[2 * X0] : X0) & ~3;
-    if (kb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb;
+    const int xb = (a.ksize ? a.bounds[2 * X0] : X0) & ~15;
+    if (sb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb;
     const int g = lane >> 2, t = lane & 3;
     const int X = X0 + g;
     int xmin = 0, n = 0;
@@ -987,41 +992,84 @@ __global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
             n = 1;
         }
     }
-    uint32_t r[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+    uint2* frag = base + ((a.ntiles + 1) >> 1) + ((int64_t)(tile * a.nsb + sb) * 6) * 32 + lane;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int kbl = 0; kbl < 2; ++kbl) {
+        uint32_t r[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = xb + 32 * kb + 16 * half + 4 * t + j - xmin;
-            int wgt = 0;
-            if (idx >= 0 && idx < n) wgt = k ? k[idx] : (1 << kPrec);
-            r[0][half] |= ((uint32_t)wgt & 255u) << (8 * j);
-            r[1][half] |= (((uint32_t)wgt >> 8) & 255u) << (8 * j);
-            r[2][half] |= (((uint32_t)wgt >> 16) & 255u) << (8 * j);      // signed byte: |wgt| < 2^23
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = xb + 64 * sb + 16 * t + 4 * (2 * kbl + half) + j - xmin;
+                int wgt = 0;
+                if (idx >= 0 && idx < n) wgt = k ? k[idx] : (1 << kPrec);
+                r[0][half] |= ((uint32_t)wgt & 255u) << (8 * j);
+                r[1][half] |= (((uint32_t)wgt >> 8) & 255u) << (8 * j);
+                r[2][half] |= (((uint32_t)wgt >> 16) & 255u) << (8 * j);      // signed byte: |wgt| < 2^23
+            }
+        }
+        frag[(3 * kbl + 0) * 32] = make_uint2(r[0][0], r[0][1]);
+        frag[(3 * kbl + 1) * 32] = make_uint2(r[1][0], r[1][1]);
+        frag[(3 * kbl + 2) * 32] = make_uint2(r[2][0], r[2][1]);
+    }
+}
+
+// the six MMAs of one super-block: data words lo (row g) / hi (row g + 8), coefficient fragments b[0..5]
+__device__ __forceinline__ void mma_superblock(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint2 (&b)[6]) {
+    const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y}, a1[4] = {lo.z, hi.z, lo.w, hi.w};
+    mma_u8u8(acc[0], a0, b[0]); mma_u8u8(acc[1], a0, b[1]); mma_u8s8(acc[2], a0, b[2]);
+    mma_u8u8(acc[0], a1, b[3]); mma_u8u8(acc[1], a1, b[4]); mma_u8s8(acc[2], a1, b[5]);
+}
+__device__ __forceinline__ void load_band(uint2 (&b)[6], const uint2* frag) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) b[q] = __ldg(frag + q * 32);
+}
+// 16 rows of one byte plane -> acc.  lo / hi: the (prefetched) first super-block words of rows g, g+8;
+// r_lo / r_hi point at them (further super-blocks are fetched here).
+__device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint8_t* r_lo, const uint8_t* r_hi,
+                                         const uint2 (&b0)[6], const uint2* frag, int nsb) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[p][i] = 0;
+    mma_superblock(acc, lo, hi, b0);
+    for (int sb = 1; sb < nsb; ++sb) {                              // rare: scale factors above ~3.5
+        uint2 b[6];
+        load_band(b, frag + sb * 192);
+        const uint4 lo2 = *reinterpret_cast<const uint4*>(r_lo + 64 * sb), hi2 = *reinterpret_cast<const uint4*>(r_hi + 64 * sb);
+        mma_superblock(acc, lo2, hi2, b);
+    }
+}
+
+// ---- data pipeline of the two passes.  A miss to HBM costs > 1000 cycles here while a tile's MMAs + epilogue are
+// ~100 instructions, so every warp keeps kRing - 1 tiles (16 rows x 64 bytes = 1 KB each) in flight with 16-byte
+// cp.async (LDGSTS: no registers held while the data travels).  Chunk id = lane + 32 j sits at byte 16 * id of the
+// stage: lane (g, t) = 4g + t stages exactly the two 16-byte pieces (row g, row g + 8; column 16 t) it later reads
+// back as its A-fragment words — no cross-lane traffic, conflict-free 128-bit shared accesses.
+constexpr int kRing = 4;
+__device__ __forceinline__ void ring_issue(uint8_t* stage, const uint8_t* plane, int64_t pitch, int row0, int n_rows, bool valid, int lane) {
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int id = lane + 32 * j;
+            const uint8_t* gsrc = plane + (int64_t)min(row0 + (id >> 2), n_rows - 1) * pitch + 16 * (id & 3);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stage + 16 * id)), "l"(gsrc) : "memory");
         }
     }
-    uint2* frag = base + ((a.ntiles + 1) >> 1) + ((int64_t)(tile * a.nkb + kb) * 3) * 32 + lane;
-    frag[0] = make_uint2(r[0][0], r[0][1]);
-    frag[32] = make_uint2(r[1][0], r[1][1]);
-    frag[64] = make_uint2(r[2][0], r[2][1]);
+    asm volatile("cp.async.commit_group;" ::: "memory");          // (possibly empty) group: keeps the wait count uniform
+}
+__device__ __forceinline__ void ring_wait() {
+    asm volatile("cp.async.wait_group %0;" :: "n"(kRing - 2) : "memory");
 }
 
-// A fragment of m16n8k32 for rows r_lo (= tile row g) and r_hi (= g + 8) of a byte plane:
-// registers {row g, k 4t..}, {row g+8, k 4t..}, {row g, k 16+4t..}, {row g+8, k 16+4t..}
-__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const uint8_t* r_lo, const uint8_t* r_hi, int koff) {
-    a[0] = *reinterpret_cast<const uint32_t*>(r_lo + koff);
-    a[1] = *reinterpret_cast<const uint32_t*>(r_hi + koff);
-    a[2] = *reinterpret_cast<const uint32_t*>(r_lo + koff + 16);
-    a[3] = *reinterpret_cast<const uint32_t*>(r_hi + koff + 16);
-}
-
-// horizontal pass.  CTA = (item, byte plane, group of 64 outputs); warp = 8 outputs; loop over the rows,
-// 32 at a time.  Result is written TRANSPOSED, [plane][X][y] with pitch Hp, so that the vertical pass
-// finds its reduction index contiguous: a warp transposes its 32 x 8 byte tile through shared memory
-// and stores 32-byte runs.
+// horizontal pass.  CTA = (item, byte plane, group of 64 outputs); warp = 8 outputs, whose first super-block of
+// coefficients stays in registers; loop over the rows, 32 at a time.  Result is written TRANSPOSED,
+// [plane][X][y] with pitch Hp, so that the vertical pass finds its reduction index contiguous: a warp
+// transposes its 32 x 8 byte tile through shared memory and stores 32-byte runs.
 __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     __shared__ __align__(16) uint8_t s_t[8][8 * 36];
+    __shared__ __align__(128) uint8_t s_ring[8][kRing][1024];
     if (threadIdx.x == 0)
         s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.h_tile_start; });
     __syncthreads();
@@ -1031,57 +1079,53 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int new_w = it.new_w, spr_h = it.spr_h;
-    const int ntiles = (new_w + 7) >> 3, nkb = it.nkb & 0xffff;
+    const int ntiles = (new_w + 7) >> 3, nsb = it.nkb & 0xffff;
     const int tile = xgroup * 8 + warp;
     if (tile >= ntiles) return;
     const uint2* base = c.band + it.hband_off;
     const int xb = reinterpret_cast<const int32_t*>(base)[tile];
-    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nkb * 96 + lane;
-    const int64_t Wp = (it.spr_w + 3) & ~3, Hp = (spr_h + 3) & ~3;
-    const uint8_t* src = c.sprite_ws + it.rot_off + (int64_t)pl * spr_h * Wp + xb + 4 * t;
+    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+    const int64_t Wp = (it.spr_w + 15) & ~15, Hp = (spr_h + 15) & ~15;
+    const uint8_t* src = c.sprite_ws + it.rot_off + (int64_t)pl * spr_h * Wp + xb + 16 * t;
     uint8_t* dst = c.sprite_ws + it.tmp_off + (int64_t)pl * new_w * Hp;
     uint8_t* st = s_t[warp];
-    for (int y0 = 0; y0 < spr_h; y0 += 32) {
-        int acc[2][3][4];
+    uint2 b0[6];
+    load_band(b0, frag);
+    const int n_rt = (spr_h + 15) >> 4;
+    uint8_t* ring = s_ring[warp][0];
+    const uint8_t* col0 = src - 16 * t;                            // first column of the window (src includes the lane's 16 t)
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int p = 0; p < 3; ++p)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[m][p][i] = 0;
-        const uint8_t* r0 = src + (int64_t)min(y0 + g, spr_h - 1) * Wp;
-        const uint8_t* r1 = src + (int64_t)min(y0 + g + 8, spr_h - 1) * Wp;
-        const uint8_t* r2 = src + (int64_t)min(y0 + g + 16, spr_h - 1) * Wp;
-        const uint8_t* r3 = src + (int64_t)min(y0 + g + 24, spr_h - 1) * Wp;
-        for (int kb = 0; kb < nkb; ++kb) {
-            uint32_t a0[4], a1[4];
-            load_a_frag(a0, r0, r1, 32 * kb);
-            load_a_frag(a1, r2, r3, 32 * kb);
-            const uint2 b0 = __ldg(frag + kb * 96), b1 = __ldg(frag + kb * 96 + 32), b2 = __ldg(frag + kb * 96 + 64);
-            mma_u8u8(acc[0][0], a0, b0); mma_u8u8(acc[1][0], a1, b0);
-            mma_u8u8(acc[0][1], a0, b1); mma_u8u8(acc[1][1], a1, b1);
-            mma_u8s8(acc[0][2], a0, b2); mma_u8s8(acc[1][2], a1, b2);
-        }
+    for (int d = 0; d < kRing - 1; ++d) ring_issue(ring + 1024 * d, col0, Wp, 16 * d, spr_h, d < n_rt, lane);
+    auto row_ptr = [&](int ti, int half) { return src + (int64_t)min(16 * ti + g + 8 * half, spr_h - 1) * Wp; };
+    for (int ti = 0; ti < n_rt; ++ti) {
+        ring_wait();                                               // tile ti has landed (this lane's own two pieces)
+        const uint8_t* stg = ring + 1024 * (ti % kRing);
+        const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
+        ring_issue(ring + 1024 * ((ti + kRing - 1) % kRing), col0, Wp, 16 * (ti + kRing - 1), spr_h, ti + kRing - 1 < n_rt, lane);
+        const uint8_t* r_lo = row_ptr(ti, 0);
+        const uint8_t* r_hi = row_ptr(ti, 1);
+        int acc[3][4];
+        mma_rows(acc, lo, hi, r_lo, r_hi, b0, frag, nsb);
+        const int m = ti & 1, y0 = (ti & ~1) << 4;
         // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1}
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
+        for (int i = 0; i < 4; ++i) {
+            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
+            const int yl = 16 * m + g + 8 * (i >> 1), xl = 2 * t + (i & 1);
+            st[xl * 36 + yl] = (uint8_t)c_clip8(v);
+        }
+        if (m == 1 || ti + 1 == n_rt) {
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int v = acc[m][0][i] + (acc[m][1][i] << 8) + (acc[m][2][i] << 16) + (1 << (kPrec - 1));
-                const int yl = 16 * m + g + 8 * (i >> 1), xl = 2 * t + (i & 1);
-                st[xl * 36 + yl] = (uint8_t)c_clip8(v);
+            for (int h = 0; h < 2; ++h) {
+                const int wi = lane + 32 * h;                       // 8 columns x 8 words
+                const int xl = wi >> 3, q = wi & 7;
+                const int X = tile * 8 + xl, y = y0 + 4 * q;
+                if (X < new_w && y < spr_h)
+                    *reinterpret_cast<uint32_t*>(dst + (int64_t)X * Hp + y) = *reinterpret_cast<const uint32_t*>(st + xl * 36 + 4 * q);
             }
+            __syncwarp();
         }
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int wi = lane + 32 * h;                       // 8 columns x 8 words
-            const int xl = wi >> 3, q = wi & 7;
-            const int X = tile * 8 + xl, y = y0 + 4 * q;
-            if (X < new_w && y < spr_h)
-                *reinterpret_cast<uint32_t*>(dst + (int64_t)X * Hp + y) = *reinterpret_cast<const uint32_t*>(st + xl * 36 + 4 * q);
-        }
-        __syncwarp();
     }
 }
 
@@ -1091,6 +1135,7 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
 // C fragment element (row = column X of the sprite, col = output row Y).
 __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     __shared__ int s_rec;
+    __shared__ __align__(128) uint8_t s_ring[8][kRing][1024];
     if (threadIdx.x == 0)
         s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
     __syncthreads();
@@ -1101,45 +1146,56 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     const int ygroup = lt / xchunks, xchunk = lt - ygroup * xchunks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int ntiles = (new_h + 7) >> 3, nkb = it.nkb >> 16;
+    const int ntiles = (new_h + 7) >> 3, nsb = it.nkb >> 16;
     const int tile = ygroup * 8 + warp;
     if (tile >= ntiles) return;
     const uint2* base = c.band + it.vband_off;
     const int yb = reinterpret_cast<const int32_t*>(base)[tile];
-    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nkb * 96 + lane;
-    const int64_t Hp = (spr_h + 3) & ~3;
+    const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+    const int64_t Hp = (spr_h + 15) & ~15;
     const int64_t plane = (int64_t)new_w * Hp;
-    const uint8_t* src = c.sprite_ws + it.tmp_off + yb + 4 * t;
+    const uint8_t* src = c.sprite_ws + it.tmp_off + yb + 16 * t;
     uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off);
     const int x_end = min(new_w, (xchunk + 1) * 128);
-    for (int X0 = xchunk * 128; X0 < x_end; X0 += 16) {
-        const uint8_t* r0 = src + (int64_t)min(X0 + g, new_w - 1) * Hp;
-        const uint8_t* r1 = src + (int64_t)min(X0 + g + 8, new_w - 1) * Hp;
-        uint32_t px[4] = {0u, 0u, 0u, 0u};
+    uint2 b0[6];
+    load_band(b0, frag);
+    // steps = (16 columns, byte plane), planes innermost; kRing - 1 steps of data in flight (see ring_issue)
+    const int x_begin = xchunk * 128;
+    const int n_steps = ((x_end - x_begin + 15) >> 4) * 4;
+    uint8_t* ring = s_ring[warp][0];
+    const uint8_t* col0 = src - 16 * t;
+    auto issue = [&](int step) {
+        ring_issue(ring + 1024 * (step % kRing), col0 + (int64_t)(step & 3) * plane, Hp, x_begin + 16 * (step >> 2), new_w, step < n_steps, lane);
+    };
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl) {
-            int acc[3][4];
-#pragma unroll
-            for (int p = 0; p < 3; ++p)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[p][i] = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                uint32_t a[4];
-                load_a_frag(a, r0 + pl * plane, r1 + pl * plane, 32 * kb);
-                mma_u8u8(acc[0], a, __ldg(frag + kb * 96));
-                mma_u8u8(acc[1], a, __ldg(frag + kb * 96 + 32));
-                mma_u8s8(acc[2], a, __ldg(frag + kb * 96 + 64));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
-                px[i] |= c_clip8(v) << (8 * pl);
-            }
-        }
+    for (int d = 0; d < kRing - 1; ++d) issue(d);
+    auto row_ptr = [&](int step, int half) {
+        return src + (int64_t)(step & 3) * plane + (int64_t)min(x_begin + 16 * (step >> 2) + g + 8 * half, new_w - 1) * Hp;
+    };
+    uint32_t px[4] = {0u, 0u, 0u, 0u};
+    for (int step = 0; step < n_steps; ++step) {
+        ring_wait();
+        const uint8_t* stg = ring + 1024 * (step % kRing);
+        const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
+        issue(step + kRing - 1);
+        const uint8_t* r_lo = row_ptr(step, 0);
+        const uint8_t* r_hi = row_ptr(step, 1);
+        int acc[3][4];
+        mma_rows(acc, lo, hi, r_lo, r_hi, b0, frag, nsb);
+        const int pl = step & 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int X = X0 + g + 8 * (i >> 1), Y = tile * 8 + 2 * t + (i & 1);
-            if (X < x_end && Y < new_h) dst[(int64_t)Y * new_w + X] = c_unpremultiply(px[i]);
+            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
+            px[i] |= c_clip8(v) << (8 * pl);
+        }
+        if (pl == 3) {
+            const int X0 = x_begin + 16 * (step >> 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int X = X0 + g + 8 * (i >> 1), Y = tile * 8 + 2 * t + (i & 1);
+                if (X < x_end && Y < new_h) dst[(int64_t)Y * new_w + X] = c_unpremultiply(px[i]);
+                px[i] = 0u;
+            }
         }
     }
 }

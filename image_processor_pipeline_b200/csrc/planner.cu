@@ -258,23 +258,23 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
         tab_rows += rows;
         max_rows = std::max(max_rows, rows);
         IPP_REQUIRE(toff < (1LL << 31) && tab_rows < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: coefficient tables exceed 2^31 entries");
-        // banded fragment tables: an 8-output tile reads at most ceil(7 * in / out) + ksize + 4 source positions
-        // (window drift over 7 outputs + one window + alignment of the first position to 4), in blocks of 32
-        auto kblocks = [](int in, int out, int ks) { return (int)(((7LL * in + out - 1) / out + std::max(ks, 1) + 4 + 31) / 32); };
-        const int nkb_h = kblocks(sw, nw, it->h_ksize), nkb_v = kblocks(sh, nh, it->v_ksize);
+        // banded fragment tables: an 8-output tile reads at most ceil(7 * in / out) + ksize + 16 source positions
+        // (window drift over 7 outputs + one window + alignment of the first position to 16), in super-blocks of 64
+        auto sblocks = [](int in, int out, int ks) { return (int)(((7LL * in + out - 1) / out + std::max(ks, 1) + 16 + 63) / 64); };
+        const int nsb_h = sblocks(sw, nw, it->h_ksize), nsb_v = sblocks(sh, nh, it->v_ksize);
         const int nt_h = (nw + 7) / 8, nt_v = (nh + 7) / 8;
-        it->nkb = nkb_h | (nkb_v << 16);
-        it->hband_off = (int32_t)boff; boff += (nt_h + 1) / 2 + (int64_t)nt_h * nkb_h * 96;
-        it->vband_off = (int32_t)boff; boff += (nt_v + 1) / 2 + (int64_t)nt_v * nkb_v * 96;
+        it->nkb = nsb_h | (nsb_v << 16);
+        it->hband_off = (int32_t)boff; boff += (nt_h + 1) / 2 + (int64_t)nt_h * nsb_h * 192;
+        it->vband_off = (int32_t)boff; boff += (nt_v + 1) / 2 + (int64_t)nt_v * nsb_v * 192;
         IPP_REQUIRE(boff < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: fragment tables exceed 16 GiB; use a smaller batch");
-        max_band_warps = std::max(max_band_warps, nt_h * nkb_h + nt_v * nkb_v);
+        max_band_warps = std::max(max_band_warps, nt_h * nsb_h + nt_v * nsb_v);
         it->gather_tile_start = (int32_t)gt; it->h_tile_start = (int32_t)ht; it->v_tile_start = (int32_t)vt;
         gt += (long long)((sw + 31) / 32) * ((sh + 31) / 32);
         ht += (long long)((nw + 63) / 64) * 4;
         vt += (long long)((nh + 63) / 64) * ((nw + 127) / 128);
         IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: too many tiles");
         // planar premultiplied sprite [4][sh][Wp], transposed planar h-pass result [4][nw][Hp], final RGBA sprite
-        const int64_t Wp = (sw + 3) & ~3, Hp = (sh + 3) & ~3;
+        const int64_t Wp = (sw + 15) & ~15, Hp = (sh + 15) & ~15;
         it->rot_off = woff; woff = align_up(woff + 4 * (int64_t)sh * Wp + 512, 256);
         it->tmp_off = woff; woff = align_up(woff + 4 * (int64_t)nw * Hp + 512, 256);
         it->spr_off = woff; woff = align_up(woff + (int64_t)nw * nh * 4, 256);

@@ -252,10 +252,10 @@ typedef struct ipp_chain_item {
     int32_t tab_row_start;                  /* first coefficient-table row of this item (h rows, then v rows) */
     int32_t out_slot;                       /* index of the output image this item writes            */
     int32_t hband_off, vband_off;           /* 8-byte offsets of this item's banded int8 fragment tables (h, v) */
-    int32_t nkb;                            /* 32-wide k-blocks per 8-output tile: h | v << 16       */
+    int32_t nkb;                            /* 64-wide super-blocks (two MMA k-blocks) per 8-output tile: h | v << 16 */
     int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace: planar premultiplied sprite
                                                [4][spr_h][Wp], transposed planar h-pass result [4][new_w][Hp],
-                                               final RGBA sprite [new_h][new_w][4]; Wp/Hp = spr_w/spr_h rounded up to 4 */
+                                               final RGBA sprite [new_h][new_w][4]; Wp/Hp = spr_w/spr_h rounded up to 16 */
 } ipp_chain_item;
 
 /* ---- host planner (C++ twin of chain.py's planner; no device work) ------------------
