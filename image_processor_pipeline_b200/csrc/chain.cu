@@ -836,6 +836,7 @@ struct B2Common {
 // gather: sprite pixel (X, Y) after flip <- canvas (X' + fit_x0, Y' + fit_y0) <- frame pixel.
 // Stored premultiplied (alpha is 0 or 255 here) as FOUR BYTE PLANES [R, G, B, A][spr_h][Wp] (Wp = spr_w
 // rounded up to 16): the layout the tensor-core LANCZOS pass reads its A fragments from.
+constexpr int kGatherRows = 8;          // rows per lane: tile = 32 columns x 64 rows
 __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     __shared__ int s_rec;
     if (threadIdx.x == 0)
@@ -848,26 +849,28 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int X = tx * 32 + lane;
-    if (X >= spr_w) return;
+    const int Y0 = ty * (8 * kGatherRows) + warp * kGatherRows;
+    if (X >= spr_w || Y0 >= spr_h) return;
     const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, it.cc_w, it.cc_h};
     const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride + (int64_t)it.cc_y * c.wpr;
     const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride + (int64_t)(c.crop_t + it.cc_y) * c.pitch +
                            (int64_t)(c.crop_l + it.cc_x) * 3;
     const int64_t Wp = (spr_w + 15) & ~15;
     const int64_t plane = (int64_t)spr_h * Wp;
-    uint8_t* dst = c.sprite_ws + it.rot_off + X;
+    uint8_t* dst = c.sprite_ws + it.rot_off + X + (int64_t)Y0 * Wp;
     const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
-    const int Y0 = ty * 32 + warp * 4;
     // affine case: canvas row cy = fit_y0 + (flip_v ? spr_h-1-Y : Y) moves by +-1 per sprite row
     const int cy0 = (it.flip_v ? (spr_h - 1 - Y0) : Y0) + it.fit_y0;
     const int dy = it.flip_v ? -1 : 1;
     int xx = it.a2 + cy0 * it.a1 + cx * it.a0, yy = it.a5 + cy0 * it.a4 + cx * it.a3;
     const int sx = dy * it.a1, sy = dy * it.a4;
+    // phase 1: all mask words and all pixel bytes of the lane's rows are requested before anything is used
+    // (the bit test and the three byte loads of a pixel do not wait for each other; pixels outside the
+    // component rect are fetched from a clamped in-rect address and discarded)
+    uint32_t word[kGatherRows], b0[kGatherRows], b1[kGatherRows], b2[kGatherRows];
+    int sh[kGatherRows];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int Y = Y0 + j;
-        if (Y >= spr_h) break;
-        uint32_t px = 0;
+    for (int j = 0; j < kGatherRows; ++j) {
         int xin, yin;
         bool inside;
         if (it.kind == 0) {
@@ -879,18 +882,24 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
         }
         xx += sx;
         yy += sy;
-        if (inside) {
-            const int fx = it.cc_x + xin;
-            if ((fb[yin * c.wpr + (fx >> 5)] >> (fx & 31)) & 1u) {
-                const uint8_t* s = frame + (int64_t)yin * c.pitch + xin * 3;
-                px = (uint32_t)s[2] | ((uint32_t)s[1] << 8) | ((uint32_t)s[0] << 16) | 0xff000000u;   // BGR -> RGBA
-            }
-        }
-        uint8_t* d = dst + (int64_t)Y * Wp;
-        d[0] = (uint8_t)px;
-        d[plane] = (uint8_t)(px >> 8);
-        d[2 * plane] = (uint8_t)(px >> 16);
-        d[3 * plane] = (uint8_t)(px >> 24);
+        const bool use = inside && Y0 + j < spr_h;
+        if (!use) { xin = 0; yin = 0; }
+        const int fx = it.cc_x + xin;
+        sh[j] = use ? (fx & 31) : -1;
+        word[j] = fb[yin * c.wpr + (fx >> 5)];
+        const uint8_t* s = frame + (int64_t)yin * c.pitch + xin * 3;
+        b0[j] = s[0]; b1[j] = s[1]; b2[j] = s[2];
+    }
+    // phase 2: select, premultiply (alpha is 0 or 255), store the four planes
+#pragma unroll
+    for (int j = 0; j < kGatherRows; ++j) {
+        if (Y0 + j >= spr_h) break;
+        const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
+        uint8_t* d = dst + (int64_t)j * Wp;
+        d[0] = on ? (uint8_t)b2[j] : (uint8_t)0;           // BGR -> R, G, B, A planes
+        d[plane] = on ? (uint8_t)b1[j] : (uint8_t)0;
+        d[2 * plane] = on ? (uint8_t)b0[j] : (uint8_t)0;
+        d[3 * plane] = on ? (uint8_t)255 : (uint8_t)0;
     }
 }
 

@@ -29,35 +29,6 @@ struct PasteParams {
 
 constexpr int kPasteThreads = 256;
 
-__device__ __forceinline__ uint32_t sprite_px(const PasteParams& p, int sx, int sy) {
-    return __ldg(reinterpret_cast<const uint32_t*>(p.sprite + (int64_t)sy * p.sprite_pitch) + sx);
-}
-
-// blend `cnt` output bytes starting at output byte ob of the row whose sprite row is sy
-__device__ __forceinline__ void blend_bytes(const PasteParams& p, uint8_t* bytes, uint32_t ob, int cnt, int sy) {
-    uint32_t q = ob / 3u;
-    uint32_t c = ob - q * 3u;
-    int sx = (int)q + p.crop_x0 - p.pos_x;
-    uint32_t spx = 0;
-    bool have = false;
-    for (int k = 0; k < cnt; ++k) {
-        if (sx >= 0 && sx < p.sprite_w) {
-            if (!have) {
-                spx = sprite_px(p, sx, sy);
-                have = true;
-            }
-            const uint32_t a = spx >> 24;
-            const uint32_t s = (spx >> (8 * c)) & 255u;
-            bytes[k] = (uint8_t)div255((uint32_t)bytes[k] * (255u - a) + s * a);
-        }
-        if (++c == 3u) {
-            c = 0;
-            ++sx;
-            have = false;
-        }
-    }
-}
-
 // 16 output bytes cut from two aligned vectors of the staged window; WS = word shift (0..3),
 // bs = byte shift inside the word in bits — both uniform for a whole row.
 template <int WS>
@@ -71,10 +42,9 @@ __device__ __forceinline__ uint4 cut16(const uint4& lo, const uint4& hi, uint32_
                       __funnelshift_r(v3, v4, bs));
 }
 
-// aligned 16-byte body of one output row, lanes striding over the chunks
+// aligned 16-byte body of one output row (background only), lanes striding over the chunks
 template <int WS>
-__device__ __forceinline__ void paste_row_body(const PasteParams& p, const uint8_t* win, uint32_t off0, uint8_t* d,
-                                               uint32_t head, uint32_t nb, bool row_hit, int hit_b0, int hit_b1, int sy, int lane) {
+__device__ __forceinline__ void copy_row_body(const uint8_t* win, uint32_t off0, uint8_t* d, uint32_t head, uint32_t nb, int lane) {
     const uint32_t bs = (off0 & 3u) * 8u;
     const uint8_t* src = win + (off0 & ~15u);
     const bool aligned = (off0 & 15u) == 0u;
@@ -85,27 +55,26 @@ __device__ __forceinline__ void paste_row_body(const PasteParams& p, const uint8
             const uint4 hi = *reinterpret_cast<const uint4*>(src + (c << 4) + 16);
             val = cut16<WS>(lo, hi, bs);
         }
-        const uint32_t ob = head + (c << 4);
-        if (row_hit && (int)(ob + 15u) >= hit_b0 && (int)ob < hit_b1) {
-            __align__(16) uint8_t bytes[16];
-            *reinterpret_cast<uint4*>(bytes) = val;
-            blend_bytes(p, bytes, ob, 16, sy);
-            val = *reinterpret_cast<uint4*>(bytes);
-        }
-        stg_stream16(d + ob, val);
+        stg_stream16(d + head + (c << 4), val);
     }
 }
 
 // emit rows [row0, row0+nrows) of the cropped composite from staged background windows.
-// One warp per row (row-uniform alignment, sprite-hit range and pointers live in uniform
-// registers); lanes stride over the aligned 16-byte output vectors of the row.
+// One warp per row (row-uniform alignment and pointers live in uniform registers), two passes:
+//  1. the background row streams out as aligned 16-byte vectors (plus < 16 head / tail bytes, one lane each);
+//  2. rows that cross the sprite: after a __syncwarp (orders the stores of pass 1 before those of pass 2 for
+//     the whole warp) the lanes walk the sprite's pixels of this row — coalesced sprite loads, background bytes
+//     from the staged window, libImaging's DIV255 blend, three byte stores.  Transparent pixels (alpha 0:
+//     DIV255(255 * bg) = bg) are skipped, opaque ones (alpha 255: DIV255(255 * s) = s) copied.
+// The sprite covers a few percent of the image, so pass 2 re-touches little; keeping the blend out of the
+// vector loop removes the per-byte phase arithmetic (pixels are 3 bytes, vectors 16) that dominated it.
 __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const uint8_t* smem, uint32_t smem_row_stride,
                                                      int row0, int nrows, int tid) {
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
     const int lane = tid & 31, warp = tid >> 5;
-    // output byte range of a row that can intersect the sprite
-    const int hit_b0 = max(p.pos_x - p.crop_x0, 0) * 3;
-    const int hit_b1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w) * 3;   // exclusive
+    // output pixel range of a row that can intersect the sprite
+    const int hit_x0 = max(p.pos_x - p.crop_x0, 0);
+    const int hit_x1 = min(p.pos_x + p.sprite_w - p.crop_x0, p.crop_w);      // exclusive
     for (int r = warp; r < nrows; r += kPasteThreads / 32) {
         const int y = row0 + r;
         uint8_t* d = p.dst + (int64_t)y * p.dst_pitch;
@@ -113,23 +82,36 @@ __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const
         const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + y) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
         const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
         const RowSplit sp = split_row(d, rowbytes);
-        const int sy = p.crop_y0 + y - p.pos_y;
-        const bool row_hit = (sy >= 0 && sy < p.sprite_h && hit_b1 > hit_b0);
         const uint32_t off0 = shift + sp.head;            // window offset of the first aligned output vector
         switch ((off0 & 15u) >> 2) {
-            case 0: paste_row_body<0>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
-            case 1: paste_row_body<1>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
-            case 2: paste_row_body<2>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
-            default: paste_row_body<3>(p, win, off0, d, sp.head, sp.nb, row_hit, hit_b0, hit_b1, sy, lane); break;
+            case 0: copy_row_body<0>(win, off0, d, sp.head, sp.nb, lane); break;
+            case 1: copy_row_body<1>(win, off0, d, sp.head, sp.nb, lane); break;
+            case 2: copy_row_body<2>(win, off0, d, sp.head, sp.nb, lane); break;
+            default: copy_row_body<3>(win, off0, d, sp.head, sp.nb, lane); break;
         }
-        if (lane < 2) {                                   // lane 0: unaligned head bytes, lane 1: tail bytes
-            const uint32_t b0 = lane == 0 ? 0u : sp.head + (sp.nb << 4);
-            const int cnt = (int)(lane == 0 ? sp.head : sp.tail);
-            if (cnt > 0) {
-                uint8_t bytes[16];
-                for (int k = 0; k < cnt; ++k) bytes[k] = win[shift + b0 + k];
-                if (row_hit) blend_bytes(p, bytes, b0, cnt, sy);
-                for (int k = 0; k < cnt; ++k) d[b0 + k] = bytes[k];
+        if ((uint32_t)lane < sp.head) d[lane] = win[shift + lane];
+        if (lane >= 16 && (uint32_t)(lane - 16) < sp.tail) {
+            const uint32_t b = sp.head + (sp.nb << 4) + (uint32_t)(lane - 16);
+            d[b] = win[shift + b];
+        }
+        const int sy = p.crop_y0 + y - p.pos_y;
+        if (sy >= 0 && sy < p.sprite_h && hit_x1 > hit_x0) {
+            __syncwarp();
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(p.sprite + (int64_t)sy * p.sprite_pitch) + (p.crop_x0 - p.pos_x);
+            for (int x = hit_x0 + lane; x < hit_x1; x += 32) {
+                const uint32_t spx = __ldg(srow + x);
+                const uint32_t a = spx >> 24;
+                if (a == 0u) continue;
+                uint32_t o0 = spx & 255u, o1 = (spx >> 8) & 255u, o2 = (spx >> 16) & 255u;
+                if (a != 255u) {
+                    const uint8_t* b = win + shift + 3 * x;
+                    const uint32_t na = 255u - a;
+                    o0 = div255((uint32_t)b[0] * na + o0 * a);
+                    o1 = div255((uint32_t)b[1] * na + o1 * a);
+                    o2 = div255((uint32_t)b[2] * na + o2 * a);
+                }
+                uint8_t* o = d + 3 * x;
+                o[0] = (uint8_t)o0; o[1] = (uint8_t)o1; o[2] = (uint8_t)o2;
             }
         }
     }

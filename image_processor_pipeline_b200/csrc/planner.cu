@@ -269,7 +269,7 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
         IPP_REQUIRE(boff < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: fragment tables exceed 16 GiB; use a smaller batch");
         max_band_warps = std::max(max_band_warps, nt_h * nsb_h + nt_v * nsb_v);
         it->gather_tile_start = (int32_t)gt; it->h_tile_start = (int32_t)ht; it->v_tile_start = (int32_t)vt;
-        gt += (long long)((sw + 31) / 32) * ((sh + 31) / 32);
+        gt += (long long)((sw + 31) / 32) * ((sh + 63) / 64);          // chain_gather_kernel: 32 x 64 tiles
         ht += (long long)((nw + 63) / 64) * 4;
         vt += (long long)((nh + 63) / 64) * ((nw + 127) / 128);
         IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: too many tiles");
