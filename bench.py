@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
+    ap.add_argument("--main-priority", type=int, default=0, help="priority boost of the stream that runs stages B2/C (0 = default stream)")
     ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
@@ -301,7 +302,10 @@ def main():
             n_out = int(c.item())
         return ms, n_out, launches
 
-    with ClockSampler(local) as clk:
+    # stages B2/C (the caller's stream) get a higher priority than stage A of the next batch (side stream):
+    # the big persistent mask CTAs then fill SMs as the finishing batch drains instead of delaying it
+    main_stream = torch.cuda.Stream(dev, priority=-args.main_priority) if args.main_priority else torch.cuda.current_stream()
+    with ClockSampler(local) as clk, torch.cuda.stream(main_stream):
         if args.no_pipeline:
             ms, n_out, launches = timed(step_resident, args.steps, args.warmup)
         else:

@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 import random as _random
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -548,7 +549,7 @@ class ChainStream:
     def _b1_stream(self, dev):
         key = dev.index if dev.index is not None else torch.cuda.current_device()
         if key not in self._b1:
-            self._b1[key] = torch.cuda.Stream(dev)
+            self._b1[key] = torch.cuda.Stream(dev, priority=int(os.environ.get('IPP_PRIO_B1', '-1')))
         return self._b1[key]
 
     def _resolve_pending(self):
@@ -926,5 +927,5 @@ _SIDE = {}
 def _side_streams(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE:
-        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _SIDE[key] = (torch.cuda.Stream(dev, priority=int(os.environ.get('IPP_PRIO_A', '0'))), torch.cuda.Stream(dev))
     return _SIDE[key]
