@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
@@ -321,7 +321,6 @@ def main():
     rep = _native.timing_report()
     _native.timing_enable(False)
     alg = {"chain_mask_kernel": B * 3 * FW * FH,                       # frame read once (generic mask kernel)
-           "chain_mask_fast_kernel": B * 3 * FW * FH,                  # frame read once (table-driven ring kernel)
            "chain_mask_seg_kernel": B * 3 * FW * FH,                   # frame read once (table-driven per-warp segment kernel)
            "chain_paste_kernel": B * 2 * 3 * 1080 * 1080}              # background crop read + output write
     peak, peak_src = measured_peak()

@@ -100,20 +100,13 @@ __global__ void __launch_bounds__(kMaskThreads) chain_mask_kernel(const MaskPara
     }
 }
 
-// ===================================================================== stage A: mask, fast path
-// Persistent LUT variant used when every filter covers the whole image (no zones) and there
-// are at most 8 filters — the reference's own use (filtres_liste.py:186-199).
-//
-//  * V and S of OpenCV's HSV depend only on (v = max, d = max - min), so "which filters accept
-//    this pixel's V and S" is one byte of a 64 KB table T[v][d] living in shared memory for the
-//    whole kernel (built once per call by hsv_lut_kernel; exact, same sdiv table).  A filter
-//    whose H range is [0, >=180] needs nothing else: the pixel is keyed out by one table hit.
-//    Hue is computed only for pixels that pass V/S of a filter with a real H range.
-//  * max/min of (b, g, r) for TWO pixels per instruction with the DPX 16x2 three-input
-//    min/max (VIMNMX3), after byte->halfword unpacking with PRMT.
-//  * one CTA per SM, 1024 threads, loops over (frame, row group) work units; a 3-stage ring
-//    of bulk-copy (UBLKCP) row windows completes on mbarriers while the previous unit is
-//    being converted, so HBM reads never wait for the ALU work.
+// ===================================================================== stage A: mask, table-driven path
+// Used when every filter covers the whole image (no zones) and at most 7 filters have a real hue range —
+// the reference's own use (filtres_liste.py:186-199).  V and S of OpenCV's HSV depend only on
+// (v = max, d = max - min), so "which filters accept this pixel's V and S" is one byte of a 64 KB table
+// T[v][d] living in shared memory for the whole kernel (built once per call by hsv_lut_kernel; exact, same
+// sdiv table).  A filter whose H range is [0, >=180] needs nothing else: the pixel is keyed out by one table
+// hit.  Hue is computed only for pixels that pass V/S of a filter with a real H range.
 struct HsvFast {
     int n_hue;                       // filters with a real hue range (<= 7), table bits 0..6
     int h_lo[7], h_hi[7];
@@ -152,24 +145,6 @@ __global__ void hsv_lut_kernel(const HsvFilterSet f, uint8_t* __restrict__ lut) 
     lut[v * 256 + d] = (uint8_t)m;
 }
 
-struct MaskFastParams {
-    const uint8_t* frames;
-    int64_t pitch, stride;
-    int crop_l, crop_t, w, h;
-    int wpr;
-    uint32_t* bits;
-    int64_t bits_stride;
-    int rows_per_unit, units_per_frame, n_units;
-    uint32_t smem_row_stride;
-    uint32_t stage_bytes;
-    int contiguous;                  // rows of a unit are adjacent in memory (full-width crop, dense pitch): ONE bulk copy per unit
-    const uint8_t* lut;
-    HsvFast f;
-};
-
-constexpr int kFastThreads = 1024;
-constexpr int kFastStages = 3;
-
 __device__ __forceinline__ int hue_of(int b, int g, int r, int v, int d, const int* hdiv) {
     int hn;
     if (v == r) hn = g - b;
@@ -184,243 +159,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised: warp 31 = producer (one lane issues the bulk copies of the next units as soon
-// as the 31 consumer warps have released a ring stage), warps 0..30 = consumers.  No block-wide
-// barrier inside the unit loop.
-constexpr int kFastConsumers = kFastThreads / 32 - 1;
-
-__global__ void __launch_bounds__(kFastThreads, 1) chain_mask_fast_kernel(const MaskFastParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t full[kFastStages], empty[kFastStages];
-    __shared__ int hdiv[256];
-    __shared__ uint32_t s_rowoff[kFastStages][32];        // byte offset of pixel 0 of each row inside its stage
-    __shared__ int q_count[3], q_head[3];                 // CTA-wide queues of groups for pass 2, three rotating slots
-    uint8_t* lut = smem;                                  // 64 KB
-    uint8_t* ring = smem + 65536;
-    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + 65536 + (size_t)kFastStages * p.stage_bytes + 128);
-    const int qcap = p.rows_per_unit * p.wpr * 4;         // every group of a unit fits
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t rowbytes = (uint32_t)p.w * 3u;
-    const uint32_t stage_bytes = p.stage_bytes;
-
-    if (tid == 0) {
-        for (int s = 0; s < kFastStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kFastConsumers);
-        }
-        for (int s = 0; s < 3; ++s) { q_count[s] = 0; q_head[s] = 0; }
-    }
-    // the table: 64 KB, L2 resident, coalesced 16-byte copies
-    for (int i = tid; i < 65536 / 16; i += kFastThreads)
-        reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(p.lut) + i);
-    for (int i = tid; i < 256; i += kFastThreads) hdiv[i] = g_hsv_hdiv[i];
-    __syncthreads();
-
-    if (warp == kFastConsumers) {
-        // ------------------------------------------------------------------ producer warp
-        // lane r owns row r of the unit: row offsets for the consumers, byte counts, bulk-copy issue
-        int it = 0;
-        for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
-            const int stage = it % kFastStages, use = it / kFastStages;
-            if (use > 0) {
-                if (lane == 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
-                __syncwarp();
-            }
-            const int img = unit / p.units_per_frame;
-            const int row0 = (unit - img * p.units_per_frame) * p.rows_per_unit;
-            const int nrows = min(p.rows_per_unit, p.h - row0);
-            const uint8_t* src = p.frames + (int64_t)img * p.stride + (int64_t)(p.crop_t + row0) * p.pitch + (int64_t)p.crop_l * 3;
-            Window w;
-            w.base = nullptr; w.bytes = 0; w.shift = 0;
-            if (p.contiguous) {                             // the unit is one contiguous byte range: one bulk copy
-                const uint32_t unit_shift = (uint32_t)((uintptr_t)src & 15);
-                if (lane < nrows) s_rowoff[stage][lane] = unit_shift + (uint32_t)lane * rowbytes;
-                if (lane == 0) w = make_window(src, (uint32_t)nrows * rowbytes);
-            } else if (lane < nrows) {
-                w = make_window(src + (int64_t)lane * p.pitch, rowbytes);
-                s_rowoff[stage][lane] = (uint32_t)lane * p.smem_row_stride + w.shift;
-            }
-            const uint32_t total = __reduce_add_sync(0xffffffffu, w.bytes);
-            __syncwarp();                                   // row offsets visible before the barrier is armed
-            if (lane == 0) mbar_expect_tx(&full[stage], total);
-            __syncwarp();
-            if (w.bytes)
-                bulk_g2s(ring + (size_t)stage * stage_bytes + (p.contiguous ? 0 : (size_t)lane * p.smem_row_stride), w.base, w.bytes,
-                         &full[stage]);
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- consumer warps
-    // The mask is produced one BYTE (8 pixels, 24 staged bytes) at a time.
-    //  pass 1, every group: with a filter "V <= T, any H, any S", a group whose bytes are all <= T is
-    //    keyed out entirely.  A lane owns 16 pixels (48 bytes) and tests the four ALIGNED 16-byte vectors
-    //    that cover them with three SWAR ops per word (a superset of the bytes: conservative, never
-    //    wrong); which vectors belong to which of its two groups is uniform for the whole row.
-    //    Groups that are not all-dark are pushed on a CTA-wide queue (ballot + popc, one atomic per warp).
-    //  pass 2, queued groups only: after a named barrier of the 31 consumer warps, every warp pops 32
-    //    groups at a time — all lanes busy, and the work of an object that covers a few chunks is spread
-    //    over the whole CTA instead of serialising the warps that own those chunks.  Table-driven V/S
-    //    classification + hue test of the candidates.
-    // Three queue slots rotate (unit u uses slot u % 3): while slow warps still pop unit u, fast ones may
-    // already push unit u+1; slot (u+2) % 3 is reset by warp 0 right after the barrier of unit u.
-    const int gpr = p.wpr * 4;                            // mask bytes (8-pixel groups) per row
-    const int cpr = (gpr + 63) >> 6;                      // warp chunks (64 groups = 512 px) per row
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t dark_add = p.f.dark_add;
-    const int dark_mode = p.f.dark_mode;
-    int it = 0;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++it) {
-        const int stage = it % kFastStages;
-        const int slot = it % 3;
-        uint16_t* q = queues + (size_t)slot * qcap;
-        mbar_wait(&full[stage], (uint32_t)(it / kFastStages) & 1u);
-        const int img = unit / p.units_per_frame;
-        const int row0 = (unit - img * p.units_per_frame) * p.rows_per_unit;
-        const int nrows = min(p.rows_per_unit, p.h - row0);
-        const uint8_t* tile = ring + (size_t)stage * stage_bytes;
-        const uint32_t* rowoff = s_rowoff[stage];
-        uint8_t* out_unit = reinterpret_cast<uint8_t*>(p.bits + (int64_t)img * p.bits_stride + (int64_t)row0 * p.wpr);
-        const int out_pitch = p.wpr * 4;
-
-        // ---- pass 1: chunk list of this warp: warp, warp + 31, ... mapped to (row, chunk-in-row)
-        int r = warp / cpr, c = warp - r * cpr;
-        while (r < nrows) {
-            const int g0 = (c * 32 + lane) * 2;                             // the lane's two groups: g0, g0 + 1
-            const int x = g0 * 8;
-            const uint32_t ro = rowoff[r];
-            bool needA = false, needB = false;
-            if (g0 < gpr) {
-                uint8_t* out_row = out_unit + r * out_pitch;
-                const bool inA = x < p.w, inB = (g0 + 1 < gpr) && (x + 8 < p.w);
-                bool darkA = !inA, darkB = !inB;                            // padding groups of the last mask word are written as 0
-                if (dark_mode == 0) {
-                    needA = inA;                                            // no "V <= T" filter: every group is classified
-                    needB = inB;
-                } else if (inA) {
-                    const uint32_t boff = ro + (uint32_t)x * 3u;            // 48 bytes per lane: boff % 16 is the same for every lane
-                    const uint4* vec = reinterpret_cast<const uint4*>(tile + (boff & ~15u));
-                    uint32_t f[4];
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {                           // any byte > T in aligned vector v ?
-                        const uint4 d = vec[v];
-                        const uint32_t l0 = (d.x & 0x7f7f7f7fu) + dark_add, l1 = (d.y & 0x7f7f7f7fu) + dark_add;
-                        const uint32_t l2 = (d.z & 0x7f7f7f7fu) + dark_add, l3 = (d.w & 0x7f7f7f7fu) + dark_add;
-                        f[v] = (dark_mode == 2) ? ((l0 & d.x) | (l1 & d.y) | (l2 & d.z) | (l3 & d.w))
-                                                : (l0 | d.x | l1 | d.y | l2 | d.z | l3 | d.w);
-                    }
-                    const uint32_t off = boff & 15u;                        // row-uniform
-                    // group A = bytes [off, off+24) of the 64, group B = [off+24, off+48)
-                    const uint32_t brA = f[0] | f[1] | (off > 8u ? f[2] : 0u);
-                    const uint32_t brB = (off < 8u ? f[1] : 0u) | f[2] | (off > 0u ? f[3] : 0u);
-                    needA = (brA & 0x80808080u) != 0u;
-                    needB = inB && (brB & 0x80808080u) != 0u;
-                    darkA = !needA;
-                    darkB = darkB || !needB;
-                }
-                if (darkA && darkB && g0 + 1 < gpr) {
-                    *reinterpret_cast<uint16_t*>(out_row + g0) = 0;         // 16 pixels keyed out (g0 is even: aligned)
-                } else {
-                    if (darkA) out_row[g0] = 0;
-                    if (darkB && g0 + 1 < gpr) out_row[g0 + 1] = 0;
-                }
-            }
-            const uint32_t balA = __ballot_sync(0xffffffffu, needA);
-            const uint32_t balB = __ballot_sync(0xffffffffu, needB);
-            const int nA = __popc(balA), nB = __popc(balB);
-            if (nA + nB) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&q_count[slot], nA + nB);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (needA) q[base + __popc(balA & lt_mask)] = (uint16_t)((r << 12) | g0);
-                if (needB) q[base + nA + __popc(balB & lt_mask)] = (uint16_t)((r << 12) | (g0 + 1));
-            }
-            c += kFastConsumers;                                            // next chunk of this warp
-            const int dr = c / cpr;
-            r += dr;
-            c -= dr * cpr;
-        }
-        asm volatile("bar.sync 1, %0;" :: "n"(kFastConsumers * 32) : "memory");   // all pushes of this unit are visible
-        if (tid == 0) {                                     // every warp is past unit it-1: recycle the slot of unit it+2
-            q_count[(it + 2) % 3] = 0;
-            q_head[(it + 2) % 3] = 0;
-        }
-
-        // ---- pass 2: pop 32 queued groups at a time
-        const int qn = *reinterpret_cast<volatile int*>(&q_count[slot]);
-        for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&q_head[slot], 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= qn) break;
-            const int i = base + lane;
-            if (i < qn) {
-                const uint32_t e = q[i];
-                const int rr_ = (int)(e >> 12), gidx = (int)(e & 0xfffu);
-                const int x = gidx * 8;
-                const uint32_t boff = rowoff[rr_] + (uint32_t)x * 3u;
-                const uint32_t bs = (boff & 3u) * 8u;
-                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(tile) + (boff >> 2);
-                uint32_t qd[7];
-#pragma unroll
-                for (int j = 0; j < 7; ++j) qd[j] = w32[j];
-                if (bs) {
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) qd[j] = __funnelshift_r(qd[j], qd[j + 1], bs);
-                }
-                uint32_t ex = 0, M2[2];
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t rx = qd[3 * g], ry = qd[3 * g + 1], rz = qd[3 * g + 2];   // b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-                    const uint32_t B01 = __byte_perm(rx, 0u, 0x4340), G01 = __byte_perm(rx, ry, 0x0401) & 0x00ff00ffu;
-                    const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
-                    const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
-                    const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
-                    const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
-                    const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
-                    const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
-                    const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
-                                       ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
-                    // bit 7 of every byte -> 4 adjacent bits (the multiply gathers them at bits 21..24)
-                    const uint32_t hit = (M & 0x80808080u) >> 7;
-                    ex |= (((hit * 0x00204081u) >> 21) & 15u) << (4 * g);
-                    M2[g] = M & 0x7f7f7f7fu & ~(hit * 0x7fu);               // hue-filter candidates of pixels not keyed out yet
-                }
-                if (M2[0] | M2[1]) {                                        // hue test of the candidates (pixels re-read from the tile)
-                    const uint8_t* px8 = tile + boff;
-#pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {
-                        uint32_t Mg = M2[g];
-                        while (Mg) {
-                            const int kb = (__ffs(Mg) - 1) >> 3;             // pixel inside the group
-                            uint32_t cand = (Mg >> (8 * kb)) & 0x7fu;
-                            Mg &= ~(0xffu << (8 * kb));
-                            const uint8_t* t = px8 + 3 * (4 * g + kb);
-                            const int b = t[0], gg = t[1], rd = t[2];
-                            const int v = max(max(b, gg), rd), d = v - min(min(b, gg), rd);
-                            const int h = hue_of(b, gg, rd, v, d, hdiv);
-                            bool hitp = false;
-                            while (cand) {
-                                const int f = __ffs(cand) - 1;
-                                cand &= cand - 1;
-                                hitp |= (h >= p.f.h_lo[f] && h <= p.f.h_hi[f]);
-                            }
-                            if (hitp) ex |= 1u << (4 * g + kb);
-                        }
-                    }
-                }
-                uint32_t byte = ~ex & 255u;
-                if (x + 8 > p.w) byte &= (1u << (p.w - x)) - 1u;            // partial last group of the row
-                out_unit[rr_ * out_pitch + gidx] = (uint8_t)byte;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-    }
-}
-
 // ===================================================================== stage A: mask, segment kernel
-// Same table-driven classification as chain_mask_fast_kernel, but every WARP runs its own pipeline:
+// Every WARP runs its own pipeline:
 //
 //  * work unit = a SEGMENT: up to 512 pixels of one row (1536 bytes, 16 mask words).  Warps draw
 //    batches of 16 consecutive segments from a global counter (dynamic balance: segments that cross
@@ -1366,20 +1106,6 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
     const uint32_t rowbytes = (uint32_t)g->crop_w * 3u;
     const uint32_t row_stride = staged_row_stride(rowbytes);
     IPP_REQUIRE(row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_a: row too long");
-    int fast_rows = (int)((196 * 1024 - 65536) / (kFastStages * row_stride + 3 * cg.wpr * 8));
-    if (fast_rows > 8) fast_rows = 8;
-    {   // pass 1 hands (rows x chunks-per-row) chunks to 31 consumer warps in rounds: pick the row count
-        // that keeps the most warps busy per round (e.g. 7 rows x 4 chunks = 28 of 31, not 8 x 4 = 32 -> 2 rounds)
-        const int cpr = (cg.wpr * 4 + 63) / 64;
-        double best = -1.0;
-        int best_rows = fast_rows;
-        for (int rws = fast_rows; rws >= 1 && rws >= fast_rows - 3; --rws) {
-            const int chunks = rws * cpr, rounds = (chunks + 30) / 31;
-            const double util = (double)chunks / (31.0 * rounds);
-            if (util > best + 1e-9) { best = util; best_rows = rws; }
-        }
-        fast_rows = best_rows;
-    }
     // the 64 KB V/S table borrows the head of the label/area scratch: ccl_init (which runs after
     // the mask kernel) writes the run-start entries there before anything reads them
     const bool lut_fits = (int64_t)cg.lab_stride * 4 * n_frames >= 65536;
@@ -1388,7 +1114,9 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
         const int lo = 512 - (int)(fs.clo[k] & 0x3ffu), hi = (int)(fs.chi[k] & 0x3ffu) - 512;
         n_hue_filters += !(lo <= 0 && hi >= 180);
     }
-    const bool fast = fs.all_zones_full && n_hue_filters <= 7 && fast_rows >= 1 && lut_fits && getenv("IPP_MASK_GENERIC") == nullptr;
+    const int64_t n_segs = (int64_t)ceil_div(g->crop_w, kSegPx) * g->crop_h * n_frames;
+    const bool fast = fs.all_zones_full && n_hue_filters <= 7 && lut_fits && n_segs < (1LL << 31) &&
+                      cg.bits_stride * n_frames < (1LL << 32) && getenv("IPP_MASK_GENERIC") == nullptr;
     if (fast) {
         HsvFast hf{};
         int dark_t = -1;
@@ -1419,9 +1147,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
         uint8_t* lut = (uint8_t*)b.la;
         { ipp::LaunchTimer _lt("hsv_lut_kernel", st); hsv_lut_kernel<<<256, 256, 0, st>>>(fs, lut); }
         IPP_LAUNCH_CHECK();
-        const int64_t n_segs = (int64_t)ceil_div(g->crop_w, kSegPx) * g->crop_h * n_frames;
-        const bool seg_ok = n_segs < (1LL << 31) && cg.bits_stride * n_frames < (1LL << 32) && getenv("IPP_MASK_RING") == nullptr;
-        if (seg_ok) {
+        {
             MaskSegParams p{};
             p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
             p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
@@ -1441,31 +1167,7 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
             const int grid = (int)std::min<int64_t>(sm_count(), ceil_div(n_segs, kSegWarps));
             { ipp::LaunchTimer _lt("chain_mask_seg_kernel", st); chain_mask_seg_kernel<<<grid, kSegThreads, kSegSmem, st>>>(p); }
             IPP_LAUNCH_CHECK();
-        } else {
-        MaskFastParams p{};
-        p.frames = frames; p.pitch = frame_pitch; p.stride = frame_stride;
-        p.crop_l = g->crop_l; p.crop_t = g->crop_t; p.w = g->crop_w; p.h = g->crop_h;
-        p.wpr = cg.wpr; p.bits = b.bits; p.bits_stride = cg.bits_stride;
-        p.rows_per_unit = fast_rows;
-        p.units_per_frame = ceil_div(g->crop_h, fast_rows);
-        p.n_units = p.units_per_frame * n_frames;
-        p.smem_row_stride = row_stride;
-        p.contiguous = (frame_pitch == (int64_t)rowbytes && g->crop_l == 0 && g->crop_w == g->frame_w &&
-                        getenv("IPP_MASK_ROWCOPIES") == nullptr) ? 1 : 0;
-        p.stage_bytes = p.contiguous ? (((uint32_t)fast_rows * rowbytes + 30u) & ~15u) + 64u : (uint32_t)fast_rows * row_stride;
-        p.lut = lut;
-        p.f = hf;
-        // LUT + ring (+128: pass 1 reads whole aligned vectors past a row's end) + three queue slots of uint16
-        const size_t smem = 65536 + (size_t)kFastStages * p.stage_bytes + 128 + (size_t)3 * fast_rows * cg.wpr * 4 * sizeof(uint16_t);
-        static size_t smem_set = 0;     // the attribute only ever grows; setting it is not free
-        if (smem > smem_set) {
-            IPP_CUDA(cudaFuncSetAttribute(chain_mask_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
         }
-        const int grid = std::min(sm_count(), p.n_units);
-        { ipp::LaunchTimer _lt("chain_mask_fast_kernel", st); chain_mask_fast_kernel<<<grid, kFastThreads, smem, st>>>(p); }
-        IPP_LAUNCH_CHECK();
-            }
     }
     if (!fast) {
     MaskParams p{};

@@ -1,4 +1,4 @@
-"""Where does chain_mask_fast_kernel's time go?  Same frames, different filter lists / contents."""
+"""Where does the stage-A mask kernel's time go?  Same frames, different filter lists / contents."""
 import ctypes as C, sys
 sys.path.insert(0, '.')
 import numpy as np, torch

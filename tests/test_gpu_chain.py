@@ -89,6 +89,22 @@ def test_chain_1080p():
     _compare(*_run_both(frames, bgs, 23, **kw))
 
 
+def test_chain_4k_frames_config5():
+    """BASELINE.json config 5: the full chain over 3840x2160 frames (a video.py frame stream) with 4K backgrounds:
+    2160x2160 outputs, sprites that need more than one 64-wide super-block in the LANCZOS passes."""
+    H, W = 2160, 3840
+    frames = [synth.frame(71, i, H, W, speck_density=0.002) for i in range(2)]
+    bgs = [synth.background(71, i, H, W) for i in range(2)]
+    kw = dict(crop_margins=(0.01, 8, 0.02, 0), color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1,
+              include_original=False, pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False,
+              scale_min=0.05, scale_max=0.12)
+    res, *ref = _run_both(frames, bgs, 29, **kw)
+    _compare(res, *ref)
+    assert res.images.shape[1:] == (2160, 2160, 3)
+    nsb = res._arrays[0]["nkb"]
+    assert ((nsb & 0xffff) > 1).any() or ((nsb >> 16) > 1).any()        # the multi-super-block path really ran
+
+
 def test_device_lanczos_tables_equal_host_tables():
     """Device-computed coefficient tables (CUDA sin) vs libm tables for many size pairs; every row that
     differs must have been flagged as ambiguous (then the host fixes it) — in practice none differs."""
