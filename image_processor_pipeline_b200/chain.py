@@ -574,7 +574,8 @@ class ChainStream:
 
 def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
               planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
-              _ticket: Optional[dict] = None, _upload_stream=None, _pipe: Optional["ChainStream"] = None):
+              _ticket: Optional[dict] = None, _upload_stream=None, _pipe: Optional["ChainStream"] = None,
+              _before_sync=None):
     """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB,
     either on the same device or in PINNED HOST memory.  Host backgrounds are never uploaded whole:
     once the square-crop offsets are planned, only each item's crop window crosses PCIe
@@ -755,6 +756,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             res.tables_flagged_rows = res.tables_fixed_items = None   # known once the next finish() / flush() has looked
             _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev))
         elif device_tables:
+            if _before_sync is not None:
+                _before_sync()                                        # e.g. queue the next uploads before the host waits
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
             _mark("sync3_amb")
             if n_amb:
@@ -848,16 +851,24 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
             raise ValueError("chunked run_chain_host pairs slice c with backgrounds[c*chunk:(c+1)*chunk]: pass one background per frame")
         compute = torch.cuda.current_stream()
         up, down = _side_streams(dev)
+        n_slots, ahead = 3, 2                             # frames of two slices are queued ahead of the slice being chained
         slots = [dict(f=_scratch(f"h2d_f{i}", chunk * frames_host[0].numel(), dev).view((chunk,) + tuple(frames_host.shape[1:])),
                       b=None if windows else
                       _scratch(f"h2d_b{i}", chunk * backgrounds_host[0].numel(), dev).view((chunk,) + tuple(backgrounds_host.shape[1:])),
-                      ready=torch.cuda.Event(), free=torch.cuda.Event()) for i in range(2)]
+                      ready=torch.cuda.Event(), free=torch.cuda.Event()) for i in range(n_slots)]
         bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
         h2d_bytes = 0
+        uploaded = [0]
 
-        def upload(c):
+        def upload_next():
+            """Queue the frames of the next slice on the copy stream.  Called right before the host waits for a slice's
+            stage C (and its crop windows, already queued): the copy engine never drains while the host is blocked."""
+            c = uploaded[0]
+            if c >= len(bounds):
+                return
+            uploaded[0] += 1
             lo, hi = bounds[c]
-            s = slots[c % 2]
+            s = slots[c % n_slots]
             up.wait_event(s["free"])                      # the chain that last used this slot has finished
             with torch.cuda.stream(up):
                 s["f"][:hi - lo].copy_(frames_host[lo:hi], non_blocking=True)
@@ -867,7 +878,8 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
 
         for s in slots:
             s["free"].record(compute)
-        upload(0)
+        for _ in range(ahead):
+            upload_next()
         labels: List[str] = []
         arrays = []
         k_total = 0
@@ -875,12 +887,13 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
         if out_host is None:
             out_host = torch.empty((n * 4, cs, cs, 3), dtype=torch.uint8).pin_memory()
         for c, (lo, hi) in enumerate(bounds):
-            if c + 1 < len(bounds):
-                upload(c + 1)                             # frames of the next slice go first; this slice's windows queue behind them
-            s = slots[c % 2]
+            s = slots[c % n_slots]
             compute.wait_event(s["ready"])
             bgs = backgrounds_host[lo:hi] if windows else s["b"][:hi - lo]
-            res = run_chain(s["f"][:hi - lo], bgs, params, rng, _upload_stream=up, **kw)
+            before = uploaded[0]
+            res = run_chain(s["f"][:hi - lo], bgs, params, rng, _upload_stream=up, _before_sync=upload_next, **kw)
+            if uploaded[0] == before:
+                upload_next()                             # the chain returned early (nothing to paste): keep the queue fed
             s["free"].record(compute)
             h2d_bytes += (hi - lo) * int(frames_host[0].numel())
             h2d_bytes += res.h2d_background_bytes if windows else (hi - lo) * int(backgrounds_host[0].numel())
