@@ -29,7 +29,6 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
-import os
 import random as _random
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -466,7 +465,7 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
 
 # =========================================================================== the chain
 def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, slot: int = 0,
-                     wait_events: Sequence = (), wait_current: bool = True) -> dict:
+                     wait_events: Sequence = (), wait_current: bool = True, tag: str = "", stream=None) -> dict:
     """Launch stage A (frame -> keep-mask + largest component; no random draws) of a batch on a side
     stream, into the scratch of ``slot`` (0 or 1), and return a ticket for ``run_chain(..., _ticket=)``.
     Lets the HBM-bound pass of batch k+1 run while the host plans / the GPU finishes batch k.
@@ -483,10 +482,10 @@ def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: Ch
     ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
     geom = _geom_struct(FW, FH, rect, BW, BH, ranges)
     with torch.cuda.device(dev):
-        side = _side_streams(dev)[0]
+        side = stream if stream is not None else _side_streams(dev)[0]
         ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-        ws = _scratch(f"mask_s{slot}", ws_bytes, dev)
-        info_d = _scratch(f"info_s{slot}", n * 32, dev, torch.int32).view(n, 8)
+        ws = _scratch(f"mask_s{slot}{tag}", ws_bytes, dev)
+        info_d = _scratch(f"info_s{slot}{tag}", n * 32, dev, torch.int32).view(n, 8)
         if wait_current:
             side.wait_stream(torch.cuda.current_stream())        # inputs / previous users of this slot
         for ev in wait_events:
@@ -518,6 +517,8 @@ class ChainStream:
     (resident batches, or the caller synchronised) — stage A then does not wait for the work queued
     on the current stream.  Default False: it waits (safe, but serialises behind stages B2/C)."""
 
+    _count = 0
+
     def __init__(self, params: ChainParams, inputs_ready: bool = False, slots: int = 2, **run_kw):
         if slots < 2:
             raise ValueError("ChainStream needs at least two keep-mask slots")
@@ -527,13 +528,16 @@ class ChainStream:
         self._slot_free = [None] * self.slots   # event: stages B2/C of the batch that last used the slot are done
         self._pending = None                    # deferred table verification of the previous batch
         self._b1 = {}
+        self._side = {}
         self._amb_host = None
+        ChainStream._count += 1
+        self.tag = f"#{ChainStream._count}"     # own workspaces: several ChainStreams may be in flight on one device
 
     def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor):
         slot = self._n % self.slots
         waits = [self._slot_free[slot]] if self._slot_free[slot] is not None else []
         ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=slot, wait_events=waits,
-                                  wait_current=not self.inputs_ready)
+                                  wait_current=not self.inputs_ready, tag=self.tag, stream=self._stream(self._side, frames.device, 0))
         ticket["backgrounds"] = backgrounds
         self._n += 1
         return ticket
@@ -546,11 +550,15 @@ class ChainStream:
         self._resolve_pending()
 
     # ---- used by run_chain
-    def _b1_stream(self, dev):
+    @staticmethod
+    def _stream(cache, dev, priority):
         key = dev.index if dev.index is not None else torch.cuda.current_device()
-        if key not in self._b1:
-            self._b1[key] = torch.cuda.Stream(dev, priority=int(os.environ.get('IPP_PRIO_B1', '-1')))
-        return self._b1[key]
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(dev, priority=priority)
+        return cache[key]
+
+    def _b1_stream(self, dev):
+        return self._stream(self._b1, dev, -1)                # B1 is tiny and on the host's critical path: high priority
 
     def _resolve_pending(self):
         pend, self._pending = self._pending, None
@@ -611,6 +619,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     pp = _plan_params(params, BW, BH, m)
     bridge = _RngBridge(rng) if planner == "native" else None
     lo, hi = (0, n) if _shard is None else (_shard["lo"], _shard["hi"])
+    tag = _pipe.tag if _pipe is not None else ""
 
     def finish(res, own):
         if bridge is not None:
@@ -624,8 +633,8 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             torch.cuda.current_stream().wait_event(_ticket["done"])
         else:
             ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-            ws = _scratch("mask", ws_bytes, dev)
-            info_d = _scratch("info", n * 32, dev, torch.int32).view(n, 8)
+            ws = _scratch("mask" + tag, ws_bytes, dev)
+            info_d = _scratch("info" + tag, n * 32, dev, torch.int32).view(n, 8)
             _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
                                                 ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
         _mark("stage_a_issued")
@@ -648,7 +657,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         rots_loc["frame"] -= lo
         tiles = _b1_tiles(rots_loc)
         rots_loc["tile_start"] = _excl(tiles)
-        bbox_d = _scratch("bbox", max(1, len(rots_loc)) * 16, dev, torch.int32).view(-1, 4)
+        bbox_d = _scratch("bbox" + tag, max(1, len(rots_loc)) * 16, dev, torch.int32).view(-1, 4)
         rot_d = None
         # pipelined: B1 runs on its own stream (stage A of this batch is complete — its info was read back),
         # so it does not queue behind stages B2/C of the previous batch on the current stream
@@ -689,12 +698,12 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         if _pipe is not None:
             _pipe._resolve_pending()          # previous batch's table check, before its workspaces are overwritten
         items_d = _upload("items", items, dev)
-        spr_ws = _scratch("sprites", max(tot["ws"], 256), dev)
-        band_d = _scratch("bands", max(tot["band_bytes"], 256), dev)
+        spr_ws = _scratch("sprites" + tag, max(tot["ws"], 256), dev)
+        band_d = _scratch("bands" + tag, max(tot["band_bytes"], 256), dev)
         amb_d = None
         if device_tables:
-            tab_d = _scratch("tables", max(1, tot["table_ints"]) * 4, dev, torch.int32)
-            amb_d = _scratch("amb", (1 + 3 * AMB_CAPACITY) * 4, dev, torch.int32)
+            tab_d = _scratch("tables" + tag, max(1, tot["table_ints"]) * 4, dev, torch.int32)
+            amb_d = _scratch("amb" + tag, (1 + 3 * AMB_CAPACITY) * 4, dev, torch.int32)
             _native.check(lib.ipp_chain_tables(items_d.data_ptr(), K, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
                                                AMB_CAPACITY, float(ambiguity_eps), _stream()), "ipp_chain_tables")
         else:
@@ -715,7 +724,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
             items_c["sq_x0"] = 0
             items_c["sq_y0"] = 0
             items_c_d = _upload("items_c", items_c, dev)
-            bg_dev = _scratch("bg_windows", K * cs * cs * 3, dev)
+            bg_dev = _scratch("bg_windows" + tag, K * cs * cs * 3, dev)
             geom_c = _geom_struct(FW, FH, rect, cs, cs, ranges)
             bg_pitch, bg_stride = cs * 3, cs * cs * 3
             up = _upload_stream if _upload_stream is not None else _side_streams(dev)[0]
@@ -940,5 +949,5 @@ _SIDE = {}
 def _side_streams(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE:
-        _SIDE[key] = (torch.cuda.Stream(dev, priority=int(os.environ.get('IPP_PRIO_A', '0'))), torch.cuda.Stream(dev))
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
     return _SIDE[key]
