@@ -607,8 +607,8 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     // phase 1: all mask words and all pixel bytes of the lane's rows are requested before anything is used
     // (the bit test and the three byte loads of a pixel do not wait for each other; pixels outside the
     // component rect are fetched from a clamped in-rect address and discarded)
-    uint32_t word[kGatherRows], b0[kGatherRows], b1[kGatherRows], b2[kGatherRows];
-    int sh[kGatherRows];
+    uint32_t word[kGatherRows], w0[kGatherRows], w1[kGatherRows];
+    int sh[kGatherRows], bsh[kGatherRows];
 #pragma unroll
     for (int j = 0; j < kGatherRows; ++j) {
         int xin, yin;
@@ -627,8 +627,13 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
         const int fx = it.cc_x + xin;
         sh[j] = use ? (fx & 31) : -1;
         word[j] = fb[yin * c.wpr + (fx >> 5)];
-        const uint8_t* s = frame + (int64_t)yin * c.pitch + xin * 3;
-        b0[j] = s[0]; b1[j] = s[1]; b2[j] = s[2];
+        // the pixel's three bytes come from the aligned word that holds its first byte and, only when they
+        // spill over (half of the pixels), the next one: 1.5 loads per pixel instead of three byte loads
+        const uintptr_t a = (uintptr_t)(frame + (int64_t)yin * c.pitch + xin * 3);
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        bsh[j] = (int)(a & 3) * 8;
+        w0[j] = aw[0];
+        w1[j] = bsh[j] > 8 ? aw[1] : 0u;
     }
     // phase 2: select, premultiply (alpha is 0 or 255), store the four planes
 #pragma unroll
@@ -636,9 +641,10 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
         if (Y0 + j >= spr_h) break;
         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
         uint8_t* d = dst + (int64_t)j * Wp;
-        d[0] = on ? (uint8_t)b2[j] : (uint8_t)0;           // BGR -> R, G, B, A planes
-        d[plane] = on ? (uint8_t)b1[j] : (uint8_t)0;
-        d[2 * plane] = on ? (uint8_t)b0[j] : (uint8_t)0;
+        const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
+        d[0] = (uint8_t)(bgr >> 16);                         // BGR -> R, G, B, A planes
+        d[plane] = (uint8_t)(bgr >> 8);
+        d[2 * plane] = (uint8_t)bgr;
         d[3 * plane] = on ? (uint8_t)255 : (uint8_t)0;
     }
 }
