@@ -231,7 +231,7 @@ def _rot_records(rots: List[dict]):
         cw, ch = plan.size
         arr[i] = (r["frame"], *r["cc"], KIND[plan.kind], *a, cw, ch, tile, 0)
         x, _, w, h = r["cc"]
-        tile += ((((x + w + 31) >> 5) - (x >> 5)) * h + 255) // 256
+        tile += ((((((x + w + 31) >> 5) + 3) >> 2) - ((x >> 5) >> 2)) * h + 255) // 256
     return arr, tile
 
 
@@ -412,10 +412,11 @@ def native_plan_items(rots: np.ndarray, rot_index: np.ndarray, bbox: np.ndarray,
 
 
 def _b1_tiles(rots: np.ndarray) -> np.ndarray:
-    """Stage B1 work list: one tile = 256 mask words of a sprite's component rect (chain_rot_bbox_kernel)."""
+    """Stage B1 work list: one tile = 256 aligned quads of mask words of a sprite's component rect
+    (chain_rot_bbox_kernel: one thread per four words)."""
     x, w, h = (rots[n].astype(np.int64) for n in ("cc_x", "cc_w", "cc_h"))
-    nw = ((x + w + 31) >> 5) - (x >> 5)
-    return (nw * h + 255) // 256
+    nq = ((((x + w + 31) >> 5) + 3) >> 2) - ((x >> 5) >> 2)
+    return (nq * h + 255) // 256
 
 
 def _excl(a):

@@ -452,7 +452,7 @@ __device__ __forceinline__ int find_record(const Rec* recs, int n, int tile, Get
 // So: scan the component rect's mask words (bits only), peel the 8-boundary with shifts and ANDs,
 // forward-map each boundary pixel in float, and test the 3x3 canvas pixels around it with the EXACT
 // integer inverse map.  Work ~ perimeter instead of canvas area; the result is identical.
-// One thread = one mask word; a CTA = 256 consecutive words of one sprite's rect (flat tile list).
+// One thread = four mask words; a CTA = 256 consecutive word quads of one sprite's rect (flat tile list).
 __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot* __restrict__ rots, int n_rot,
                                                              const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
                                                              int frame_h, int32_t* bbox_out) {
@@ -468,59 +468,77 @@ __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot
         if (chunk == 0 && threadIdx.x == 0) { out[0] = 0; out[1] = 0; out[2] = rec.canvas_w; out[3] = rec.canvas_h; }
         return;
     }
-    const int w0 = rec.cc_x >> 5;
-    const int nw = ((rec.cc_x + rec.cc_w + 31) >> 5) - w0;
+    // one thread = FOUR consecutive mask words of a row (a 16-byte load when rows are 16-byte aligned):
+    // 9 loads per 128 pixels for the 3 x 3 neighbourhood instead of 9 per 32
+    const int q0 = (rec.cc_x >> 5) >> 2;
+    const int nq = ((((rec.cc_x + rec.cc_w + 31) >> 5) + 3) >> 2) - q0;
     const int q = chunk * 256 + (int)threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t* fb = bits + (int64_t)rec.frame * bits_stride;
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
-    // ---- phase 1: boundary pixels of this thread's word
-    uint32_t bnd = 0;
+    // ---- phase 1: boundary pixels of this thread's four words
+    uint32_t bnd[4] = {0u, 0u, 0u, 0u};
     int row = 0, wi = 0;
-    if (q < nw * rec.cc_h) {
-        row = q / nw;
-        wi = w0 + (q - row * nw);
+    if (q < nq * rec.cc_h) {
+        row = q / nq;
+        wi = 4 * (q0 + (q - row * nq));
         const int fy = rec.cc_y + row;
-        const uint32_t* pr = fb + (int64_t)fy * wpr + wi;
-        const uint32_t m = pr[0];
-        if (m) {
-            const bool hasl = wi > 0, hasr = wi + 1 < wpr;
-            // pixels whose left, own and right neighbours are all set, for one row (zero row when it does not exist)
-            auto hcore = [&](const uint32_t* r, bool exists) -> uint32_t {
-                if (!exists) return 0u;
-                const uint32_t x = r[0];
-                const uint32_t l = (x << 1) | (hasl ? (r[-1] >> 31) : 0u);
-                const uint32_t rr = (x >> 1) | (hasr ? (r[1] << 31) : 0u);
-                return x & l & rr;
-            };
-            const uint32_t interior = hcore(pr, true) & hcore(pr - wpr, fy > 0) & hcore(pr + wpr, fy + 1 < frame_h);
-            bnd = m & ~interior;
+        const bool vec = ((wpr & 3) == 0) && ((((uintptr_t)fb) & 15) == 0);
+        // words wi-1 .. wi+4 of a mask row (zero outside the row / when the row does not exist)
+        auto load6 = [&](int y, bool exists, uint32_t (&v)[6]) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = 0u;
+            if (!exists) return;
+            const uint32_t* r = fb + (int64_t)y * wpr;
+            if (vec) {
+                const uint4 t = *reinterpret_cast<const uint4*>(r + wi);
+                v[1] = t.x; v[2] = t.y; v[3] = t.z; v[4] = t.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (wi + k < wpr) v[1 + k] = r[wi + k];
+            }
+            if (wi > 0) v[0] = r[wi - 1];
+            if (wi + 4 < wpr) v[5] = r[wi + 4];
+        };
+        uint32_t mid[6];
+        load6(fy, true, mid);
+        if (mid[1] | mid[2] | mid[3] | mid[4]) {
+            uint32_t up[6], dn[6];
+            load6(fy - 1, fy > 0, up);
+            load6(fy + 1, fy + 1 < frame_h, dn);
+            // pixels whose left, own and right neighbours are all set, for one row
+            auto hcore = [](const uint32_t (&v)[6], int k) { return v[k] & ((v[k] << 1) | (v[k - 1] >> 31)) & ((v[k] >> 1) | (v[k + 1] << 31)); };
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bnd[k] = mid[1 + k] & ~(hcore(mid, 1 + k) & hcore(up, 1 + k) & hcore(dn, 1 + k));
         }
     }
-    // ---- phase 2: the warp's boundary pixels, compacted (a flat edge puts 32 of them in one lane's word)
+    // ---- phase 2: the warp's boundary pixels, compacted (a flat edge puts 32 of them in one word), word slot by word slot
     __shared__ uint32_t s_q[8][1024];
-    const int cnt = __popc(bnd);
-    int incl = cnt;
+    // forward map (float): canvas = A^-1 * (65536 * (S + 0.5) - (a2, a5))
+    const double det = (double)rec.a0 * (double)rec.a4 - (double)rec.a1 * (double)rec.a3;
+    const float i00 = (float)((double)rec.a4 / det), i01 = (float)(-(double)rec.a1 / det);
+    const float i10 = (float)(-(double)rec.a3 / det), i11 = (float)((double)rec.a0 / det);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        uint32_t bk = bnd[k];
+        const int cnt = __popc(bk);
+        int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;                                  // warp-uniform
         int off = incl - cnt;
         const uint32_t hi = (uint32_t)row << 16;
-        const int xbase = wi * 32 - rec.cc_x;
-        while (bnd) {
-            const int bit = __ffs(bnd) - 1;
-            bnd &= bnd - 1;
+        const int xbase = (wi + k) * 32 - rec.cc_x;
+        while (bk) {
+            const int bit = __ffs(bk) - 1;
+            bk &= bk - 1;
             s_q[warp][off++] = (uint32_t)(xbase + bit) | hi;
         }
         __syncwarp();
-        // forward map (float): canvas = A^-1 * (65536 * (S + 0.5) - (a2, a5))
-        const double det = (double)rec.a0 * (double)rec.a4 - (double)rec.a1 * (double)rec.a3;
-        const float i00 = (float)((double)rec.a4 / det), i01 = (float)(-(double)rec.a1 / det);
-        const float i10 = (float)(-(double)rec.a3 / det), i11 = (float)((double)rec.a0 / det);
         for (int i = lane; i < total; i += 32) {
             const uint32_t e = s_q[warp][i];
             const int xin = (int)(e & 0xffffu), yin = (int)(e >> 16);
@@ -548,6 +566,7 @@ __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot
                 }
             }
         }
+        __syncwarp();                                              // the queue is refilled by the next word slot
     }
     minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
     if ((threadIdx.x & 31) == 0 && maxx1 > 0) {

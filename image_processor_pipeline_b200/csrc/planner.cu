@@ -212,9 +212,9 @@ int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_pa
             }
             rot_index_out[n] = i;
             r->tile_start = (int32_t)tiles;
-            {   // stage B1 tile = 256 mask words of the component rect (chain_rot_bbox_kernel)
-                const long long nw = ((r->cc_x + r->cc_w + 31) >> 5) - (r->cc_x >> 5);
-                tiles += (nw * r->cc_h + 255) / 256;
+            {   // stage B1 tile = 256 aligned quads of mask words of the component rect (chain_rot_bbox_kernel)
+                const long long nq = ((((r->cc_x + r->cc_w + 31) >> 5) + 3) >> 2) - ((r->cc_x >> 5) >> 2);
+                tiles += (nq * r->cc_h + 255) / 256;
             }
             IPP_REQUIRE(tiles < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_rotations_host: too many tiles");
             ++n;

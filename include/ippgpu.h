@@ -232,8 +232,9 @@ typedef struct ipp_chain_rot {
     int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (kind 0)           */
     int32_t canvas_w, canvas_h;
     int32_t tile_start;                 /* first stage-B1 tile of this sprite in the flat grid; a tile =
-                                           256 mask words of the component rect, whose rows span
-                                           nw = ((cc_x+cc_w+31)>>5) - (cc_x>>5) words: ceil(nw*cc_h/256) tiles */
+                                           256 aligned quads of mask words of the component rect, whose rows span
+                                           nq = ((((cc_x+cc_w+31)>>5)+3)>>2) - ((cc_x>>5)>>2) quads:
+                                           ceil(nq*cc_h/256) tiles */
     int32_t _pad;
 } ipp_chain_rot;
 
