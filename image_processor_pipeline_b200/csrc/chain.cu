@@ -798,19 +798,19 @@ __device__ __forceinline__ void load_band(uint2 (&b)[6], const uint2* frag) {
 #pragma unroll
     for (int q = 0; q < 6; ++q) b[q] = __ldg(frag + q * 32);
 }
-// 16 rows of one byte plane -> acc.  lo / hi: the (prefetched) first super-block words of rows g, g+8;
-// r_lo / r_hi point at them (further super-blocks are fetched here).
-__device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint8_t* r_lo, const uint8_t* r_hi,
-                                         const uint2 (&b0)[6], const uint2* frag, int nsb) {
+// 16 rows of one byte plane -> acc.  lo / hi: the staged first super-block words of rows g, g+8; further
+// super-blocks (rare: scale factors above ~3.5) are fetched here from the rows row_lo / row_hi of `plane`.
+// acc[0] starts at the rounding constant 2^21 of clip8((2^21 + sum) >> 22).
+__device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint8_t* plane, int64_t pitch,
+                                         int row_lo, int row_hi, const uint2 (&b0)[6], const uint2* frag, int nsb) {
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[p][i] = 0;
+    for (int i = 0; i < 4; ++i) { acc[0][i] = 1 << (kPrec - 1); acc[1][i] = 0; acc[2][i] = 0; }
     mma_superblock(acc, lo, hi, b0);
-    for (int sb = 1; sb < nsb; ++sb) {                              // rare: scale factors above ~3.5
+    for (int sb = 1; sb < nsb; ++sb) {
         uint2 b[6];
         load_band(b, frag + sb * 192);
-        const uint4 lo2 = *reinterpret_cast<const uint4*>(r_lo + 64 * sb), hi2 = *reinterpret_cast<const uint4*>(r_hi + 64 * sb);
+        const uint4 lo2 = *reinterpret_cast<const uint4*>(plane + (int64_t)row_lo * pitch + 64 * sb);
+        const uint4 hi2 = *reinterpret_cast<const uint4*>(plane + (int64_t)row_hi * pitch + 64 * sb);
         mma_superblock(acc, lo2, hi2, b);
     }
 }
@@ -870,21 +870,18 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     const uint8_t* col0 = src - 16 * t;                            // first column of the window (src includes the lane's 16 t)
 #pragma unroll
     for (int d = 0; d < kRing - 1; ++d) ring_issue(ring + 1024 * d, col0, Wp, 16 * d, spr_h, d < n_rt, lane);
-    auto row_ptr = [&](int ti, int half) { return src + (int64_t)min(16 * ti + g + 8 * half, spr_h - 1) * Wp; };
     for (int ti = 0; ti < n_rt; ++ti) {
         ring_wait();                                               // tile ti has landed (this lane's own two pieces)
         const uint8_t* stg = ring + 1024 * (ti % kRing);
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
         ring_issue(ring + 1024 * ((ti + kRing - 1) % kRing), col0, Wp, 16 * (ti + kRing - 1), spr_h, ti + kRing - 1 < n_rt, lane);
-        const uint8_t* r_lo = row_ptr(ti, 0);
-        const uint8_t* r_hi = row_ptr(ti, 1);
         int acc[3][4];
-        mma_rows(acc, lo, hi, r_lo, r_hi, b0, frag, nsb);
+        mma_rows(acc, lo, hi, src, Wp, min(16 * ti + g, spr_h - 1), min(16 * ti + g + 8, spr_h - 1), b0, frag, nsb);
         const int m = ti & 1, y0 = (ti & ~1) << 4;
         // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1}
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
+            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16);
             const int yl = 16 * m + g + 8 * (i >> 1), xl = 2 * t + (i & 1);
             st[xl * 36 + yl] = (uint8_t)c_clip8(v);
         }
@@ -943,23 +940,19 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     };
 #pragma unroll
     for (int d = 0; d < kRing - 1; ++d) issue(d);
-    auto row_ptr = [&](int step, int half) {
-        return src + (int64_t)(step & 3) * plane + (int64_t)min(x_begin + 16 * (step >> 2) + g + 8 * half, new_w - 1) * Hp;
-    };
     uint32_t px[4] = {0u, 0u, 0u, 0u};
     for (int step = 0; step < n_steps; ++step) {
         ring_wait();
         const uint8_t* stg = ring + 1024 * (step % kRing);
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
         issue(step + kRing - 1);
-        const uint8_t* r_lo = row_ptr(step, 0);
-        const uint8_t* r_hi = row_ptr(step, 1);
         int acc[3][4];
-        mma_rows(acc, lo, hi, r_lo, r_hi, b0, frag, nsb);
+        const int xr = x_begin + 16 * (step >> 2) + g;
+        mma_rows(acc, lo, hi, src + (int64_t)(step & 3) * plane, Hp, min(xr, new_w - 1), min(xr + 8, new_w - 1), b0, frag, nsb);
         const int pl = step & 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16) + (1 << (kPrec - 1));
+            const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16);
             px[i] |= c_clip8(v) << (8 * pl);
         }
         if (pl == 3) {
