@@ -78,15 +78,19 @@ struct GroupIdx {
     int img, by, k;
     bool ok;
 };
+// grid = (ceil(groups per image / 256), images): 32-bit index math, a CTA never straddles two images
 __device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n) {
     GroupIdx r;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = (int64_t)g.bh * g.bww;
-    r.ok = t < per * n;
-    r.img = (int)(t / per);
-    const int rem = (int)(t - (int64_t)r.img * per);
-    r.by = rem / g.bww;
-    r.k = rem - r.by * g.bww;
+    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x;
+    r.img = (int)blockIdx.y;
+    r.ok = rem < (uint32_t)(g.bh * g.bww) && r.img < n;
+    uint32_t q = rem;                                      // rem / bww
+    if (g.bww > 1) {
+        q = __umulhi(rem, g.bww_inv);                      // bww_inv = floor(2^32 / bww) + 1: exact or one too large
+        if (q * (uint32_t)g.bww > rem) --q;
+    }
+    r.by = (int)q;
+    r.k = (int)(rem - q * (uint32_t)g.bww);
     return r;
 }
 
@@ -290,9 +294,18 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
             key = (long long)(uintptr_t)slot;
             nfg += cnt;
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const int sum = __reduce_add_sync(peers, cnt);
-        if (slot && lane == __ffs(peers) - 1) atomicAdd(slot, sum);
+        // neighbouring groups mostly sit in ONE component (the object): when every active lane has the same root a
+        // single reduction and atomic do; only mixed warps pay for match.any
+        const uint32_t active = __ballot_sync(0xffffffffu, slot != nullptr);
+        const long long key0 = __shfl_sync(0xffffffffu, key, __ffs(active) - 1);
+        if (__all_sync(0xffffffffu, slot == nullptr || key == key0)) {
+            const int sum = __reduce_add_sync(0xffffffffu, cnt);
+            if (slot && lane == __ffs(active) - 1) atomicAdd(slot, sum);
+        } else {
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const int sum = __reduce_add_sync(peers, cnt);
+            if (slot && lane == __ffs(peers) - 1) atomicAdd(slot, sum);
+        }
     }
     // foreground pixel count per image: one atomic per warp when the warp sits in one image
     const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
@@ -419,8 +432,7 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
 }
 
 int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
-    const int64_t groups = (int64_t)g.bh * g.bww * n;
-    const int gb = ceil_div(groups, 256);
+    const dim3 gb(ceil_div((int64_t)g.bh * g.bww, 256), n);
     { ipp::LaunchTimer _lt("ccl_reset_kernel", st); ccl_reset_kernel<<<ceil_div(n, 256), 256, 0, st>>>(b, n); }
     IPP_LAUNCH_CHECK();
     { ipp::LaunchTimer _lt("ccl_init_kernel", st); ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n); }

@@ -30,6 +30,7 @@ struct CclGeom {
     int wpr;         // 32-bit words per pixel row
     int bw, bh;      // blocks
     int bww;         // 32-bit words per block row
+    uint32_t bww_inv;    // floor(2^32 / bww) + 1: __umulhi(x, bww_inv) = x / bww or one more (x * bww < 2^32)
     // per-image strides (in elements of the respective arrays)
     int64_t bits_stride;   // uint32 words
     int64_t cf_stride;     // uint32 words (C and F have the same shape)
@@ -53,6 +54,7 @@ static inline CclGeom make_ccl_geom(int w, int h) {
     g.bw = (w + 1) / 2;
     g.bh = (h + 1) / 2;
     g.bww = (g.bw + 31) / 32;
+    g.bww_inv = (uint32_t)((1ull << 32) / (uint64_t)g.bww) + 1u;
     g.bits_stride = (int64_t)h * g.wpr;
     g.cf_stride = (int64_t)g.bh * g.bww;
     g.lab_stride = (int64_t)g.bh * g.bw;

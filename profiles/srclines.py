@@ -11,8 +11,10 @@ def main():
     path = sys.argv[1]
     want = sys.argv[2] if len(sys.argv) > 2 else ""
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                         capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+    if want:
+        cmd += ["-k", "regex:" + want]       # without a filter ncu prints only the first kernels of a big report
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     state = dict(kernel=None, data=[], ie=None, si=None)
 
