@@ -364,14 +364,21 @@ __global__ void __launch_bounds__(kSegThreads, 1) chain_mask_seg_kernel(const Ma
                     const uint32_t R01 = __byte_perm(rx, ry, 0x0502) & 0x00ff00ffu;
                     const uint32_t B23 = __byte_perm(ry, rz, 0x0502) & 0x00ff00ffu, G23 = __byte_perm(ry, rz, 0x0603) & 0x00ff00ffu;
                     const uint32_t R23 = __byte_perm(rz, 0u, 0x4340);
-                    const uint32_t V01 = __vimax3_s16x2(B01, G01, R01), V23 = __vimax3_s16x2(B23, G23, R23);
+                    // max with predicates (DPX): gb = (g >= b), rm = (r >= max(b, g)) per pixel — OpenCV's hue sector
+                    // (v == r first, then v == g, else b) falls out of the max computation for free
+                    bool gb0, gb1, gb2, gb3, rm0, rm1, rm2, rm3;
+                    const uint32_t X01 = __vibmax_s16x2(G01, B01, &gb1, &gb0), X23 = __vibmax_s16x2(G23, B23, &gb3, &gb2);
+                    const uint32_t V01 = __vibmax_s16x2(R01, X01, &rm1, &rm0), V23 = __vibmax_s16x2(R23, X23, &rm3, &rm2);
                     const uint32_t D01 = V01 - __vimin3_s16x2(B01, G01, R01), D23 = V23 - __vimin3_s16x2(B23, G23, R23);
                     const uint32_t I01 = (V01 << 8) | D01, I23 = (V23 << 8) | D23;
                     const uint32_t M = (uint32_t)lut[I01 & 0xffffu] | ((uint32_t)lut[I01 >> 16] << 8) |
                                        ((uint32_t)lut[I23 & 0xffffu] << 16) | ((uint32_t)lut[I23 >> 16] << 24);
                     const uint32_t hit = (M & 0x80808080u) >> 7;
                     uint32_t ex = ((hit * 0x00204081u) >> 21) & 15u;        // bit 7 of every byte -> 4 adjacent bits
-                    const uint32_t M2 = M & 0x7f7f7f7fu & ~(hit * 0x7fu);   // hue-filter candidates of pixels not keyed out yet
+                    // hue filters whose range the pixel's sector can reach at all (a bluish object never meets an orange filter)
+                    const uint32_t S = (rm0 ? sm_r : gb0 ? sm_g : sm_b) | ((rm1 ? sm_r : gb1 ? sm_g : sm_b) << 8) |
+                                       ((rm2 ? sm_r : gb2 ? sm_g : sm_b) << 16) | ((rm3 ? sm_r : gb3 ? sm_g : sm_b) << 24);
+                    const uint32_t M2 = M & S & ~(hit * 0x7fu);             // hue-filter candidates of pixels not keyed out yet
                     // hue test of the candidates, one pixel per iteration and lane (bytes re-read from the tile): a lane
                     // with a single bright speck loops once, a lane inside the object four times
                     uint32_t m = M2;
@@ -382,12 +389,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) chain_mask_seg_kernel(const Ma
                         const uint8_t* t = tile + boff + 3 * k;
                         const int b = t[0], g = t[1], r = t[2];
                         const int v = max(max(b, g), r), d = v - min(min(b, g), r);
-                        // hue sector of the pixel (max channel) -> filters whose hue range can contain it at all
-                        const uint32_t sm = (v == r) ? sm_r : (v == g) ? sm_g : sm_b;
-                        if (cand & sm) {
-                            const int hh = hue_of(b, g, r, v, d, hdiv);
-                            if (h2f[hh] & cand) ex |= 1u << k;
-                        }
+                        const int hh = hue_of(b, g, r, v, d, hdiv);
+                        if (h2f[hh] & cand) ex |= 1u << k;
                     }
                     uint32_t nb = ~ex & 15u;
                     const int left = npx - 4 * hg;                          // partial last group of the row
