@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
     ap.add_argument("--main-priority", type=int, default=0, help="priority boost of the stream that runs stages B2/C (0 = default stream)")
+    ap.add_argument("--stage-a-stream", default="side", choices=["side", "caller"])
+    ap.add_argument("--slots", type=int, default=2, help="keep-mask workspaces of the ChainStream (>= ahead + 1)")
     ap.add_argument("--pipes", type=int, default=1, help="independent chain streams per GPU, each on batch/pipes frames")
     ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
@@ -251,7 +253,7 @@ def main():
     P = max(1, args.pipes)
     part = B // P
     assert part * P == B, "--batch must be a multiple of --pipes"
-    pipes = [chain.ChainStream(params, inputs_ready=True, slots=args.ahead + 1) for _ in range(P)]   # inputs are resident
+    pipes = [chain.ChainStream(params, inputs_ready=True, slots=max(args.slots, args.ahead + 1), stage_a_stream=args.stage_a_stream) for _ in range(P)]   # inputs are resident
     pstreams = [torch.cuda.Stream(dev) for _ in range(P)] if P > 1 else [None]
     prngs = [random.Random() for _ in range(P)] if P > 1 else [random]
     parts = [(frames_d[i * part:(i + 1) * part], bgs_d[i * part:(i + 1) * part]) for i in range(P)]

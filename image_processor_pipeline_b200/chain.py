@@ -520,11 +520,14 @@ class ChainStream:
 
     _count = 0
 
-    def __init__(self, params: ChainParams, inputs_ready: bool = False, slots: int = 2, **run_kw):
+    def __init__(self, params: ChainParams, inputs_ready: bool = False, slots: int = 2, stage_a_stream: str = "side", **run_kw):
         if slots < 2:
             raise ValueError("ChainStream needs at least two keep-mask slots")
         self.params, self.run_kw, self._n = params, run_kw, 0
         self.inputs_ready = bool(inputs_ready)
+        if stage_a_stream not in ("side", "caller"):
+            raise ValueError("stage_a_stream must be 'side' or 'caller'")
+        self.stage_a_stream = stage_a_stream    # "caller": stage A is queued on the caller's stream (no kernel concurrency)
         self.slots = int(slots)                 # batches that may be between submit() and the end of their stage B2
         self._slot_free = [None] * self.slots   # event: stages B2/C of the batch that last used the slot are done
         self._pending = None                    # deferred table verification of the previous batch
@@ -538,7 +541,9 @@ class ChainStream:
         slot = self._n % self.slots
         waits = [self._slot_free[slot]] if self._slot_free[slot] is not None else []
         ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=slot, wait_events=waits,
-                                  wait_current=not self.inputs_ready, tag=self.tag, stream=self._stream(self._side, frames.device, 0))
+                                  wait_current=not self.inputs_ready, tag=self.tag,
+                                  stream=torch.cuda.current_stream(frames.device) if self.stage_a_stream == "caller"
+                                  else self._stream(self._side, frames.device, 0))
         ticket["backgrounds"] = backgrounds
         self._n += 1
         return ticket
