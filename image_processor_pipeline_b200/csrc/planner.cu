@@ -84,11 +84,62 @@ struct PyRandom {
     }
 };
 
-// round(x, 15) of Python: exact decimal rounding (half-even on the exact binary value), then back
+// round_half_even(|x| * 10^digits) on the EXACT binary value of x (128-bit integer arithmetic) — what printf("%.*f")
+// and Python's round(x, n) compute, without going through a decimal string.  false: outside the fast range.
+static bool scaled_round(double x, int digits, uint64_t* out) {
+    static const uint64_t P10[16] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+                                     1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+                                     100000000000000ull, 1000000000000000ull};
+    if (!(x == x) || digits < 0 || digits > 15) return false;
+    const double ax = std::fabs(x);
+    if (ax >= 4096.0) return false;
+    if (ax == 0.0) { *out = 0; return true; }
+    int ex;
+    const double f = std::frexp(ax, &ex);                       // ax = f * 2^ex, f in [0.5, 1)
+    const uint64_t m = (uint64_t)std::ldexp(f, 53);             // exact: 53-bit integer
+    const int sh = 53 - ex;                                     // ax = m * 2^-sh, sh >= 41 here
+    const unsigned __int128 N = (unsigned __int128)m * P10[digits];     // < 2^53 * 2^50
+    if (sh >= 127) { *out = 0; return true; }                   // ax * 10^digits < 2^-24: rounds to 0
+    const unsigned __int128 one = 1;
+    unsigned __int128 q = N >> sh;
+    const unsigned __int128 r = N & ((one << sh) - 1), half = one << (sh - 1);
+    if (r > half || (r == half && (q & 1))) ++q;
+    *out = (uint64_t)q;
+    return true;
+}
+
+// round(x, 15) of Python: exact decimal rounding (half-even on the exact binary value), then the nearest double
+// to that decimal = the correctly rounded quotient of two exactly representable numbers
 static double round15(double x) {
+    uint64_t q;
+    if (scaled_round(x, 15, &q) && q < (1ull << 53)) return std::copysign((double)q / 1e15, x);
     char buf[400];
     snprintf(buf, sizeof(buf), "%.15f", x);
     return strtod(buf, nullptr);
+}
+
+// "%.6f" of a non-negative value + the float64 np.loadtxt reads back from that text.  Returns the number of
+// characters written (no terminator).
+static int fmt6(char* dst, double v, double* parsed) {
+    uint64_t q;
+    if (v >= 0.0 && scaled_round(v, 6, &q)) {
+        const uint64_t ip = q / 1000000ull;
+        uint32_t fp = (uint32_t)(q % 1000000ull);
+        char tmp[24];
+        int n = 0;
+        uint64_t t = ip;
+        do { tmp[n++] = (char)('0' + t % 10); t /= 10; } while (t);
+        int len = 0;
+        while (n) dst[len++] = tmp[--n];
+        dst[len++] = '.';
+        for (int i = 5; i >= 0; --i) { dst[len + i] = (char)('0' + fp % 10); fp /= 10; }
+        len += 6;
+        if (parsed) *parsed = (double)q / 1e6;
+        return len;
+    }
+    const int len = snprintf(dst, 48, "%.6f", v);
+    if (parsed) *parsed = strtod(dst, nullptr);
+    return len;
 }
 static double py_fmod360(double a) {
     double m = std::fmod(a, 360.0);
@@ -113,7 +164,8 @@ static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r) {
     if (angle == 90.0 || angle == 270.0) { r->kind = angle == 90.0 ? 3 : 4; r->canvas_w = h; r->canvas_h = w; return 0; }
     const double cx = w / 2.0, cy = h / 2.0;
     const double a = -(angle * (M_PI / 180.0));
-    double m[6] = {round15(std::cos(a)), round15(std::sin(a)), 0.0, round15(-std::sin(a)), round15(std::cos(a)), 0.0};
+    const double rc = round15(std::cos(a)), rs = round15(std::sin(a));       // round(-x, 15) == -round(x, 15)
+    double m[6] = {rc, rs, 0.0, -rs, rc, 0.0};
     auto tfx = [&](double x, double y) { return m[0] * x + m[1] * y + m[2]; };
     auto tfy = [&](double x, double y) { return m[3] * x + m[4] * y + m[5]; };
     {
@@ -338,7 +390,7 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
             if (present[by_name[k]]) variants.push_back({r, by_name[k], fx, fy, sw, sh});
     }
     // ---- overlay step (overlays.py:104-149)
-    struct Ov { Var v; int bg, nw, nh, px, py; double ratio; char label[96]; };
+    struct Ov { Var v; int bg, nw, nh, px, py; double ratio; double box[4]; };   // box: the label's numbers as np.loadtxt reads them
     std::vector<Ov> overlays;
     overlays.reserve(variants.size());
     for (size_t k = 0; k < variants.size(); ++k) {
@@ -356,7 +408,11 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
         const long long x1 = o.px, y1 = o.py, x2 = o.px + o.nw, y2 = o.py + o.nh;
         const float cx = (float)(((double)(x1 + x2) / 2.0) / (double)BW), cy = (float)(((double)(y1 + y2) / 2.0) / (double)BH);
         const float wn = (float)((double)(x2 - x1) / (double)BW), hn = (float)((double)(y2 - y1) / (double)BH);
-        snprintf(o.label, sizeof(o.label), "%d %.6f %.6f %.6f %.6f", p->yolo_class_id, (double)cx, (double)cy, (double)wn, (double)hn);
+        {   // label text "{cls} {cx:.6f} {cy:.6f} {w:.6f} {h:.6f}" (overlays.py:149): only its parsed-back numbers are needed
+            char scratch[48];
+            fmt6(scratch, (double)cx, &o.box[0]); fmt6(scratch, (double)cy, &o.box[1]);
+            fmt6(scratch, (double)wn, &o.box[2]); fmt6(scratch, (double)hn, &o.box[3]);
+        }
         overlays.push_back(o);
     }
     // ---- square-crop step (crop_square.py:62-65,163-217) + records
@@ -365,14 +421,8 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
     const int cs = BW < BH ? BW : BH;
     for (const Ov& o : overlays) {
         // np.loadtxt: class id and the four 6-decimal numbers back to float64
-        int cls = 0;
-        double b[4];
-        {
-            const char* s = o.label;
-            char* end;
-            cls = (int)strtod(s, &end);       // data[:, 0].astype(int)
-            for (int i = 0; i < 4; ++i) { s = end; b[i] = strtod(s, &end); }
-        }
+        const int cls = p->yolo_class_id;      // data[:, 0].astype(int)
+        const double* b = o.box;
         // xywhn2xyxy: float64 expression, float32 store
         const float ax1 = (float)((double)BW * (b[0] - b[2] / 2.0)), ay1 = (float)((double)BH * (b[1] - b[3] / 2.0));
         const float ax2 = (float)((double)BW * (b[0] + b[2] / 2.0)), ay2 = (float)((double)BH * (b[1] + b[3] / 2.0));
@@ -390,8 +440,15 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
         const float nwn = (float)((x2 - x1) / (double)cs), nhn = (float)((y2 - y1) / (double)cs);
 
         IPP_REQUIRE(n < capacity, IPP_ERR_WORKSPACE, "ipp_plan_items_host: capacity %d too small", capacity);
-        char row[160];
-        const int len = snprintf(row, sizeof(row), "%d %.6f %.6f %.6f %.6f\n", cls, (double)ncx, (double)ncy, (double)nwn, (double)nhn);
+        char row[256];
+        int len = snprintf(row, 16, "%d", cls);
+        const float vals[4] = {ncx, ncy, nwn, nhn};
+        for (int i = 0; i < 4; ++i) {
+            row[len++] = ' ';
+            len += fmt6(row + len, (double)vals[i], nullptr);
+        }
+        row[len++] = '\n';
+        row[len] = 0;
         IPP_REQUIRE(lpos + (size_t)len + 1 <= (size_t)labels_capacity, IPP_ERR_WORKSPACE, "ipp_plan_items_host: label buffer too small");
         memcpy(labels_out + lpos, row, (size_t)len + 1);
         lpos += (size_t)len + 1;
@@ -416,6 +473,15 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
     if (lrc != IPP_OK) return lrc;
     totals_out->labels_bytes = (int32_t)lpos;
     return IPP_OK;
+}
+
+// the planner's exact-decimal helpers, exported so that tests can hold them against Python's round() / "%.6f"
+double ipp_host_round15(double x) { return ipp::plan::round15(x); }
+int ipp_host_format6(double v, char* text_out48, double* parsed_out) {
+    if (!text_out48) return -1;
+    const int len = ipp::plan::fmt6(text_out48, v, parsed_out);
+    text_out48[len] = 0;
+    return len;
 }
 
 // one exact table row (libm sin) for the rare fix-up of rows the device flagged as ambiguous

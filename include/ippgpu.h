@@ -294,6 +294,11 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
                         ipp_chain_item* items_out, ipp_plan_aux* aux_out, int capacity, int32_t* n_items_out,
                         char* labels_out, int labels_capacity, ipp_plan_totals* totals_out);
 int ipp_lanczos_row_host(int in_size, int out_size, int xx, int32_t* bounds2_host, int32_t* kk_row_host);
+/* Exact-decimal helpers of the planner (128-bit integer arithmetic on the binary value, no printf on the hot
+ * path): Python's round(x, 15) (PIL:Image.py:2541-2548 rounds the rotation matrix) and "%.6f" of a label number
+ * together with the float64 np.loadtxt reads back from that text (overlays.py:149, crop_square.py:62-65,98-101). */
+double ipp_host_round15(double x);
+int ipp_host_format6(double v, char* text_out48, double* parsed_out);
 /* Device-side schedule of an item array (sizes, kind, flips, positions already set): coefficient-table
  * and fragment-table offsets, flat tile starts, sprite-workspace offsets, out_slot = index.  Called by
  * ipp_plan_items_host; exported for callers that assemble item arrays themselves. */

@@ -107,3 +107,31 @@ def test_hypot_and_round15_conventions():
         x = r.uniform(-1, 1)
         assert float(f"{x:.15f}") == round(x, 15)
     assert math.hypot(1920, 1080) == math.sqrt(1920 ** 2 + 1080 ** 2)
+
+
+def test_exact_decimal_helpers_match_python():
+    """round(x, 15) and "%.6f" + float() of the planner's integer fast paths vs Python, incl. exact ties,
+    values next to ties, tiny / large magnitudes and float32-valued inputs (what labels hold)."""
+    import ctypes as C
+    import math
+    import struct
+    lib = _native.load()
+    r = np.random.default_rng(3)
+    xs = list(r.uniform(-1, 1, 20000)) + list(np.cos(r.uniform(0, 7, 5000))) + [0.0, 1.0, -1.0, 0.5, 1e-16, -3e-17, 2.5e-16, 0.1, 0.3,
+                                                                                   1e-300, 5e-16, 15e-16 / 2, 0.9999999999999996]
+    for k in range(2000):                                      # neighbours of 15-decimal ties
+        t = (int(r.integers(0, 10 ** 15)) + 0.5) / 1e15
+        xs += [t, math.nextafter(t, 0.0), math.nextafter(t, 2.0)]
+    for x in xs:
+        assert lib.ipp_host_round15(float(x)) == round(float(x), 15), x
+    vs = list(r.uniform(0, 1, 20000).astype(np.float32).astype(np.float64)) + list(r.uniform(0, 1, 5000)) + [0.0, 1.0, 0.5, 1e-7, 5e-7, 4.9999999e-7,
+                                                                                                            0.9999995, 0.99999949, 2.0000005, 1234.5678915, 1e-30]
+    for k in range(2000):                                      # exact 6-decimal ties representable in binary: k / 64 + odd multiples of 2^-k
+        vs += [(int(r.integers(0, 10 ** 6)) + 0.5) / 1e6, int(r.integers(0, 2 ** 20)) / 2 ** 20, int(r.integers(0, 2 ** 7)) / 2 ** 7]
+    buf = C.create_string_buffer(64)
+    parsed = C.c_double()
+    for v in vs:
+        n = lib.ipp_host_format6(float(v), buf, C.byref(parsed))
+        want = "%.6f" % float(v)
+        assert buf.value.decode() == want and n == len(want), (v, buf.value, want)
+        assert parsed.value == float(want), v
