@@ -693,8 +693,9 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
 // the input bytes exactly, so both kernels have a single code path.
 constexpr int kPrec = 32 - 8 - 2;
 __device__ __forceinline__ uint32_t c_clip8(int v) {
-    v >>= kPrec;
-    return (uint32_t)min(max(v, 0), 255);
+    uint32_t r;
+    asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v >> kPrec));      // clamp to [0, 255] in one instruction
+    return r;
 }
 __device__ __forceinline__ uint32_t c_unpremultiply(uint32_t v) {
     const uint32_t a = v >> 24;
@@ -802,18 +803,18 @@ __device__ __forceinline__ void load_band(uint2 (&b)[6], const uint2* frag) {
     for (int q = 0; q < 6; ++q) b[q] = __ldg(frag + q * 32);
 }
 // 16 rows of one byte plane -> acc.  lo / hi: the staged first super-block words of rows g, g+8; further
-// super-blocks (rare: scale factors above ~3.5) are fetched here from the rows row_lo / row_hi of `plane`.
+// super-blocks (rare: scale factors above ~3.5) are fetched here through r_lo (row g; row g + 8 is 8 * pitch further).
 // acc[0] starts at the rounding constant 2^21 of clip8((2^21 + sum) >> 22).
-__device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint8_t* plane, int64_t pitch,
-                                         int row_lo, int row_hi, const uint2 (&b0)[6], const uint2* frag, int nsb) {
+__device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, const uint4& hi, const uint8_t* r_lo, int64_t pitch,
+                                         const uint2 (&b0)[6], const uint2* frag, int nsb) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { acc[0][i] = 1 << (kPrec - 1); acc[1][i] = 0; acc[2][i] = 0; }
     mma_superblock(acc, lo, hi, b0);
     for (int sb = 1; sb < nsb; ++sb) {
         uint2 b[6];
         load_band(b, frag + sb * 192);
-        const uint4 lo2 = *reinterpret_cast<const uint4*>(plane + (int64_t)row_lo * pitch + 64 * sb);
-        const uint4 hi2 = *reinterpret_cast<const uint4*>(plane + (int64_t)row_hi * pitch + 64 * sb);
+        const uint4 lo2 = *reinterpret_cast<const uint4*>(r_lo + 64 * sb);
+        const uint4 hi2 = *reinterpret_cast<const uint4*>(r_lo + 8 * pitch + 64 * sb);
         mma_superblock(acc, lo2, hi2, b);
     }
 }
@@ -824,14 +825,13 @@ __device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, cons
 // stage: lane (g, t) = 4g + t stages exactly the two 16-byte pieces (row g, row g + 8; column 16 t) it later reads
 // back as its A-fragment words — no cross-lane traffic, conflict-free 128-bit shared accesses.
 constexpr int kRing = 4;
-__device__ __forceinline__ void ring_issue(uint8_t* stage, const uint8_t* plane, int64_t pitch, int row0, int n_rows, bool valid, int lane) {
+// g0: this lane's piece of rows 0..7 of the tile (row lane / 4, column 16 * (lane % 4)); rows 8..15 are 8 * pitch further.
+// Rows past the end of a plane are NOT clamped: the planes of a sprite are adjacent and its workspace is padded by
+// 16 rows (ipp_chain_layout_host), so the reads stay inside the buffer; their results are never stored.
+__device__ __forceinline__ void ring_issue(uint8_t* stage, const uint8_t* g0, int64_t pitch, bool valid, int lane) {
     if (valid) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int id = lane + 32 * j;
-            const uint8_t* gsrc = plane + (int64_t)min(row0 + (id >> 2), n_rows - 1) * pitch + 16 * (id & 3);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stage + 16 * id)), "l"(gsrc) : "memory");
-        }
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stage + 16 * lane)), "l"(g0) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(stage + 16 * lane + 512)), "l"(g0 + 8 * pitch) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");          // (possibly empty) group: keeps the wait count uniform
 }
@@ -870,16 +870,23 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     load_band(b0, frag);
     const int n_rt = (spr_h + 15) >> 4;
     uint8_t* ring = s_ring[warp][0];
-    const uint8_t* col0 = src - 16 * t;                            // first column of the window (src includes the lane's 16 t)
+    const int64_t tile_step = 16 * Wp;
+    const uint8_t* gnext = src - 16 * t + (int64_t)(lane >> 2) * Wp + 16 * (lane & 3);     // this lane's staging piece of tile 0
+    const uint8_t* rcur = src + (int64_t)g * Wp;                                            // row g of the current tile (extra super-blocks)
 #pragma unroll
-    for (int d = 0; d < kRing - 1; ++d) ring_issue(ring + 1024 * d, col0, Wp, 16 * d, spr_h, d < n_rt, lane);
+    for (int d = 0; d < kRing - 1; ++d) {
+        ring_issue(ring + 1024 * d, gnext, Wp, d < n_rt, lane);
+        gnext += tile_step;
+    }
     for (int ti = 0; ti < n_rt; ++ti) {
         ring_wait();                                               // tile ti has landed (this lane's own two pieces)
         const uint8_t* stg = ring + 1024 * (ti % kRing);
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
-        ring_issue(ring + 1024 * ((ti + kRing - 1) % kRing), col0, Wp, 16 * (ti + kRing - 1), spr_h, ti + kRing - 1 < n_rt, lane);
+        ring_issue(ring + 1024 * ((ti + kRing - 1) % kRing), gnext, Wp, ti + kRing - 1 < n_rt, lane);
+        gnext += tile_step;
         int acc[3][4];
-        mma_rows(acc, lo, hi, src, Wp, min(16 * ti + g, spr_h - 1), min(16 * ti + g + 8, spr_h - 1), b0, frag, nsb);
+        mma_rows(acc, lo, hi, rcur, Wp, b0, frag, nsb);
+        rcur += tile_step;
         const int m = ti & 1, y0 = (ti & ~1) << 4;
         // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1}
 #pragma unroll
@@ -937,21 +944,27 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     const int x_begin = xchunk * 128;
     const int n_steps = ((x_end - x_begin + 15) >> 4) * 4;
     uint8_t* ring = s_ring[warp][0];
-    const uint8_t* col0 = src - 16 * t;
-    auto issue = [&](int step) {
-        ring_issue(ring + 1024 * (step % kRing), col0 + (int64_t)(step & 3) * plane, Hp, x_begin + 16 * (step >> 2), new_w, step < n_steps, lane);
+    // pointers advance plane by plane (4 steps), then to the next 16 columns
+    const int64_t back = 16 * Hp - 3 * plane;
+    const uint8_t* gnext = src - 16 * t + (int64_t)(x_begin + (lane >> 2)) * Hp + 16 * (lane & 3);
+    const uint8_t* rcur = src + (int64_t)(x_begin + g) * Hp;
+    int issued = 0;
+    auto issue = [&]() {
+        ring_issue(ring + 1024 * (issued % kRing), gnext, Hp, issued < n_steps, lane);
+        gnext += ((issued & 3) == 3) ? back : plane;
+        ++issued;
     };
 #pragma unroll
-    for (int d = 0; d < kRing - 1; ++d) issue(d);
+    for (int d = 0; d < kRing - 1; ++d) issue();
     uint32_t px[4] = {0u, 0u, 0u, 0u};
     for (int step = 0; step < n_steps; ++step) {
         ring_wait();
         const uint8_t* stg = ring + 1024 * (step % kRing);
         const uint4 lo = *reinterpret_cast<const uint4*>(stg + 16 * lane), hi = *reinterpret_cast<const uint4*>(stg + 16 * lane + 512);
-        issue(step + kRing - 1);
+        issue();
         int acc[3][4];
-        const int xr = x_begin + 16 * (step >> 2) + g;
-        mma_rows(acc, lo, hi, src + (int64_t)(step & 3) * plane, Hp, min(xr, new_w - 1), min(xr + 8, new_w - 1), b0, frag, nsb);
+        mma_rows(acc, lo, hi, rcur, Hp, b0, frag, nsb);
+        rcur += ((step & 3) == 3) ? back : plane;
         const int pl = step & 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

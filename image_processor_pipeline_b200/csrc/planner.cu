@@ -327,8 +327,9 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
         IPP_REQUIRE(gt < (1LL << 31) && ht < (1LL << 31) && vt < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_chain_layout_host: too many tiles");
         // planar premultiplied sprite [4][sh][Wp], transposed planar h-pass result [4][nw][Hp], final RGBA sprite
         const int64_t Wp = (sw + 15) & ~15, Hp = (sh + 15) & ~15;
-        it->rot_off = woff; woff = align_up(woff + 4 * (int64_t)sh * Wp + 512, 256);
-        it->tmp_off = woff; woff = align_up(woff + 4 * (int64_t)nw * Hp + 512, 256);
+        // + 16 rows and 1 KB: the LANCZOS passes read whole 16-row tiles and 64-byte windows without clamping
+        it->rot_off = woff; woff = align_up(woff + (4 * (int64_t)sh + 16) * Wp + 1024, 256);
+        it->tmp_off = woff; woff = align_up(woff + (4 * (int64_t)nw + 16) * Hp + 1024, 256);
         it->spr_off = woff; woff = align_up(woff + (int64_t)nw * nh * 4, 256);
         it->out_slot = i;
     }
