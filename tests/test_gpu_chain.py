@@ -276,3 +276,55 @@ def test_chain_stream_pipelining_is_transparent(inputs_ready, run_kw):
         assert sum(flagged) > 0
     for (a, la), r in zip(plain, results):
         assert la == r.labels and np.array_equal(a, r.images.cpu().numpy())
+
+
+@pytest.mark.parametrize("sizes", [((37, 53), (37, 20)),        # width unchanged: identity band in the horizontal pass
+                                   ((64, 40), (23, 40)),        # height unchanged: identity band in the vertical pass
+                                   ((40, 30), (95, 77)),        # up-scaling (3-tap support, scale < 1)
+                                   ((700, 520), (41, 33)),      # 17x down: several 64-wide super-blocks per tile
+                                   ((301, 7), (9, 5)), ((5, 300), (4, 11)), ((1, 1), (3, 2)), ((129, 130), (128, 129))])
+def test_tensor_core_lanczos_passes_vs_pillow(sizes):
+    """The two LANCZOS kernels alone (stage B2 without the gather): planar premultiplied sprites written by the
+    test, device tables + exact fix-up, result against PIL.Image.resize(LANCZOS) — bit-exact, for identity
+    passes, up-scaling and extreme down-scaling (paths the chain's own size distribution rarely reaches)."""
+    import ctypes as C
+    from PIL import Image
+    from image_processor_pipeline_b200 import _native, hostmath
+    lib = _native.load()
+    (sw, sh), (nw, nh) = sizes
+    r = np.random.default_rng(sw * 1000 + nw)
+    n = 3
+    rgba = r.integers(0, 256, (n, sh, sw, 4), dtype=np.uint8)
+    rgba[..., 3] = np.where(r.random((n, sh, sw)) < 0.7, 255, 0)          # alpha as the chain has it: 0 or 255
+    rgba[rgba[..., 3] == 0] = 0
+    items = np.zeros(n, dtype=chain.ITEM_DTYPE)
+    items["spr_w"], items["spr_h"], items["new_w"], items["new_h"] = sw, sh, nw, nh
+    tot = chain._layout(items)
+    ws = torch.zeros(tot["ws"], dtype=torch.uint8, device=DEV)
+    Wp = (sw + 15) & ~15
+    for i in range(n):                                                     # [4][sh][Wp] byte planes at rot_off
+        planes = np.zeros((4, sh, Wp), np.uint8)
+        planes[:, :, :sw] = np.moveaxis(rgba[i], 2, 0)
+        off = int(items[i]["rot_off"])
+        ws[off:off + planes.size] = torch.from_numpy(planes.reshape(-1)).to(DEV)
+    geom = chain._geom_struct(64, 64, (0, 0, 64, 64), 64, 64, hostmath.pack_hsv_ranges(synth.REFERENCE_FILTERS))
+    items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)
+    tab_d = torch.zeros(max(1, tot["table_ints"]), dtype=torch.int32, device=DEV)
+    amb_d = torch.zeros(1 + 3 * chain.AMB_CAPACITY, dtype=torch.int32, device=DEV)
+    band_d = torch.zeros(max(tot["band_bytes"], 256), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    if tot["max_rows"]:
+        _native.check(lib.ipp_chain_tables(items_d.data_ptr(), n, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
+                                           chain.AMB_CAPACITY, chain.AMBIGUITY_EPS, st), "tables")
+        host = chain._host_tables(items, lib, tot["table_ints"])
+        assert np.array_equal(tab_d.cpu().numpy()[:len(host)], host) or int(amb_d[0]) > 0
+        tab_d[:len(host)] = torch.from_numpy(host).to(DEV)                 # exact tables: this test is about the passes
+    dummy = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)           # frames / mask workspace are not touched (no gather)
+    _native.check(lib.ipp_chain_stage_b2(dummy.data_ptr(), 64 * 3, 64 * 64 * 3, C.byref(geom), items_d.data_ptr(), n, 0, tot["ht"], tot["vt"],
+                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], dummy.data_ptr(), ws.data_ptr(), st), "b2")
+    out = ws.cpu().numpy()
+    for i in range(n):
+        off = int(items[i]["spr_off"])
+        mine = out[off:off + nw * nh * 4].reshape(nh, nw, 4)
+        ref = np.asarray(Image.fromarray(rgba[i], "RGBA").resize((nw, nh), Image.Resampling.LANCZOS))
+        assert np.array_equal(mine, ref), (i, int((mine != ref).sum()))
