@@ -383,6 +383,8 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
             const int2* L = b.la + (int64_t)t.img * g.lab_stride;
             const int rowbase = t.by * g.bw, gb0 = t.k << 5;
             uint32_t starts = Fall & (~C | 1u), keep = 0;
+            // only isolated runs here and the winner is not one of them: nothing is kept, no need to walk the runs
+            if (F == 0u && (unsigned)(best_root - (rowbase + gb0)) >= 32u) starts = 0u;
             while (starts) {
                 const int i = __ffs(starts) - 1;
                 starts &= starts - 1;
