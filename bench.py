@@ -55,8 +55,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _shifts(n: int, seed: int, first: int):
+    out = []
+    for i in range(n):
+        r = np.random.default_rng(seed * 7_000_003 + first + i)
+        out.append((int(r.integers(-120, 121)), int(r.integers(-300, 301)), int(r.integers(0, FH)), int(r.integers(0, FW))))
+    return out
+
+
 def make_inputs(n: int, seed: int, first: int = 0, base: int = 8):
-    """n frames + n backgrounds.  `base` distinct synthetic frames are generated with numpy
+    """n frames + n backgrounds (numpy, host).  `base` distinct synthetic frames are generated with numpy
     (synth.frame, ~0.4 s each) and multiplied by cyclic shifts so that every frame of the
     batch has different content and object position at negligible generation cost."""
     from image_processor_pipeline_b200 import synth
@@ -64,12 +72,26 @@ def make_inputs(n: int, seed: int, first: int = 0, base: int = 8):
     bgb = [synth.background(seed, k, FH, FW) for k in range(base)]
     frames = np.empty((n, FH, FW, 3), np.uint8)
     bgs = np.empty((n, FH, FW, 3), np.uint8)
-    for i in range(n):
+    for i, (dy, dx, by, bx) in enumerate(_shifts(n, seed, first)):
         g = first + i
-        r = np.random.default_rng(seed * 7_000_003 + g)
-        dy, dx = int(r.integers(-120, 121)), int(r.integers(-300, 301))
         frames[i] = np.roll(bases[g % base], (dy, dx), axis=(0, 1))
-        bgs[i] = np.roll(bgb[g % base], (int(r.integers(0, FH)), int(r.integers(0, FW))), axis=(0, 1))
+        bgs[i] = np.roll(bgb[g % base], (by, bx), axis=(0, 1))
+    return frames, bgs
+
+
+def make_inputs_device(n: int, seed: int, first: int, dev, base: int = 8):
+    """The same n frames + backgrounds as make_inputs, built on the device: only the `base` images are generated on
+    the host; the cyclic shifts are torch.roll on the GPU (no n x 12 MB host copies per rank)."""
+    import torch
+    from image_processor_pipeline_b200 import synth
+    bases = torch.from_numpy(np.stack([synth.frame(seed, k, FH, FW) for k in range(base)])).to(dev)
+    bgb = torch.from_numpy(np.stack([synth.background(seed, k, FH, FW) for k in range(base)])).to(dev)
+    frames = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
+    bgs = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
+    for i, (dy, dx, by, bx) in enumerate(_shifts(n, seed, first)):
+        g = first + i
+        frames[i] = torch.roll(bases[g % base], (dy, dx), dims=(0, 1))
+        bgs[i] = torch.roll(bgb[g % base], (by, bx), dims=(0, 1))
     return frames, bgs
 
 
@@ -207,6 +229,7 @@ def main():
     ap.add_argument("--pipes", type=int, default=1, help="independent chain streams per GPU, each on batch/pipes frames")
     ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames of the batch used by the end-to-end leg (0 = all)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -230,11 +253,7 @@ def main():
     params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
 
     # each rank owns a contiguous slice of the global work list (weak scaling: B frames per GPU)
-    frames_h, bgs_h = make_inputs(B, seed=1, first=rank * B)
-    frames_pin = torch.from_numpy(frames_h).pin_memory()
-    bgs_pin = torch.from_numpy(bgs_h).pin_memory()
-    frames_d = frames_pin.to(dev, non_blocking=True)
-    bgs_d = bgs_pin.to(dev, non_blocking=True)
+    frames_d, bgs_d = make_inputs_device(B, seed=1, first=rank * B, dev=dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -373,7 +392,13 @@ def main():
     # end to end through the host API: pinned host inputs, H2D + chain + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        out_pin = torch.empty((B, 1080, 1080, 3), dtype=torch.uint8).pin_memory()
+        # host buffers of the end-to-end leg: the same batch in pinned memory (B = 512: 8 GB per rank; the first slice's
+        # upload is not overlapped, so short batches under-report the PCIe-bound steady state: 4.80 k at 256, 5.05 k at 512)
+        E = min(B, args.e2e_frames) if args.e2e_frames else B
+        frames_pin = torch.empty((E, FH, FW, 3), dtype=torch.uint8).pin_memory()
+        bgs_pin = torch.empty((E, FH, FW, 3), dtype=torch.uint8).pin_memory()
+        frames_pin.copy_(frames_d[:E]); bgs_pin.copy_(bgs_d[:E])
+        out_pin = torch.empty((E, 1080, 1080, 3), dtype=torch.uint8).pin_memory()
 
         last = {}
 
@@ -386,7 +411,7 @@ def main():
 
         ems, en, _ = timed(step_e2e, max(2, args.steps // 2), 1)
         e2e = {"value": en / (ems * 1e-3), "unit": "images/s", "pipelined_slice_frames": args.e2e_chunk,
-               "h2d_bytes_per_step": int(last["h2d"]), "d2h_bytes_per_step": int(last["d2h"]),
+               "frames_per_step": E, "h2d_bytes_per_step": int(last["h2d"]), "d2h_bytes_per_step": int(last["d2h"]),
                "background_upload": "whole images" if args.no_bg_windows else
                "square-crop windows only (planned offsets known before the copy; cudaMemcpy2DAsync per item)"}
 
