@@ -256,7 +256,9 @@ typedef struct ipp_chain_item {
     int32_t nkb;                            /* 64-wide super-blocks (two MMA k-blocks) per 8-output tile: h | v << 16 */
     int64_t rot_off, tmp_off, spr_off;      /* byte offsets in the sprite workspace: planar premultiplied sprite
                                                [4][spr_h][Wp], transposed planar h-pass result [4][new_w][Hp],
-                                               final RGBA sprite [new_h][new_w][4]; Wp/Hp = spr_w/spr_h rounded up to 16 */
+                                               final RGBA sprite [new_h][new_w][4]; Wp/Hp = spr_w/spr_h rounded up to 16;
+                                               the two planar buffers carry 16 extra rows + 1 KB (the passes read
+                                               whole 16-row tiles and 64-byte windows without clamping) */
 } ipp_chain_item;
 
 /* ---- host planner (C++ twin of chain.py's planner; no device work) ------------------
