@@ -437,13 +437,18 @@ def _layout(items: np.ndarray):
     tot = _native.PlanTotals()
     _native.check(lib.ipp_chain_layout_host(items.ctypes.data, len(items), C.byref(tot)), "ipp_chain_layout_host")
     return dict(table_ints=int(tot.table_ints), max_rows=int(tot.max_rows), ws=int(tot.sprite_ws_bytes), gt=int(tot.gather_tiles),
-                ht=int(tot.h_tiles), vt=int(tot.v_tiles), band_bytes=int(tot.band_units) * 8, max_band_warps=int(tot.max_band_warps))
+                ht=int(tot.h_tiles), vt=int(tot.v_tiles), band_bytes=int(tot.band_units) * 8, max_band_warps=int(tot.max_band_warps),
+                fused_smem=int(tot.fused_smem_bytes))
 
 
-def _pass_tiles(items: np.ndarray):
-    """Flat tile counts of the two LANCZOS passes per item (chain_hpass_kernel / chain_vpass_kernel grids)."""
-    nw, nh = items["new_w"].astype(np.int64), items["new_h"].astype(np.int64)
-    return ((nw + 63) // 64) * 4, ((nh + 63) // 64) * ((nw + 127) // 128)
+def _pass_tiles(items: np.ndarray, fused: bool):
+    """Flat tile counts per item of the kernels a table fix-up re-runs: (gather, h, v).  Fused mode: the gather + h
+    kernel (one tile per 16 sprite rows) and the v pass; two-kernel mode: h and v passes on the gathered sprites."""
+    sh, nw, nh = (items[n].astype(np.int64) for n in ("spr_h", "new_w", "new_h"))
+    vt = ((nh + 63) // 64) * ((nw + 127) // 128)
+    if fused:
+        return (sh + 15) // 16, np.zeros_like(sh), vt
+    return np.zeros_like(sh), ((nw + 63) // 64) * 4, vt
 
 
 def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
@@ -538,6 +543,9 @@ class ChainStream:
         self.tag = f"#{ChainStream._count}"     # own workspaces: several ChainStreams may be in flight on one device
 
     def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor):
+        # the deferred table check of the last finished batch is looked at BEFORE a new stage A is queued: a fix-up
+        # re-gathers its sprites and needs that batch's keep-mask, which the new stage A may overwrite
+        self._resolve_pending()
         slot = self._n % self.slots
         waits = [self._slot_free[slot]] if self._slot_free[slot] is not None else []
         ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=slot, wait_events=waits,
@@ -747,7 +755,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         # ------------------------------------------------------------------ stage B2 + C
         def run_b2_c(items_dev, items_c_dev, k, gt, ht, vt):
             _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
-                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"],
+                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], tot["fused_smem"],
                                                  ws.data_ptr(), spr_ws.data_ptr(), _stream()),
                           "ipp_chain_stage_b2")
             if bg_ready is not None:
@@ -769,14 +777,14 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         res = ChainResult(out, labels, record_arrays=rec_arrays)
         if device_tables and _pipe is not None:
             res.tables_flagged_rows = res.tables_fixed_items = None   # known once the next finish() / flush() has looked
-            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev))
+            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev, tot["fused_smem"] > 0))
         elif device_tables:
             if _before_sync is not None:
                 _before_sync()                                        # e.g. queue the next uploads before the host waits
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
             _mark("sync3_amb")
             if n_amb:
-                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev)
+                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, tot["fused_smem"] > 0)
         for t in (rot_d, items_d, items_c_d):
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
@@ -788,7 +796,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     return finish(res, own.tolist())
 
 
-def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev) -> int:
+def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, fused: bool) -> int:
     """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C
     library's sin() (ipp_lanczos_row_host).  If a row really differs it is patched on the device and
     the h/v passes + paste of the affected items are re-run (their gathered sprites are still valid).
@@ -814,14 +822,14 @@ def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev)
             dirty.add(item)
     if dirty:
         sub = items[sorted(dirty)].copy()
-        ht, vt = _pass_tiles(sub)
-        sub["h_tile_start"], sub["v_tile_start"] = _excl(ht), _excl(vt)
+        gt, ht, vt = _pass_tiles(sub, fused)
+        sub["gather_tile_start"], sub["h_tile_start"], sub["v_tile_start"] = _excl(gt), _excl(ht), _excl(vt)
         sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
         sub_c = items_c[sorted(dirty)].copy()                  # stage C's view of the same items (host-window mode: shifted copies)
-        for name in ("h_tile_start", "v_tile_start"):
+        for name in ("gather_tile_start", "h_tile_start", "v_tile_start"):
             sub_c[name] = sub[name]
         sub_c_d = torch.from_numpy(sub_c.view(np.uint8)).to(dev)
-        run_b2_c(sub_d, sub_c_d, len(sub), 0, int(ht.sum()), int(vt.sum()))
+        run_b2_c(sub_d, sub_c_d, len(sub), int(gt.sum()), int(ht.sum()), int(vt.sum()))
         torch.cuda.current_stream().synchronize()
     return len(dirty)
 

@@ -910,6 +910,126 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     }
 }
 
+// ---- fused gather + horizontal pass.  The two kernels above exchange the gathered sprite through global memory
+// (1.7 MB written and re-read ~3.5x per 1080p sprite).  Here a CTA gathers SIXTEEN SPRITE ROWS x all columns x four byte
+// planes straight into shared memory (rows padded to 64 mod 128 bytes: the 128-bit A-fragment reads of a quarter warp
+// then hit all 32 banks) and its eight warps run the MMA tiles of those rows from there: no planar sprite in global
+// memory, no load latency in the MMA loop.  Used whenever the widest sprite of the batch fits (ipp_chain_layout_host).
+__host__ __device__ inline int gh_row_pitch(int spr_w) { return ((spr_w + 64 + 127) / 128) * 128 + 64; }   // >= spr_w + 128, == 64 mod 128
+constexpr int kGhTail = 1024;          // slack behind the planes: windows of multi-super-block tiles may run past the last row
+
+__global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
+    extern __shared__ __align__(128) uint8_t gh_smem[];
+    __shared__ int s_rec;
+    __shared__ __align__(16) uint8_t s_t[8][8 * 20];
+    if (threadIdx.x == 0)
+        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+    __syncthreads();
+    const ipp_chain_item& it = c.items[s_rec];
+    const int spr_w = it.spr_w, spr_h = it.spr_h, new_w = it.new_w;
+    const int y0 = ((int)blockIdx.x - it.gather_tile_start) * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Wps = gh_row_pitch(spr_w);
+    const int plane_bytes = 16 * Wps;
+
+    // ---------------------------------------------------------------- phase 1: gather rows y0 .. y0+15 into shared memory
+    {
+        const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, it.cc_w, it.cc_h};
+        const uint32_t* fb = c.bits + (int64_t)it.frame * c.bits_stride + (int64_t)it.cc_y * c.wpr;
+        const uint8_t* frame = c.frames + (int64_t)it.frame * c.stride + (int64_t)(c.crop_t + it.cc_y) * c.pitch +
+                               (int64_t)(c.crop_l + it.cc_x) * 3;
+        const uint32_t frame_lsb = (uint32_t)((uintptr_t)frame & 3);     // rect origin = 4-byte aligned base + 0..3
+        const uint8_t* frame_al = frame - frame_lsb;
+        const uint32_t pitch32 = (uint32_t)c.pitch;
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * warp + rr, Y = y0 + r;
+            if (Y >= spr_h) break;
+            const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
+            const int xx0 = it.a2 + cy * it.a1, yy0 = it.a5 + cy * it.a4;
+            uint8_t* drow = gh_smem + r * Wps;
+            for (int X0 = 0; X0 < spr_w; X0 += 128) {                   // four columns per lane in flight
+                uint32_t word[4], w0[4], w1[4];
+                int sh[4], bsh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int X = X0 + 32 * j + lane;
+                    const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
+                    int xin, yin;
+                    bool inside;
+                    if (it.kind == 0) {
+                        xin = (xx0 + cx * it.a0) >> 16;
+                        yin = (yy0 + cx * it.a3) >> 16;
+                        inside = (unsigned)xin < (unsigned)it.cc_w && (unsigned)yin < (unsigned)it.cc_h;
+                    } else {
+                        inside = map_canvas(m, cx, cy, xin, yin);
+                    }
+                    const bool use = inside && X < spr_w;
+                    if (!use) { xin = 0; yin = 0; }
+                    const int fx = it.cc_x + xin;
+                    sh[j] = use ? (fx & 31) : -1;
+                    word[j] = fb[(uint32_t)(yin * c.wpr + (fx >> 5))];
+                    // 32-bit byte offset inside the component rect (a frame is far smaller than 4 GB)
+                    const uint32_t off = (uint32_t)yin * pitch32 + (uint32_t)xin * 3u + frame_lsb;
+                    const uint32_t* aw = reinterpret_cast<const uint32_t*>(frame_al + (off & ~3u));
+                    bsh[j] = (int)(off & 3u) * 8;
+                    w0[j] = aw[0];
+                    w1[j] = bsh[j] > 8 ? aw[1] : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int X = X0 + 32 * j + lane;
+                    if (X < spr_w) {
+                        const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
+                        const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
+                        drow[X] = (uint8_t)(bgr >> 16);                 // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
+                        drow[plane_bytes + X] = (uint8_t)(bgr >> 8);
+                        drow[2 * plane_bytes + X] = (uint8_t)bgr;
+                        drow[3 * plane_bytes + X] = on ? (uint8_t)255 : (uint8_t)0;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 2: MMA tiles of these 16 rows, all planes
+    const int g = lane >> 2, t = lane & 3;
+    const int ntiles = (new_w + 7) >> 3, nsb = it.nkb & 0xffff;
+    const uint2* base = c.band + it.hband_off;
+    const int64_t Hp = (spr_h + 15) & ~15;
+    const int64_t plane_out = (int64_t)new_w * Hp;
+    uint8_t* st = s_t[warp];
+    for (int tile = warp; tile < ntiles; tile += 8) {
+        const int xb = reinterpret_cast<const int32_t*>(base)[tile];
+        const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+        uint2 b0[6];
+        load_band(b0, frag);
+        const uint8_t* r_lo = gh_smem + g * Wps + xb + 16 * t;          // row g of plane 0, this lane's 16-byte column
+        const int xl = lane >> 2, q = lane & 3;                         // transposed store: 8 columns x 4 words of 4 rows
+        const int X = tile * 8 + xl, y = y0 + 4 * q;
+        uint8_t* outp = c.sprite_ws + it.tmp_off + (int64_t)X * Hp + y;
+        const bool out_ok = X < new_w && y < spr_h;
+#pragma unroll 1
+        for (int pl = 0; pl < 4; ++pl) {
+            const uint8_t* rp = r_lo + pl * plane_bytes;
+            const uint4 lo = *reinterpret_cast<const uint4*>(rp), hi = *reinterpret_cast<const uint4*>(rp + 8 * Wps);
+            int acc[3][4];
+            mma_rows(acc, lo, hi, rp, Wps, b0, frag, nsb);
+            // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1} -> transposed [X][y]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int v = acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16);
+                st[(2 * t + (i & 1)) * 20 + g + 8 * (i >> 1)] = (uint8_t)c_clip8(v);
+            }
+            __syncwarp();
+            if (out_ok) *reinterpret_cast<uint32_t*>(outp) = *reinterpret_cast<const uint32_t*>(st + xl * 20 + 4 * q);
+            outp += plane_out;
+            __syncwarp();
+        }
+    }
+}
+
 // vertical pass + un-premultiply.  CTA = (item, group of 64 output rows, chunk of 128 columns); warp = 8 output
 // rows; the reduction runs over y, contiguous in the transposed planar intermediate.  All four byte planes of a
 // tile are accumulated by the same warp, so un-premultiply and the interleaved RGBA store are lane-local:
@@ -1248,16 +1368,18 @@ int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, void* band, int max_band_warps,
+                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes,
                        const void* workspace, uint8_t* sprite_ws, void* stream) {
     using namespace ipp;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = chain_check_geom(g);
     if (rc != IPP_OK) return rc;
-    IPP_REQUIRE(frames && items && workspace && sprite_ws && tables && band && n_items >= 0 && max_band_warps >= 0, IPP_ERR_BAD_ARG,
-                "ipp_chain_stage_b2: bad arguments");
+    IPP_REQUIRE(frames && items && workspace && sprite_ws && tables && band && n_items >= 0 && max_band_warps >= 0 && fused_smem_bytes >= 0,
+                IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: bad arguments");
     IPP_REQUIRE((((uintptr_t)sprite_ws) & 255) == 0 && (((uintptr_t)band) & 15) == 0, IPP_ERR_BAD_ARG,
                 "ipp_chain_stage_b2: sprite workspace must be 256-byte aligned, fragment tables 16-byte aligned");
+    IPP_REQUIRE(fused_smem_bytes <= 200 * 1024 && (fused_smem_bytes == 0 || h_tiles == 0), IPP_ERR_BAD_ARG,
+                "ipp_chain_stage_b2: fused mode takes its tiles in gather_tiles (h_tiles = 0) and at most 200 KB of shared memory");
     if (n_items == 0) return IPP_OK;
     const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
     B2Common c{};
@@ -1265,18 +1387,30 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
     c.crop_l = g->crop_l; c.crop_t = g->crop_t;
     c.bits = (const uint32_t*)workspace; c.bits_stride = cg.bits_stride; c.wpr = cg.wpr;
     c.items = items; c.n_items = n_items; c.tables = tables; c.band = (uint2*)band; c.sprite_ws = sprite_ws;
-    if (max_band_warps > 0 && (h_tiles > 0 || v_tiles > 0)) {
+    if (max_band_warps > 0 && (gather_tiles > 0 || h_tiles > 0 || v_tiles > 0)) {
         dim3 grid(ceil_div(max_band_warps, 8), n_items);
         { ipp::LaunchTimer _lt("chain_band_kernel", st); chain_band_kernel<<<grid, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }
-    if (gather_tiles > 0) {
-        { ipp::LaunchTimer _lt("chain_gather_kernel", st); chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c); }
-        IPP_LAUNCH_CHECK();
-    }
-    if (h_tiles > 0) {
-        { ipp::LaunchTimer _lt("chain_hpass_kernel", st); chain_hpass_kernel<<<h_tiles, 256, 0, st>>>(c); }
-        IPP_LAUNCH_CHECK();
+    if (fused_smem_bytes > 0) {
+        if (gather_tiles > 0) {
+            static int smem_set = 0;         // the attribute only ever grows
+            if (fused_smem_bytes > smem_set) {
+                IPP_CUDA(cudaFuncSetAttribute(chain_gh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes));
+                smem_set = fused_smem_bytes;
+            }
+            { ipp::LaunchTimer _lt("chain_gh_kernel", st); chain_gh_kernel<<<gather_tiles, 256, fused_smem_bytes, st>>>(c); }
+            IPP_LAUNCH_CHECK();
+        }
+    } else {
+        if (gather_tiles > 0) {
+            { ipp::LaunchTimer _lt("chain_gather_kernel", st); chain_gather_kernel<<<gather_tiles, 256, 0, st>>>(c); }
+            IPP_LAUNCH_CHECK();
+        }
+        if (h_tiles > 0) {
+            { ipp::LaunchTimer _lt("chain_hpass_kernel", st); chain_hpass_kernel<<<h_tiles, 256, 0, st>>>(c); }
+            IPP_LAUNCH_CHECK();
+        }
     }
     if (v_tiles > 0) {
         { ipp::LaunchTimer _lt("chain_vpass_kernel", st); chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c); }

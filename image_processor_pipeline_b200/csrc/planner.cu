@@ -26,7 +26,7 @@
 
 static_assert(sizeof(ipp_chain_rot) == 64, "ipp_chain_rot layout (chain.py ROT_DTYPE)");
 static_assert(sizeof(ipp_chain_item) == 184, "ipp_chain_item layout (chain.py ITEM_DTYPE)");
-static_assert(sizeof(ipp_plan_params) == 88 && sizeof(ipp_plan_aux) == 16 && sizeof(ipp_plan_totals) == 56, "planner struct layout");
+static_assert(sizeof(ipp_plan_params) == 88 && sizeof(ipp_plan_aux) == 16 && sizeof(ipp_plan_totals) == 64, "planner struct layout");
 
 namespace ipp {
 namespace plan {
@@ -333,6 +333,24 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
         it->spr_off = woff; woff = align_up(woff + (int64_t)nw * nh * 4, 256);
         it->out_slot = i;
     }
+    // gather + h pass fused (16 gathered rows x 4 planes in shared memory) when the widest sprite fits; then the
+    // gather tile list is "one tile per 16 sprite rows" and there are no h tiles
+    int max_w = 0;
+    for (int i = 0; i < n_items; ++i) max_w = std::max(max_w, items[i].spr_w);
+    const int pitch = ((max_w + 64 + 127) / 128) * 128 + 64;              // gh_row_pitch (chain.cu)
+    const int64_t fused_smem = n_items ? (int64_t)64 * pitch + 1024 : 0;   // 4 planes x 16 rows + tail slack
+    const bool fused = n_items > 0 && fused_smem <= 200 * 1024 && getenv("IPP_B2_UNFUSED") == nullptr;
+    if (fused) {
+        gt = 0;
+        ht = 0;
+        for (int i = 0; i < n_items; ++i) {
+            items[i].gather_tile_start = (int32_t)gt;
+            items[i].h_tile_start = 0;
+            gt += (items[i].spr_h + 15) / 16;
+        }
+    }
+    totals_out->fused_smem_bytes = fused ? (int32_t)fused_smem : 0;
+    totals_out->_pad = 0;
     totals_out->table_ints = toff;
     totals_out->table_rows = tab_rows;
     totals_out->sprite_ws_bytes = woff;

@@ -286,6 +286,8 @@ typedef struct ipp_plan_totals {
     int64_t band_units;                     /* size of the fragment-table buffer in 8-byte units      */
     int32_t gather_tiles, h_tiles, v_tiles, labels_bytes;
     int32_t max_rows, max_band_warps;       /* per-item maxima: coefficient rows, fragment-table warps */
+    int32_t fused_smem_bytes;               /* > 0: the fused gather + h pass kernel is used with this much shared memory */
+    int32_t _pad;
 } ipp_plan_totals;
 
 int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
@@ -333,11 +335,16 @@ int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rot
  * The two passes are exact integer banded GEMMs on the tensor cores (mma.sync m16n8k32, u8 data x
  * coefficients split into three byte planes, int32 accumulation = Pillow's own arithmetic); `band`
  * (totals.band_units * 8 bytes) receives the coefficient bands in fragment order, derived from
- * `tables` by this call (max_band_warps = totals.max_band_warps). */
+ * `tables` by this call (max_band_warps = totals.max_band_warps).
+ * fused_smem_bytes = totals.fused_smem_bytes: when > 0 (every sprite of the batch is narrow enough) gather and h
+ * pass are ONE kernel that keeps 16 gathered rows x 4 planes in shared memory (gather_tiles = its tiles: one per 16
+ * sprite rows, h_tiles = 0); when 0 they are two kernels exchanging the planar sprite through sprite_ws
+ * (gather_tiles of 32 x 64 pixels, h_tiles of 64 outputs x plane).  gather_tiles = 0 skips the gather in the
+ * two-kernel mode only (h / v passes re-run on the sprites already gathered). */
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, void* band, int max_band_warps,
+                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes,
                        const void* workspace, uint8_t* sprite_ws, void* stream);
 /* stage C: out[i] (sq x sq x 3, RGB) = crop(paste(background[bg], sprite_i, pos), square) */
 int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,

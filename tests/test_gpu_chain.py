@@ -142,6 +142,19 @@ def test_device_lanczos_tables_equal_host_tables():
     assert len(bad) <= 2 and n_amb < 200, (len(bad), n_amb)
 
 
+def test_chain_two_kernel_gather_and_hpass_still_match(monkeypatch):
+    """Stage B2 has two modes: gather + h pass fused through shared memory (default whenever the sprites are narrow
+    enough) and two kernels exchanging the planar sprite through global memory.  Force the second one."""
+    monkeypatch.setenv("IPP_B2_UNFUSED", "1")
+    H, W = 270, 480
+    frames = [synth.frame(33, i, H, W) for i in range(3)]
+    bgs = [synth.background(33, i, H, W) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=2, include_original=True,
+              pool=["o", "h", "v", "hv"], choose_random=2, sym_include_original=False)
+    for run_kw in (dict(), dict(ambiguity_eps=0.2)):
+        _compare(*_run_both(frames, bgs, 6, run_kw=run_kw, **kw))
+
+
 def test_chain_generic_mask_kernel_still_matches(monkeypatch):
     """Stage A has two mask kernels: the persistent table-driven one (no zones, <= 8 filters) and the
     generic one.  Force the generic one on a configuration the fast one would take."""
@@ -283,11 +296,12 @@ def test_chain_stream_pipelining_is_transparent(inputs_ready, run_kw):
                                    ((40, 30), (95, 77)),        # up-scaling (3-tap support, scale < 1)
                                    ((700, 520), (41, 33)),      # 17x down: several 64-wide super-blocks per tile
                                    ((301, 7), (9, 5)), ((5, 300), (4, 11)), ((1, 1), (3, 2)), ((129, 130), (128, 129))])
-def test_tensor_core_lanczos_passes_vs_pillow(sizes):
-    """The two LANCZOS kernels alone (stage B2 without the gather): planar premultiplied sprites written by the
-    test, device tables + exact fix-up, result against PIL.Image.resize(LANCZOS) — bit-exact, for identity
-    passes, up-scaling and extreme down-scaling (paths the chain's own size distribution rarely reaches)."""
+def test_tensor_core_lanczos_passes_vs_pillow(sizes, monkeypatch):
+    """The two LANCZOS kernels alone (stage B2 in its two-kernel mode, without the gather): planar premultiplied
+    sprites written by the test, device tables + exact fix-up, result against PIL.Image.resize(LANCZOS) — bit-exact,
+    for identity passes, up-scaling and extreme down-scaling (paths the chain's own size distribution rarely reaches)."""
     import ctypes as C
+    monkeypatch.setenv("IPP_B2_UNFUSED", "1")
     from PIL import Image
     from image_processor_pipeline_b200 import _native, hostmath
     lib = _native.load()
@@ -321,7 +335,7 @@ def test_tensor_core_lanczos_passes_vs_pillow(sizes):
         tab_d[:len(host)] = torch.from_numpy(host).to(DEV)                 # exact tables: this test is about the passes
     dummy = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)           # frames / mask workspace are not touched (no gather)
     _native.check(lib.ipp_chain_stage_b2(dummy.data_ptr(), 64 * 3, 64 * 64 * 3, C.byref(geom), items_d.data_ptr(), n, 0, tot["ht"], tot["vt"],
-                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], dummy.data_ptr(), ws.data_ptr(), st), "b2")
+                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], 0, dummy.data_ptr(), ws.data_ptr(), st), "b2")
     out = ws.cpu().numpy()
     for i in range(n):
         off = int(items[i]["spr_off"])
