@@ -196,8 +196,14 @@ constexpr int kSegThreads = 1024;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegStages = 3;
 constexpr uint32_t kSegStageBytes = 1552;          // 1536 + 15 bytes of misalignment, rounded up to 16 (covers every whole-vector / whole-word read)
-constexpr int kSegBatch = 16;
-constexpr int kSegRefine = 20;                      // more cheaply-flagged groups than this: run the exact dark test
+#ifndef IPP_SEG_BATCH
+#define IPP_SEG_BATCH 16
+#endif
+constexpr int kSegBatch = IPP_SEG_BATCH;
+#ifndef IPP_SEG_REFINE
+#define IPP_SEG_REFINE 20
+#endif
+constexpr int kSegRefine = IPP_SEG_REFINE;          // more cheaply-flagged groups than this: run the exact dark test
 constexpr size_t kSegSmem = 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192;
 
 __global__ void __launch_bounds__(kSegThreads, 1) chain_mask_seg_kernel(const MaskSegParams p) {
@@ -824,7 +830,10 @@ __device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, cons
 // cp.async (LDGSTS: no registers held while the data travels).  Chunk id = lane + 32 j sits at byte 16 * id of the
 // stage: lane (g, t) = 4g + t stages exactly the two 16-byte pieces (row g, row g + 8; column 16 t) it later reads
 // back as its A-fragment words — no cross-lane traffic, conflict-free 128-bit shared accesses.
-constexpr int kRing = 4;
+#ifndef IPP_RING
+#define IPP_RING 4
+#endif
+constexpr int kRing = IPP_RING;
 // g0: this lane's piece of rows 0..7 of the tile (row lane / 4, column 16 * (lane % 4)); rows 8..15 are 8 * pitch further.
 // Rows past the end of a plane are NOT clamped: the planes of a sprite are adjacent and its workspace is padded by
 // 16 rows (ipp_chain_layout_host), so the reads stay inside the buffer; their results are never stored.
