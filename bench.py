@@ -88,10 +88,14 @@ def make_inputs_device(n: int, seed: int, first: int, dev, base: int = 8):
     bgb = torch.from_numpy(np.stack([synth.background(seed, k, FH, FW) for k in range(base)])).to(dev)
     frames = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
     bgs = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
-    for i, (dy, dx, by, bx) in enumerate(_shifts(n, seed, first)):
-        g = first + i
-        frames[i] = torch.roll(bases[g % base], (dy, dx), dims=(0, 1))
-        bgs[i] = torch.roll(bgb[g % base], (by, bx), dims=(0, 1))
+    sh = torch.tensor(_shifts(n, seed, first), dtype=torch.int64, device=dev)          # [n, 4] = dy, dx, by, bx
+    which = (first + torch.arange(n, device=dev)) % base
+    ys, xs = torch.arange(FH, device=dev), torch.arange(FW, device=dev)
+    for lo in range(0, n, 64):                                                          # rolled[y, x] = src[(y - dy) % H, (x - dx) % W]: one gather per 64 images
+        sl = slice(lo, min(lo + 64, n))
+        w = which[sl, None, None]
+        frames[sl] = bases[w, ((ys[None, :] - sh[sl, 0:1]) % FH)[:, :, None], ((xs[None, :] - sh[sl, 1:2]) % FW)[:, None, :]]
+        bgs[sl] = bgb[w, ((ys[None, :] - sh[sl, 2:3]) % FH)[:, :, None], ((xs[None, :] - sh[sl, 3:4]) % FW)[:, None, :]]
     return frames, bgs
 
 
