@@ -17,6 +17,11 @@ __device__ __forceinline__ uint32_t compress_even(uint64_t x) {
 
 // pixels 64k .. 64k+63 of one mask row
 __device__ __forceinline__ uint64_t load_px64(const uint32_t* row, int k, int wpr) {
+    if ((wpr & 1) == 0) {                               // even row length (mask base is 256-byte aligned): rows are 8-byte aligned
+        if (2 * k >= wpr) return 0ull;
+        const uint2 v = *reinterpret_cast<const uint2*>(row + 2 * k);
+        return (uint64_t)v.x | ((uint64_t)v.y << 32);
+    }
     const uint32_t lo = (2 * k < wpr) ? row[2 * k] : 0u;
     const uint32_t hi = (2 * k + 1 < wpr) ? row[2 * k + 1] : 0u;
     return (uint64_t)lo | ((uint64_t)hi << 32);
