@@ -14,6 +14,7 @@
 #include "staging.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 namespace ipp {
@@ -950,12 +951,12 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
         const uint32_t frame_lsb = (uint32_t)((uintptr_t)frame & 3);     // rect origin = 4-byte aligned base + 0..3
         const uint8_t* frame_al = frame - frame_lsb;
         const uint32_t pitch32 = (uint32_t)c.pitch;
-#pragma unroll 1
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = 2 * warp + rr, Y = y0 + r;
-            if (Y >= spr_h) break;
-            const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
-            const int xx0 = it.a2 + cy * it.a1, yy0 = it.a5 + cy * it.a4;
+        // column X of the sprite is canvas column cxb + cxs * X (flip folded in); in the affine case the fixed-point source
+        // coordinates are then linear in X: (ax + X * dax) >> 16, (ay + X * day) >> 16
+        const int cxs = it.flip_h ? -1 : 1, cxb = (it.flip_h ? spr_w - 1 : 0) + it.fit_x0;
+        const int dax = cxs * it.a0, day = cxs * it.a3;
+        auto gather_row = [&](auto affine, int r, int cy) {
+            const int ax = it.a2 + cy * it.a1 + cxb * it.a0, ay = it.a5 + cy * it.a4 + cxb * it.a3;
             uint8_t* drow = gh_smem + r * Wps;
             for (int X0 = 0; X0 < spr_w; X0 += 128) {                   // four columns per lane in flight
                 uint32_t word[4], w0[4], w1[4];
@@ -963,15 +964,14 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int X = X0 + 32 * j + lane;
-                    const int cx = (it.flip_h ? (spr_w - 1 - X) : X) + it.fit_x0;
                     int xin, yin;
                     bool inside;
-                    if (it.kind == 0) {
-                        xin = (xx0 + cx * it.a0) >> 16;
-                        yin = (yy0 + cx * it.a3) >> 16;
+                    if constexpr (decltype(affine)::value) {
+                        xin = (ax + X * dax) >> 16;
+                        yin = (ay + X * day) >> 16;
                         inside = (unsigned)xin < (unsigned)it.cc_w && (unsigned)yin < (unsigned)it.cc_h;
                     } else {
-                        inside = map_canvas(m, cx, cy, xin, yin);
+                        inside = map_canvas(m, cxb + cxs * X, cy, xin, yin);
                     }
                     const bool use = inside && X < spr_w;
                     if (!use) { xin = 0; yin = 0; }
@@ -998,6 +998,14 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                     }
                 }
             }
+        };
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * warp + rr, Y = y0 + r;
+            if (Y >= spr_h) break;
+            const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
+            if (it.kind == 0) gather_row(std::true_type{}, r, cy);
+            else gather_row(std::false_type{}, r, cy);
         }
     }
     __syncthreads();
