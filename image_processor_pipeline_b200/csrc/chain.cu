@@ -1154,15 +1154,14 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
 
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int r = 0; r < nrows; ++r)
-            total += make_window(p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes).bytes;
-        mbar_expect_tx(&bar, total);
-        for (int r = 0; r < nrows; ++r) {
-            const Window w = make_window(p.bg + (int64_t)(p.crop_y0 + row0 + r) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes);
-            bulk_g2s(smem + (size_t)r * c.smem_row_stride, w.base, w.bytes, &bar);
-        }
+    if (tid < 32) {                                   // lane r issues the bulk copy of row r (rows_per_cta <= 8): no serial loop in front of the loads
+        Window w;
+        w.base = nullptr; w.bytes = 0; w.shift = 0;
+        if (tid < nrows) w = make_window(p.bg + (int64_t)(p.crop_y0 + row0 + tid) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes);
+        const uint32_t total = __reduce_add_sync(0xffffffffu, w.bytes);
+        if (tid == 0) mbar_expect_tx(&bar, total);
+        __syncwarp();                                 // the barrier is armed before any copy can complete on it
+        if (w.bytes) bulk_g2s(smem + (size_t)tid * c.smem_row_stride, w.base, w.bytes, &bar);
     }
     mbar_wait(&bar, 0);
     paste_rows_from_smem(p, smem, c.smem_row_stride, row0, nrows, tid);
