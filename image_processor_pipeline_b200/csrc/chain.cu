@@ -1329,10 +1329,12 @@ int ipp_chain_stage_a(const uint8_t* frames, int64_t frame_pitch, int64_t frame_
             p.lut = lut;
             p.f = hf;
             IPP_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
-            static bool attr_set = false;
-            if (!attr_set) {
+            static bool attr_set[64] = {};              // per device: the attribute belongs to the device's context
+            int dev_id = 0;
+            IPP_CUDA(cudaGetDevice(&dev_id));
+            if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
                 IPP_CUDA(cudaFuncSetAttribute(chain_mask_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem));
-                attr_set = true;
+                if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
             }
             const int grid = (int)std::min<int64_t>(sm_count(), ceil_div(n_segs, kSegWarps));
             { ipp::LaunchTimer _lt("chain_mask_seg_kernel", st); chain_mask_seg_kernel<<<grid, kSegThreads, kSegSmem, st>>>(p); }
@@ -1410,10 +1412,12 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
     }
     if (fused_smem_bytes > 0) {
         if (gather_tiles > 0) {
-            static int smem_set = 0;         // the attribute only ever grows
-            if (fused_smem_bytes > smem_set) {
+            static int smem_set[64] = {};     // per device; the attribute only ever grows
+            int dev_id = 0;
+            IPP_CUDA(cudaGetDevice(&dev_id));
+            if (dev_id < 0 || dev_id >= 64 || fused_smem_bytes > smem_set[dev_id]) {
                 IPP_CUDA(cudaFuncSetAttribute(chain_gh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes));
-                smem_set = fused_smem_bytes;
+                if (dev_id >= 0 && dev_id < 64) smem_set[dev_id] = fused_smem_bytes;
             }
             { ipp::LaunchTimer _lt("chain_gh_kernel", st); chain_gh_kernel<<<gather_tiles, 256, fused_smem_bytes, st>>>(c); }
             IPP_LAUNCH_CHECK();
