@@ -52,7 +52,7 @@ class PlanTotals(C.Structure):
     _fields_ = [("table_ints", C.c_int64), ("table_rows", C.c_int64), ("sprite_ws_bytes", C.c_int64),
                 ("band_units", C.c_int64),
                 ("gather_tiles", C.c_int32), ("h_tiles", C.c_int32), ("v_tiles", C.c_int32), ("labels_bytes", C.c_int32),
-                ("max_rows", C.c_int32), ("max_band_warps", C.c_int32), ("fused_smem_bytes", C.c_int32), ("_pad", C.c_int32)]
+                ("max_rows", C.c_int32), ("max_band_warps", C.c_int32), ("fused_smem_bytes", C.c_int32), ("vstaged_smem_bytes", C.c_int32)]
 
 
 _u8p = C.c_void_p      # device pointers travel as integers
@@ -99,7 +99,7 @@ PROTOTYPES = {
     "ipp_chain_stage_a": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _i32p, _vp, _i64, _int, _vp]),
     "ipp_chain_stage_b1": (_int, [C.POINTER(ChainGeom), _vp, _int, _int, _vp, _i32p, _vp]),
     "ipp_chain_stage_b2": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _int, _int, _int,
-                                  _i32p, _vp, _int, _int, _vp, _u8p, _vp]),
+                                  _i32p, _vp, _int, _int, _int, _vp, _u8p, _vp]),
     "ipp_chain_layout_host": (_int, [_vp, _int, C.POINTER(PlanTotals)]),
     "ipp_host_round15": (C.c_double, [C.c_double]),
     "ipp_host_format6": (_int, [C.c_double, C.c_char_p, C.POINTER(C.c_double)]),

@@ -438,14 +438,14 @@ def _layout(items: np.ndarray):
     _native.check(lib.ipp_chain_layout_host(items.ctypes.data, len(items), C.byref(tot)), "ipp_chain_layout_host")
     return dict(table_ints=int(tot.table_ints), max_rows=int(tot.max_rows), ws=int(tot.sprite_ws_bytes), gt=int(tot.gather_tiles),
                 ht=int(tot.h_tiles), vt=int(tot.v_tiles), band_bytes=int(tot.band_units) * 8, max_band_warps=int(tot.max_band_warps),
-                fused_smem=int(tot.fused_smem_bytes))
+                fused_smem=int(tot.fused_smem_bytes), vstaged_smem=int(tot.vstaged_smem_bytes))
 
 
-def _pass_tiles(items: np.ndarray, fused: bool):
+def _pass_tiles(items: np.ndarray, fused: bool, vstaged: bool):
     """Flat tile counts per item of the kernels a table fix-up re-runs: (gather, h, v).  Fused mode: the gather + h
     kernel (one tile per 16 sprite rows) and the v pass; two-kernel mode: h and v passes on the gathered sprites."""
     sh, nw, nh = (items[n].astype(np.int64) for n in ("spr_h", "new_w", "new_h"))
-    vt = ((nh + 63) // 64) * ((nw + 127) // 128)
+    vt = (nw + 15) // 16 if vstaged else ((nh + 63) // 64) * ((nw + 127) // 128)
     if fused:
         return (sh + 15) // 16, np.zeros_like(sh), vt
     return np.zeros_like(sh), ((nw + 63) // 64) * 4, vt
@@ -755,7 +755,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         # ------------------------------------------------------------------ stage B2 + C
         def run_b2_c(items_dev, items_c_dev, k, gt, ht, vt):
             _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
-                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], tot["fused_smem"],
+                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], tot["fused_smem"], tot["vstaged_smem"],
                                                  ws.data_ptr(), spr_ws.data_ptr(), _stream()),
                           "ipp_chain_stage_b2")
             if bg_ready is not None:
@@ -777,14 +777,14 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         res = ChainResult(out, labels, record_arrays=rec_arrays)
         if device_tables and _pipe is not None:
             res.tables_flagged_rows = res.tables_fixed_items = None   # known once the next finish() / flush() has looked
-            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev, tot["fused_smem"] > 0))
+            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev, tot["fused_smem"] > 0, tot["vstaged_smem"] > 0))
         elif device_tables:
             if _before_sync is not None:
                 _before_sync()                                        # e.g. queue the next uploads before the host waits
             n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
             _mark("sync3_amb")
             if n_amb:
-                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, tot["fused_smem"] > 0)
+                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, tot["fused_smem"] > 0, tot["vstaged_smem"] > 0)
         for t in (rot_d, items_d, items_c_d):
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
@@ -796,7 +796,7 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
     return finish(res, own.tolist())
 
 
-def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, fused: bool) -> int:
+def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, fused: bool, vstaged: bool) -> int:
     """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C
     library's sin() (ipp_lanczos_row_host).  If a row really differs it is patched on the device and
     the h/v passes + paste of the affected items are re-run (their gathered sprites are still valid).
@@ -822,7 +822,7 @@ def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev,
             dirty.add(item)
     if dirty:
         sub = items[sorted(dirty)].copy()
-        gt, ht, vt = _pass_tiles(sub, fused)
+        gt, ht, vt = _pass_tiles(sub, fused, vstaged)
         sub["gather_tile_start"], sub["h_tile_start"], sub["v_tile_start"] = _excl(gt), _excl(ht), _excl(vt)
         sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
         sub_c = items_c[sorted(dirty)].copy()                  # stage C's view of the same items (host-window mode: shifted copies)

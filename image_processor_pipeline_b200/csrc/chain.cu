@@ -1120,6 +1120,66 @@ __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     }
 }
 
+// ---- vertical pass with the intermediate staged per CTA.  chain_vpass_kernel lets every warp re-read its 64-byte window of
+// every column through a private cp.async ring (3.4x read amplification, ring bookkeeping in the MMA loop).  Here a CTA owns
+// 16 columns of the sprite: the 64 rows [4 planes][16 columns] of the transposed intermediate are contiguous in global memory and
+// are bulk-copied once into shared memory (rows padded like chain_gh_kernel's); the warps then run the output tiles (8 rows of
+// the final sprite each, all four planes, un-premultiply lane-local) from there.  Used when the tallest sprite of the batch fits.
+__global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
+    extern __shared__ __align__(128) uint8_t vs_smem[];
+    __shared__ int s_rec;
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0)
+        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+    if (threadIdx.x == 32) mbar_init(&bar, 1);
+    __syncthreads();
+    const ipp_chain_item& it = c.items[s_rec];
+    const int new_w = it.new_w, new_h = it.new_h, spr_h = it.spr_h;
+    const int X0 = ((int)blockIdx.x - it.v_tile_start) * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t Hp = (spr_h + 15) & ~15;
+    const int Hps = gh_row_pitch(spr_h);
+    const int plane_bytes = 16 * Hps;
+    // ---- phase 1: 64 rows (plane, column) of Hp bytes each, one bulk copy per row (columns past the edge repeat the last one)
+    // (the phase cannot complete before thread 0's arrive.expect_tx: its single arrival is still pending, so copies that land
+    //  earlier only run the transaction count negative for a moment)
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, 64u * (uint32_t)Hp);
+    if (threadIdx.x < 64) {
+        const int pl = threadIdx.x >> 4, r = threadIdx.x & 15;
+        const uint8_t* gsrc = c.sprite_ws + it.tmp_off + ((int64_t)pl * new_w + min(X0 + r, new_w - 1)) * Hp;
+        bulk_g2s(vs_smem + pl * plane_bytes + r * Hps, gsrc, (uint32_t)Hp, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    // ---- phase 2: output tiles of 8 rows, all planes per warp
+    const int g = lane >> 2, t = lane & 3;
+    const int ntiles = (new_h + 7) >> 3, nsb = it.nkb >> 16;
+    const uint2* base = c.band + it.vband_off;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off);
+    for (int tile = warp; tile < ntiles; tile += 8) {
+        const int yb = reinterpret_cast<const int32_t*>(base)[tile];
+        const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+        uint2 b0[6];
+        load_band(b0, frag);
+        const uint8_t* r_lo = vs_smem + g * Hps + yb + 16 * t;
+        uint32_t px[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+            const uint8_t* rp = r_lo + pl * plane_bytes;
+            const uint4 lo = *reinterpret_cast<const uint4*>(rp), hi = *reinterpret_cast<const uint4*>(rp + 8 * Hps);
+            int acc[3][4];
+            mma_rows(acc, lo, hi, rp, Hps, b0, frag, nsb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) px[i] |= c_clip8(acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16)) << (8 * pl);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int X = X0 + g + 8 * (i >> 1), Y = tile * 8 + 2 * t + (i & 1);
+            if (X < new_w && Y < new_h) dst[(int64_t)Y * new_w + X] = c_unpremultiply(px[i]);
+        }
+    }
+}
+
 // ===================================================================== stage C
 struct CParams {
     const uint8_t* bgs;
@@ -1386,13 +1446,14 @@ int ipp_chain_stage_b1(const ipp_chain_geom* g, const ipp_chain_rot* rots, int n
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes,
+                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes, int vstaged_smem_bytes,
                        const void* workspace, uint8_t* sprite_ws, void* stream) {
     using namespace ipp;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = chain_check_geom(g);
     if (rc != IPP_OK) return rc;
-    IPP_REQUIRE(frames && items && workspace && sprite_ws && tables && band && n_items >= 0 && max_band_warps >= 0 && fused_smem_bytes >= 0,
+    IPP_REQUIRE(frames && items && workspace && sprite_ws && tables && band && n_items >= 0 && max_band_warps >= 0 && fused_smem_bytes >= 0 &&
+                    vstaged_smem_bytes >= 0 && vstaged_smem_bytes <= 200 * 1024,
                 IPP_ERR_BAD_ARG, "ipp_chain_stage_b2: bad arguments");
     IPP_REQUIRE((((uintptr_t)sprite_ws) & 255) == 0 && (((uintptr_t)band) & 15) == 0, IPP_ERR_BAD_ARG,
                 "ipp_chain_stage_b2: sprite workspace must be 256-byte aligned, fragment tables 16-byte aligned");
@@ -1432,7 +1493,17 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
             IPP_LAUNCH_CHECK();
         }
     }
-    if (v_tiles > 0) {
+    if (v_tiles > 0 && vstaged_smem_bytes > 0) {
+        static int vsmem_set[64] = {};     // per device; the attribute only ever grows
+        int dev_id = 0;
+        IPP_CUDA(cudaGetDevice(&dev_id));
+        if (dev_id < 0 || dev_id >= 64 || vstaged_smem_bytes > vsmem_set[dev_id]) {
+            IPP_CUDA(cudaFuncSetAttribute(chain_vs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vstaged_smem_bytes));
+            if (dev_id >= 0 && dev_id < 64) vsmem_set[dev_id] = vstaged_smem_bytes;
+        }
+        { ipp::LaunchTimer _lt("chain_vs_kernel", st); chain_vs_kernel<<<v_tiles, 256, vstaged_smem_bytes, st>>>(c); }
+        IPP_LAUNCH_CHECK();
+    } else if (v_tiles > 0) {
         { ipp::LaunchTimer _lt("chain_vpass_kernel", st); chain_vpass_kernel<<<v_tiles, 256, 0, st>>>(c); }
         IPP_LAUNCH_CHECK();
     }

@@ -350,7 +350,20 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
         }
     }
     totals_out->fused_smem_bytes = fused ? (int32_t)fused_smem : 0;
-    totals_out->_pad = 0;
+    // vertical pass staged per CTA (16 columns x 4 planes of the transposed intermediate) when the tallest sprite fits
+    int max_h = 0;
+    for (int i = 0; i < n_items; ++i) max_h = std::max(max_h, items[i].spr_h);
+    const int vpitch = ((max_h + 64 + 127) / 128) * 128 + 64;
+    const int64_t vs_smem = n_items ? (int64_t)64 * vpitch + 1024 : 0;
+    const bool vstaged = n_items > 0 && vs_smem <= 200 * 1024 && getenv("IPP_B2_UNFUSED") == nullptr;
+    if (vstaged) {
+        vt = 0;
+        for (int i = 0; i < n_items; ++i) {
+            items[i].v_tile_start = (int32_t)vt;
+            vt += (items[i].new_w + 15) / 16;
+        }
+    }
+    totals_out->vstaged_smem_bytes = vstaged ? (int32_t)vs_smem : 0;
     totals_out->table_ints = toff;
     totals_out->table_rows = tab_rows;
     totals_out->sprite_ws_bytes = woff;

@@ -287,7 +287,7 @@ typedef struct ipp_plan_totals {
     int32_t gather_tiles, h_tiles, v_tiles, labels_bytes;
     int32_t max_rows, max_band_warps;       /* per-item maxima: coefficient rows, fragment-table warps */
     int32_t fused_smem_bytes;               /* > 0: the fused gather + h pass kernel is used with this much shared memory */
-    int32_t _pad;
+    int32_t vstaged_smem_bytes;             /* > 0: the CTA-staged vertical pass is used with this much shared memory       */
 } ipp_plan_totals;
 
 int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_params* p, uint32_t* rng_mt624, int32_t* rng_index,
@@ -340,11 +340,14 @@ int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rot
  * pass are ONE kernel that keeps 16 gathered rows x 4 planes in shared memory (gather_tiles = its tiles: one per 16
  * sprite rows, h_tiles = 0); when 0 they are two kernels exchanging the planar sprite through sprite_ws
  * (gather_tiles of 32 x 64 pixels, h_tiles of 64 outputs x plane).  gather_tiles = 0 skips the gather in the
- * two-kernel mode only (h / v passes re-run on the sprites already gathered). */
+ * two-kernel mode only (h / v passes re-run on the sprites already gathered).
+ * vstaged_smem_bytes = totals.vstaged_smem_bytes: when > 0 the vertical pass stages 16 columns x 4 planes of the
+ * transposed intermediate per CTA in shared memory (v_tiles: one per 16 sprite columns); when 0 every warp streams
+ * its windows through a private cp.async ring (v_tiles of 64 output rows x 128 columns). */
 int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride,
                        const ipp_chain_geom* geom_host, const ipp_chain_item* items, int n_items,
                        int gather_tiles, int h_tiles, int v_tiles,
-                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes,
+                       const int32_t* tables, void* band, int max_band_warps, int fused_smem_bytes, int vstaged_smem_bytes,
                        const void* workspace, uint8_t* sprite_ws, void* stream);
 /* stage C: out[i] (sq x sq x 3, RGB) = crop(paste(background[bg], sprite_i, pos), square) */
 int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,

@@ -335,7 +335,7 @@ def test_tensor_core_lanczos_passes_vs_pillow(sizes, monkeypatch):
         tab_d[:len(host)] = torch.from_numpy(host).to(DEV)                 # exact tables: this test is about the passes
     dummy = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)           # frames / mask workspace are not touched (no gather)
     _native.check(lib.ipp_chain_stage_b2(dummy.data_ptr(), 64 * 3, 64 * 64 * 3, C.byref(geom), items_d.data_ptr(), n, 0, tot["ht"], tot["vt"],
-                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], 0, dummy.data_ptr(), ws.data_ptr(), st), "b2")
+                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], 0, 0, dummy.data_ptr(), ws.data_ptr(), st), "b2")
     out = ws.cpu().numpy()
     for i in range(n):
         off = int(items[i]["spr_off"])
