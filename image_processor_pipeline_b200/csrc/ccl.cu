@@ -204,6 +204,8 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const Cc
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const CclGeom g, const CclBuffers b, int n) {
     const GroupIdx t = group_index(g, n);
     if (!t.ok || t.by == 0) return;
+    // F == 0: nothing here, or only isolated runs (finished by the init pass; by definition they touch nothing above)
+    if (b.fbits[(int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k] == 0u) return;
     const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
     const uint32_t* rowT = bits + (int64_t)(2 * t.by) * g.wpr;
     const uint32_t* rowB = rowT - g.wpr;
