@@ -193,7 +193,10 @@ struct MaskSegParams {
 };
 
 constexpr int kSegPx = 512;
-constexpr int kSegThreads = 1024;
+#ifndef IPP_SEG_THREADS
+#define IPP_SEG_THREADS 1024
+#endif
+constexpr int kSegThreads = IPP_SEG_THREADS;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegStages = 3;
 constexpr uint32_t kSegStageBytes = 1552;          // 1536 + 15 bytes of misalignment, rounded up to 16 (covers every whole-vector / whole-word read)
@@ -207,7 +210,7 @@ constexpr int kSegBatch = IPP_SEG_BATCH;
 constexpr int kSegRefine = IPP_SEG_REFINE;          // more cheaply-flagged groups than this: run the exact dark test
 constexpr size_t kSegSmem = 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192;
 
-__global__ void __launch_bounds__(kSegThreads, 1) chain_mask_seg_kernel(const MaskSegParams p) {
+__global__ void __launch_bounds__(kSegThreads, 1024 / kSegThreads) chain_mask_seg_kernel(const MaskSegParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full[kSegWarps][kSegStages];
     __shared__ int hdiv[256];
@@ -930,6 +933,7 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
 // then hit all 32 banks) and its eight warps run the MMA tiles of those rows from there: no planar sprite in global
 // memory, no load latency in the MMA loop.  Used whenever the widest sprite of the batch fits (ipp_chain_layout_host).
 __host__ __device__ inline int gh_row_pitch(int spr_w) { return ((spr_w + 64 + 127) / 128) * 128 + 64; }   // >= spr_w + 128, == 64 mod 128
+__host__ __device__ inline int gh_row_skew(int r) { return (r & 2) * 16; }      // rows 2, 3 (mod 4): +32 bytes (same for r and r + 8)
 constexpr int kGhTail = 1024;          // slack behind the planes: windows of multi-super-block tiles may run past the last row
 
 __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
@@ -959,15 +963,23 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
         // coordinates are then linear in X: (ax + X * dax) >> 16, (ay + X * day) >> 16
         const int cxs = it.flip_h ? -1 : 1, cxb = (it.flip_h ? spr_w - 1 : 0) + it.fit_x0;
         const int dax = cxs * it.a0, day = cxs * it.a3;
-        auto gather_row = [&](auto affine, int r, int cy) {
+        // A warp gathers 8 x 4 patches (lane = column lx of row ly of the patch): the source pixels of a patch are a
+        // rotated 8 x 4 block of the frame, i.e. ~10 sectors per request where 32 pixels along one rotated line touch up to
+        // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 32 columns; four patches per lane are in flight.
+        // Rows 2, 3 (mod 4) sit 32 bytes further right in shared memory (gh_row_skew), which puts the four rows of a
+        // patch into different banks and keeps the fragment loads of phase 2 conflict-free.
+        auto gather_rows = [&](auto affine) {
+            const int lx = lane & 7, r = 4 * (warp & 3) + (lane >> 3), Y = y0 + r;
+            const bool row_ok = Y < spr_h;
+            const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
             const int ax = it.a2 + cy * it.a1 + cxb * it.a0, ay = it.a5 + cy * it.a4 + cxb * it.a3;
-            uint8_t* drow = gh_smem + r * Wps;
-            for (int X0 = 0; X0 < spr_w; X0 += 128) {                   // four columns per lane in flight
+            uint8_t* drow = gh_smem + r * Wps + gh_row_skew(r);
+            for (int X0 = (warp >> 2) * 32; X0 < spr_w; X0 += 64) {
                 uint32_t word[4], w0[4], w1[4];
                 int sh[4], bsh[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int X = X0 + 32 * j + lane;
+                    const int X = X0 + 8 * j + lx;
                     int xin, yin;
                     bool inside;
                     if constexpr (decltype(affine)::value) {
@@ -977,7 +989,7 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                     } else {
                         inside = map_canvas(m, cxb + cxs * X, cy, xin, yin);
                     }
-                    const bool use = inside && X < spr_w;
+                    const bool use = inside && X < spr_w && row_ok;
                     if (!use) { xin = 0; yin = 0; }
                     const int fx = it.cc_x + xin;
                     sh[j] = use ? (fx & 31) : -1;
@@ -991,8 +1003,8 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int X = X0 + 32 * j + lane;
-                    if (X < spr_w) {
+                    const int X = X0 + 8 * j + lx;
+                    if (X < spr_w && row_ok) {
                         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
                         const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
                         drow[X] = (uint8_t)(bgr >> 16);                 // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
@@ -1003,14 +1015,8 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                 }
             }
         };
-#pragma unroll 1
-        for (int rr = 0; rr < 2; ++rr) {
-            const int r = 2 * warp + rr, Y = y0 + r;
-            if (Y >= spr_h) break;
-            const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
-            if (it.kind == 0) gather_row(std::true_type{}, r, cy);
-            else gather_row(std::false_type{}, r, cy);
-        }
+        if (it.kind == 0) gather_rows(std::true_type{});
+        else gather_rows(std::false_type{});
     }
     __syncthreads();
 
@@ -1026,7 +1032,7 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
         const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
         uint2 b0[6];
         load_band(b0, frag);
-        const uint8_t* r_lo = gh_smem + g * Wps + xb + 16 * t;          // row g of plane 0, this lane's 16-byte column
+        const uint8_t* r_lo = gh_smem + g * Wps + gh_row_skew(g) + xb + 16 * t;     // row g of plane 0, this lane's 16-byte column
         const int xl = lane >> 2, q = lane & 3;                         // transposed store: 8 columns x 4 words of 4 rows
         const int X = tile * 8 + xl, y = y0 + 4 * q;
         uint8_t* outp = c.sprite_ws + it.tmp_off + (int64_t)X * Hp + y;
