@@ -603,6 +603,7 @@ struct B2Common {
     const int32_t* tables;
     uint2* band;                 // banded int8 fragment tables (chain_band_kernel)
     uint8_t* sprite_ws;
+    int h_blocks32, v_blocks32;  // fragment tables of that axis in 32-position blocks (shared-memory passes) instead of 64-position super-blocks
 };
 
 // gather: sprite pixel (X, Y) after flip <- canvas (X' + fit_x0, Y' + fit_y0) <- frame pixel.
@@ -767,9 +768,10 @@ __global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
     if (w >= a.ntiles * a.nsb) return;
     const int tile = w / a.nsb, sb = w - tile * a.nsb;
     uint2* base = c.band + (axis ? it.vband_off : it.hband_off);
+    const bool blocks32 = axis ? c.v_blocks32 : c.h_blocks32;
     const int X0 = tile * 8;
-    const int xb = (a.ksize ? a.bounds[2 * X0] : X0) & ~15;
-    if (sb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb;
+    const int xfirst = a.ksize ? a.bounds[2 * X0] : X0;
+    const int xb = blocks32 ? (xfirst & ~7) : (xfirst & ~15);
     const int g = lane >> 2, t = lane & 3;
     const int X = X0 + g;
     int xmin = 0, n = 0;
@@ -784,7 +786,35 @@ __global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
             n = 1;
         }
     }
+    auto weight = [&](int pos) {
+        const int idx = pos - xmin;
+        return (idx >= 0 && idx < n) ? (k ? k[idx] : (1 << kPrec)) : 0;
+    };
     uint2* frag = base + ((a.ntiles + 1) >> 1) + ((int64_t)(tile * a.nsb + sb) * 6) * 32 + lane;
+    if (blocks32) {
+        // 32-position blocks 2 sb, 2 sb + 1 of the tile; the tile's entry carries how many blocks hold a non-zero tap
+        const int last = __reduce_max_sync(0xffffffffu, xmin + n);                  // one past the last source position of the tile
+        if (sb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb | (max(1, (last - xb + 31) >> 5) << 24);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            uint32_t r[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int wgt = weight(xb + 32 * (2 * sb + blk) + 8 * t + 4 * half + j);
+                    r[0][half] |= ((uint32_t)wgt & 255u) << (8 * j);
+                    r[1][half] |= (((uint32_t)wgt >> 8) & 255u) << (8 * j);
+                    r[2][half] |= (((uint32_t)wgt >> 16) & 255u) << (8 * j);
+                }
+            }
+            frag[(3 * blk + 0) * 32] = make_uint2(r[0][0], r[0][1]);
+            frag[(3 * blk + 1) * 32] = make_uint2(r[1][0], r[1][1]);
+            frag[(3 * blk + 2) * 32] = make_uint2(r[2][0], r[2][1]);
+        }
+        return;
+    }
+    if (sb == 0 && lane == 0) reinterpret_cast<int32_t*>(base)[tile] = xb;
 #pragma unroll
     for (int kbl = 0; kbl < 2; ++kbl) {
         uint32_t r[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
@@ -792,9 +822,7 @@ __global__ void __launch_bounds__(256) chain_band_kernel(const B2Common c) {
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int idx = xb + 64 * sb + 16 * t + 4 * (2 * kbl + half) + j - xmin;
-                int wgt = 0;
-                if (idx >= 0 && idx < n) wgt = k ? k[idx] : (1 << kPrec);
+                const int wgt = weight(xb + 64 * sb + 16 * t + 4 * (2 * kbl + half) + j);
                 r[0][half] |= ((uint32_t)wgt & 255u) << (8 * j);
                 r[1][half] |= (((uint32_t)wgt >> 8) & 255u) << (8 * j);
                 r[2][half] |= (((uint32_t)wgt >> 16) & 255u) << (8 * j);      // signed byte: |wgt| < 2^23
@@ -830,6 +858,26 @@ __device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, cons
         const uint4 lo2 = *reinterpret_cast<const uint4*>(r_lo + 64 * sb);
         const uint4 hi2 = *reinterpret_cast<const uint4*>(r_lo + 8 * pitch + 64 * sb);
         mma_superblock(acc, lo2, hi2, b);
+    }
+}
+
+// Shared-memory passes: 32-position blocks.  Lane (g, t) reads 8 bytes of rows g and g + 8 per block (positions 8t .. 8t+7
+// of the block = both k-halves of its A fragment); the tile's entry says how many blocks carry non-zero taps, usually one
+// for down-scales up to ~2.5x — half the MMAs of a 64-position super-block.
+__device__ __forceinline__ void mma_rows32(int (&acc)[3][4], const uint8_t* r_lo, int64_t pitch, const uint2 (&b0)[3],
+                                           const uint2* frag, int nblk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[0][i] = 1 << (kPrec - 1); acc[1][i] = 0; acc[2][i] = 0; }
+    {
+        const uint2 lo = *reinterpret_cast<const uint2*>(r_lo), hi = *reinterpret_cast<const uint2*>(r_lo + 8 * pitch);
+        const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+        mma_u8u8(acc[0], a, b0[0]); mma_u8u8(acc[1], a, b0[1]); mma_u8s8(acc[2], a, b0[2]);
+    }
+    for (int blk = 1; blk < nblk; ++blk) {
+        const uint2 b[3] = {__ldg(frag + blk * 96), __ldg(frag + blk * 96 + 32), __ldg(frag + blk * 96 + 64)};
+        const uint2 lo = *reinterpret_cast<const uint2*>(r_lo + 32 * blk), hi = *reinterpret_cast<const uint2*>(r_lo + 8 * pitch + 32 * blk);
+        const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+        mma_u8u8(acc[0], a, b[0]); mma_u8u8(acc[1], a, b[1]); mma_u8s8(acc[2], a, b[2]);
     }
 }
 
@@ -934,9 +982,13 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
 // memory, no load latency in the MMA loop.  Used whenever the widest sprite of the batch fits (ipp_chain_layout_host).
 __host__ __device__ inline int gh_row_pitch(int spr_w) { return ((spr_w + 64 + 127) / 128) * 128 + 64; }   // >= spr_w + 128, == 64 mod 128
 __host__ __device__ inline int gh_row_skew(int r) { return (r & 2) * 16; }      // rows 2, 3 (mod 4): +32 bytes (same for r and r + 8)
+#ifndef IPP_GH_FLY
+#define IPP_GH_FLY 6
+#endif
+constexpr int kGhFly = IPP_GH_FLY;      // patches per lane in flight
 constexpr int kGhTail = 1024;          // slack behind the planes: windows of multi-super-block tiles may run past the last row
 
-__global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
+__global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
     extern __shared__ __align__(128) uint8_t gh_smem[];
     __shared__ int s_rec;
     __shared__ __align__(16) uint8_t s_t[8][8 * 20];
@@ -965,7 +1017,7 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
         const int dax = cxs * it.a0, day = cxs * it.a3;
         // A warp gathers 8 x 4 patches (lane = column lx of row ly of the patch): the source pixels of a patch are a
         // rotated 8 x 4 block of the frame, i.e. ~10 sectors per request where 32 pixels along one rotated line touch up to
-        // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 32 columns; four patches per lane are in flight.
+        // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 8 * kGhFly columns; kGhFly patches per lane are in flight.
         // Rows 2, 3 (mod 4) sit 32 bytes further right in shared memory (gh_row_skew), which puts the four rows of a
         // patch into different banks and keeps the fragment loads of phase 2 conflict-free.
         auto gather_rows = [&](auto affine) {
@@ -974,11 +1026,11 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
             const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
             const int ax = it.a2 + cy * it.a1 + cxb * it.a0, ay = it.a5 + cy * it.a4 + cxb * it.a3;
             uint8_t* drow = gh_smem + r * Wps + gh_row_skew(r);
-            for (int X0 = (warp >> 2) * 32; X0 < spr_w; X0 += 64) {
-                uint32_t word[4], w0[4], w1[4];
-                int sh[4], bsh[4];
+            for (int X0 = (warp >> 2) * (8 * kGhFly); X0 < spr_w; X0 += 16 * kGhFly) {
+                uint32_t word[kGhFly], w0[kGhFly], w1[kGhFly];
+                int sh[kGhFly], bsh[kGhFly];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kGhFly; ++j) {
                     const int X = X0 + 8 * j + lx;
                     int xin, yin;
                     bool inside;
@@ -1002,7 +1054,7 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                     w1[j] = bsh[j] > 8 ? aw[1] : 0u;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kGhFly; ++j) {
                     const int X = X0 + 8 * j + lx;
                     if (X < spr_w && row_ok) {
                         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
@@ -1015,8 +1067,10 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
                 }
             }
         };
+#ifndef IPP_GH_SKIP1
         if (it.kind == 0) gather_rows(std::true_type{});
         else gather_rows(std::false_type{});
+#endif
     }
     __syncthreads();
 
@@ -1027,22 +1081,23 @@ __global__ void __launch_bounds__(256) chain_gh_kernel(const B2Common c) {
     const int64_t Hp = (spr_h + 15) & ~15;
     const int64_t plane_out = (int64_t)new_w * Hp;
     uint8_t* st = s_t[warp];
+#ifdef IPP_GH_SKIP2
+    if (c.n_items >= 0) return;
+#endif
     for (int tile = warp; tile < ntiles; tile += 8) {
-        const int xb = reinterpret_cast<const int32_t*>(base)[tile];
+        const int entry = reinterpret_cast<const int32_t*>(base)[tile];
+        const int xb = entry & 0xffffff, nblk = entry >> 24;
         const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
-        uint2 b0[6];
-        load_band(b0, frag);
-        const uint8_t* r_lo = gh_smem + g * Wps + gh_row_skew(g) + xb + 16 * t;     // row g of plane 0, this lane's 16-byte column
+        const uint2 b0[3] = {__ldg(frag), __ldg(frag + 32), __ldg(frag + 64)};
+        const uint8_t* r_lo = gh_smem + g * Wps + gh_row_skew(g) + xb + 8 * t;      // row g of plane 0, this lane's 8-byte column
         const int xl = lane >> 2, q = lane & 3;                         // transposed store: 8 columns x 4 words of 4 rows
         const int X = tile * 8 + xl, y = y0 + 4 * q;
         uint8_t* outp = c.sprite_ws + it.tmp_off + (int64_t)X * Hp + y;
         const bool out_ok = X < new_w && y < spr_h;
 #pragma unroll 1
         for (int pl = 0; pl < 4; ++pl) {
-            const uint8_t* rp = r_lo + pl * plane_bytes;
-            const uint4 lo = *reinterpret_cast<const uint4*>(rp), hi = *reinterpret_cast<const uint4*>(rp + 8 * Wps);
             int acc[3][4];
-            mma_rows(acc, lo, hi, rp, Wps, b0, frag, nsb);
+            mma_rows32(acc, r_lo + pl * plane_bytes, Wps, b0, frag, nblk);
             // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1} -> transposed [X][y]
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1157,7 +1212,7 @@ __global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
     if (threadIdx.x < 64) {
         const int pl = threadIdx.x >> 4, r = threadIdx.x & 15;
         const uint8_t* gsrc = c.sprite_ws + it.tmp_off + ((int64_t)pl * new_w + min(X0 + r, new_w - 1)) * Hp;
-        bulk_g2s(vs_smem + pl * plane_bytes + r * Hps, gsrc, (uint32_t)Hp, &bar);
+        bulk_g2s(vs_smem + pl * plane_bytes + r * Hps + gh_row_skew(r), gsrc, (uint32_t)Hp, &bar);
     }
     mbar_wait(&bar, 0);
 
@@ -1167,18 +1222,16 @@ __global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
     const uint2* base = c.band + it.vband_off;
     uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off);
     for (int tile = warp; tile < ntiles; tile += 8) {
-        const int yb = reinterpret_cast<const int32_t*>(base)[tile];
+        const int entry = reinterpret_cast<const int32_t*>(base)[tile];
+        const int yb = entry & 0xffffff, nblk = entry >> 24;
         const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
-        uint2 b0[6];
-        load_band(b0, frag);
-        const uint8_t* r_lo = vs_smem + g * Hps + yb + 16 * t;
+        const uint2 b0[3] = {__ldg(frag), __ldg(frag + 32), __ldg(frag + 64)};
+        const uint8_t* r_lo = vs_smem + g * Hps + gh_row_skew(g) + yb + 8 * t;
         uint32_t px[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int pl = 0; pl < 4; ++pl) {
-            const uint8_t* rp = r_lo + pl * plane_bytes;
-            const uint4 lo = *reinterpret_cast<const uint4*>(rp), hi = *reinterpret_cast<const uint4*>(rp + 8 * Hps);
             int acc[3][4];
-            mma_rows(acc, lo, hi, rp, Hps, b0, frag, nsb);
+            mma_rows32(acc, r_lo + pl * plane_bytes, Hps, b0, frag, nblk);
 #pragma unroll
             for (int i = 0; i < 4; ++i) px[i] |= c_clip8(acc[0][i] + (acc[1][i] << 8) + (acc[2][i] << 16)) << (8 * pl);
         }
@@ -1476,6 +1529,7 @@ int ipp_chain_stage_b2(const uint8_t* frames, int64_t frame_pitch, int64_t frame
     c.crop_l = g->crop_l; c.crop_t = g->crop_t;
     c.bits = (const uint32_t*)workspace; c.bits_stride = cg.bits_stride; c.wpr = cg.wpr;
     c.items = items; c.n_items = n_items; c.tables = tables; c.band = (uint2*)band; c.sprite_ws = sprite_ws;
+    c.h_blocks32 = fused_smem_bytes > 0; c.v_blocks32 = vstaged_smem_bytes > 0;
     if (max_band_warps > 0 && (gather_tiles > 0 || h_tiles > 0 || v_tiles > 0)) {
         dim3 grid(ceil_div(max_band_warps, 8), n_items);
         { ipp::LaunchTimer _lt("chain_band_kernel", st); chain_band_kernel<<<grid, 256, 0, st>>>(c); }

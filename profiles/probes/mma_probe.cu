@@ -19,6 +19,15 @@ __global__ void __launch_bounds__(256) probe(int iters, int* out) {
             if (KIND == 0)
                 asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                              : "+r"(c[j][0]), "+r"(c[j][1]), "+r"(c[j][2]), "+r"(c[j][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            else if (KIND == 2)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(f[j][0]), "+f"(f[j][1]), "+f"(f[j][2]), "+f"(f[j][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            else if (KIND == 3)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+r"(c[j][0]), "+r"(c[j][1]), "+r"(c[j][2]), "+r"(c[j][3]) : "r"(a0), "r"(a1), "r"(b0));
+            else if (KIND == 4)
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+f"(f[j][0]), "+f"(f[j][1]), "+f"(f[j][2]), "+f"(f[j][3]) : "r"(a0), "r"(a1), "r"(b0));
             else
                 asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                              : "+f"(f[j][0]), "+f"(f[j][1]), "+f"(f[j][2]), "+f"(f[j][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -55,5 +64,8 @@ void run(const char* name, double macs_per_mma) {
 int main() {
     run<0>("IMMA m16n8k32 u8.s8", 16.0 * 8 * 32);
     run<1>("HMMA m16n8k16 f16  ", 16.0 * 8 * 16);
+    run<2>("HMMA m16n8k16 bf16 ", 16.0 * 8 * 16);
+    run<3>("IMMA m16n8k16 u8.s8", 16.0 * 8 * 16);
+    run<4>("HMMA m16n8k8 f16   ", 16.0 * 8 * 8);
     return 0;
 }
