@@ -861,6 +861,11 @@ __device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, cons
     }
 }
 
+// Pull the first two 32-position blocks of a tile's fragment table (1536 bytes = 12 lines) into L1 ahead of use: the
+// table reads are the only global loads of a tile and would otherwise cost one L2 round trip per tile and warp.
+__device__ __forceinline__ void band_prefetch(const uint2* tile_frags, int lane) {
+    if (lane < 12) asm volatile("prefetch.global.L1 [%0];" :: "l"(tile_frags + lane * 16));
+}
 // Shared-memory passes: 32-position blocks.  Lane (g, t) reads 8 bytes of rows g and g + 8 per block (positions 8t .. 8t+7
 // of the block = both k-halves of its A fragment); the tile's entry says how many blocks carry non-zero taps, usually one
 // for down-scales up to ~2.5x — half the MMAs of a 64-position super-block.
@@ -877,6 +882,25 @@ __device__ __forceinline__ void mma_rows32(int (&acc)[3][4], const uint8_t* r_lo
         const uint2 b[3] = {__ldg(frag + blk * 96), __ldg(frag + blk * 96 + 32), __ldg(frag + blk * 96 + 64)};
         const uint2 lo = *reinterpret_cast<const uint2*>(r_lo + 32 * blk), hi = *reinterpret_cast<const uint2*>(r_lo + 8 * pitch + 32 * blk);
         const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+        mma_u8u8(acc[0], a, b[0]); mma_u8u8(acc[1], a, b[1]); mma_u8s8(acc[2], a, b[2]);
+    }
+}
+
+// Same, for rows stored pairwise interleaved (the fused gather's layout): words of rows g and g + 8 alternate every four
+// positions, so ONE 16-byte load per lane and block is the whole A fragment {a0, a1, a2, a3} — no register shuffling.
+__device__ __forceinline__ void mma_rows32i(int (&acc)[3][4], const uint8_t* pair, const uint2 (&b0)[3], const uint2* frag, int nblk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[0][i] = 1 << (kPrec - 1); acc[1][i] = 0; acc[2][i] = 0; }
+    {
+        const uint4 q = *reinterpret_cast<const uint4*>(pair);
+        const uint32_t a[4] = {q.x, q.y, q.z, q.w};
+        mma_u8u8(acc[0], a, b0[0]); mma_u8u8(acc[1], a, b0[1]); mma_u8s8(acc[2], a, b0[2]);
+    }
+#pragma unroll 1
+    for (int blk = 1; blk < nblk; ++blk) {
+        const uint2 b[3] = {__ldg(frag + blk * 96), __ldg(frag + blk * 96 + 32), __ldg(frag + blk * 96 + 64)};
+        const uint4 q = *reinterpret_cast<const uint4*>(pair + 64 * blk);
+        const uint32_t a[4] = {q.x, q.y, q.z, q.w};
         mma_u8u8(acc[0], a, b[0]); mma_u8u8(acc[1], a, b[1]); mma_u8s8(acc[2], a, b[2]);
     }
 }
@@ -986,12 +1010,14 @@ __host__ __device__ inline int gh_row_skew(int r) { return (r & 2) * 16; }      
 #define IPP_GH_FLY 6
 #endif
 constexpr int kGhFly = IPP_GH_FLY;      // patches per lane in flight
+constexpr int kGhEntries = 256;      // tile entries kept in shared memory (sprites up to 2048 columns; wider ones read the rest from global)
 constexpr int kGhTail = 1024;          // slack behind the planes: windows of multi-super-block tiles may run past the last row
 
 __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
     extern __shared__ __align__(128) uint8_t gh_smem[];
     __shared__ int s_rec;
     __shared__ __align__(16) uint8_t s_t[8][8 * 20];
+    __shared__ int s_ent[kGhEntries];
     if (threadIdx.x == 0)
         s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
     __syncthreads();
@@ -999,8 +1025,16 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
     const int spr_w = it.spr_w, spr_h = it.spr_h, new_w = it.new_w;
     const int y0 = ((int)blockIdx.x - it.gather_tile_start) * 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Wps = gh_row_pitch(spr_w);
-    const int plane_bytes = 16 * Wps;
+    // shared-memory layout of a plane: eight row pairs (r, r + 8) of pitch P2 = 64 mod 128, the two rows of a pair
+    // interleaved every four columns: byte (r, x) at (r & 7) * P2 + skew + 8 * (x / 4) + 4 * (r / 8) + x % 4
+    const int P2 = 2 * gh_row_pitch(spr_w) - 64;
+    const int plane_bytes = 8 * P2;
+    // tile entries and the first tile's fragments are requested before the gather so that phase 2 finds them on chip
+    const int ntiles = (new_w + 7) >> 3, nsb = it.nkb & 0xffff;
+    const uint2* base = c.band + it.hband_off;
+    const uint2* frags = base + ((ntiles + 1) >> 1);
+    for (int i = threadIdx.x; i < min(ntiles, kGhEntries); i += 256) s_ent[i] = reinterpret_cast<const int32_t*>(base)[i];
+    if (warp < ntiles) band_prefetch(frags + (int64_t)warp * nsb * 192, lane);
 
     // ---------------------------------------------------------------- phase 1: gather rows y0 .. y0+15 into shared memory
     {
@@ -1018,14 +1052,14 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
         // A warp gathers 8 x 4 patches (lane = column lx of row ly of the patch): the source pixels of a patch are a
         // rotated 8 x 4 block of the frame, i.e. ~10 sectors per request where 32 pixels along one rotated line touch up to
         // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 8 * kGhFly columns; kGhFly patches per lane are in flight.
-        // Rows 2, 3 (mod 4) sit 32 bytes further right in shared memory (gh_row_skew), which puts the four rows of a
+        // Row pairs 2, 3 (mod 4) sit 32 bytes further right in shared memory (gh_row_skew), which puts the four rows of a
         // patch into different banks and keeps the fragment loads of phase 2 conflict-free.
         auto gather_rows = [&](auto affine) {
             const int lx = lane & 7, r = 4 * (warp & 3) + (lane >> 3), Y = y0 + r;
             const bool row_ok = Y < spr_h;
             const int cy = (it.flip_v ? (spr_h - 1 - Y) : Y) + it.fit_y0;
             const int ax = it.a2 + cy * it.a1 + cxb * it.a0, ay = it.a5 + cy * it.a4 + cxb * it.a3;
-            uint8_t* drow = gh_smem + r * Wps + gh_row_skew(r);
+            uint8_t* drow = gh_smem + (r & 7) * P2 + gh_row_skew(r) + 4 * (r >> 3) + lx + (lx & 4);
             for (int X0 = (warp >> 2) * (8 * kGhFly); X0 < spr_w; X0 += 16 * kGhFly) {
                 uint32_t word[kGhFly], w0[kGhFly], w1[kGhFly];
                 int sh[kGhFly], bsh[kGhFly];
@@ -1059,10 +1093,11 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
                     if (X < spr_w && row_ok) {
                         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
                         const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
-                        drow[X] = (uint8_t)(bgr >> 16);                 // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
-                        drow[plane_bytes + X] = (uint8_t)(bgr >> 8);
-                        drow[2 * plane_bytes + X] = (uint8_t)bgr;
-                        drow[3 * plane_bytes + X] = on ? (uint8_t)255 : (uint8_t)0;
+                        uint8_t* d = drow + 2 * X0 + 16 * j;            // X0 is a multiple of 8: 8 * (X / 4) + X % 4 = 2 * X0 + 16 j + lx + (lx & 4)
+                        d[0] = (uint8_t)(bgr >> 16);                    // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
+                        d[plane_bytes] = (uint8_t)(bgr >> 8);
+                        d[2 * plane_bytes] = (uint8_t)bgr;
+                        d[3 * plane_bytes] = on ? (uint8_t)255 : (uint8_t)0;
                     }
                 }
             }
@@ -1076,8 +1111,6 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
 
     // ---------------------------------------------------------------- phase 2: MMA tiles of these 16 rows, all planes
     const int g = lane >> 2, t = lane & 3;
-    const int ntiles = (new_w + 7) >> 3, nsb = it.nkb & 0xffff;
-    const uint2* base = c.band + it.hband_off;
     const int64_t Hp = (spr_h + 15) & ~15;
     const int64_t plane_out = (int64_t)new_w * Hp;
     uint8_t* st = s_t[warp];
@@ -1085,11 +1118,12 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
     if (c.n_items >= 0) return;
 #endif
     for (int tile = warp; tile < ntiles; tile += 8) {
-        const int entry = reinterpret_cast<const int32_t*>(base)[tile];
+        const int entry = tile < kGhEntries ? s_ent[tile] : reinterpret_cast<const int32_t*>(base)[tile];
         const int xb = entry & 0xffffff, nblk = entry >> 24;
-        const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+        const uint2* frag = frags + (int64_t)tile * nsb * 192 + lane;
         const uint2 b0[3] = {__ldg(frag), __ldg(frag + 32), __ldg(frag + 64)};
-        const uint8_t* r_lo = gh_smem + g * Wps + gh_row_skew(g) + xb + 8 * t;      // row g of plane 0, this lane's 8-byte column
+        if (tile + 8 < ntiles) band_prefetch(frags + (int64_t)(tile + 8) * nsb * 192, lane);
+        const uint8_t* r_lo = gh_smem + g * P2 + gh_row_skew(g) + 2 * xb + 16 * t;  // row pair (g, g + 8) of plane 0, this lane's 8 columns
         const int xl = lane >> 2, q = lane & 3;                         // transposed store: 8 columns x 4 words of 4 rows
         const int X = tile * 8 + xl, y = y0 + 4 * q;
         uint8_t* outp = c.sprite_ws + it.tmp_off + (int64_t)X * Hp + y;
@@ -1097,7 +1131,7 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
 #pragma unroll 1
         for (int pl = 0; pl < 4; ++pl) {
             int acc[3][4];
-            mma_rows32(acc, r_lo + pl * plane_bytes, Wps, b0, frag, nblk);
+            mma_rows32i(acc, r_lo + pl * plane_bytes, b0, frag, nblk);
             // C fragment: {row g, col 2t}, {row g, col 2t+1}, {row g+8, col 2t}, {row g+8, col 2t+1} -> transposed [X][y]
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1214,18 +1248,24 @@ __global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
         const uint8_t* gsrc = c.sprite_ws + it.tmp_off + ((int64_t)pl * new_w + min(X0 + r, new_w - 1)) * Hp;
         bulk_g2s(vs_smem + pl * plane_bytes + r * Hps + gh_row_skew(r), gsrc, (uint32_t)Hp, &bar);
     }
+    const int ntiles = (new_h + 7) >> 3, nsb = it.nkb >> 16;
+    const uint2* base = c.band + it.vband_off;
+    const uint2* frags = base + ((ntiles + 1) >> 1);
+    if (warp < ntiles) band_prefetch(frags + (int64_t)warp * nsb * 192, lane);
+    int entry = warp < ntiles ? reinterpret_cast<const int32_t*>(base)[warp] : 0;
     mbar_wait(&bar, 0);
 
     // ---- phase 2: output tiles of 8 rows, all planes per warp
     const int g = lane >> 2, t = lane & 3;
-    const int ntiles = (new_h + 7) >> 3, nsb = it.nkb >> 16;
-    const uint2* base = c.band + it.vband_off;
     uint32_t* dst = reinterpret_cast<uint32_t*>(c.sprite_ws + it.spr_off);
     for (int tile = warp; tile < ntiles; tile += 8) {
-        const int entry = reinterpret_cast<const int32_t*>(base)[tile];
         const int yb = entry & 0xffffff, nblk = entry >> 24;
-        const uint2* frag = base + ((ntiles + 1) >> 1) + (int64_t)tile * nsb * 192 + lane;
+        const uint2* frag = frags + (int64_t)tile * nsb * 192 + lane;
         const uint2 b0[3] = {__ldg(frag), __ldg(frag + 32), __ldg(frag + 64)};
+        if (tile + 8 < ntiles) {                                         // next tile: entry in flight, fragments towards L1
+            entry = reinterpret_cast<const int32_t*>(base)[tile + 8];
+            band_prefetch(frags + (int64_t)(tile + 8) * nsb * 192, lane);
+        }
         const uint8_t* r_lo = vs_smem + g * Hps + gh_row_skew(g) + yb + 8 * t;
         uint32_t px[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
