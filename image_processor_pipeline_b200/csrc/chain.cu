@@ -866,6 +866,11 @@ __device__ __forceinline__ void mma_rows(int (&acc)[3][4], const uint4& lo, cons
 __device__ __forceinline__ void band_prefetch(const uint2* tile_frags, int lane) {
     if (lane < 12) asm volatile("prefetch.global.L1 [%0];" :: "l"(tile_frags + lane * 16));
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 // Shared-memory passes: 32-position blocks.  Lane (g, t) reads 8 bytes of rows g and g + 8 per block (positions 8t .. 8t+7
 // of the block = both k-halves of its A fragment); the tile's entry says how many blocks carry non-zero taps, usually one
 // for down-scales up to ~2.5x — half the MMAs of a 64-position super-block.
@@ -873,15 +878,16 @@ __device__ __forceinline__ void mma_rows32(int (&acc)[3][4], const uint8_t* r_lo
                                            const uint2* frag, int nblk) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { acc[0][i] = 1 << (kPrec - 1); acc[1][i] = 0; acc[2][i] = 0; }
+    // four 32-bit loads straight into the fragment's register order (64-bit loads would need the halves re-shuffled)
+    const uint32_t s_lo = smem_u32(r_lo), s_hi = smem_u32(r_lo + 8 * pitch);
     {
-        const uint2 lo = *reinterpret_cast<const uint2*>(r_lo), hi = *reinterpret_cast<const uint2*>(r_lo + 8 * pitch);
-        const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+        const uint32_t a[4] = {lds32(s_lo), lds32(s_hi), lds32(s_lo + 4), lds32(s_hi + 4)};
         mma_u8u8(acc[0], a, b0[0]); mma_u8u8(acc[1], a, b0[1]); mma_u8s8(acc[2], a, b0[2]);
     }
+#pragma unroll 1
     for (int blk = 1; blk < nblk; ++blk) {
         const uint2 b[3] = {__ldg(frag + blk * 96), __ldg(frag + blk * 96 + 32), __ldg(frag + blk * 96 + 64)};
-        const uint2 lo = *reinterpret_cast<const uint2*>(r_lo + 32 * blk), hi = *reinterpret_cast<const uint2*>(r_lo + 8 * pitch + 32 * blk);
-        const uint32_t a[4] = {lo.x, hi.x, lo.y, hi.y};
+        const uint32_t a[4] = {lds32(s_lo + 32 * blk), lds32(s_hi + 32 * blk), lds32(s_lo + 32 * blk + 4), lds32(s_hi + 32 * blk + 4)};
         mma_u8u8(acc[0], a, b[0]); mma_u8u8(acc[1], a, b[1]); mma_u8s8(acc[2], a, b[2]);
     }
 }
