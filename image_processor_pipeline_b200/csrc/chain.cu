@@ -441,13 +441,20 @@ __device__ __forceinline__ bool map_canvas(const SrcMap& m, int cx, int cy, int&
     return xin >= 0 && xin < m.w && yin >= 0 && yin < m.h;
 }
 
-// flat tile index -> (record index, tile inside the record) by binary search on tile_start
+// flat tile index -> record index (the last record whose tile_start is <= tile).  Called by the 32 lanes of one warp: every
+// round probes 32 records at once and narrows the range 33-fold, i.e. two dependent L2 round trips for up to 1089 records
+// where a scalar binary search needs ten — the search sits at the head of every CTA of the tile-list kernels.
 template <typename Rec, typename GetStart>
 __device__ __forceinline__ int find_record(const Rec* recs, int n, int tile, GetStart start_of) {
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (start_of(recs[mid]) <= tile) lo = mid; else hi = mid - 1;
+    const int lane = threadIdx.x & 31;
+    int lo = 0, hi = n;                             // the answer lies in [lo, hi)
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 32) / 33;
+        const int idx = lo + step * (lane + 1);
+        const bool le = idx < hi && start_of(recs[idx]) <= tile;        // monotone over the lanes
+        const int k = __popc(__ballot_sync(0xffffffffu, le));
+        hi = min(hi, lo + step * (k + 1));
+        lo += step * k;
     }
     return lo;
 }
@@ -470,8 +477,10 @@ __global__ void __launch_bounds__(256) chain_rot_bbox_kernel(const ipp_chain_rot
                                                              const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
                                                              int frame_h, int32_t* bbox_out) {
     __shared__ int s_rec;
-    if (threadIdx.x == 0)
-        s_rec = find_record(rots, n_rot, (int)blockIdx.x, [](const ipp_chain_rot& r) { return r.tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(rots, n_rot, (int)blockIdx.x, [](const ipp_chain_rot& r) { return r.tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     __syncthreads();
     const ipp_chain_rot rec = rots[s_rec];
     const int chunk = (int)blockIdx.x - rec.tile_start;
@@ -612,8 +621,10 @@ struct B2Common {
 constexpr int kGatherRows = 8;          // rows per lane: tile = 32 columns x 64 rows
 __global__ void __launch_bounds__(256) chain_gather_kernel(const B2Common c) {
     __shared__ int s_rec;
-    if (threadIdx.x == 0)
-        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int spr_w = it.spr_w, spr_h = it.spr_h;
@@ -942,8 +953,10 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     __shared__ __align__(16) uint8_t s_t[8][8 * 36];
     __shared__ __align__(128) uint8_t s_ring[8][kRing][1024];
-    if (threadIdx.x == 0)
-        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.h_tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.h_tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int lt = (int)blockIdx.x - it.h_tile_start;
@@ -1024,8 +1037,10 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
     __shared__ int s_rec;
     __shared__ __align__(16) uint8_t s_t[8][8 * 20];
     __shared__ int s_ent[kGhEntries];
-    if (threadIdx.x == 0)
-        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.gather_tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int spr_w = it.spr_w, spr_h = it.spr_h, new_w = it.new_w;
@@ -1159,8 +1174,10 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
 __global__ void __launch_bounds__(256) chain_vpass_kernel(const B2Common c) {
     __shared__ int s_rec;
     __shared__ __align__(128) uint8_t s_ring[8][kRing][1024];
-    if (threadIdx.x == 0)
-        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
     const int lt = (int)blockIdx.x - it.v_tile_start;
@@ -1234,8 +1251,10 @@ __global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
     extern __shared__ __align__(128) uint8_t vs_smem[];
     __shared__ int s_rec;
     __shared__ uint64_t bar;
-    if (threadIdx.x == 0)
-        s_rec = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+    if (threadIdx.x < 32) {
+        const int found = find_record(c.items, c.n_items, (int)blockIdx.x, [](const ipp_chain_item& r) { return r.v_tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
     if (threadIdx.x == 32) mbar_init(&bar, 1);
     __syncthreads();
     const ipp_chain_item& it = c.items[s_rec];
