@@ -1024,6 +1024,9 @@ __global__ void __launch_bounds__(256) chain_hpass_kernel(const B2Common c) {
 // then hit all 32 banks) and its eight warps run the MMA tiles of those rows from there: no planar sprite in global
 // memory, no load latency in the MMA loop.  Used whenever the widest sprite of the batch fits (ipp_chain_layout_host).
 __host__ __device__ inline int gh_row_pitch(int spr_w) { return ((spr_w + 64 + 127) / 128) * 128 + 64; }   // >= spr_w + 128, == 64 mod 128
+// rows of the staged vertical pass: Hp bytes (multiple of 16) + room for the 32-byte skew, == 64 mod 128.  Windows that run
+// past a row's end read the next row's bytes against zero coefficients.
+__host__ __device__ inline int vs_row_pitch(int spr_h) { return ((((spr_h + 15) & ~15) + 32 - 64 + 127) / 128) * 128 + 64; }
 __host__ __device__ inline int gh_row_skew(int r) { return (r & 2) * 16; }      // rows 2, 3 (mod 4): +32 bytes (same for r and r + 8)
 #ifndef IPP_GH_FLY
 #define IPP_GH_FLY 6
@@ -1262,7 +1265,7 @@ __global__ void __launch_bounds__(256) chain_vs_kernel(const B2Common c) {
     const int X0 = ((int)blockIdx.x - it.v_tile_start) * 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t Hp = (spr_h + 15) & ~15;
-    const int Hps = gh_row_pitch(spr_h);
+    const int Hps = vs_row_pitch(spr_h);
     const int plane_bytes = 16 * Hps;
     // ---- phase 1: 64 rows (plane, column) of Hp bytes each, one bulk copy per row (columns past the edge repeat the last one)
     // (the phase cannot complete before thread 0's arrive.expect_tx: its single arrival is still pending, so copies that land

@@ -353,7 +353,7 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
     // vertical pass staged per CTA (16 columns x 4 planes of the transposed intermediate) when the tallest sprite fits
     int max_h = 0;
     for (int i = 0; i < n_items; ++i) max_h = std::max(max_h, items[i].spr_h);
-    const int vpitch = ((max_h + 64 + 127) / 128) * 128 + 64;
+    const int vpitch = ((((max_h + 15) & ~15) + 32 - 64 + 127) / 128) * 128 + 64;   // vs_row_pitch (chain.cu)
     const int64_t vs_smem = n_items ? (int64_t)64 * vpitch + 1024 : 0;
     const bool vstaged = n_items > 0 && vs_smem <= 200 * 1024 && getenv("IPP_B2_UNFUSED") == nullptr;
     if (vstaged) {
