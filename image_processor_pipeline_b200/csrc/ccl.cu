@@ -83,10 +83,17 @@ struct GroupIdx {
     int img, by, k;
     bool ok;
 };
-// grid = (ceil(groups per image / 256), images): 32-bit index math, a CTA never straddles two images
-__device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n) {
+// grid = (ceil(groups per image / (256 * kRep)), images): 32-bit index math, a CTA never straddles two images.
+// Every thread visits kRep groups (rep = 0 .. kRep-1, 256 apart so that each visit of a warp is coalesced) and issues the
+// first loads of all of them before it looks at any: most groups of a keyed frame are empty, and one thread per group
+// spent its life waiting for a single load (the passes were bound by resident threads / latency, not by bandwidth).
+// measured per pass (512 keyed 1080p frames): the scans over mostly empty groups gain from 2-4 visits per thread, the
+// passes dominated by the union-find work of the big component want the threads (area: 1, merge: 2)
+constexpr int kRepInit = 4, kRepMerge = 2, kRepArea = 1, kRepBest = 4, kRepKeep = 2;
+template <int kRep>
+__device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n, int rep) {
     GroupIdx r;
-    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rem = (blockIdx.x * kRep + rep) * blockDim.x + threadIdx.x;
     r.img = (int)blockIdx.y;
     r.ok = rem < (uint32_t)(g.bh * g.bww) && r.img < n;
     uint32_t q = rem;                                      // rem / bww
@@ -134,20 +141,33 @@ __global__ void ccl_reset_kernel(const CclBuffers b, int n) {
 // (F then means "block of a run that needs union-find"; a set pixel whose F bit is clear belongs to an
 // isolated run, whose identity is its first block.)
 __global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
     unsigned long long cand = 0ull;
     int nfg_iso = 0;
-    if (t.ok) {
+    uint64_t P0[kRepInit], P1[kRepInit];
+#pragma unroll
+    for (int rep = 0; rep < kRepInit; ++rep) {
+        const GroupIdx t = group_index<kRepInit>(g, n, rep);
+        P0[rep] = 0ull; P1[rep] = 0ull;
+        if (t.ok) {
+            const uint32_t* r0 = b.bits + (int64_t)t.img * g.bits_stride + (int64_t)(2 * t.by) * g.wpr;
+            P0[rep] = load_px64(r0, t.k, g.wpr);
+            if ((2 * t.by + 1) < g.h) P1[rep] = load_px64(r0 + g.wpr, t.k, g.wpr);
+        }
+    }
+#pragma unroll
+    for (int rep = 0; rep < kRepInit; ++rep) {
+        const GroupIdx t = group_index<kRepInit>(g, n, rep);
+        if (!t.ok) continue;
         const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
         const uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
         const bool has1 = (2 * t.by + 1) < g.h;
         const uint32_t* r1 = r0 + g.wpr;
-        const uint64_t p0 = load_px64(r0, t.k, g.wpr), p1 = has1 ? load_px64(r1, t.k, g.wpr) : 0ull;
+        const uint64_t p0 = P0[rep], p1 = P1[rep];
         const uint64_t any = p0 | p1;
         const uint32_t Lc = compress_even(any), Rc = compress_even(any >> 1);
         uint32_t F = Lc | Rc;
         uint32_t carry = 0;
-        if (t.k > 0) carry = (r0[2 * t.k - 1] | (has1 ? r1[2 * t.k - 1] : 0u)) >> 31;
+        if (t.k > 0 && (Lc & 1u)) carry = (r0[2 * t.k - 1] | (has1 ? r1[2 * t.k - 1] : 0u)) >> 31;   // only bit 0 of C needs it
         const uint32_t C = ((Rc << 1) | carry) & Lc;
         const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
         if (F) {
@@ -185,27 +205,31 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const CclGeom g, const Cc
         b.cbits[cf] = C;
         b.fbits[cf] = F;
     }
-    // isolated runs: one argmax / pixel-count atomic per warp (warps straddle images only at image boundaries)
-    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
-    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
-        const unsigned long long m = warp_max_u64(cand);
-        const int tot = __reduce_add_sync(0xffffffffu, nfg_iso);
-        if ((threadIdx.x & 31) == 0 && tot) {
-            if (m > __ldcg(&b.best[img0])) atomicMax(&b.best[img0], m);   // best only grows: a stale read can only cause a redundant atomic
-            atomicAdd(&b.acc[8 * img0 + 4], tot);
-        }
-    } else if (nfg_iso) {
-        atomicMax(&b.best[t.img], cand);
-        atomicAdd(&b.acc[8 * t.img + 4], nfg_iso);
+    // isolated runs: one argmax / pixel-count atomic per warp (blockIdx.y is the image: a warp never straddles two)
+    const int img = (int)blockIdx.y;
+    const unsigned long long m = warp_max_u64(cand);
+    const int tot = __reduce_add_sync(0xffffffffu, nfg_iso);
+    if ((threadIdx.x & 31) == 0 && tot && img < n) {
+        if (m > __ldcg(&b.best[img])) atomicMax(&b.best[img], m);   // best only grows: a stale read can only cause a redundant atomic
+        atomicAdd(&b.acc[8 * img + 4], tot);
     }
 }
 
 // ---- phase 2: unions between runs of adjacent block rows (once per contact segment)
+__device__ __forceinline__ void ccl_merge_group(const CclGeom& g, const CclBuffers& b, const GroupIdx& t);
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
-    if (!t.ok || t.by == 0) return;
     // F == 0: nothing here, or only isolated runs (finished by the init pass; by definition they touch nothing above)
-    if (b.fbits[(int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k] == 0u) return;
+    uint32_t Fv[kRepMerge];
+#pragma unroll
+    for (int rep = 0; rep < kRepMerge; ++rep) {
+        const GroupIdx t = group_index<kRepMerge>(g, n, rep);
+        Fv[rep] = (t.ok && t.by > 0) ? b.fbits[(int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k] : 0u;
+    }
+#pragma unroll
+    for (int rep = 0; rep < kRepMerge; ++rep)
+        if (Fv[rep]) ccl_merge_group(g, b, group_index<kRepMerge>(g, n, rep));
+}
+__device__ __forceinline__ void ccl_merge_group(const CclGeom& g, const CclBuffers& b, const GroupIdx& t) {
     const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
     const uint32_t* rowT = bits + (int64_t)(2 * t.by) * g.wpr;
     const uint32_t* rowB = rowT - g.wpr;
@@ -259,16 +283,26 @@ __device__ __forceinline__ int segment_end(uint32_t C, int i) {
 // single atomicAdd per distinct root and round reaches L2 — a big blob costs ~1 atomic per
 // warp instead of one per run segment (same-address atomics serialise in L2).
 __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
-    uint32_t starts = 0, C = 0;
-    uint64_t p0 = 0, p1 = 0;
-    const uint32_t* crow = nullptr;
-    int2* L = nullptr;
-    int rowbase = 0, gb0 = 0;
-    if (t.ok) {
-        const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
-        const uint32_t F = b.fbits[cf + t.k];
+    uint32_t Fv[kRepArea];
+#pragma unroll
+    for (int rep = 0; rep < kRepArea; ++rep) {
+        const GroupIdx t = group_index<kRepArea>(g, n, rep);
+        Fv[rep] = t.ok ? b.fbits[(int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k] : 0u;
+    }
+    int nfg = 0;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int rep = 0; rep < kRepArea; ++rep) {
+        const uint32_t F = Fv[rep];
+        if (!__any_sync(0xffffffffu, F != 0u)) continue;
+        const GroupIdx t = group_index<kRepArea>(g, n, rep);
+        uint32_t starts = 0, C = 0;
+        uint64_t p0 = 0, p1 = 0;
+        const uint32_t* crow = nullptr;
+        int2* L = nullptr;
+        int rowbase = 0, gb0 = 0;
         if (F) {
+            const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
             C = b.cbits[cf + t.k];
             crow = b.cbits + cf;
             const uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
@@ -280,80 +314,78 @@ __global__ void __launch_bounds__(256) ccl_area_kernel(const CclGeom g, const Cc
             gb0 = t.k << 5;
             starts = F & (~C | 1u);
         }
-    }
-    int nfg = 0;
-    const int lane = threadIdx.x & 31;
-    while (__any_sync(0xffffffffu, starts != 0u)) {
-        long long key = -1 - (long long)lane;          // unique per lane when it has nothing to add
-        int cnt = 0;
-        int32_t* slot = nullptr;
-        if (starts) {
-            const int i = __ffs(starts) - 1;
-            starts &= starts - 1;
-            const int e = segment_end(C, i);
-            const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
-            cnt = __popcll(p0 & pm) + __popcll(p1 & pm);
-            const bool own = ((C >> i) & 1u) == 0u;
-            const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
-            const int root = find_root(L, rowbase + s);
-            if (own) L[rowbase + gb0 + i].x = root;
-            slot = &L[root].y;
-            key = (long long)(uintptr_t)slot;
-            nfg += cnt;
-        }
-        // neighbouring groups mostly sit in ONE component (the object): when every active lane has the same root a
-        // single reduction and atomic do; only mixed warps pay for match.any
-        const uint32_t active = __ballot_sync(0xffffffffu, slot != nullptr);
-        const long long key0 = __shfl_sync(0xffffffffu, key, __ffs(active) - 1);
-        if (__all_sync(0xffffffffu, slot == nullptr || key == key0)) {
-            const int sum = __reduce_add_sync(0xffffffffu, cnt);
-            if (slot && lane == __ffs(active) - 1) atomicAdd(slot, sum);
-        } else {
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            const int sum = __reduce_add_sync(peers, cnt);
-            if (slot && lane == __ffs(peers) - 1) atomicAdd(slot, sum);
+        while (__any_sync(0xffffffffu, starts != 0u)) {
+            long long key = -1 - (long long)lane;          // unique per lane when it has nothing to add
+            int cnt = 0;
+            int32_t* slot = nullptr;
+            if (starts) {
+                const int i = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const int e = segment_end(C, i);
+                const uint64_t pm = ((e == 32) ? ~0ull : ((1ull << (2 * e)) - 1ull)) & ~((1ull << (2 * i)) - 1ull);
+                cnt = __popcll(p0 & pm) + __popcll(p1 & pm);
+                const bool own = ((C >> i) & 1u) == 0u;
+                const int s = own ? (gb0 + i) : run_start(crow, gb0 + i);
+                const int root = find_root(L, rowbase + s);
+                if (own) L[rowbase + gb0 + i].x = root;
+                slot = &L[root].y;
+                key = (long long)(uintptr_t)slot;
+                nfg += cnt;
+            }
+            // neighbouring groups mostly sit in ONE component (the object): when every active lane has the same root a
+            // single reduction and atomic do; only mixed warps pay for match.any
+            const uint32_t active = __ballot_sync(0xffffffffu, slot != nullptr);
+            const long long key0 = __shfl_sync(0xffffffffu, key, __ffs(active) - 1);
+            if (__all_sync(0xffffffffu, slot == nullptr || key == key0)) {
+                const int sum = __reduce_add_sync(0xffffffffu, cnt);
+                if (slot && lane == __ffs(active) - 1) atomicAdd(slot, sum);
+            } else {
+                const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                const int sum = __reduce_add_sync(peers, cnt);
+                if (slot && lane == __ffs(peers) - 1) atomicAdd(slot, sum);
+            }
         }
     }
-    // foreground pixel count per image: one atomic per warp when the warp sits in one image
-    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
-    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
-        const int tot = __reduce_add_sync(0xffffffffu, nfg);
-        if (lane == 0 && tot) atomicAdd(&b.acc[8 * img0 + 4], tot);
-    } else if (nfg) {
-        atomicAdd(&b.acc[8 * t.img + 4], nfg);
-    }
+    // foreground pixel count per image: one atomic per warp (blockIdx.y is the image)
+    const int tot = __reduce_add_sync(0xffffffffu, nfg);
+    if (lane == 0 && tot) atomicAdd(&b.acc[8 * (int)blockIdx.y + 4], tot);
 }
 
 // ---- phase 4: argmax over roots of (area, smallest block index); one atomic per warp
 __global__ void __launch_bounds__(256) ccl_best_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
     unsigned long long best = 0ull;
-    if (t.ok) {
-        const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
-        uint32_t S = b.fbits[cf] & ~b.cbits[cf];
-        if (S) {
-            const int2* L = b.la + (int64_t)t.img * g.lab_stride;
-            const int base = t.by * g.bw + (t.k << 5);
-            while (S) {
-                const int i = __ffs(S) - 1;
-                S &= S - 1;
-                const int bi = base + i;
-                const int2 la = L[bi];
-                if (la.x == bi) {
-                    const unsigned long long key =
-                        ((unsigned long long)(uint32_t)la.y << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
-                    best = key > best ? key : best;
-                }
+    uint32_t Sv[kRepBest];
+#pragma unroll
+    for (int rep = 0; rep < kRepBest; ++rep) {
+        const GroupIdx t = group_index<kRepBest>(g, n, rep);
+        Sv[rep] = 0u;
+        if (t.ok) {
+            const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww + t.k;
+            const uint32_t F = b.fbits[cf];
+            if (F) Sv[rep] = F & ~b.cbits[cf];
+        }
+    }
+#pragma unroll
+    for (int rep = 0; rep < kRepBest; ++rep) {
+        uint32_t S = Sv[rep];
+        if (!S) continue;
+        const GroupIdx t = group_index<kRepBest>(g, n, rep);
+        const int2* L = b.la + (int64_t)t.img * g.lab_stride;
+        const int base = t.by * g.bw + (t.k << 5);
+        while (S) {
+            const int i = __ffs(S) - 1;
+            S &= S - 1;
+            const int bi = base + i;
+            const int2 la = L[bi];
+            if (la.x == bi) {
+                const unsigned long long key =
+                    ((unsigned long long)(uint32_t)la.y << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bi);
+                best = key > best ? key : best;
             }
         }
     }
-    const int img0 = __shfl_sync(0xffffffffu, t.img, 0);
-    if (__all_sync(0xffffffffu, !t.ok || t.img == img0)) {
-        const unsigned long long m = warp_max_u64(best);
-        if ((threadIdx.x & 31) == 0 && m) atomicMax(&b.best[img0], m);
-    } else if (best) {
-        atomicMax(&b.best[t.img], best);
-    }
+    const unsigned long long m = warp_max_u64(best);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&b.best[(int)blockIdx.y], m);
 }
 
 // each of the 32 low bits doubled: block bit i -> pixel bits 2i, 2i+1
@@ -371,16 +403,27 @@ __device__ __forceinline__ uint64_t spread_pairs(uint32_t v) {
 // (64 pixels x 2 rows).  Run segments are classified once for both pixel rows; isolated runs (pixels
 // whose F bit is clear) need no label lookup at all.
 __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const CclBuffers b, int n) {
-    const GroupIdx t = group_index(g, n);
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
-    if (t.ok) {
-        uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
-        uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
-        uint32_t* r1 = r0 + g.wpr;
-        const bool has1 = (2 * t.by + 1) < g.h;
-        const uint64_t p0 = load_px64(r0, t.k, g.wpr), p1 = has1 ? load_px64(r1, t.k, g.wpr) : 0ull;
+    uint64_t P0[kRepKeep], P1[kRepKeep];
+#pragma unroll
+    for (int rep = 0; rep < kRepKeep; ++rep) {
+        const GroupIdx t = group_index<kRepKeep>(g, n, rep);
+        P0[rep] = 0ull; P1[rep] = 0ull;
+        if (t.ok) {
+            const uint32_t* r0 = b.bits + (int64_t)t.img * g.bits_stride + (int64_t)(2 * t.by) * g.wpr;
+            P0[rep] = load_px64(r0, t.k, g.wpr);
+            if ((2 * t.by + 1) < g.h) P1[rep] = load_px64(r0 + g.wpr, t.k, g.wpr);
+        }
+    }
+#pragma unroll
+    for (int rep = 0; rep < kRepKeep; ++rep) {
+        const uint64_t p0 = P0[rep], p1 = P1[rep];
         const uint64_t any = p0 | p1;
         if (any) {
+            const GroupIdx t = group_index<kRepKeep>(g, n, rep);
+            uint32_t* bits = b.bits + (int64_t)t.img * g.bits_stride;
+            uint32_t* r0 = bits + (int64_t)(2 * t.by) * g.wpr;
+            uint32_t* r1 = r0 + g.wpr;
             const unsigned long long bk = b.best[t.img];
             const int best_root = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffull));
             const int64_t cf = (int64_t)t.img * g.cf_stride + (int64_t)t.by * g.bww;
@@ -418,41 +461,36 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
             }
             const uint64_t ka = k0 | k1;
             if (ka) {
-                minx = 64 * t.k + __ffsll((long long)ka) - 1;
-                maxx1 = 64 * t.k + 64 - __clzll((long long)ka);
-                miny = k0 ? 2 * t.by : 2 * t.by + 1;
-                maxy1 = k1 ? 2 * t.by + 2 : 2 * t.by + 1;
+                const int x0 = 64 * t.k + __ffsll((long long)ka) - 1, x1 = 64 * t.k + 64 - __clzll((long long)ka);
+                minx = min(minx, x0);
+                maxx1 = max(maxx1, x1);
+                miny = min(miny, k0 ? 2 * t.by : 2 * t.by + 1);
+                maxy1 = max(maxy1, k1 ? 2 * t.by + 2 : 2 * t.by + 1);
             }
         }
     }
-    // a warp may straddle two images only at image boundaries; reduce per warp, then atomics
-    const int wimg = __shfl_sync(0xffffffffu, t.img, 0);
-    const bool uniform = __all_sync(0xffffffffu, t.img == wimg || !t.ok);
-    if (uniform) {
-        minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
-        if ((threadIdx.x & 31) == 0 && maxx1 > 0) {
-            int32_t* acc = b.acc + 8 * wimg;
-            atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
-        }
-    } else if (t.ok && maxx1 > 0) {
-        int32_t* acc = b.acc + 8 * t.img;
+    // reduce per warp (blockIdx.y is the image), then atomics
+    minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
+    if ((threadIdx.x & 31) == 0 && maxx1 > 0) {
+        int32_t* acc = b.acc + 8 * (int)blockIdx.y;
         atomicMin(&acc[0], minx); atomicMin(&acc[1], miny); atomicMax(&acc[2], maxx1); atomicMax(&acc[3], maxy1);
     }
 }
 
 int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
-    const dim3 gb(ceil_div((int64_t)g.bh * g.bww, 256), n);
+    const int64_t groups = (int64_t)g.bh * g.bww;
+    auto grid = [&](int rep) { return dim3((unsigned)ceil_div(groups, 256 * rep), (unsigned)n); };
     { ipp::LaunchTimer _lt("ccl_reset_kernel", st); ccl_reset_kernel<<<ceil_div(n, 256), 256, 0, st>>>(b, n); }
     IPP_LAUNCH_CHECK();
-    { ipp::LaunchTimer _lt("ccl_init_kernel", st); ccl_init_kernel<<<gb, 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_init_kernel", st); ccl_init_kernel<<<grid(kRepInit), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    { ipp::LaunchTimer _lt("ccl_merge_kernel", st); ccl_merge_kernel<<<gb, 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_merge_kernel", st); ccl_merge_kernel<<<grid(kRepMerge), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    { ipp::LaunchTimer _lt("ccl_area_kernel", st); ccl_area_kernel<<<gb, 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_area_kernel", st); ccl_area_kernel<<<grid(kRepArea), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    { ipp::LaunchTimer _lt("ccl_best_kernel", st); ccl_best_kernel<<<gb, 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_best_kernel", st); ccl_best_kernel<<<grid(kRepBest), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
-    { ipp::LaunchTimer _lt("ccl_keep_kernel", st); ccl_keep_kernel<<<gb, 256, 0, st>>>(g, b, n); }
+    { ipp::LaunchTimer _lt("ccl_keep_kernel", st); ccl_keep_kernel<<<grid(kRepKeep), 256, 0, st>>>(g, b, n); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
