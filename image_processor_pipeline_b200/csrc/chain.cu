@@ -1320,13 +1320,13 @@ struct CParams {
     uint8_t* out;
     int64_t out_pitch, out_stride;
     int out_size;
-    int rows_per_cta;
+    int rows_per_cta, chunks_per_cta;
     uint32_t smem_row_stride;
 };
 
 __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParams c) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     const int tid = threadIdx.x;
     const ipp_chain_item& it = c.items[blockIdx.y];
     PasteParams p;
@@ -1338,24 +1338,37 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
     p.crop_x0 = it.sq_x0; p.crop_y0 = it.sq_y0; p.crop_w = it.sq_size; p.crop_h = it.sq_size;
     p.dst = c.out + (int64_t)it.out_slot * c.out_stride;
     p.dst_pitch = c.out_pitch;
-    const int row0 = blockIdx.x * c.rows_per_cta;
-    if (row0 >= p.crop_h) return;
-    const int nrows = min(c.rows_per_cta, p.crop_h - row0);
+    // A CTA walks chunks_per_cta consecutive chunks of rows_per_cta rows through two shared-memory buffers: the bulk copies of
+    // chunk j + 1 are in flight while chunk j is blended and written, and the item record is fetched once per CTA.
+    const int first = blockIdx.x * c.rows_per_cta * c.chunks_per_cta;
+    if (first >= p.crop_h) return;
+    const int nchunks = min(c.chunks_per_cta, (p.crop_h - first + c.rows_per_cta - 1) / c.rows_per_cta);
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
+    const size_t buf_bytes = (size_t)c.rows_per_cta * c.smem_row_stride;
 
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     __syncthreads();
-    if (tid < 32) {                                   // lane r issues the bulk copy of row r (rows_per_cta <= 8): no serial loop in front of the loads
+    auto issue = [&](int j) {                           // warp 0: lane r issues the bulk copy of row r of chunk j (rows_per_cta <= 8)
+        const int row0 = first + j * c.rows_per_cta;
+        const int nrows = min(c.rows_per_cta, p.crop_h - row0);
         Window w;
         w.base = nullptr; w.bytes = 0; w.shift = 0;
         if (tid < nrows) w = make_window(p.bg + (int64_t)(p.crop_y0 + row0 + tid) * p.bg_pitch + (int64_t)p.crop_x0 * 3, rowbytes);
         const uint32_t total = __reduce_add_sync(0xffffffffu, w.bytes);
-        if (tid == 0) mbar_expect_tx(&bar, total);
-        __syncwarp();                                 // the barrier is armed before any copy can complete on it
-        if (w.bytes) bulk_g2s(smem + (size_t)tid * c.smem_row_stride, w.base, w.bytes, &bar);
+        if (tid == 0) mbar_expect_tx(&bar[j & 1], total);
+        __syncwarp();                                   // the barrier is armed before any copy can complete on it
+        if (w.bytes) bulk_g2s(smem + (j & 1) * buf_bytes + (size_t)tid * c.smem_row_stride, w.base, w.bytes, &bar[j & 1]);
+    };
+    if (tid < 32) issue(0);
+    for (int j = 0; j < nchunks; ++j) {
+        if (j + 1 < nchunks) {
+            __syncthreads();                            // every warp is done reading the buffer chunk j + 1 lands in (chunk j - 1)
+            if (tid < 32) issue(j + 1);
+        }
+        mbar_wait(&bar[j & 1], (uint32_t)(j >> 1) & 1u);
+        const int row0 = first + j * c.rows_per_cta;
+        paste_rows_from_smem(p, smem + (j & 1) * buf_bytes, c.smem_row_stride, row0, min(c.rows_per_cta, p.crop_h - row0), tid);
     }
-    mbar_wait(&bar, 0);
-    paste_rows_from_smem(p, smem, c.smem_row_stride, row0, nrows, tid);
 }
 
 // ===================================================================== device LANCZOS tables
@@ -1680,10 +1693,20 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
     if (rows < 1) rows = 1;
     if (rows > out_size) rows = out_size;
     c.rows_per_cta = rows;
-    const size_t smem = (size_t)rows * c.smem_row_stride;
-    if (smem > 48 * 1024)
-        IPP_CUDA(cudaFuncSetAttribute(chain_paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(out_size, rows), n_items);
+    static const int chunks_env = getenv("IPP_PASTE_CHUNKS") ? atoi(getenv("IPP_PASTE_CHUNKS")) : 0;
+    c.chunks_per_cta = chunks_env > 0 ? chunks_env : 4;
+    const size_t smem = 2 * (size_t)rows * c.smem_row_stride;          // two chunk buffers
+    IPP_REQUIRE(smem <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
+    if (smem > 48 * 1024) {
+        static size_t smem_set[64] = {};          // per device; the attribute only ever grows
+        int dev_id = 0;
+        IPP_CUDA(cudaGetDevice(&dev_id));
+        if (dev_id < 0 || dev_id >= 64 || smem > smem_set[dev_id]) {
+            IPP_CUDA(cudaFuncSetAttribute(chain_paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev_id >= 0 && dev_id < 64) smem_set[dev_id] = smem;
+        }
+    }
+    dim3 grid(ceil_div(out_size, rows * c.chunks_per_cta), n_items);
     { ipp::LaunchTimer _lt("chain_paste_kernel", st); chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
