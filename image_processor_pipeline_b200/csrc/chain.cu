@@ -1073,6 +1073,7 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
         // coordinates are then linear in X: (ax + X * dax) >> 16, (ay + X * day) >> 16
         const int cxs = it.flip_h ? -1 : 1, cxb = (it.flip_h ? spr_w - 1 : 0) + it.fit_x0;
         const int dax = cxs * it.a0, day = cxs * it.a3;
+        const int cc_w = it.cc_w, cc_h = it.cc_h, cc_x = it.cc_x;       // registers: the record itself lives in global memory
         // A warp gathers 8 x 4 patches (lane = column lx of row ly of the patch): the source pixels of a patch are a
         // rotated 8 x 4 block of the frame, i.e. ~10 sectors per request where 32 pixels along one rotated line touch up to
         // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 8 * kGhFly columns; kGhFly patches per lane are in flight.
@@ -1095,13 +1096,13 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
                     if constexpr (decltype(affine)::value) {
                         xin = (ax + X * dax) >> 16;
                         yin = (ay + X * day) >> 16;
-                        inside = (unsigned)xin < (unsigned)it.cc_w && (unsigned)yin < (unsigned)it.cc_h;
+                        inside = ((unsigned)xin < (unsigned)cc_w) & ((unsigned)yin < (unsigned)cc_h);
                     } else {
                         inside = map_canvas(m, cxb + cxs * X, cy, xin, yin);
                     }
                     const bool use = inside && X < spr_w && row_ok;
                     if (!use) { xin = 0; yin = 0; }
-                    const int fx = it.cc_x + xin;
+                    const int fx = cc_x + xin;
                     sh[j] = use ? (fx & 31) : -1;
                     word[j] = fb[(uint32_t)(yin * c.wpr + (fx >> 5))];
                     // 32-bit byte offset inside the component rect (a frame is far smaller than 4 GB)
@@ -1113,8 +1114,7 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
                 }
 #pragma unroll
                 for (int j = 0; j < kGhFly; ++j) {
-                    const int X = X0 + 8 * j + lx;
-                    if (X < spr_w && row_ok) {
+                    {   // columns past the sprite / rows past its end are written too (zeros, into the padding of the row pair)
                         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
                         const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
                         uint8_t* d = drow + 2 * X0 + 16 * j;            // X0 is a multiple of 8: 8 * (X / 4) + X % 4 = 2 * X0 + 16 j + lx + (lx & 4)
