@@ -1074,6 +1074,8 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
         const int cxs = it.flip_h ? -1 : 1, cxb = (it.flip_h ? spr_w - 1 : 0) + it.fit_x0;
         const int dax = cxs * it.a0, day = cxs * it.a3;
         const int cc_w = it.cc_w, cc_h = it.cc_h, cc_x = it.cc_x;       // registers: the record itself lives in global memory
+        const uint8_t* fb_bytes = reinterpret_cast<const uint8_t*>(fb);
+        const int wpr = c.wpr;
         // A warp gathers 8 x 4 patches (lane = column lx of row ly of the patch): the source pixels of a patch are a
         // rotated 8 x 4 block of the frame, i.e. ~10 sectors per request where 32 pixels along one rotated line touch up to
         // 32.  Warp w owns rows 4*(w&3) .. +3 and every other group of 8 * kGhFly columns; kGhFly patches per lane are in flight.
@@ -1104,7 +1106,7 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
                     if (!use) { xin = 0; yin = 0; }
                     const int fx = cc_x + xin;
                     sh[j] = use ? (fx & 31) : -1;
-                    word[j] = fb[(uint32_t)(yin * c.wpr + (fx >> 5))];
+                    word[j] = *reinterpret_cast<const uint32_t*>(fb_bytes + ((uint32_t)(yin * wpr + (fx >> 5)) << 2));   // 32-bit byte offset
                     // 32-bit byte offset inside the component rect (a frame is far smaller than 4 GB)
                     const uint32_t off = (uint32_t)yin * pitch32 + (uint32_t)xin * 3u + frame_lsb;
                     const uint32_t* aw = reinterpret_cast<const uint32_t*>(frame_al + (off & ~3u));
@@ -1112,16 +1114,20 @@ __global__ void __launch_bounds__(256, 3) chain_gh_kernel(const B2Common c) {
                     w0[j] = aw[0];
                     w1[j] = bsh[j] > 8 ? aw[1] : 0u;
                 }
+                uint8_t* q0 = drow + 2 * X0;
+                uint8_t* q1 = q0 + plane_bytes;
+                uint8_t* q2 = q1 + plane_bytes;
+                uint8_t* q3 = q2 + plane_bytes;
 #pragma unroll
                 for (int j = 0; j < kGhFly; ++j) {
                     {   // columns past the sprite / rows past its end are written too (zeros, into the padding of the row pair)
                         const bool on = sh[j] >= 0 && ((word[j] >> sh[j]) & 1u);
                         const uint32_t bgr = on ? __funnelshift_r(w0[j], w1[j], bsh[j]) : 0u;
-                        uint8_t* d = drow + 2 * X0 + 16 * j;            // X0 is a multiple of 8: 8 * (X / 4) + X % 4 = 2 * X0 + 16 j + lx + (lx & 4)
-                        d[0] = (uint8_t)(bgr >> 16);                    // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
-                        d[plane_bytes] = (uint8_t)(bgr >> 8);
-                        d[2 * plane_bytes] = (uint8_t)bgr;
-                        d[3 * plane_bytes] = on ? (uint8_t)255 : (uint8_t)0;
+                        // X0 is a multiple of 8: 8 * (X / 4) + X % 4 = 2 * X0 + 16 j + lx + (lx & 4)
+                        q0[16 * j] = (uint8_t)(bgr >> 16);              // BGR -> R, G, B, A planes (premultiplied, alpha 0 / 255)
+                        q1[16 * j] = (uint8_t)(bgr >> 8);
+                        q2[16 * j] = (uint8_t)bgr;
+                        q3[16 * j] = on ? (uint8_t)255 : (uint8_t)0;
                     }
                 }
             }
