@@ -1700,7 +1700,9 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
     if (rows > out_size) rows = out_size;
     c.rows_per_cta = rows;
     static const int chunks_env = getenv("IPP_PASTE_CHUNKS") ? atoi(getenv("IPP_PASTE_CHUNKS")) : 0;
-    c.chunks_per_cta = chunks_env > 0 ? chunks_env : 4;
+    // four chunks per CTA once that still leaves ~8 waves of CTAs; small batches keep short CTAs (tail effect)
+    const int64_t chunk_ctas = (int64_t)ceil_div(out_size, rows) * n_items;
+    c.chunks_per_cta = chunks_env > 0 ? chunks_env : (int)std::max<int64_t>(1, std::min<int64_t>(4, chunk_ctas / ((int64_t)sm_count() * 32)));
     const size_t smem = 2 * (size_t)rows * c.smem_row_stride;          // two chunk buffers
     IPP_REQUIRE(smem <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
     if (smem > 48 * 1024) {
