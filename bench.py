@@ -251,6 +251,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=dev)
     _native.load()
     B = args.batch
