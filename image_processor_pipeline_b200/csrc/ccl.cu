@@ -94,15 +94,16 @@ template <int kRep>
 __device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n, int rep) {
     GroupIdx r;
     const uint32_t rem = (blockIdx.x * kRep + rep) * blockDim.x + threadIdx.x;
-    r.img = (int)blockIdx.y;
-    r.ok = rem < (uint32_t)(g.bh * g.bww) && r.img < n;
-    uint32_t q = rem;                                      // rem / bww
-    if (g.bww > 1) {
-        q = __umulhi(rem, g.bww_inv);                      // bww_inv = floor(2^32 / bww) + 1: exact or one too large
-        if (q * (uint32_t)g.bww > rem) --q;
+    const uint32_t p = rem >> 5, l = rem & 31u;            // patch, lane inside the patch
+    uint32_t q = p;                                        // p / pw
+    if (g.pw > 1) {
+        q = __umulhi(p, g.pw_inv);                         // pw_inv = floor(2^32 / pw) + 1: exact or one too large
+        if (q * (uint32_t)g.pw > p) --q;
     }
-    r.by = (int)q;
-    r.k = (int)(rem - q * (uint32_t)g.bww);
+    r.img = (int)blockIdx.y;
+    r.by = (int)(q * kCclPatchH + l / kCclPatchW);
+    r.k = (int)((p - q * (uint32_t)g.pw) * kCclPatchW + l % kCclPatchW);
+    r.ok = r.by < g.bh && r.k < g.bww && r.img < n;
     return r;
 }
 
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(256) ccl_keep_kernel(const CclGeom g, const Cc
 }
 
 int ccl_run(const CclGeom& g, const CclBuffers& b, int n, cudaStream_t st) {
-    const int64_t groups = (int64_t)g.bh * g.bww;
+    const int64_t groups = (int64_t)g.npatch * 32;          // threads: one per group slot of every warp patch
     auto grid = [&](int rep) { return dim3((unsigned)ceil_div(groups, 256 * rep), (unsigned)n); };
     { ipp::LaunchTimer _lt("ccl_reset_kernel", st); ccl_reset_kernel<<<ceil_div(n, 256), 256, 0, st>>>(b, n); }
     IPP_LAUNCH_CHECK();

@@ -25,12 +25,21 @@
 
 namespace ipp {
 
+// A warp of the group passes covers a PATCH of kCclPatchW x kCclPatchH groups (not 32 consecutive groups of one block row):
+// a compact object then fills whole warps and the background leaves whole warps empty, where a row-wise mapping ran the
+// long path of every pass at ~25 % lane efficiency.
+#ifndef IPP_CCL_PATCH_W
+#define IPP_CCL_PATCH_W 2
+#endif
+constexpr int kCclPatchW = IPP_CCL_PATCH_W, kCclPatchH = 32 / kCclPatchW;
 struct CclGeom {
     int w, h;        // pixels
     int wpr;         // 32-bit words per pixel row
     int bw, bh;      // blocks
     int bww;         // 32-bit words per block row
     uint32_t bww_inv;    // floor(2^32 / bww) + 1: __umulhi(x, bww_inv) = x / bww or one more (x * bww < 2^32)
+    int pw, npatch;      // warp patches (kCclPatchW x kCclPatchH groups) per band of block rows, and per image
+    uint32_t pw_inv;     // floor(2^32 / pw) + 1
     // per-image strides (in elements of the respective arrays)
     int64_t bits_stride;   // uint32 words
     int64_t cf_stride;     // uint32 words (C and F have the same shape)
@@ -55,6 +64,9 @@ static inline CclGeom make_ccl_geom(int w, int h) {
     g.bh = (h + 1) / 2;
     g.bww = (g.bw + 31) / 32;
     g.bww_inv = (uint32_t)((1ull << 32) / (uint64_t)g.bww) + 1u;
+    g.pw = (g.bww + kCclPatchW - 1) / kCclPatchW;
+    g.npatch = g.pw * ((g.bh + kCclPatchH - 1) / kCclPatchH);
+    g.pw_inv = (uint32_t)((1ull << 32) / (uint64_t)g.pw) + 1u;
     g.bits_stride = (int64_t)h * g.wpr;
     g.cf_stride = (int64_t)g.bh * g.bww;
     g.lab_stride = (int64_t)g.bh * g.bw;
