@@ -88,8 +88,15 @@ struct GroupIdx {
 // first loads of all of them before it looks at any: most groups of a keyed frame are empty, and one thread per group
 // spent its life waiting for a single load (the passes were bound by resident threads / latency, not by bandwidth).
 // measured per pass (512 keyed 1080p frames): the scans over mostly empty groups gain from 2-4 visits per thread, the
-// passes dominated by the union-find work of the big component want the threads (area: 1, merge: 2)
-constexpr int kRepInit = 4, kRepMerge = 2, kRepArea = 1, kRepBest = 4, kRepKeep = 2;
+// passes dominated by the union-find work of the big component want the threads (2 visits)
+#ifndef IPP_CCL_R_INIT
+#define IPP_CCL_R_INIT 4
+#define IPP_CCL_R_MERGE 2
+#define IPP_CCL_R_AREA 2
+#define IPP_CCL_R_BEST 4
+#define IPP_CCL_R_KEEP 2
+#endif
+constexpr int kRepInit = IPP_CCL_R_INIT, kRepMerge = IPP_CCL_R_MERGE, kRepArea = IPP_CCL_R_AREA, kRepBest = IPP_CCL_R_BEST, kRepKeep = IPP_CCL_R_KEEP;
 template <int kRep>
 __device__ __forceinline__ GroupIdx group_index(const CclGeom& g, int n, int rep) {
     GroupIdx r;
