@@ -68,6 +68,7 @@ __device__ __forceinline__ void copy_row_body(const uint8_t* win, uint32_t off0,
 //     DIV255(255 * bg) = bg) are skipped, opaque ones (alpha 255: DIV255(255 * s) = s) copied.
 // The sprite covers a few percent of the image, so pass 2 re-touches little; keeping the blend out of the
 // vector loop removes the per-byte phase arithmetic (pixels are 3 bytes, vectors 16) that dominated it.
+constexpr int kSprFly = 4;          // sprite pixels per lane in flight
 __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const uint8_t* smem, uint32_t smem_row_stride,
                                                      int row0, int nrows, int tid) {
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
@@ -82,6 +83,17 @@ __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const
         const uint8_t* s = p.bg + (int64_t)(p.crop_y0 + y) * p.bg_pitch + (int64_t)p.crop_x0 * 3;
         const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
         const RowSplit sp = split_row(d, rowbytes);
+        // sprite pixels of this row: the first kSprFly * 32 are requested BEFORE the row is streamed out, so that their L2 round
+        // trip overlaps the copy instead of heading a dependent load -> blend -> store loop (one round trip per 32 pixels)
+        const int sy = p.crop_y0 + y - p.pos_y;
+        const bool has_sprite = sy >= 0 && sy < p.sprite_h && hit_x1 > hit_x0;
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(p.sprite + (int64_t)(has_sprite ? sy : 0) * p.sprite_pitch) + (p.crop_x0 - p.pos_x);
+        uint32_t v[kSprFly];
+#pragma unroll
+        for (int k = 0; k < kSprFly; ++k) {
+            const int x = hit_x0 + 32 * k + lane;
+            v[k] = (has_sprite && x < hit_x1) ? __ldg(srow + x) : 0u;        // alpha 0: nothing to blend
+        }
         const uint32_t off0 = shift + sp.head;            // window offset of the first aligned output vector
         switch ((off0 & 15u) >> 2) {
             case 0: copy_row_body<0>(win, off0, d, sp.head, sp.nb, lane); break;
@@ -94,14 +106,11 @@ __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const
             const uint32_t b = sp.head + (sp.nb << 4) + (uint32_t)(lane - 16);
             d[b] = win[shift + b];
         }
-        const int sy = p.crop_y0 + y - p.pos_y;
-        if (sy >= 0 && sy < p.sprite_h && hit_x1 > hit_x0) {
+        if (has_sprite) {
             __syncwarp();
-            const uint32_t* srow = reinterpret_cast<const uint32_t*>(p.sprite + (int64_t)sy * p.sprite_pitch) + (p.crop_x0 - p.pos_x);
-            for (int x = hit_x0 + lane; x < hit_x1; x += 32) {
-                const uint32_t spx = __ldg(srow + x);
+            auto blend = [&](uint32_t spx, int x) {
                 const uint32_t a = spx >> 24;
-                if (a == 0u) continue;
+                if (a == 0u) return;
                 uint32_t o0 = spx & 255u, o1 = (spx >> 8) & 255u, o2 = (spx >> 16) & 255u;
                 if (a != 255u) {
                     const uint8_t* b = win + shift + 3 * x;
@@ -112,6 +121,18 @@ __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const
                 }
                 uint8_t* o = d + 3 * x;
                 o[0] = (uint8_t)o0; o[1] = (uint8_t)o1; o[2] = (uint8_t)o2;
+            };
+            for (int x0 = hit_x0; x0 < hit_x1; x0 += 32 * kSprFly) {
+                uint32_t nv[kSprFly];
+#pragma unroll
+                for (int k = 0; k < kSprFly; ++k) {                           // next batch in flight while this one is blended
+                    const int x = x0 + 32 * (kSprFly + k) + lane;
+                    nv[k] = x < hit_x1 ? __ldg(srow + x) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < kSprFly; ++k) blend(v[k], x0 + 32 * k + lane);
+#pragma unroll
+                for (int k = 0; k < kSprFly; ++k) v[k] = nv[k];
             }
         }
     }
