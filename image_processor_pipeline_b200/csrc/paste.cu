@@ -68,7 +68,10 @@ __device__ __forceinline__ void copy_row_body(const uint8_t* win, uint32_t off0,
 //     DIV255(255 * bg) = bg) are skipped, opaque ones (alpha 255: DIV255(255 * s) = s) copied.
 // The sprite covers a few percent of the image, so pass 2 re-touches little; keeping the blend out of the
 // vector loop removes the per-byte phase arithmetic (pixels are 3 bytes, vectors 16) that dominated it.
-constexpr int kSprFly = 4;          // sprite pixels per lane in flight
+#ifndef IPP_SPR_FLY
+#define IPP_SPR_FLY 4
+#endif
+constexpr int kSprFly = IPP_SPR_FLY;          // sprite pixels per lane in flight
 __device__ __forceinline__ void paste_rows_from_smem(const PasteParams& p, const uint8_t* smem, uint32_t smem_row_stride,
                                                      int row0, int nrows, int tid) {
     const uint32_t rowbytes = (uint32_t)p.crop_w * 3u;
