@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--pipes", type=int, default=1, help="independent chain streams per GPU, each on batch/pipes frames")
     ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
-    ap.add_argument("--e2e-frames", type=int, default=0, help="frames of the batch used by the end-to-end leg (0 = all)")
+    ap.add_argument("--e2e-frames", type=int, default=512, help="frames of the batch used by the end-to-end leg (0 = all; 512 = 8 GB of pinned host memory per rank)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
     args = ap.parse_args()
     if args.impl == "reference":
