@@ -336,6 +336,8 @@ int ipp_chain_stage_b1(const ipp_chain_geom* geom_host, const ipp_chain_rot* rot
  * coefficients split into three byte planes, int32 accumulation = Pillow's own arithmetic); `band`
  * (totals.band_units * 8 bytes) receives the coefficient bands in fragment order, derived from
  * `tables` by this call (max_band_warps = totals.max_band_warps).
+ * (Fragment format per axis: 64-position super-blocks for the passes that stream from global memory, 32-position blocks
+ * with a per-tile block count for the passes that work from shared memory; it follows the two *_smem_bytes arguments below.)
  * fused_smem_bytes = totals.fused_smem_bytes: when > 0 (every sprite of the batch is narrow enough) gather and h
  * pass are ONE kernel that keeps 16 gathered rows x 4 planes in shared memory (gather_tiles = its tiles: one per 16
  * sprite rows, h_tiles = 0); when 0 they are two kernels exchanging the planar sprite through sprite_ws
