@@ -342,3 +342,66 @@ def test_tensor_core_lanczos_passes_vs_pillow(sizes, monkeypatch):
         mine = out[off:off + nw * nh * 4].reshape(nh, nw, 4)
         ref = np.asarray(Image.fromarray(rgba[i], "RGBA").resize((nw, nh), Image.Resampling.LANCZOS))
         assert np.array_equal(mine, ref), (i, int((mine != ref).sum()))
+
+
+@pytest.mark.parametrize("flips", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("sizes", [((37, 53), (37, 20)), ((64, 40), (23, 40)), ((40, 30), (95, 77)), ((700, 520), (41, 33)),
+                                   ((301, 7), (9, 5)), ((5, 300), (4, 11)), ((1, 1), (3, 2)), ((129, 130), (128, 129)),
+                                   ((783, 756), (495, 468)), ((457, 451), (191, 185)), ((95, 49), (500, 17))])
+def test_fused_gather_and_staged_lanczos_vs_pillow(sizes, flips):
+    """Stage B2 in its shared-memory mode (fused gather + horizontal pass, CTA-staged vertical pass, 32-position
+    fragment blocks): frames and mask bits written by the test, identity map (+ both flips), result against
+    PIL.Image.resize(LANCZOS) of the (flipped) sprite — bit-exact, over identity passes, up-scaling, 17x down-scaling
+    and the largest / smallest sprites of the bench workload."""
+    import ctypes as C
+    from PIL import Image
+    from image_processor_pipeline_b200 import _native, hostmath
+    lib = _native.load()
+    (sw, sh), (nw, nh) = sizes
+    fh, fv = flips
+    r = np.random.default_rng(sw * 1000 + nw + 7 * fh)
+    n = 3
+    rgba = r.integers(0, 256, (n, sh, sw, 4), dtype=np.uint8)
+    alpha = r.random((n, sh, sw)) < 0.7
+    rgba[..., 3] = np.where(alpha, 255, 0)
+    frames = np.ascontiguousarray(rgba[..., [2, 1, 0]])                     # frames are BGR; pixels under a clear mask bit are ignored
+    items = np.zeros(n, dtype=chain.ITEM_DTYPE)
+    items["frame"] = np.arange(n)
+    items["kind"] = chain.KIND["copy"]
+    items["cc_w"], items["cc_h"], items["spr_w"], items["spr_h"] = sw, sh, sw, sh
+    items["flip_h"], items["flip_v"] = fh, fv
+    items["new_w"], items["new_h"] = nw, nh
+    tot = chain._layout(items)
+    assert tot["fused_smem"] > 0 and tot["vstaged_smem"] > 0 and tot["ht"] == 0
+    wpr = (sw + 31) // 32
+    bits = np.zeros((n, sh, wpr * 32), dtype=np.uint8)
+    bits[:, :, :sw] = alpha
+    words = np.packbits(bits.reshape(n, sh, wpr, 32), axis=-1, bitorder="little").view("<u4").reshape(n, sh, wpr)
+    bits_d = torch.from_numpy(np.ascontiguousarray(words).view(np.uint8).reshape(-1)).to(DEV)
+    pad = torch.zeros(4096, dtype=torch.uint8, device=DEV)
+    bits_d = torch.cat([bits_d, pad])
+    frames_d = torch.cat([torch.from_numpy(frames.reshape(-1)).to(DEV), pad])     # aligned word loads may look past the last pixel
+    ws = torch.zeros(tot["ws"], dtype=torch.uint8, device=DEV)
+    geom = chain._geom_struct(sw, sh, (0, 0, sw, sh), max(nw, 8), max(nh, 8), hostmath.pack_hsv_ranges(synth.REFERENCE_FILTERS))
+    items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)
+    tab_d = torch.zeros(max(1, tot["table_ints"]), dtype=torch.int32, device=DEV)
+    band_d = torch.zeros(max(tot["band_bytes"], 256), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    if tot["max_rows"]:
+        host = chain._host_tables(items, lib, tot["table_ints"])
+        tab_d[:len(host)] = torch.from_numpy(host).to(DEV)                 # exact tables: this test is about the passes
+    _native.check(lib.ipp_chain_stage_b2(frames_d.data_ptr(), sw * 3, sh * sw * 3, C.byref(geom), items_d.data_ptr(), n, tot["gt"], 0, tot["vt"],
+                                         tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], tot["fused_smem"], tot["vstaged_smem"],
+                                         bits_d.data_ptr(), ws.data_ptr(), st), "b2")
+    out = ws.cpu().numpy()
+    for i in range(n):
+        off = int(items[i]["spr_off"])
+        mine = out[off:off + nw * nh * 4].reshape(nh, nw, 4)
+        src = rgba[i].copy()
+        src[src[..., 3] == 0] = 0
+        if fh:
+            src = src[:, ::-1]
+        if fv:
+            src = src[::-1]
+        ref = np.asarray(Image.fromarray(np.ascontiguousarray(src), "RGBA").resize((nw, nh), Image.Resampling.LANCZOS))
+        assert np.array_equal(mine, ref), (i, int((mine != ref).sum()))
