@@ -251,8 +251,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line only: NCCL prints its version banner there when the communicator comes up, so the
+        # communicator is created (init + one barrier) with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _native.load()
     B = args.batch
     params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
