@@ -227,11 +227,6 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
-    ap.add_argument("--main-priority", type=int, default=0, help="priority boost of the stream that runs stages B2/C (0 = default stream)")
-    ap.add_argument("--stage-a-stream", default="side", choices=["side", "caller"])
-    ap.add_argument("--slots", type=int, default=2, help="keep-mask workspaces of the ChainStream (>= ahead + 1)")
-    ap.add_argument("--pipes", type=int, default=1, help="independent chain streams per GPU, each on batch/pipes frames")
-    ap.add_argument("--ahead", type=int, default=1, help="steps whose stage A is submitted ahead of the step being finished")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames of the batch used by the end-to-end leg (0 = all; 512 = 8 GB of pinned host memory per rank)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
@@ -281,45 +276,16 @@ def main():
         random.seed(1000 * rank + s)
         return chain.run_chain(frames_d, bgs_d, params)
 
-    # --pipes P: the batch is cut into P equal parts, each with its own ChainStream, CUDA stream and generator
-    # (like P pipeline processes sharing the GPU); their kernels overlap on the device.  Most chain kernels are
-    # latency-bound when alone (25-50 % issue utilisation), so interleaving two independent streams of them
-    # raises throughput.  P = 1: one stream, draw order identical to run_chain over the whole batch.
-    P = max(1, args.pipes)
-    part = B // P
-    assert part * P == B, "--batch must be a multiple of --pipes"
-    pipes = [chain.ChainStream(params, inputs_ready=True, slots=max(args.slots, args.ahead + 1), stage_a_stream=args.stage_a_stream) for _ in range(P)]   # inputs are resident
-    pstreams = [torch.cuda.Stream(dev) for _ in range(P)] if P > 1 else [None]
-    prngs = [random.Random() for _ in range(P)] if P > 1 else [random]
-    parts = [(frames_d[i * part:(i + 1) * part], bgs_d[i * part:(i + 1) * part]) for i in range(P)]
+    pipe = chain.ChainStream(params)
 
     def run_pipelined(first, count):
-        """`count` steps, software-pipelined: stage A of the next `--ahead` steps is in flight while step s is
-        planned and its stages B2/C are queued (ChainStream).  Exactly `count` stage-A launches and `count`
-        finishes per pipe."""
+        """`count` steps through ChainStream.map: the four phases of consecutive steps are interleaved on one
+        stream (finish(s-3), prepare(s-2), plan(s-1), submit(s)), so the device never waits for the host's
+        planning or for the small read-backs.  Draw order = step after step (re-seeded per step)."""
         n_out = 0
-        if P > 1:
-            cur = torch.cuda.current_stream()
-            for st in pstreams:
-                st.wait_stream(cur)
-        tickets = [collections.deque(pipes[i].submit(*parts[i]) for _ in range(min(args.ahead, count))) for i in range(P)]
-        submitted = min(args.ahead, count)
-        for s in range(count):
-            more = submitted < count
-            submitted += more
-            for i in range(P):
-                ctx = torch.cuda.stream(pstreams[i]) if P > 1 else contextlib.nullcontext()
-                with ctx:
-                    if more:
-                        tickets[i].append(pipes[i].submit(*parts[i]))
-                    prngs[i].seed(1000 * rank + first + s + 7919 * i)
-                    n_out += pipes[i].finish(tickets[i].popleft(), prngs[i]).images.shape[0]
-        for i in range(P):
-            pipes[i].flush()                                   # deferred table verification of the last batch
-        if P > 1:
-            cur = torch.cuda.current_stream()
-            for st in pstreams:
-                cur.wait_stream(st)
+        for res in pipe.map(((frames_d, bgs_d) for _ in range(count)), random,
+                            on_batch=lambda i: random.seed(1000 * rank + first + i)):
+            n_out += res.images.shape[0]
         return n_out
 
     def timed(fn, steps, warmup):
@@ -367,8 +333,7 @@ def main():
 
     # stages B2/C (the caller's stream) get a higher priority than stage A of the next batch (side stream):
     # the big persistent mask CTAs then fill SMs as the finishing batch drains instead of delaying it
-    main_stream = torch.cuda.Stream(dev, priority=-args.main_priority) if args.main_priority else torch.cuda.current_stream()
-    with ClockSampler(local) as clk, torch.cuda.stream(main_stream):
+    with ClockSampler(local) as clk:
         if args.no_pipeline:
             ms, n_out, launches = timed(step_resident, args.steps, args.warmup)
         else:
@@ -441,7 +406,7 @@ def main():
         line = {"metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline, "stage_a_steps_ahead": args.ahead, "chain_streams_per_gpu": max(1, args.pipes),
+                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline,
                            "l2": f"inputs per step {2 * B * 3 * FW * FH / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                            "host_work_in_step": "C++ planner (Python-compatible MT19937 draws) + 3 small device->host read-backs per batch (RNG bounds depend on sprite sizes; table-ambiguity count)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "ipp_launch_count": (C.c_longlong, []),
     "ipp_timing_enable": (_int, [_int]),
     "ipp_timing_report": (_int, [C.c_char_p, _int]),
+    "ipp_timing_timeline": (_int, [C.c_char_p, _int]),
     "ipp_remap_u8": (_int, [_u8p, _i64, _int, _int, _int, _int, _int, _int, _int, _int, _int,
                             _u8p, _i64, _int, _i64, _i64, _vp]),
     "ipp_symmetries_u8": (_int, [_u8p, _i64, _int, _int, _int, _u8p, _u8p, _u8p, _u8p, _i64, _int, _i64, _i64, _vp]),
@@ -155,4 +156,16 @@ def timing_report() -> dict:
         if part:
             name, cnt, ms = part.rsplit(":", 2)
             out[name] = (int(cnt), float(ms))
+    return out
+
+
+def timing_timeline() -> list:
+    """[(kernel, stream_id, start_ms, end_ms)] per launch since the previous report, in launch order (synchronises)."""
+    buf = C.create_string_buffer(1 << 22)
+    check(load().ipp_timing_timeline(buf, len(buf)), "ipp_timing_timeline")
+    out = []
+    for part in buf.value.decode().split(";"):
+        if part:
+            name, sid, t0, t1 = part.rsplit(":", 3)
+            out.append((name, int(sid), float(t0), float(t1)))
     return out

@@ -27,6 +27,7 @@ of the Python generator it is given) and ``planner="python"`` (the readable twin
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import ctypes as C
 import random as _random
@@ -80,6 +81,14 @@ class ChainParams:
     yolo_class_id: int = 0
     scale_min: float = 0.15
     scale_max: float = 0.30
+
+    def max_outputs_per_frame(self) -> int:
+        """Upper bound of images one frame can yield: rotations (+ original) x symmetry variants."""
+        pool, choose = self.resolved_pool()
+        variants = min(len(set(pool)), choose)
+        if self.sym_include_original and (choose < len(pool) or "o" not in pool):
+            variants += 1
+        return max(0, int(self.num_rotations) + int(bool(self.include_original))) * max(0, min(4, variants))
 
     def resolved_pool(self):
         pool = self.pool if self.pool else ["o", "h", "v", "hv"]
@@ -170,6 +179,7 @@ def release_scratch():
     """Drop the cached workspaces (they are re-created on demand)."""
     _SCRATCH.clear()
     _PINNED.clear()
+    _HOSTBUF.clear()
 
 
 # Small host->device uploads (plan records) go through rotating PINNED staging buffers: a copy from
@@ -470,143 +480,46 @@ def _host_tables(items: np.ndarray, lib, n_ints: int) -> np.ndarray:
 
 
 # =========================================================================== the chain
-def prefetch_stage_a(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, slot: int = 0,
-                     wait_events: Sequence = (), wait_current: bool = True, tag: str = "", stream=None) -> dict:
-    """Launch stage A (frame -> keep-mask + largest component; no random draws) of a batch on a side
-    stream, into the scratch of ``slot`` (0 or 1), and return a ticket for ``run_chain(..., _ticket=)``.
-    Lets the HBM-bound pass of batch k+1 run while the host plans / the GPU finishes batch k.
-    The launch waits for ``wait_events`` (previous readers of the slot) and, when ``wait_current``, for
-    everything queued so far on the current stream (the producer of ``frames``)."""
-    if not frames.is_cuda:
-        raise RuntimeError("prefetch_stage_a needs CUDA tensors (there is no CPU fallback)")
-    lib = _native.load()
-    dev = frames.device
-    frames = frames.contiguous()
-    n, FH, FW, _ = frames.shape
-    m, BH, BW, _ = backgrounds.shape
-    rect = hostmath.border_crop_rect(FW, FH, params.crop_margins)
-    ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
-    geom = _geom_struct(FW, FH, rect, BW, BH, ranges)
-    with torch.cuda.device(dev):
-        side = stream if stream is not None else _side_streams(dev)[0]
-        ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-        ws = _scratch(f"mask_s{slot}{tag}", ws_bytes, dev)
-        info_d = _scratch(f"info_s{slot}{tag}", n * 32, dev, torch.int32).view(n, 8)
-        if wait_current:
-            side.wait_stream(torch.cuda.current_stream())        # inputs / previous users of this slot
-        for ev in wait_events:
-            side.wait_event(ev)
-        _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
-                                            ws.data_ptr(), ws_bytes, n, side.cuda_stream), "ipp_chain_stage_a")
-        done = torch.cuda.Event()
-        done.record(side)
-    return dict(frames=frames, ws=ws, ws_bytes=ws_bytes, info_d=info_d, done=done, geom=geom, n=n, slot=slot)
+# One batch flows through four device phases separated only where a data-dependent size has to reach the
+# host generator (randint bounds depend on the sprite sizes):
+#
+#   A   mask + largest component            -> info  (32 B / frame)   read back
+#   B1  rotation draws, rotated bbox        -> bbox  (16 B / sprite)  read back
+#   T   item draws, layout, LANCZOS tables  -> rows whose rounding was ambiguous, WITH their content, read back
+#   B2C exact-row patches (rare), gather + LANCZOS + paste + square crop
+#
+# Every read-back is an asynchronous copy into pinned memory followed by an event; the host only ever waits
+# for the event of the phase it needs.  run_chain runs the four phases back to back (the waits are then plain
+# synchronisations); ChainStream interleaves the phases of consecutive batches on ONE stream so that the GPU
+# always has the later phases of older batches queued while the host waits / plans (software pipeline).
+AMB_REC = 64                  # int32 per flagged-row record (ippgpu.h, ipp_chain_tables)
+AMB_INLINE = 64               # records fetched with the count in the one asynchronous read-back
 
 
-class ChainStream:
-    """Software pipeline over consecutive batches.  ``submit`` launches stage A of a batch on a side
-    stream right away; ``finish`` does the rest: host planning, stage B1 on a third stream, stages
-    B2 + C queued on the current stream — and returns WITHOUT waiting for them (the images are ordinary
-    stream-ordered CUDA tensors).  With batch k+1 submitted before batch k is finished, the GPU always
-    has a stage A and a stage B2/C to run while the host plans: no device idle time between batches.
-
-    The one read-back stages B2/C need (the count of LANCZOS table rows flagged for exact host
-    verification) is copied to pinned memory asynchronously and looked at during the NEXT ``finish``
-    (before anything overwrites the shared workspaces), or by ``flush()``.  Random draws still happen
-    batch after batch, step-major inside a batch (no draw is made by ``submit``).
-
-    ``slots``: number of keep-mask workspaces = how many batches may be submitted ahead of the one being
-    finished, plus one (2: one batch ahead; 3: two ahead — stage A of batch k+2 is already done when
-    batch k+1 is planned, so the host never waits for it).
-
-    ``inputs_ready=True``: the caller guarantees that the tensors passed to ``submit`` are complete
-    (resident batches, or the caller synchronised) — stage A then does not wait for the work queued
-    on the current stream.  Default False: it waits (safe, but serialises behind stages B2/C)."""
-
-    _count = 0
-
-    def __init__(self, params: ChainParams, inputs_ready: bool = False, slots: int = 2, stage_a_stream: str = "side", **run_kw):
-        if slots < 2:
-            raise ValueError("ChainStream needs at least two keep-mask slots")
-        self.params, self.run_kw, self._n = params, run_kw, 0
-        self.inputs_ready = bool(inputs_ready)
-        if stage_a_stream not in ("side", "caller"):
-            raise ValueError("stage_a_stream must be 'side' or 'caller'")
-        self.stage_a_stream = stage_a_stream    # "caller": stage A is queued on the caller's stream (no kernel concurrency)
-        self.slots = int(slots)                 # batches that may be between submit() and the end of their stage B2
-        self._slot_free = [None] * self.slots   # event: stages B2/C of the batch that last used the slot are done
-        self._pending = None                    # deferred table verification of the previous batch
-        self._b1 = {}
-        self._side = {}
-        self._amb_host = None
-        ChainStream._count += 1
-        self.tag = f"#{ChainStream._count}"     # own workspaces: several ChainStreams may be in flight on one device
-
-    def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor):
-        # the deferred table check of the last finished batch is looked at BEFORE a new stage A is queued: a fix-up
-        # re-gathers its sprites and needs that batch's keep-mask, which the new stage A may overwrite
-        self._resolve_pending()
-        slot = self._n % self.slots
-        waits = [self._slot_free[slot]] if self._slot_free[slot] is not None else []
-        ticket = prefetch_stage_a(frames, backgrounds, self.params, slot=slot, wait_events=waits,
-                                  wait_current=not self.inputs_ready, tag=self.tag,
-                                  stream=torch.cuda.current_stream(frames.device) if self.stage_a_stream == "caller"
-                                  else self._stream(self._side, frames.device, 0))
-        ticket["backgrounds"] = backgrounds
-        self._n += 1
-        return ticket
-
-    def finish(self, ticket, rng=_random) -> "ChainResult":
-        return run_chain(ticket["frames"], ticket["backgrounds"], self.params, rng, _ticket=ticket, _pipe=self, **self.run_kw)
-
-    def flush(self):
-        """Resolve the deferred verification of the last finished batch (synchronises with it)."""
-        self._resolve_pending()
-
-    # ---- used by run_chain
-    @staticmethod
-    def _stream(cache, dev, priority):
-        key = dev.index if dev.index is not None else torch.cuda.current_device()
-        if key not in cache:
-            cache[key] = torch.cuda.Stream(dev, priority=priority)
-        return cache[key]
-
-    def _b1_stream(self, dev):
-        return self._stream(self._b1, dev, -1)                # B1 is tiny and on the host's critical path: high priority
-
-    def _resolve_pending(self):
-        pend, self._pending = self._pending, None
-        if pend is None:
-            return
-        pend["event"].synchronize()
-        n_amb = int(pend["host"][0])
-        res = pend["res"]
-        res.tables_flagged_rows = n_amb
-        res.tables_fixed_items = pend["fix"](n_amb) if n_amb else 0
-
-    def _defer(self, amb_d, res, fix):
-        if self._amb_host is None:
-            self._amb_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
-        host = self._amb_host[self._n % 2]
-        host.copy_(amb_d[:1], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self._pending = dict(event=ev, host=host, res=res, fix=fix)
+def amb_ints(capacity: int = AMB_CAPACITY) -> int:
+    return AMB_REC * (capacity + 1)
 
 
-def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
-              planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
-              _ticket: Optional[dict] = None, _upload_stream=None, _pipe: Optional["ChainStream"] = None,
-              _before_sync=None):
-    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB,
-    either on the same device or in PINNED HOST memory.  Host backgrounds are never uploaded whole:
-    once the square-crop offsets are planned, only each item's crop window crosses PCIe
-    (ipp_chain_upload_windows, on a side stream, overlapping stage B2).
-    Returns a ChainResult.  ``planner``: "native" (C++) or "python"; ``device_tables``: compute the
-    LANCZOS tables on the GPU (default with the native planner) with exact host fix-up of ambiguous
-    rows.  ``_shard`` (set by sharding.run_chain_sharded): this call holds frames [lo, hi) of a larger
-    job; stage-A / B1 metadata is gathered across ranks, the plan is made for ALL items with the shared
-    ``rng`` and only the items of the local frames are executed; returns (ChainResult, global indices)."""
+_HOSTBUF = {}
+
+
+def _pinned(name: str, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
+    """Grow-only pinned host buffer (read-back target), keyed by name."""
+    item = torch.empty(0, dtype=dtype).element_size()
+    n = max(1, (int(nbytes) + item - 1) // item)
+    buf = _HOSTBUF.get(name)
+    if buf is None or buf.numel() < n or buf.dtype != dtype:
+        buf = torch.empty(int(n * 1.25) + 256, dtype=dtype).pin_memory()
+        _HOSTBUF[name] = buf
+    return buf[:n]
+
+
+class _Batch:
+    """State of one batch between the phases."""
+    pass
+
+
+def _begin(frames, backgrounds, params, planner, device_tables, ambiguity_eps, shard, tag, slot=0) -> _Batch:
     if not frames.is_cuda:
         raise RuntimeError("run_chain needs CUDA frames (there is no CPU fallback)")
     host_bgs = not backgrounds.is_cuda
@@ -616,222 +529,372 @@ def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainPara
         raise TypeError("frames / backgrounds must be uint8 [N, H, W, 3]")
     if planner not in ("native", "python"):
         raise ValueError("planner must be 'native' or 'python'")
-    if device_tables is None:
-        device_tables = planner == "native"
-    lib = _native.load()
-    dev = frames.device
-    frames = frames.contiguous()
     if host_bgs and not backgrounds.is_contiguous():
         raise ValueError("host backgrounds must be contiguous")
-    backgrounds = backgrounds.contiguous()
-    n, FH, FW, _ = frames.shape
-    m, BH, BW, _ = backgrounds.shape
-    rect = hostmath.border_crop_rect(FW, FH, params.crop_margins)
-    ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
-    geom = _geom_struct(FW, FH, rect, BW, BH, ranges)
-    cs = min(BH, BW)
-    pp = _plan_params(params, BW, BH, m)
-    bridge = _RngBridge(rng) if planner == "native" else None
-    lo, hi = (0, n) if _shard is None else (_shard["lo"], _shard["hi"])
-    tag = _pipe.tag if _pipe is not None else ""
+    b = _Batch()
+    b.lib = _native.load()
+    b.dev = frames.device
+    b.frames = frames.contiguous()
+    b.backgrounds = backgrounds.contiguous()
+    b.host_bgs = host_bgs
+    b.params, b.planner = params, planner
+    b.device_tables = (planner == "native") if device_tables is None else bool(device_tables)
+    b.eps = float(ambiguity_eps)
+    b.n, b.FH, b.FW, _ = b.frames.shape
+    b.m, b.BH, b.BW, _ = b.backgrounds.shape
+    b.rect = hostmath.border_crop_rect(b.FW, b.FH, params.crop_margins)
+    b.ranges = hostmath.pack_hsv_ranges(params.color_ranges_to_exclude_hsv, params.zones, params.use_gimp_scale)
+    b.geom = _geom_struct(b.FW, b.FH, b.rect, b.BW, b.BH, b.ranges)
+    b.cs = min(b.BH, b.BW)
+    b.pp = _plan_params(params, b.BW, b.BH, b.m)
+    b.shard = shard
+    b.lo, b.hi = (0, b.n) if shard is None else (shard["lo"], shard["hi"])
+    b.tag, b.slot = tag, slot
+    b.phase = 0
+    return b
 
-    def finish(res, own):
-        if bridge is not None:
-            bridge.commit()
-        return res if _shard is None else (res, own)
 
-    with torch.cuda.device(dev):
-        # ------------------------------------------------------------------ stage A
-        if _ticket is not None:                                       # stage A was launched ahead on a side stream
-            ws, ws_bytes, info_d = _ticket["ws"], _ticket["ws_bytes"], _ticket["info_d"]
-            torch.cuda.current_stream().wait_event(_ticket["done"])
+def _phase_a(b: _Batch):
+    """Stage A on the current stream + asynchronous read-back of its 32 bytes per frame."""
+    lib, dev, n = b.lib, b.dev, b.n
+    b.info_host = _pinned(f"info{b.tag}/{b.slot}", max(1, n) * 32, torch.int32).view(-1, 8)[:n]
+    if n:
+        b.ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(b.geom), n)
+        b.ws = _scratch(f"mask{b.tag}/{b.slot}", b.ws_bytes, dev)
+        info_d = _scratch(f"info{b.tag}/{b.slot}", n * 32, dev, torch.int32).view(n, 8)
+        _native.check(lib.ipp_chain_stage_a(b.frames.data_ptr(), b.FW * 3, b.FH * b.FW * 3, C.byref(b.geom), info_d.data_ptr(),
+                                            b.ws.data_ptr(), b.ws_bytes, n, _stream()), "ipp_chain_stage_a")
+        b.info_host.copy_(info_d, non_blocking=True)
+    else:
+        b.ws, b.ws_bytes = _scratch(f"mask{b.tag}/{b.slot}", 256, dev), 256       # a rank that owns no frame still takes part in the gathers
+    b.ev_info = torch.cuda.Event()
+    b.ev_info.record(torch.cuda.current_stream())
+    b.phase = 1
+    _mark("stage_a_issued")
+
+
+def _phase_rot(b: _Batch, rng):
+    """Rotation step (host draws) + stage B1 + asynchronous read-back of the rotated boxes."""
+    lib, dev = b.lib, b.dev
+    b.ev_info.synchronize()                                           # wait #1: component boxes of this batch
+    _mark("sync1_info")
+    info = b.info_host.numpy().copy()
+    if b.shard is not None:
+        info = b.shard["gather"](info)                                # 32 bytes of metadata per frame
+    b.bridge = _RngBridge(rng) if b.planner == "native" else None
+    if b.planner == "native":
+        b.rots_all, b.angles, b.rot_index = native_plan_rotations(info, b.pp, b.bridge)
+        b.py_rots = None
+        b.bridge.commit()
+    else:
+        b.py_rots = plan_rotations(info, b.params, rng)
+        b.rots_all, _ = _rot_records(b.py_rots)
+        b.angles = np.array([np.nan if r["angle"] is None else r["angle"] for r in b.py_rots], dtype=np.float64)
+        b.rot_index = np.array([r["rot_index"] for r in b.py_rots], dtype=np.int32)
+    local = (b.rots_all["frame"] >= b.lo) & (b.rots_all["frame"] < b.hi)
+    rots_loc = b.rots_all[local].copy()
+    rots_loc["frame"] -= b.lo
+    tiles = _b1_tiles(rots_loc)
+    rots_loc["tile_start"] = _excl(tiles)
+    nr = len(rots_loc)
+    b.n_rot_loc = nr
+    b.bbox_host = _pinned(f"bbox{b.tag}/{b.slot}", max(1, nr) * 16, torch.int32).view(-1, 4)[:nr]
+    b.rot_d = None
+    if nr:
+        bbox_d = _scratch(f"bbox{b.tag}/{b.slot}", nr * 16, dev, torch.int32).view(-1, 4)
+        b.rot_d = _upload("rots" + b.tag, rots_loc, dev)
+        _native.check(lib.ipp_chain_stage_b1(C.byref(b.geom), b.rot_d.data_ptr(), nr, int(tiles.sum()), b.ws.data_ptr(),
+                                             bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
+        b.bbox_host.copy_(bbox_d, non_blocking=True)
+    b.ev_bbox = torch.cuda.Event()
+    b.ev_bbox.record(torch.cuda.current_stream())
+    b.phase = 2
+    _mark("plan_rot+b1_issued")
+
+
+def _phase_items(b: _Batch, rng):
+    """Host plan of every later step (fit, symmetry, overlay, square crop: the remaining draws) + device
+    LANCZOS tables + asynchronous read-back of the rows whose rounding the host has to confirm."""
+    lib, dev = b.lib, b.dev
+    b.ev_bbox.synchronize()                                           # wait #2: rotated boxes
+    _mark("sync2_bbox")
+    bbox = b.bbox_host.numpy().copy()
+    if b.shard is not None:
+        bbox = b.shard["gather"](bbox)                                # 16 bytes per sprite, rank order == item order
+    if b.planner == "native":
+        bridge = _RngBridge(rng)
+        items, aux, labels = native_plan_items(b.rots_all, b.rot_index, bbox, b.pp, bridge)
+        bridge.commit()
+    else:
+        finals = plan_items(b.py_rots, bbox, b.params, rng, b.m, b.BW, b.BH)
+        items, aux = _python_plan_to_arrays(b.py_rots, finals)
+        labels = [f["label"] for f in finals]
+    own = np.flatnonzero((items["frame"] >= b.lo) & (items["frame"] < b.hi))
+    if b.shard is not None:
+        items, aux = items[own].copy(), aux[own].copy()
+        labels = [labels[i] for i in own]
+        items["frame"] -= b.lo
+    _mark("plan_items")
+    b.items, b.aux, b.labels, b.own = items, aux, labels, own.tolist()
+    b.tot = tot = _layout(items)
+    b.K = K = len(items)
+    _mark("layout")
+    b.out = torch.empty((K, b.cs, b.cs, 3), dtype=torch.uint8, device=dev)
+    b.amb_host = b.ev_amb = b.amb_d = None
+    if K:
+        b.items_d = _upload("items" + b.tag, items, dev)
+        if b.device_tables:
+            b.tab_d = _scratch("tables" + b.tag, max(1, tot["table_ints"]) * 4, dev, torch.int32)
+            b.amb_d = _scratch("amb" + b.tag, amb_ints() * 4, dev, torch.int32)
+            _native.check(lib.ipp_chain_tables(b.items_d.data_ptr(), K, tot["max_rows"], b.tab_d.data_ptr(), b.amb_d.data_ptr(),
+                                               AMB_CAPACITY, b.eps, _stream()), "ipp_chain_tables")
+            b.amb_host = _pinned(f"amb{b.tag}/{b.slot}", AMB_REC * (AMB_INLINE + 1) * 4, torch.int32)
+            b.amb_host.copy_(b.amb_d[:AMB_REC * (AMB_INLINE + 1)], non_blocking=True)
+            b.ev_amb = torch.cuda.Event()
+            b.ev_amb.record(torch.cuda.current_stream())
         else:
-            ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
-            ws = _scratch("mask" + tag, ws_bytes, dev)
-            info_d = _scratch("info" + tag, n * 32, dev, torch.int32).view(n, 8)
-            _native.check(lib.ipp_chain_stage_a(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info_d.data_ptr(),
-                                                ws.data_ptr(), ws_bytes, n, _stream()), "ipp_chain_stage_a")
-        _mark("stage_a_issued")
-        info = info_d.cpu().numpy()                                   # sync #1
-        _mark("sync1_info")
-        if _shard is not None:
-            info = _shard["gather"](info)                             # 32 bytes of metadata per frame
+            b.tab_d = torch.from_numpy(_host_tables(items, lib, tot["table_ints"])).to(dev)
+    b.phase = 3
+    _mark("tables_issued")
 
-        # ------------------------------------------------------------------ rotation step (host) + stage B1
-        if planner == "native":
-            rots_all, angles, rot_index = native_plan_rotations(info, pp, bridge)
-            py_rots = None
-        else:
-            py_rots = plan_rotations(info, params, rng)
-            rots_all, _ = _rot_records(py_rots)
-            angles = np.array([np.nan if r["angle"] is None else r["angle"] for r in py_rots], dtype=np.float64)
-            rot_index = np.array([r["rot_index"] for r in py_rots], dtype=np.int32)
-        local = (rots_all["frame"] >= lo) & (rots_all["frame"] < hi)
-        rots_loc = rots_all[local].copy()
-        rots_loc["frame"] -= lo
-        tiles = _b1_tiles(rots_loc)
-        rots_loc["tile_start"] = _excl(tiles)
-        bbox_d = _scratch("bbox" + tag, max(1, len(rots_loc)) * 16, dev, torch.int32).view(-1, 4)
-        rot_d = None
-        # pipelined: B1 runs on its own stream (stage A of this batch is complete — its info was read back),
-        # so it does not queue behind stages B2/C of the previous batch on the current stream
-        b1_ctx = torch.cuda.stream(_pipe._b1_stream(dev)) if _pipe is not None else contextlib.nullcontext()
-        with b1_ctx:
-            if len(rots_loc):
-                rot_d = _upload("rots", rots_loc, dev)
-                _native.check(lib.ipp_chain_stage_b1(C.byref(geom), rot_d.data_ptr(), len(rots_loc), int(tiles.sum()), ws.data_ptr(),
-                                                     bbox_d.data_ptr(), _stream()), "ipp_chain_stage_b1")
-            _mark("plan_rot+b1_issued")
-            bbox = bbox_d.cpu().numpy()[:len(rots_loc)]               # sync #2
-        _mark("sync2_bbox")
-        if _shard is not None:
-            bbox = _shard["gather"](bbox)                             # 16 bytes per sprite, rank order == item order
 
-        # ------------------------------------------------------------------ host: fit, symmetry, overlay, square-crop plans
-        if planner == "native":
-            items, aux, labels = native_plan_items(rots_all, rot_index, bbox, pp, bridge)
-        else:
-            finals = plan_items(py_rots, bbox, params, rng, m, BW, BH)
-            items, aux = _python_plan_to_arrays(py_rots, finals)
-            labels = [f["label"] for f in finals]
-        own = np.flatnonzero((items["frame"] >= lo) & (items["frame"] < hi))
-        if _shard is not None:
-            items, aux = items[own].copy(), aux[own].copy()
-            labels = [labels[i] for i in own]
-            items["frame"] -= lo
-        _mark("plan_items")
-        tot = _layout(items)
-        K = len(items)
-        _mark("layout")
-        out = torch.empty((K, cs, cs, 3), dtype=torch.uint8, device=dev)
-        rec_arrays = (items, aux, rot_index, angles)
-        if K == 0:
-            return finish(ChainResult(out, [], record_arrays=rec_arrays), own.tolist())
-
-        # ------------------------------------------------------------------ tables, sprite workspace
-        if _pipe is not None:
-            _pipe._resolve_pending()          # previous batch's table check, before its workspaces are overwritten
-        items_d = _upload("items", items, dev)
-        spr_ws = _scratch("sprites" + tag, max(tot["ws"], 256), dev)
-        band_d = _scratch("bands" + tag, max(tot["band_bytes"], 256), dev)
-        amb_d = None
-        if device_tables:
-            tab_d = _scratch("tables" + tag, max(1, tot["table_ints"]) * 4, dev, torch.int32)
-            amb_d = _scratch("amb" + tag, (1 + 3 * AMB_CAPACITY) * 4, dev, torch.int32)
-            _native.check(lib.ipp_chain_tables(items_d.data_ptr(), K, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
-                                               AMB_CAPACITY, float(ambiguity_eps), _stream()), "ipp_chain_tables")
-        else:
-            tab_d = torch.from_numpy(_host_tables(items, lib, tot["table_ints"])).to(dev)
-
-        # ------------------------------------------------------------------ stage C input: device backgrounds or host windows
-        h2d_bytes = 0
-        bg_ready = None
-        if host_bgs and K * cs * cs >= m * BH * BW:                   # many items per background: whole images are fewer bytes
-            backgrounds = backgrounds.to(dev, non_blocking=True)
-            h2d_bytes = int(backgrounds.numel())
-            host_bgs = False
-        if host_bgs:
-            items_c = items.copy()                                     # stage C sees window i as "background i", crop origin (0, 0)
-            items_c["bg"] = np.arange(K)
-            items_c["pos_x"] -= items["sq_x0"]
-            items_c["pos_y"] -= items["sq_y0"]
-            items_c["sq_x0"] = 0
-            items_c["sq_y0"] = 0
-            items_c_d = _upload("items_c", items_c, dev)
-            bg_dev = _scratch("bg_windows" + tag, K * cs * cs * 3, dev)
-            geom_c = _geom_struct(FW, FH, rect, cs, cs, ranges)
-            bg_pitch, bg_stride = cs * 3, cs * cs * 3
-            up = _upload_stream if _upload_stream is not None else _side_streams(dev)[0]
-            up.wait_stream(torch.cuda.current_stream())                # previous readers of the window buffer
-            _native.check(lib.ipp_chain_upload_windows(backgrounds.data_ptr(), BW * 3, BH * BW * 3, BW, BH, m, items.ctypes.data, K, cs,
-                                                       bg_dev.data_ptr(), up.cuda_stream), "ipp_chain_upload_windows")
-            bg_ready = torch.cuda.Event()
-            bg_ready.record(up)
-            h2d_bytes = K * cs * cs * 3
-        else:
-            items_c, items_c_d, bg_dev, geom_c = items, items_d, backgrounds, geom
-            bg_pitch, bg_stride = BW * 3, BH * BW * 3
-
-        # ------------------------------------------------------------------ stage B2 + C
-        def run_b2_c(items_dev, items_c_dev, k, gt, ht, vt):
-            _native.check(lib.ipp_chain_stage_b2(frames.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), items_dev.data_ptr(), k,
-                                                 gt, ht, vt, tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"], tot["fused_smem"], tot["vstaged_smem"],
-                                                 ws.data_ptr(), spr_ws.data_ptr(), _stream()),
-                          "ipp_chain_stage_b2")
-            if bg_ready is not None:
-                torch.cuda.current_stream().wait_event(bg_ready)       # the windows have landed (copied while B2 ran)
-            _native.check(lib.ipp_chain_stage_c(bg_dev.data_ptr(), bg_pitch, bg_stride, C.byref(geom_c), items_c_dev.data_ptr(), k,
-                                                spr_ws.data_ptr(), out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
-                          "ipp_chain_stage_c")
-
-        run_b2_c(items_d, items_c_d, K, tot["gt"], tot["ht"], tot["vt"])
-        _mark("tables+b2+c_issued")
-
-        if _ticket is not None and _pipe is not None:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            _pipe._slot_free[_ticket["slot"]] = ev                    # the keep-mask of this slot may be overwritten after this
-
-        # ------------------------------------------------------------------ exactness fix-up of device tables (rare)
-        n_fixed, n_amb = 0, 0
-        res = ChainResult(out, labels, record_arrays=rec_arrays)
-        if device_tables and _pipe is not None:
-            res.tables_flagged_rows = res.tables_fixed_items = None   # known once the next finish() / flush() has looked
-            _pipe._defer(amb_d, res, lambda n: _fix_ambiguous_rows(lib, items, items_c, amb_d, n, tab_d, run_b2_c, dev, tot["fused_smem"] > 0, tot["vstaged_smem"] > 0))
-        elif device_tables:
-            if _before_sync is not None:
-                _before_sync()                                        # e.g. queue the next uploads before the host waits
-            n_amb = int(amb_d[0].item())                              # sync #3 (end of batch)
-            _mark("sync3_amb")
-            if n_amb:
-                n_fixed = _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, tot["fused_smem"] > 0, tot["vstaged_smem"] > 0)
-        for t in (rot_d, items_d, items_c_d):
-            if t is not None:
-                t.record_stream(torch.cuda.current_stream())
-
-    if not (device_tables and _pipe is not None):
+def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResult":
+    """Exact-row confirmation of the device tables (patches them where the C library's sin() decides
+    otherwise — before anything has read them), then stages B2 + C."""
+    lib, dev, items, tot, K, cs = b.lib, b.dev, b.items, b.tot, b.K, b.cs
+    res = ChainResult(b.out, b.labels, record_arrays=(b.items, b.aux, b.rot_index, b.angles))
+    res.tables_flagged_rows = res.tables_fixed_items = 0
+    res.h2d_background_bytes = 0
+    b.phase = 4
+    if K == 0:
+        return res
+    if b.ev_amb is not None:
+        if before_sync is not None:
+            before_sync()                                             # e.g. queue the next uploads before the host waits
+        b.ev_amb.synchronize()                                        # wait #3: flagged rows (with their content)
+        _mark("sync3_amb")
+        n_amb = int(b.amb_host[0])
         res.tables_flagged_rows = n_amb
-        res.tables_fixed_items = n_fixed
-    res.h2d_background_bytes = h2d_bytes
-    return finish(res, own.tolist())
+        if n_amb:
+            res.tables_fixed_items = _confirm_rows(lib, items, b.amb_d, b.amb_host, n_amb, b.tab_d, dev)
+    elif before_sync is not None:
+        before_sync()
+
+    # stage C input: device backgrounds or host windows
+    backgrounds, host_bgs = b.backgrounds, b.host_bgs
+    bg_ready = None
+    if host_bgs and K * cs * cs >= b.m * b.BH * b.BW:                 # many items per background: whole images are fewer bytes
+        backgrounds = backgrounds.to(dev, non_blocking=True)
+        res.h2d_background_bytes = int(backgrounds.numel())
+        host_bgs = False
+    if host_bgs:
+        items_c = items.copy()                                        # stage C sees window i as "background i", crop origin (0, 0)
+        items_c["bg"] = np.arange(K)
+        items_c["pos_x"] -= items["sq_x0"]
+        items_c["pos_y"] -= items["sq_y0"]
+        items_c["sq_x0"] = 0
+        items_c["sq_y0"] = 0
+        items_c_d = _upload("items_c" + b.tag, items_c, dev)
+        bg_dev = _scratch("bg_windows" + b.tag, K * cs * cs * 3, dev)
+        geom_c = _geom_struct(b.FW, b.FH, b.rect, cs, cs, b.ranges)
+        bg_pitch, bg_stride = cs * 3, cs * cs * 3
+        up = upload_stream if upload_stream is not None else _side_streams(dev)[0]
+        up.wait_stream(torch.cuda.current_stream())                   # previous readers of the window buffer
+        _native.check(lib.ipp_chain_upload_windows(backgrounds.data_ptr(), b.BW * 3, b.BH * b.BW * 3, b.BW, b.BH, b.m, items.ctypes.data, K, cs,
+                                                   bg_dev.data_ptr(), up.cuda_stream), "ipp_chain_upload_windows")
+        bg_ready = torch.cuda.Event()
+        bg_ready.record(up)
+        res.h2d_background_bytes = K * cs * cs * 3
+    else:
+        items_c_d, bg_dev, geom_c = b.items_d, backgrounds, b.geom
+        bg_pitch, bg_stride = b.BW * 3, b.BH * b.BW * 3
+
+    spr_ws = _scratch("sprites" + b.tag, max(tot["ws"], 256), dev)
+    band_d = _scratch("bands" + b.tag, max(tot["band_bytes"], 256), dev)
+    _native.check(lib.ipp_chain_stage_b2(b.frames.data_ptr(), b.FW * 3, b.FH * b.FW * 3, C.byref(b.geom), b.items_d.data_ptr(), K,
+                                         tot["gt"], tot["ht"], tot["vt"], b.tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"],
+                                         tot["fused_smem"], tot["vstaged_smem"], b.ws.data_ptr(), spr_ws.data_ptr(), _stream()),
+                  "ipp_chain_stage_b2")
+    if bg_ready is not None:
+        torch.cuda.current_stream().wait_event(bg_ready)              # the windows have landed (copied while B2 ran)
+    _native.check(lib.ipp_chain_stage_c(bg_dev.data_ptr(), bg_pitch, bg_stride, C.byref(geom_c), items_c_d.data_ptr(), K,
+                                        spr_ws.data_ptr(), b.out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
+                  "ipp_chain_stage_c")
+    _mark("b2+c_issued")
+    for t in (b.rot_d, b.items_d, items_c_d):
+        if t is not None:
+            t.record_stream(torch.cuda.current_stream())
+    return res
 
 
-def _fix_ambiguous_rows(lib, items, items_c, amb_d, n_amb, tab_d, run_b2_c, dev, fused: bool, vstaged: bool) -> int:
-    """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C
-    library's sin() (ipp_lanczos_row_host).  If a row really differs it is patched on the device and
-    the h/v passes + paste of the affected items are re-run (their gathered sprites are still valid).
-    Returns the number of items that had to be redone."""
-    if n_amb > AMB_CAPACITY:          # far too many flags: check every row
+def _confirm_rows(lib, items, amb_d, amb_host, n_amb, tab_d, dev) -> int:
+    """Rows whose quantisation was within eps of a rounding boundary are re-derived with the C library's
+    sin() (ipp_lanczos_row_host) and compared with what the device computed (the rows came back with their
+    flags).  A row that really differs is patched on the device — stages B2/C have not been queued yet, so
+    nothing ever reads an unconfirmed coefficient.  Returns the number of items with a patched row."""
+    whole = None
+    if n_amb > AMB_CAPACITY:          # far too many flags: check every row against the whole table
+        whole = tab_d.cpu().numpy()
+        recs = None
         triples = [(i, a, r) for i in range(len(items)) for a in (0, 1) if items[i]["v_ksize" if a else "h_ksize"]
                    for r in range(int(items[i]["new_h" if a else "new_w"]))]
     else:
-        triples = amb_d[1:1 + 3 * n_amb].cpu().numpy().reshape(-1, 3).tolist()
+        if n_amb > AMB_INLINE:
+            recs = amb_d[AMB_REC:AMB_REC * (n_amb + 1)].cpu().numpy().reshape(-1, AMB_REC)
+        else:
+            recs = amb_host[AMB_REC:AMB_REC * (n_amb + 1)].numpy().reshape(-1, AMB_REC)
+        triples = recs[:, :3].tolist()
     dirty = set()
-    for item, axis, row in triples:
+    for j, (item, axis, row) in enumerate(triples):
         it = items[item]
         ks = int(it["v_ksize" if axis else "h_ksize"])
         n_in, n_out = (int(it["spr_h"]), int(it["new_h"])) if axis else (int(it["spr_w"]), int(it["new_w"]))
         bo, ko = (int(it["vb_off"]), int(it["vk_off"])) if axis else (int(it["hb_off"]), int(it["hk_off"]))
-        b = np.empty(2, np.int32)
+        bnd = np.empty(2, np.int32)
         kk = np.empty(ks, np.int32)
-        _native.check(lib.ipp_lanczos_row_host(n_in, n_out, row, b.ctypes.data, kk.ctypes.data), "ipp_lanczos_row_host")
-        view = tab_d[ko + row * ks: ko + (row + 1) * ks]
-        if not np.array_equal(view.cpu().numpy(), kk):
-            view.copy_(torch.from_numpy(kk).to(dev))
-            tab_d[bo + 2 * row: bo + 2 * row + 2] = torch.from_numpy(b).to(dev)
+        _native.check(lib.ipp_lanczos_row_host(n_in, n_out, row, bnd.ctypes.data, kk.ctypes.data), "ipp_lanczos_row_host")
+        if whole is not None:
+            same = np.array_equal(whole[ko + row * ks: ko + (row + 1) * ks], kk) and np.array_equal(whole[bo + 2 * row: bo + 2 * row + 2], bnd)
+        elif ks <= AMB_REC - 6:
+            same = np.array_equal(recs[j, 6:6 + ks], kk) and int(recs[j, 3]) == int(bnd[0]) and int(recs[j, 4]) == int(bnd[1])
+        else:                         # row too long for a record (scale factors beyond ~9): compare against the table itself
+            same = np.array_equal(tab_d[ko + row * ks: ko + (row + 1) * ks].cpu().numpy(), kk)
+        if not same:
+            tab_d[ko + row * ks: ko + (row + 1) * ks].copy_(torch.from_numpy(kk).to(dev))
+            tab_d[bo + 2 * row: bo + 2 * row + 2].copy_(torch.from_numpy(bnd).to(dev))
             dirty.add(item)
-    if dirty:
-        sub = items[sorted(dirty)].copy()
-        gt, ht, vt = _pass_tiles(sub, fused, vstaged)
-        sub["gather_tile_start"], sub["h_tile_start"], sub["v_tile_start"] = _excl(gt), _excl(ht), _excl(vt)
-        sub_d = torch.from_numpy(sub.view(np.uint8)).to(dev)
-        sub_c = items_c[sorted(dirty)].copy()                  # stage C's view of the same items (host-window mode: shifted copies)
-        for name in ("gather_tile_start", "h_tile_start", "v_tile_start"):
-            sub_c[name] = sub[name]
-        sub_c_d = torch.from_numpy(sub_c.view(np.uint8)).to(dev)
-        run_b2_c(sub_d, sub_c_d, len(sub), int(gt.sum()), int(ht.sum()), int(vt.sum()))
-        torch.cuda.current_stream().synchronize()
     return len(dirty)
+
+
+def run_chain(frames: torch.Tensor, backgrounds: torch.Tensor, params: ChainParams, rng=_random, _shard=None,
+              planner: str = "native", device_tables: Optional[bool] = None, ambiguity_eps: float = AMBIGUITY_EPS,
+              _upload_stream=None, _before_sync=None, _tag: str = ""):
+    """frames: uint8 [N, H, W, 3] BGR (cv2 order) on a CUDA device; backgrounds: uint8 [M, BH, BW, 3] RGB,
+    either on the same device or in PINNED HOST memory.  Host backgrounds are never uploaded whole:
+    once the square-crop offsets are planned, only each item's crop window crosses PCIe
+    (ipp_chain_upload_windows, on a side stream, overlapping stage B2).
+    Returns a ChainResult.  ``planner``: "native" (C++) or "python"; ``device_tables``: compute the
+    LANCZOS tables on the GPU (default with the native planner); rows whose rounding is ambiguous are
+    confirmed on the host before stage B2 reads them.  ``_shard`` (set by sharding.run_chain_sharded): this
+    call holds frames [lo, hi) of a larger job; stage-A / B1 metadata is gathered across ranks, the plan is
+    made for ALL items with the shared ``rng`` and only the items of the local frames are executed;
+    returns (ChainResult, global indices)."""
+    b = _begin(frames, backgrounds, params, planner, device_tables, ambiguity_eps, _shard, _tag)
+    with torch.cuda.device(b.dev):
+        _phase_a(b)
+        _phase_rot(b, rng)
+        _phase_items(b, rng)
+        res = _phase_paste(b, _upload_stream, _before_sync)
+    return res if _shard is None else (res, b.own)
+
+
+class ChainStream:
+    """Software pipeline over consecutive batches on ONE stream (the caller's current stream).
+
+    The four phases of a batch (see above) are separate calls — ``submit`` (A), ``plan`` (B1), ``prepare`` (T),
+    ``finish`` (B2 + C, returns the ChainResult whose images are ordinary stream-ordered CUDA tensors) — so that
+    a caller can interleave consecutive batches: while the host waits for the small read-back of one phase
+    and plans, the GPU still has the later phases of older batches queued.  ``map`` does exactly that:
+
+        iteration s:  finish(s-3)   prepare(s-2)   plan(s-1)   submit(s)
+
+    Every wait then targets work that was queued a whole iteration earlier and is followed by several
+    milliseconds of queued kernels: the device never idles on the host.  ``finish`` runs the earlier
+    phases itself when they were not called (plain submit / finish use keeps working, with host stalls).
+
+    Random draws happen in ``plan`` (rotation angles) and ``prepare`` (everything else); ``map`` calls
+    prepare(s-2) before plan(s-1), which is the reference's order: all draws of batch k before those of k+1.
+    Results are exact when they are returned: ambiguous table rows are confirmed before stage B2 is queued.
+
+    ``slots``: keep-mask workspaces = batches between ``submit`` and ``finish`` (``map`` needs 3)."""
+
+    _count = 0
+
+    def __init__(self, params: ChainParams, inputs_ready: bool = True, slots: int = 4, **run_kw):
+        if slots < 1:
+            raise ValueError("ChainStream needs at least one keep-mask slot")
+        self.params, self._n = params, 0
+        self.slots = int(slots)
+        self.planner = run_kw.pop("planner", "native")
+        self.device_tables = run_kw.pop("device_tables", None)
+        self.eps = run_kw.pop("ambiguity_eps", AMBIGUITY_EPS)
+        run_kw.pop("stage_a_stream", None)                           # earlier versions ran stage A on a side stream
+        if run_kw:
+            raise TypeError(f"unexpected arguments {sorted(run_kw)}")
+        self.inputs_ready = bool(inputs_ready)                       # kept for callers; everything is stream-ordered now
+        self._live = collections.deque()
+        ChainStream._count += 1
+        self.tag = f"#{ChainStream._count}"     # own workspaces: several ChainStreams may be in flight on one device
+
+    def submit(self, frames: torch.Tensor, backgrounds: torch.Tensor) -> _Batch:
+        if len(self._live) >= self.slots:
+            raise RuntimeError(f"ChainStream: {self.slots} batches are already between submit() and finish()")
+        b = _begin(frames, backgrounds, self.params, self.planner, self.device_tables, self.eps, None, self.tag, self._n % self.slots)
+        self._n += 1
+        with torch.cuda.device(b.dev):
+            _phase_a(b)
+        self._live.append(b)
+        return b
+
+    def plan(self, b: _Batch, rng=_random):
+        if b.phase < 2:
+            with torch.cuda.device(b.dev):
+                _phase_rot(b, rng)
+
+    def prepare(self, b: _Batch, rng=_random):
+        self.plan(b, rng)
+        if b.phase < 3:
+            with torch.cuda.device(b.dev):
+                _phase_items(b, rng)
+
+    def finish(self, b: _Batch, rng=_random) -> "ChainResult":
+        self.prepare(b, rng)
+        with torch.cuda.device(b.dev):
+            res = _phase_paste(b)
+        self._live.remove(b)
+        return res
+
+    def flush(self):
+        """Kept for callers of earlier versions: results are final when finish() returns."""
+
+    def map(self, batches, rng=_random, on_batch=None):
+        """Generator: ChainResult per (frames, backgrounds) batch of the iterable, in order, software-pipelined
+        four deep.  ``on_batch(index)`` (optional) is called right before the draws of batch ``index`` start
+        (e.g. to re-seed the generator per batch)."""
+        if self.slots < 3:
+            raise ValueError("ChainStream.map needs slots >= 3")
+        it = iter(batches)
+        q = collections.deque()                                       # batches in flight, oldest first
+        k = 0
+        exhausted = False
+        while True:
+            # oldest first: finish(s-3), prepare(s-2), plan(s-1), then submit(s)
+            out = None
+            if q and q[0].phase >= 3 and (len(q) >= 3 or exhausted):
+                out = self.finish(q.popleft(), rng)
+            for b in q:
+                if b.phase == 2:
+                    self.prepare(b, rng)
+                    break
+            for b in q:
+                if b.phase == 1:
+                    if on_batch is not None:
+                        on_batch(b.index)
+                    self.plan(b, rng)
+                    break
+            if not exhausted:
+                try:
+                    f, g = next(it)
+                    b = self.submit(f, g)
+                    b.index = k
+                    k += 1
+                    q.append(b)
+                except StopIteration:
+                    exhausted = True
+            if out is not None:
+                yield out
+            if exhausted and not q:
+                return
 
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
@@ -907,8 +970,11 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
         arrays = []
         k_total = 0
         pending = []
+        cap = n * params.max_outputs_per_frame()
         if out_host is None:
-            out_host = torch.empty((n * 4, cs, cs, 3), dtype=torch.uint8).pin_memory()
+            out_host = torch.empty((cap, cs, cs, 3), dtype=torch.uint8).pin_memory()
+        elif out_host.shape[0] < cap:
+            raise ValueError(f"out_host holds {out_host.shape[0]} images; {n} frames can yield up to {cap} with these parameters")
         for c, (lo, hi) in enumerate(bounds):
             s = slots[c % n_slots]
             compute.wait_event(s["ready"])

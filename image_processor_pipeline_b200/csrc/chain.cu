@@ -1381,7 +1381,7 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
 struct TabParams {
     const ipp_chain_item* items;
     int32_t* tables;
-    int32_t* amb;      // [0] = count, then triples
+    int32_t* amb;      // [0] = count; record r at amb + 64 * (r + 1): {item, axis, row, xmin, xmax, ksize, k[0 .. 57]}
     int amb_cap;
     double eps;
 };
@@ -1439,9 +1439,10 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
     if (amb) {
         const int slot = atomicAdd(&p.amb[0], 1);
         if (slot < p.amb_cap) {
-            p.amb[1 + 3 * slot] = (int)blockIdx.y;
-            p.amb[2 + 3 * slot] = axis;
-            p.amb[3 + 3 * slot] = xx;
+            // the flagged row travels with its flag: the host verifies it from ONE read-back, without touching the tables
+            int32_t* rec = p.amb + 64 * (slot + 1);
+            rec[0] = (int)blockIdx.y; rec[1] = axis; rec[2] = xx; rec[3] = xmin; rec[4] = xmax; rec[5] = ksize;
+            for (int x = 0; x < ksize && x < 58; ++x) rec[6 + x] = k[x];
         }
     }
 }

@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <string.h>
 #include <vector>
 
 namespace ipp {
@@ -37,6 +38,7 @@ static std::atomic<int> g_timing{0};
 struct TimedLaunch {
     const char* name;
     cudaEvent_t a, b;
+    cudaStream_t st;
 };
 static std::mutex g_tmu;
 static std::vector<TimedLaunch> g_timed;
@@ -55,6 +57,7 @@ LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(s
     } else {
         if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
     }
+    t.st = st;
     cudaEventRecord(t.a, st);
     g_timed.push_back(t);
     slot_ = (int)g_timed.size() - 1;
@@ -103,6 +106,29 @@ int ipp_timing_report(char* buf_host, int buflen) {
     return IPP_OK;
 }
 
+// "name:stream:start_ms:end_ms;..." per launch since the last report (times relative to the first launch's
+// start event; events of different streams share the device clock), in launch order; synchronises and clears.
+int ipp_timing_timeline(char* buf_host, int buflen) {
+    using namespace ipp;
+    IPP_REQUIRE(buf_host && buflen > 0, IPP_ERR_BAD_ARG, "ipp_timing_timeline: bad buffer");
+    std::lock_guard<std::mutex> lock(g_tmu);
+    std::string out;
+    std::map<cudaStream_t, int> ids;
+    for (auto& t : g_timed) {
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventSynchronize(g_timed[0].a) == cudaSuccess &&
+            cudaEventElapsedTime(&t0, g_timed[0].a, t.a) == cudaSuccess && cudaEventElapsedTime(&t1, g_timed[0].a, t.b) == cudaSuccess) {
+            const int id = ids.emplace(t.st, (int)ids.size()).first->second;
+            char line[256];
+            snprintf(line, sizeof(line), "%s:%d:%.4f:%.4f;", t.name, id, t0, t1);
+            if ((int)(out.size() + strlen(line)) < buflen - 1) out += line;
+        }
+    }
+    for (auto& t : g_timed) g_event_pool.push_back({t.a, t.b});
+    g_timed.clear();
+    snprintf(buf_host, buflen, "%s", out.c_str());
+    return IPP_OK;
+}
 
 int ipp_version(void) { return IPP_VERSION; }
 

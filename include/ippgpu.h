@@ -53,6 +53,9 @@ int ipp_sm_count(int* out_host);
 long long ipp_launch_count(void);
 int ipp_timing_enable(int on);
 int ipp_timing_report(char* buf_host, int buflen);
+/* same launches as a timeline: "kernel:stream_id:start_ms:end_ms;..." in launch order, times relative to the
+ * first launch (events of all streams share the device clock); synchronises and clears like the report. */
+int ipp_timing_timeline(char* buf_host, int buflen);
 
 /* ---------------------------------------------------------------------------------
  * 1. flip x crop x copy as one load-address remap.
@@ -310,10 +313,13 @@ int ipp_chain_layout_host(ipp_chain_item* items_host, int n_items, ipp_plan_tota
 
 /* LANCZOS coefficient tables of all items computed ON THE DEVICE (double precision, the
  * libImaging operation order).  The C library's sin() cannot be reproduced bit for bit on the
- * GPU, so every coefficient whose rounding decision lies within `eps` (in units of 2^-22) of
- * a boundary is reported: amb_out[0] = count, then {item, axis, row} triples (capacity
- * amb_capacity).  The caller re-derives those rows with ipp_lanczos_row_host and re-runs
- * the affected items if a row really differs — results stay bit-exact. */
+ * GPU, so every row with a coefficient whose rounding decision lies within `eps` (in units of
+ * 2^-22) of a boundary is reported together with its device-computed content:
+ * amb_out[0] = count; record r < amb_capacity at amb_out + 64 * (r + 1) =
+ * {item, axis, row, xmin, xmax, ksize, k[0 .. min(ksize, 58) - 1]}  (amb_out holds
+ * 64 * (amb_capacity + 1) int32).  The caller re-derives those rows with ipp_lanczos_row_host
+ * and patches `tables` where a row really differs BEFORE ipp_chain_stage_b2 reads them —
+ * results stay bit-exact. */
 int ipp_chain_tables(const ipp_chain_item* items, int n_items, int max_rows_per_item, int32_t* tables,
                      int32_t* amb_out, int amb_capacity, double eps, void* stream);
 

@@ -10,21 +10,15 @@ frames_h, bgs_h = bench.make_inputs(B, seed=1)
 dev = torch.device('cuda:0')
 f = torch.from_numpy(frames_h).to(dev); b = torch.from_numpy(bgs_h).to(dev)
 params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **bench.CHAIN_KW)
-pipe = chain.ChainStream(params, inputs_ready=True)
+pipe = chain.ChainStream(params)
 
 
 def run(count, first):
-    t = pipe.submit(f, b)
-    for s in range(count):
-        chain._mark("submit_next")
-        nxt = pipe.submit(f, b) if s + 1 < count else None
-        random.seed(first + s)
-        pipe.finish(t)
-        t = nxt
-    pipe.flush()
+    for _ in pipe.map(((f, b) for _ in range(count)), random, on_batch=lambda i: random.seed(first + i)):
+        chain._mark("yield")
 
 
-run(3, 0)
+run(5, 0)
 torch.cuda.synchronize()
 chain.TRACE = []
 t0 = time.perf_counter()

@@ -121,12 +121,12 @@ def test_device_lanczos_tables_equal_host_tables():
     host = chain._host_tables(items, lib, tot["table_ints"])
     items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)
     tab_d = torch.zeros(tot["table_ints"], dtype=torch.int32, device=DEV)
-    amb_d = torch.zeros(1 + 3 * chain.AMB_CAPACITY, dtype=torch.int32, device=DEV)
+    amb_d = torch.zeros(chain.amb_ints(), dtype=torch.int32, device=DEV)
     _native.check(lib.ipp_chain_tables(items_d.data_ptr(), k, tot["max_rows"], tab_d.data_ptr(), amb_d.data_ptr(),
                                        chain.AMB_CAPACITY, chain.AMBIGUITY_EPS, torch.cuda.current_stream().cuda_stream), "tables")
     dev_tab = tab_d.cpu().numpy()
     n_amb = int(amb_d[0].item())
-    flagged = set(map(tuple, amb_d[1:1 + 3 * n_amb].cpu().numpy().reshape(-1, 3).tolist()))
+    flagged = set(map(tuple, amb_d[chain.AMB_REC:chain.AMB_REC * (n_amb + 1)].cpu().numpy().reshape(-1, chain.AMB_REC)[:, :3].tolist()))
     bad = np.flatnonzero(dev_tab != host)
     for idx in bad:                                               # map the flat index back to (item, axis, row)
         i = int(np.searchsorted(items["hb_off"] + (items["h_ksize"] == 0) * 0, idx, side="right") - 1)
@@ -256,14 +256,15 @@ def test_host_backgrounds_upload_only_crop_windows(bg_shape, run_kw):
         chain.run_chain(fd, torch.from_numpy(np.stack(bgs)), chain.ChainParams(**kw))      # pageable host memory
 
 
-@pytest.mark.parametrize("inputs_ready", [False, True])
+@pytest.mark.parametrize("mode", ["submit_finish", "phases", "map"])
 @pytest.mark.parametrize("run_kw", [dict(), dict(ambiguity_eps=0.2)])
-def test_chain_stream_pipelining_is_transparent(inputs_ready, run_kw):
-    """ChainStream (stage A of batch k+1 launched before batch k is finished, B1 on its own stream,
-    table verification deferred to the next finish / flush) gives the same images, labels and
+def test_chain_stream_pipelining_is_transparent(mode, run_kw):
+    """ChainStream (the four phases of consecutive batches interleaved on one stream, small read-backs through
+    pinned memory + events, table rows confirmed before stage B2 reads them) gives the same images, labels and
     generator state as plain run_chain calls — also when rows ARE flagged and re-derived."""
     H, W = 200, 320
-    batches = [([synth.frame(50 + b, i, H, W) for i in range(3)], [synth.background(50 + b, i, 240, 300) for i in range(2)]) for b in range(4)]
+    NB = 6
+    batches = [([synth.frame(50 + b, i, H, W) for i in range(3)], [synth.background(50 + b, i, 240, 300) for i in range(2)]) for b in range(NB)]
     kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
               pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
     dev_batches = [(torch.from_numpy(np.stack(f)).to(DEV), torch.from_numpy(np.stack(b)).to(DEV)) for f, b in batches]
@@ -274,19 +275,34 @@ def test_chain_stream_pipelining_is_transparent(inputs_ready, run_kw):
     plain = [(r.images.cpu().numpy(), r.labels) for r in plain]
     state = random.getstate()
     random.seed(77)
-    pipe = chain.ChainStream(chain.ChainParams(**kw), inputs_ready=inputs_ready, **run_kw)
-    ticket = pipe.submit(*dev_batches[0])
-    results = []
-    for k in range(4):
-        nxt = pipe.submit(*dev_batches[k + 1]) if k + 1 < 4 else None
-        results.append(pipe.finish(ticket))
-        ticket = nxt
-    assert results[-1].tables_flagged_rows is None          # not looked at yet
-    pipe.flush()
+    pipe = chain.ChainStream(chain.ChainParams(**kw), **run_kw)
+    if mode == "map":
+        results = list(pipe.map(iter(dev_batches)))
+    elif mode == "submit_finish":                 # one batch ahead; finish() runs the missing phases itself
+        ticket = pipe.submit(*dev_batches[0])
+        results = []
+        for k in range(NB):
+            nxt = pipe.submit(*dev_batches[k + 1]) if k + 1 < NB else None
+            results.append(pipe.finish(ticket))
+            ticket = nxt
+    else:                                         # hand-written interleaving, draws in batch order
+        results, q = [], []
+        for k in range(NB + 2):
+            if len(q) == 3 or (k >= NB and q):
+                results.append(pipe.finish(q.pop(0)))
+            if len(q) >= 2:
+                pipe.prepare(q[-2])
+            if q:
+                pipe.plan(q[-1])
+            if k < NB:
+                q.append(pipe.submit(*dev_batches[k]))
+        while q:
+            results.append(pipe.finish(q.pop(0)))
     assert random.getstate() == state
     assert [r.tables_flagged_rows for r in results] == flagged
     if run_kw:
         assert sum(flagged) > 0
+    assert len(results) == NB
     for (a, la), r in zip(plain, results):
         assert la == r.labels and np.array_equal(a, r.images.cpu().numpy())
 
@@ -324,7 +340,7 @@ def test_tensor_core_lanczos_passes_vs_pillow(sizes, monkeypatch):
     geom = chain._geom_struct(64, 64, (0, 0, 64, 64), 64, 64, hostmath.pack_hsv_ranges(synth.REFERENCE_FILTERS))
     items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)
     tab_d = torch.zeros(max(1, tot["table_ints"]), dtype=torch.int32, device=DEV)
-    amb_d = torch.zeros(1 + 3 * chain.AMB_CAPACITY, dtype=torch.int32, device=DEV)
+    amb_d = torch.zeros(chain.amb_ints(), dtype=torch.int32, device=DEV)
     band_d = torch.zeros(max(tot["band_bytes"], 256), dtype=torch.uint8, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     if tot["max_rows"]:
