@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
+    ap.add_argument("--stage-a-stream", default="caller", choices=["side", "caller"], help="stage A of new batches on a second stream")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames of the batch used by the end-to-end leg (0 = all; 512 = 8 GB of pinned host memory per rank)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
@@ -276,7 +277,7 @@ def main():
         random.seed(1000 * rank + s)
         return chain.run_chain(frames_d, bgs_d, params)
 
-    pipe = chain.ChainStream(params)
+    pipe = chain.ChainStream(params, stage_a_stream=args.stage_a_stream)
 
     def run_pipelined(first, count):
         """`count` steps through ChainStream.map: the four phases of consecutive steps are interleaved on one

@@ -106,6 +106,15 @@ PROTOTYPES = {
     "ipp_host_format6": (_int, [C.c_double, C.c_char_p, C.POINTER(C.c_double)]),
     "ipp_chain_stage_c": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _u8p, _u8p, _i64, _i64, _int, _vp]),
     "ipp_chain_upload_windows": (_int, [_vp, _i64, _i64, _int, _int, _int, _vp, _int, _int, _u8p, _vp]),
+    "ipp_crop_batch_u8": (_int, [_u8p, _i64, _i64, _int, _int, _int, _i32p, _int, _int, _u8p, _i64, _i64, _int, _vp]),
+    "ipp_plan_rotate_batch_host": (_int, [_int, _int, _int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "ipp_rotate_batch_u8": (_int, [_u8p, _i64, _i64, _int, _int, _int, _int, _vp, _int, _int, _int, _u8p, _i32p, _vp]),
+    "ipp_plan_overlay_batch_host": (_int, [_int, _int, _int, _int, C.POINTER(PlanParams), _vp, _vp, _vp, _vp, _vp, _int,
+                                           C.POINTER(PlanTotals)]),
+    "ipp_chain_layout_planar_host": (_int, [_vp, _int, C.POINTER(PlanTotals)]),
+    "ipp_sprite_planes_u8": (_int, [_u8p, _i64, _i64, _int, _int, _int, _vp, _int, _u8p, _vp]),
+    "ipp_chain_stage_c_rect": (_int, [_u8p, _i64, _i64, _int, _int, _vp, _int, _u8p, _u8p, _i64, _i64, _int, _int, _vp]),
+    "ipp_sprites_export_u8": (_int, [_vp, _int, _u8p, _u8p, _vp, _vp]),
 }
 
 EXCEPTION_FOR_CODE = {-1: ValueError, -2: ValueError, -3: MemoryError, -4: NotImplementedError}

@@ -26,10 +26,13 @@ def up_to_date() -> bool:
     return all(p.stat().st_mtime <= t for p in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: Path = OUT, defines=()) -> Path:
+    """``out`` / ``defines``: tuning variants (e.g. -DIPP_SEG_THREADS=512) built next to the product library
+    and selected at run time with IPPGPU_LIB=<path>; the product build takes neither."""
+    if not force and out == OUT and up_to_date():
         return OUT
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(OUT), str(CSRC / "ippgpu_all.cu")]
+    out.parent.mkdir(parents=True, exist_ok=True)
+    cmd = ["nvcc", *NVCC_FLAGS, *defines, "-o", str(out), str(CSRC / "ippgpu_all.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -37,8 +40,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:                       # python -m ...build --variant NAME -DX=1 -DY=2
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(force=True, verbose="-v" in sys.argv, out=HERE / "_variants" / f"libippgpu_{name}.so",
+                    defines=[a for a in sys.argv if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -810,18 +810,25 @@ class ChainStream:
 
     _count = 0
 
-    def __init__(self, params: ChainParams, inputs_ready: bool = True, slots: int = 4, **run_kw):
+    def __init__(self, params: ChainParams, inputs_ready: bool = True, slots: int = 4, stage_a_stream: str = "caller", **run_kw):
         if slots < 1:
             raise ValueError("ChainStream needs at least one keep-mask slot")
+        if stage_a_stream not in ("side", "caller"):
+            raise ValueError("stage_a_stream must be 'side' or 'caller'")
         self.params, self._n = params, 0
         self.slots = int(slots)
         self.planner = run_kw.pop("planner", "native")
         self.device_tables = run_kw.pop("device_tables", None)
         self.eps = run_kw.pop("ambiguity_eps", AMBIGUITY_EPS)
-        run_kw.pop("stage_a_stream", None)                           # earlier versions ran stage A on a side stream
         if run_kw:
             raise TypeError(f"unexpected arguments {sorted(run_kw)}")
-        self.inputs_ready = bool(inputs_ready)                       # kept for callers; everything is stream-ordered now
+        # "side": stage A (mask + largest component, no draws) of a new batch runs on a second stream, concurrently with the
+        # later phases of older batches on the caller's stream.  inputs_ready=False then makes it wait for the work queued
+        # on the caller's stream so far (the producer of the frames).
+        self.stage_a_stream = stage_a_stream
+        self.inputs_ready = bool(inputs_ready)
+        self._side = {}
+        self._slot_free = [None] * self.slots   # event: stages B2/C of the batch that last used the keep-mask slot are queued-complete
         self._live = collections.deque()
         ChainStream._count += 1
         self.tag = f"#{ChainStream._count}"     # own workspaces: several ChainStreams may be in flight on one device
@@ -832,13 +839,26 @@ class ChainStream:
         b = _begin(frames, backgrounds, self.params, self.planner, self.device_tables, self.eps, None, self.tag, self._n % self.slots)
         self._n += 1
         with torch.cuda.device(b.dev):
-            _phase_a(b)
+            if self.stage_a_stream == "side":
+                key = b.dev.index if b.dev.index is not None else torch.cuda.current_device()
+                side = self._side.setdefault(key, torch.cuda.Stream(b.dev))
+                if not self.inputs_ready:
+                    side.wait_stream(torch.cuda.current_stream())
+                if self._slot_free[b.slot] is not None:
+                    side.wait_event(self._slot_free[b.slot])         # last reader of this keep-mask slot
+                with torch.cuda.stream(side):
+                    _phase_a(b)
+                b.a_done = b.ev_info
+            else:
+                _phase_a(b)
         self._live.append(b)
         return b
 
     def plan(self, b: _Batch, rng=_random):
         if b.phase < 2:
             with torch.cuda.device(b.dev):
+                if getattr(b, "a_done", None) is not None:
+                    torch.cuda.current_stream().wait_event(b.a_done)  # stage A ran on the side stream
                 _phase_rot(b, rng)
 
     def prepare(self, b: _Batch, rng=_random):
@@ -851,6 +871,10 @@ class ChainStream:
         self.prepare(b, rng)
         with torch.cuda.device(b.dev):
             res = _phase_paste(b)
+            if self.stage_a_stream == "side":
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._slot_free[b.slot] = ev
         self._live.remove(b)
         return res
 

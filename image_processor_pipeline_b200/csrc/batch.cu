@@ -1,0 +1,236 @@
+// batch.cu — batched entry points of the stand-alone operators: n images per call, per-item
+// parameter records on the device, flat tile lists (one launch per batch whatever the sizes).
+//
+// Reference behaviour replaced, per image of a directory a ProcessingStep maps a transform over
+// (pipeline.py:304-437):
+//   * rotations.py:55,96-99   convert("RGBA") + Image.rotate(expand=True) + getbbox
+//   * overlays.py:104-149     LANCZOS resize of an RGBA sprite + paste onto an RGB background
+// The single-image entry points (rotate.cu, resample.cu, paste.cu) stay; a 1080p image is 2-3 us
+// of HBM time, so only a batch can come near the memory roofline.
+#include "staging.cuh"
+
+namespace ipp {
+
+// ===================================================================== rotation
+// CTA = 32 x 32 output tile of one canvas (8 lanes x 4 px wide, 4 rows per warp): the rotated source
+// footprint of a square tile is compact (<= 46 x 46 source pixels), so the gathers of a CTA share L1 lines
+// and every source byte leaves HBM once.  Canvas rows are padded to a multiple of four pixels: every lane
+// stores one aligned 16-byte vector.
+struct RotBatchParams {
+    const uint8_t* src;
+    int64_t src_pitch, src_stride;
+    int src_w, src_h;
+    const ipp_rot_item* items;
+    int n_items;
+    uint8_t* dst_pool;
+    int32_t* bbox;
+};
+
+// pixel (xin, yin) of a CH-channel image as RGBA (CH == 3: alpha 255, bytes from the aligned word(s) holding the pixel)
+template <int CH>
+__device__ __forceinline__ uint32_t fetch_rgba(const uint8_t* img, int64_t pitch, int xin, int yin) {
+    if (CH == 4) return __ldg(reinterpret_cast<const uint32_t*>(img + (int64_t)yin * pitch) + xin);
+    const uintptr_t a = (uintptr_t)(img + (int64_t)yin * pitch + xin * 3);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const int bsh = (int)(a & 3) * 8;
+    const uint32_t w0 = __ldg(aw), w1 = bsh > 8 ? __ldg(aw + 1) : 0u;      // every word read holds a byte of the pixel
+    return (__funnelshift_r(w0, w1, bsh) & 0x00ffffffu) | 0xff000000u;
+}
+
+// arithmetic without fma contraction in either precision (libImaging evaluates v1 + (v2 - v1) * d as written)
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ void premult_t(uint32_t v, T out[4]) {
+    const uint32_t a = v >> 24;
+    out[0] = (T)div255((v & 255u) * a);
+    out[1] = (T)div255(((v >> 8) & 255u) * a);
+    out[2] = (T)div255(((v >> 16) & 255u) * a);
+    out[3] = (T)a;
+}
+template <int CH> struct InterpType { typedef float type; };      // opaque sources: single precision, <= 1 LSB
+template <> struct InterpType<4> { typedef double type; };        // real alpha: libImaging's double (un-premultiply amplifies errors)
+
+template <int MODE, int CH>
+__global__ void __launch_bounds__(256) rotate_batch_kernel(const RotBatchParams p) {
+    __shared__ int s_rec;
+    if (threadIdx.x < 32) {
+        const int found = find_record(p.items, p.n_items, (int)blockIdx.x, [](const ipp_rot_item& r) { return r.tile_start; });
+        if (threadIdx.x == 0) s_rec = found;
+    }
+    __syncthreads();
+    const int rec = s_rec;
+    const ipp_rot_item& it = p.items[rec];
+    const int tile = (int)blockIdx.x - it.tile_start;
+    const int ty = tile / it.tiles_x, tx = tile - ty * it.tiles_x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = tx * 32 + (lane & 7) * 4;
+    const int y = ty * 32 + warp * 4 + (lane >> 3);
+    const int dst_w = it.dst_w, dst_h = it.dst_h;
+    const int wpad = (dst_w + 3) & ~3;
+    const uint8_t* img = p.src + (int64_t)it.src * p.src_stride;
+    int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
+    if (y < dst_h && x < wpad) {
+        uint32_t px[4] = {0u, 0u, 0u, 0u};
+        if (MODE == 0 || it.kind != 0) {
+            const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, p.src_w, p.src_h};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int xin, yin;
+                if (x + k < dst_w && map_canvas(m, x + k, y, xin, yin)) px[k] = fetch_rgba<CH>(img, p.src_pitch, xin, yin);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (x + k >= dst_w) break;
+                // xin = m0*(x+.5) + m1*(y+.5) + m2 as C evaluates it (double, no fma contraction): the validity test and the
+                // sample position are Pillow's; the interpolation runs in single precision for opaque RGB sources (<= 1 LSB,
+                // no un-premultiply) and in double like libImaging for RGBA sources
+                typedef typename InterpType<CH>::type T;
+                const double xo = (double)(x + k) + 0.5, yo = (double)y + 0.5;
+                double xin = __dadd_rn(__dadd_rn(__dmul_rn(it.m[0], xo), __dmul_rn(it.m[1], yo)), it.m[2]);
+                double yin = __dadd_rn(__dadd_rn(__dmul_rn(it.m[3], xo), __dmul_rn(it.m[4], yo)), it.m[5]);
+                if (!(xin >= 0.0 && xin < (double)p.src_w && yin >= 0.0 && yin < (double)p.src_h)) continue;
+                xin -= 0.5;
+                yin -= 0.5;
+                const int xi = (int)floor(xin), yi = (int)floor(yin);
+                const T dx = (T)(xin - (double)xi), dy = (T)(yin - (double)yi);
+                const int xa = min(max(xi, 0), p.src_w - 1), xb = min(max(xi + 1, 0), p.src_w - 1);
+                const int ya = min(max(yi, 0), p.src_h - 1), yb = min(max(yi + 1, 0), p.src_h - 1);
+                T s00[4], s01[4], s10[4], s11[4];
+                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xa, ya), s00);
+                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xb, ya), s01);
+                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xa, yb), s10);
+                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xb, yb), s11);
+                uint32_t c[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const T v1 = add_rn(s00[b], mul_rn(sub_rn(s01[b], s00[b]), dx));
+                    const T v2 = add_rn(s10[b], mul_rn(sub_rn(s11[b], s10[b]), dx));
+                    const T v = add_rn(v1, mul_rn(sub_rn(v2, v1), dy));
+                    c[b] = (uint32_t)min(max((int)v, 0), 255);
+                }
+                const uint32_t a = c[3];
+                if (a != 0u && a != 255u) {
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) c[b] = min(255u, (255u * c[b]) / a);
+                }
+                px[k] = c[0] | (c[1] << 8) | (c[2] << 16) | (a << 24);
+            }
+        }
+        uint8_t* d = p.dst_pool + it.dst_off + ((int64_t)y * wpad + x) * 4;
+        stg_stream16(d, make_uint4(px[0], px[1], px[2], px[3]));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((px[k] >> 24) != 0u) {
+                minx = min(minx, x + k);
+                maxx1 = max(maxx1, x + k + 1);
+                miny = y;
+                maxy1 = y + 1;
+            }
+        }
+    }
+    bbox_block_reduce(p.bbox + 4 * rec, minx, miny, maxx1, maxy1);
+}
+
+// ===================================================================== overlay: RGBA sprite -> premultiplied planes
+// thread = four pixels of one sprite row (one 16-byte load, one 32-bit store per plane)
+__global__ void __launch_bounds__(256) sprite_planes_kernel(const uint8_t* __restrict__ sprites, int64_t pitch, int64_t stride,
+                                                            const ipp_chain_item* __restrict__ items, uint8_t* ws) {
+    const ipp_chain_item& it = items[blockIdx.y];
+    const int sw = it.spr_w, sh = it.spr_h;
+    const int Wp = (sw + 15) & ~15, q = Wp >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= q * sh) return;
+    const int y = idx / q, x = (idx - y * q) * 4;
+    const uint8_t* row = sprites + (int64_t)it.frame * stride + (int64_t)y * pitch;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    if (x + 3 < sw && ((((uintptr_t)row) & 15) == 0)) {
+        const uint4 t = ldg_stream16(row + 4 * x);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x + k < sw) v[k] = __ldg(reinterpret_cast<const uint32_t*>(row) + x + k);
+    }
+    uint32_t pl[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t a = v[k] >> 24;
+        pl[0] |= div255((v[k] & 255u) * a) << (8 * k);
+        pl[1] |= div255(((v[k] >> 8) & 255u) * a) << (8 * k);
+        pl[2] |= div255(((v[k] >> 16) & 255u) * a) << (8 * k);
+        pl[3] |= a << (8 * k);
+    }
+    uint8_t* d = ws + it.rot_off + (int64_t)y * Wp + x;
+    const int64_t plane = (int64_t)sh * Wp;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t*>(d + c * plane) = pl[c];
+}
+
+}  // namespace ipp
+
+extern "C" {
+
+int ipp_rotate_batch_u8(const uint8_t* src, int64_t src_pitch, int64_t src_image_stride, int src_w, int src_h,
+                        int src_channels, int n_src, const ipp_rot_item* items, int n_items, int total_tiles, int mode,
+                        uint8_t* dst_pool, int32_t* bbox_out, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(src && items && dst_pool && bbox_out, IPP_ERR_BAD_ARG, "ipp_rotate_batch_u8: NULL pointer");
+    IPP_REQUIRE((src_channels == 3 || src_channels == 4) && (mode == 0 || mode == 1) && n_src >= 1 && n_items >= 0 && total_tiles >= 0,
+                IPP_ERR_BAD_ARG, "ipp_rotate_batch_u8: channels=%d mode=%d", src_channels, mode);
+    IPP_REQUIRE(src_w > 0 && src_h > 0 && src_pitch >= (int64_t)src_w * src_channels, IPP_ERR_BAD_SHAPE, "ipp_rotate_batch_u8: bad geometry");
+    IPP_REQUIRE(src_channels == 3 || (((src_pitch | src_image_stride) & 3) == 0 && (((uintptr_t)src) & 3) == 0), IPP_ERR_BAD_ARG,
+                "ipp_rotate_batch_u8: RGBA sources must be 4-byte aligned");
+    IPP_REQUIRE((((uintptr_t)dst_pool) & 255) == 0, IPP_ERR_BAD_ARG, "ipp_rotate_batch_u8: dst_pool must be 256-byte aligned");
+    if (n_items == 0) return IPP_OK;
+    { ipp::LaunchTimer _lt("bbox_reset_kernel", st); bbox_reset_kernel<<<ceil_div(n_items, 256), 256, 0, st>>>(bbox_out, n_items); }
+    IPP_LAUNCH_CHECK();
+    if (total_tiles == 0) return IPP_OK;
+    RotBatchParams p{src, src_pitch, src_image_stride, src_w, src_h, items, n_items, dst_pool, bbox_out};
+    {
+        ipp::LaunchTimer _lt(mode == 0 ? "rotate_batch_nearest_kernel" : "rotate_batch_bilinear_kernel", st);
+        if (mode == 0 && src_channels == 3) rotate_batch_kernel<0, 3><<<total_tiles, 256, 0, st>>>(p);
+        else if (mode == 0) rotate_batch_kernel<0, 4><<<total_tiles, 256, 0, st>>>(p);
+        else if (src_channels == 3) rotate_batch_kernel<1, 3><<<total_tiles, 256, 0, st>>>(p);
+        else rotate_batch_kernel<1, 4><<<total_tiles, 256, 0, st>>>(p);
+    }
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_sprite_planes_u8(const uint8_t* sprites, int64_t sprite_pitch, int64_t sprite_stride, int spr_w, int spr_h,
+                         int n_sprites, const ipp_chain_item* items, int n_items, uint8_t* sprite_ws, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    IPP_REQUIRE(sprites && items && sprite_ws && n_sprites >= 1 && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_sprite_planes_u8: bad arguments");
+    IPP_REQUIRE(spr_w > 0 && spr_h > 0 && sprite_pitch >= (int64_t)spr_w * 4 && ((sprite_pitch | sprite_stride) & 3) == 0 &&
+                    (((uintptr_t)sprites) & 3) == 0 && (((uintptr_t)sprite_ws) & 255) == 0,
+                IPP_ERR_BAD_SHAPE, "ipp_sprite_planes_u8: sprites must be 4-byte aligned RGBA, the workspace 256-byte aligned");
+    if (n_items == 0) return IPP_OK;
+    const int q = ((spr_w + 15) & ~15) >> 2;
+    dim3 grid(ceil_div((int64_t)q * spr_h, 256), n_items);
+    { ipp::LaunchTimer _lt("sprite_planes_kernel", st); sprite_planes_kernel<<<grid, 256, 0, st>>>(sprites, sprite_pitch, sprite_stride, items, sprite_ws); }
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}
+
+int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const uint8_t* sprite_ws,
+                          uint8_t* dst, const int64_t* dst_offsets_host, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE((items_host && dst_offsets_host) || n_items == 0, IPP_ERR_BAD_ARG, "ipp_sprites_export_u8: NULL pointer");
+    IPP_REQUIRE(sprite_ws && dst && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_sprites_export_u8: bad arguments");
+    for (int i = 0; i < n_items; ++i) {
+        const ipp_chain_item& it = items_host[i];
+        IPP_CUDA(cudaMemcpyAsync(dst + dst_offsets_host[i], sprite_ws + it.spr_off, (size_t)it.new_w * it.new_h * 4,
+                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return IPP_OK;
+}
+
+}  // extern "C"

@@ -1325,7 +1325,7 @@ struct CParams {
     const uint8_t* sprite_ws;
     uint8_t* out;
     int64_t out_pitch, out_stride;
-    int out_size;
+    int out_w, out_h;                 // window size (the chain: sq_size x sq_size)
     int rows_per_cta, chunks_per_cta;
     uint32_t smem_row_stride;
 };
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
     p.sprite = c.sprite_ws + it.spr_off;
     p.sprite_pitch = (int64_t)it.new_w * 4;
     p.sprite_w = it.new_w; p.sprite_h = it.new_h; p.pos_x = it.pos_x; p.pos_y = it.pos_y;
-    p.crop_x0 = it.sq_x0; p.crop_y0 = it.sq_y0; p.crop_w = it.sq_size; p.crop_h = it.sq_size;
+    p.crop_x0 = it.sq_x0; p.crop_y0 = it.sq_y0; p.crop_w = c.out_w; p.crop_h = c.out_h;
     p.dst = c.out + (int64_t)it.out_slot * c.out_stride;
     p.dst_pitch = c.out_pitch;
     // A CTA walks chunks_per_cta (1-2) consecutive chunks of rows_per_cta rows through two shared-memory buffers: the bulk copies of
@@ -1677,36 +1677,29 @@ int ipp_chain_tables(const ipp_chain_item* items, int n_items, int max_rows_per_
     return IPP_OK;
 }
 
-int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
-                      const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
-                      const uint8_t* sprite_ws,
-                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_size, void* stream) {
+static int stage_c_launch(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride, const ipp_chain_item* items, int n_items,
+                          const uint8_t* sprite_ws, uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_w, int out_h,
+                          cudaStream_t st) {
     using namespace ipp;
-    cudaStream_t st = (cudaStream_t)stream;
-    IPP_REQUIRE(g && backgrounds && items && sprite_ws && out && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_c: bad arguments");
-    IPP_REQUIRE(out_size > 0 && out_size <= g->bg_w && out_size <= g->bg_h && bg_pitch >= (int64_t)g->bg_w * 3 &&
-                    out_pitch >= (int64_t)out_size * 3,
-                IPP_ERR_BAD_SHAPE, "ipp_chain_stage_c: bad geometry");
-    if (n_items == 0) return IPP_OK;
     CParams c{};
     c.bgs = backgrounds; c.bg_pitch = bg_pitch; c.bg_stride = bg_stride;
     c.items = items; c.sprite_ws = sprite_ws;
-    c.out = out; c.out_pitch = out_pitch; c.out_stride = out_stride; c.out_size = out_size;
-    const uint32_t rowbytes = (uint32_t)out_size * 3u;
+    c.out = out; c.out_pitch = out_pitch; c.out_stride = out_stride; c.out_w = out_w; c.out_h = out_h;
+    const uint32_t rowbytes = (uint32_t)out_w * 3u;
     c.smem_row_stride = staged_row_stride(rowbytes);
-    IPP_REQUIRE(c.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
+    IPP_REQUIRE(c.smem_row_stride <= 100 * 1024, IPP_ERR_UNSUPPORTED, "stage C: row too long");
     int rows = (int)(32768 / c.smem_row_stride);            // one warp per row: 8 rows when they fit
     if (rows > kPasteThreads / 32) rows = kPasteThreads / 32;
     if (rows < 1) rows = 1;
-    if (rows > out_size) rows = out_size;
+    if (rows > out_h) rows = out_h;
     c.rows_per_cta = rows;
     static const int chunks_env = getenv("IPP_PASTE_CHUNKS") ? atoi(getenv("IPP_PASTE_CHUNKS")) : 0;
     // two chunks per CTA (measured best: 1 / 2 / 4 / 8 chunks = 0.66 / 0.58 / 0.60 / 0.61 ms per 512 images) once that still leaves
     // ~8 waves of CTAs; small batches keep short CTAs (tail effect)
-    const int64_t chunk_ctas = (int64_t)ceil_div(out_size, rows) * n_items;
+    const int64_t chunk_ctas = (int64_t)ceil_div(out_h, rows) * n_items;
     c.chunks_per_cta = chunks_env > 0 ? chunks_env : (int)std::max<int64_t>(1, std::min<int64_t>(2, chunk_ctas / ((int64_t)sm_count() * 32)));
     const size_t smem = 2 * (size_t)rows * c.smem_row_stride;          // two chunk buffers
-    IPP_REQUIRE(smem <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_stage_c: row too long");
+    IPP_REQUIRE(smem <= 200 * 1024, IPP_ERR_UNSUPPORTED, "stage C: row too long");
     if (smem > 48 * 1024) {
         static size_t smem_set[64] = {};          // per device; the attribute only ever grows
         int dev_id = 0;
@@ -1716,10 +1709,36 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
             if (dev_id >= 0 && dev_id < 64) smem_set[dev_id] = smem;
         }
     }
-    dim3 grid(ceil_div(out_size, rows * c.chunks_per_cta), n_items);
+    dim3 grid(ceil_div(out_h, rows * c.chunks_per_cta), n_items);
     { ipp::LaunchTimer _lt("chain_paste_kernel", st); chain_paste_kernel<<<grid, kPasteThreads, smem, st>>>(c); }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
+}
+
+int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride,
+                      const ipp_chain_geom* g, const ipp_chain_item* items, int n_items,
+                      const uint8_t* sprite_ws,
+                      uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_size, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(g && backgrounds && items && sprite_ws && out && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_c: bad arguments");
+    IPP_REQUIRE(out_size > 0 && out_size <= g->bg_w && out_size <= g->bg_h && bg_pitch >= (int64_t)g->bg_w * 3 &&
+                    out_pitch >= (int64_t)out_size * 3,
+                IPP_ERR_BAD_SHAPE, "ipp_chain_stage_c: bad geometry");
+    if (n_items == 0) return IPP_OK;
+    return stage_c_launch(backgrounds, bg_pitch, bg_stride, items, n_items, sprite_ws, out, out_pitch, out_stride, out_size, out_size,
+                          (cudaStream_t)stream);
+}
+
+int ipp_chain_stage_c_rect(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h,
+                           const ipp_chain_item* items, int n_items, const uint8_t* sprite_ws,
+                           uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_w, int out_h, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(backgrounds && items && sprite_ws && out && n_items >= 0, IPP_ERR_BAD_ARG, "ipp_chain_stage_c_rect: bad arguments");
+    IPP_REQUIRE(out_w > 0 && out_h > 0 && out_w <= bg_w && out_h <= bg_h && bg_pitch >= (int64_t)bg_w * 3 && out_pitch >= (int64_t)out_w * 3,
+                IPP_ERR_BAD_SHAPE, "ipp_chain_stage_c_rect: bad geometry");
+    if (n_items == 0) return IPP_OK;
+    return stage_c_launch(backgrounds, bg_pitch, bg_stride, items, n_items, sprite_ws, out, out_pitch, out_stride, out_w, out_h,
+                          (cudaStream_t)stream);
 }
 
 int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h, int n_bgs,

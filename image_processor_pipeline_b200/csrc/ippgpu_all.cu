@@ -9,4 +9,5 @@
 #include "ccl.cu"
 #include "boxes.cu"
 #include "chain.cu"
+#include "batch.cu"
 #include "planner.cu"

@@ -156,7 +156,7 @@ static int fix16(double v) {
 }
 
 // Pillow Image.rotate(angle, expand=True) parameter math for a w x h image
-static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r) {
+static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r, double* m_out = nullptr) {
     angle = py_fmod360(angle);
     r->a0 = r->a1 = r->a2 = r->a3 = r->a4 = r->a5 = 0;
     if (angle == 0.0) { r->kind = 1; r->canvas_w = w; r->canvas_h = h; return 0; }
@@ -195,6 +195,7 @@ static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r) {
     if (!(in_range(0, 0) && in_range(nw, nh) && in_range(0, nh) && in_range(nw, 0)) || (m[1] == 0.0 && m[3] == 0.0))
         return IPP_ERR_UNSUPPORTED;      // outside libImaging's affine_fixed path
     r->kind = 0;
+    if (m_out) for (int i = 0; i < 6; ++i) m_out[i] = m[i];
     r->a0 = fix16(m[0]); r->a1 = fix16(m[1]); r->a2 = fix16(m[2] + m[0] * 0.5 + m[1] * 0.5);
     r->a3 = fix16(m[3]); r->a4 = fix16(m[4]); r->a5 = fix16(m[5] + m[3] * 0.5 + m[4] * 0.5);
     r->canvas_w = nw; r->canvas_h = nh;
@@ -280,7 +281,14 @@ int ipp_plan_rotations_host(const int32_t* info, int n_frames, const ipp_plan_pa
 // Device-side schedule of an item array: coefficient-table offsets, banded int8 fragment tables for the
 // tensor-core LANCZOS passes, flat tile starts, sprite-workspace offsets.  Shared by the planner and by
 // callers that build item arrays themselves (tests).
+static int layout_impl(ipp_chain_item* items, int n_items, ipp_plan_totals* totals_out, bool allow_fused);
 int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* totals_out) {
+    return layout_impl(items, n_items, totals_out, true);
+}
+int ipp_chain_layout_planar_host(ipp_chain_item* items, int n_items, ipp_plan_totals* totals_out) {
+    return layout_impl(items, n_items, totals_out, false);
+}
+static int layout_impl(ipp_chain_item* items, int n_items, ipp_plan_totals* totals_out, bool allow_fused) {
     using namespace ipp;
     using namespace ipp::plan;
     IPP_REQUIRE((items || n_items == 0) && n_items >= 0 && totals_out, IPP_ERR_BAD_ARG, "ipp_chain_layout_host: bad arguments");
@@ -339,7 +347,7 @@ int ipp_chain_layout_host(ipp_chain_item* items, int n_items, ipp_plan_totals* t
     for (int i = 0; i < n_items; ++i) max_w = std::max(max_w, items[i].spr_w);
     const int pitch = ((max_w + 64 + 127) / 128) * 128 + 64;              // gh_row_pitch (chain.cu)
     const int64_t fused_smem = n_items ? (int64_t)64 * pitch + 1024 : 0;   // 4 planes x 16 rows + tail slack
-    const bool fused = n_items > 0 && fused_smem <= 200 * 1024 && getenv("IPP_B2_UNFUSED") == nullptr;
+    const bool fused = allow_fused && n_items > 0 && fused_smem <= 200 * 1024 && getenv("IPP_B2_UNFUSED") == nullptr;
     if (fused) {
         gt = 0;
         ht = 0;
@@ -502,6 +510,92 @@ int ipp_plan_items_host(const ipp_chain_rot* rots, const int32_t* rot_is_origina
     }
     *n_items_out = n;
     const int lrc = ipp_chain_layout_host(items_out, n, totals_out);
+    if (lrc != IPP_OK) return lrc;
+    totals_out->labels_bytes = (int32_t)lpos;
+    return IPP_OK;
+}
+
+// Batched rotation step (rotations.py:88-99) over n images of one size: one uniform() per image.
+int ipp_plan_rotate_batch_host(int src_w, int src_h, int n, double angle_min, double angle_max,
+                               uint32_t* rng_mt624, int32_t* rng_index,
+                               ipp_rot_item* items_out, double* angles_out, int64_t* totals_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE(src_w > 0 && src_h > 0 && n >= 0 && rng_mt624 && rng_index && items_out && angles_out && totals_out, IPP_ERR_BAD_ARG,
+                "ipp_plan_rotate_batch_host: bad arguments");
+    PyRandom rng{rng_mt624, rng_index};
+    int64_t off = 0, tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const double angle = rng.uniform(angle_min, angle_max);
+        ipp_chain_rot r;
+        memset(&r, 0, sizeof(r));
+        ipp_rot_item* it = items_out + i;
+        memset(it, 0, sizeof(*it));
+        const int rc = rotation_plan(src_w, src_h, angle, &r, it->m);
+        IPP_REQUIRE(rc == 0, rc, "ipp_plan_rotate_batch_host: rotation outside libImaging's 16.16 fixed-point range");
+        angles_out[i] = angle;
+        it->src = i; it->kind = r.kind;
+        it->a0 = r.a0; it->a1 = r.a1; it->a2 = r.a2; it->a3 = r.a3; it->a4 = r.a4; it->a5 = r.a5;
+        it->dst_w = r.canvas_w; it->dst_h = r.canvas_h;
+        it->tiles_x = (r.canvas_w + 31) / 32;
+        it->tile_start = (int32_t)tiles;
+        tiles += (int64_t)it->tiles_x * ((r.canvas_h + 31) / 32);
+        IPP_REQUIRE(tiles < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_rotate_batch_host: too many tiles; use a smaller batch");
+        it->dst_off = off;
+        off = align_up(off + (int64_t)((r.canvas_w + 3) & ~3) * 4 * r.canvas_h, 256);
+    }
+    totals_out[0] = off;
+    totals_out[1] = tiles;
+    return IPP_OK;
+}
+
+// Batched overlay step (overlays.py:104-149) over n_pairs (sprite k % n_sprites, background k % n_bgs) pairs.
+int ipp_plan_overlay_batch_host(int spr_w, int spr_h, int n_sprites, int n_pairs, const ipp_plan_params* p,
+                                uint32_t* rng_mt624, int32_t* rng_index,
+                                ipp_chain_item* items_out, int32_t* n_items_out,
+                                char* labels_out, int labels_capacity, ipp_plan_totals* totals_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE(p && rng_mt624 && rng_index && items_out && n_items_out && labels_out && totals_out && spr_w > 0 && spr_h > 0 &&
+                    n_sprites >= 1 && n_pairs >= 0 && p->n_bgs >= 1,
+                IPP_ERR_BAD_ARG, "ipp_plan_overlay_batch_host: bad arguments");
+    PyRandom rng{rng_mt624, rng_index};
+    const int BW = p->bg_w, BH = p->bg_h;
+    int n = 0;
+    size_t lpos = 0;
+    for (int k = 0; k < n_pairs; ++k) {
+        const double ratio = rng.uniform(p->scale_min, p->scale_max);
+        int nw, nh;
+        if (!overlay_size(spr_w, spr_h, BW, BH, ratio, &nw, &nh)) continue;       // ValueError -> print, None
+        bool ok;
+        const int px = (int)rng.randint(0, BW - nw, &ok);
+        if (!ok) continue;
+        const int py = (int)rng.randint(0, BH - nh, &ok);
+        if (!ok) continue;
+        const long long x1 = px, y1 = py, x2 = px + nw, y2 = py + nh;
+        const float vals[4] = {(float)(((double)(x1 + x2) / 2.0) / (double)BW), (float)(((double)(y1 + y2) / 2.0) / (double)BH),
+                               (float)((double)(x2 - x1) / (double)BW), (float)((double)(y2 - y1) / (double)BH)};
+        char row[256];
+        int len = snprintf(row, 16, "%d", p->yolo_class_id);
+        for (int i = 0; i < 4; ++i) {
+            row[len++] = ' ';
+            len += fmt6(row + len, (double)vals[i], nullptr);
+        }
+        row[len] = 0;                                                              // overlays.py:149: no trailing newline
+        IPP_REQUIRE(lpos + (size_t)len + 1 <= (size_t)labels_capacity, IPP_ERR_WORKSPACE, "ipp_plan_overlay_batch_host: label buffer too small");
+        memcpy(labels_out + lpos, row, (size_t)len + 1);
+        lpos += (size_t)len + 1;
+        ipp_chain_item* it = items_out + n;
+        memset(it, 0, sizeof(*it));
+        it->frame = k % n_sprites; it->bg = k % p->n_bgs;
+        it->kind = 1; it->cc_w = spr_w; it->cc_h = spr_h; it->spr_w = spr_w; it->spr_h = spr_h;
+        it->new_w = nw; it->new_h = nh; it->pos_x = px; it->pos_y = py;
+        it->sq_size = BW < BH ? BW : BH;
+        it->cc_x = k;                                                              // pair index (items of skipped pairs are absent)
+        ++n;
+    }
+    *n_items_out = n;
+    const int lrc = ipp_chain_layout_planar_host(items_out, n, totals_out);
     if (lrc != IPP_OK) return lrc;
     totals_out->labels_bytes = (int32_t)lpos;
     return IPP_OK;

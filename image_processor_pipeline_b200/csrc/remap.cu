@@ -22,6 +22,7 @@ struct RowsParams {
     int64_t dst_pitch, dst_img_stride;
     int rows_per_cta;
     uint32_t smem_row_stride;
+    const int32_t* xy;  // optional per-image {x0, y0} (device); nullptr: x0 / y0 above for every image
 };
 
 constexpr int kRowsThreads = 256;
@@ -60,18 +61,20 @@ __global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) 
     const int nrows = min(p.rows_per_cta, p.out_h - row0);
     const uint32_t rowbytes = (uint32_t)p.out_w * (uint32_t)p.bpp;
     const uint8_t* src_img = p.src + (int64_t)img * p.src_img_stride;
+    // per-image offsets are device data: clamped to [0, src - out] (p.x0 / p.y0 then hold those maxima), never read outside the image
+    const int x0 = p.xy ? min(max(p.xy[2 * img], 0), p.x0) : p.x0, y0 = p.xy ? min(max(p.xy[2 * img + 1], 0), p.y0) : p.y0;
 
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
         uint32_t total = 0;
         for (int r = 0; r < nrows; ++r) {
-            const uint8_t* s = src_img + (int64_t)(p.y0 + row0 + r) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            const uint8_t* s = src_img + (int64_t)(y0 + row0 + r) * p.src_pitch + (int64_t)x0 * p.bpp;
             total += make_window(s, rowbytes).bytes;
         }
         mbar_expect_tx(&bar, total);
         for (int r = 0; r < nrows; ++r) {
-            const uint8_t* s = src_img + (int64_t)(p.y0 + row0 + r) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            const uint8_t* s = src_img + (int64_t)(y0 + row0 + r) * p.src_pitch + (int64_t)x0 * p.bpp;
             const Window w = make_window(s, rowbytes);
             bulk_g2s(smem + (size_t)r * p.smem_row_stride, w.base, w.bytes, &bar);
         }
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) 
             const int drow = (v & 2) ? (p.out_h - 1 - y) : y;
             uint8_t* d = dimg + (int64_t)drow * p.dst_pitch;
             const uint8_t* win = smem + (size_t)r * p.smem_row_stride;
-            const uint8_t* s = src_img + (int64_t)(p.y0 + y) * p.src_pitch + (int64_t)p.x0 * p.bpp;
+            const uint8_t* s = src_img + (int64_t)(y0 + y) * p.src_pitch + (int64_t)x0 * p.bpp;
             const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
             const RowSplit sp = split_row(d, rowbytes);
             if (c < sp.nb) {
@@ -249,6 +252,27 @@ int ipp_remap_u8(const uint8_t* src, int64_t src_pitch, int src_w, int src_h, in
     p.bpp = bpp; p.x0 = x0; p.y0 = y0; p.out_w = out_w; p.out_h = out_h;
     p.dst[(flip_h ? 1 : 0) | (flip_v ? 2 : 0)] = dst;
     p.dst_pitch = dst_pitch; p.dst_img_stride = dst_image_stride;
+    return launch_rows(p, n, (cudaStream_t)stream);
+}
+
+int ipp_crop_batch_u8(const uint8_t* src, int64_t src_pitch, int64_t src_image_stride, int src_w, int src_h, int bpp,
+                      const int32_t* xy_offsets, int out_w, int out_h,
+                      uint8_t* dst, int64_t dst_pitch, int64_t dst_image_stride, int n, void* stream) {
+    using namespace ipp;
+    IPP_REQUIRE(src && dst && xy_offsets, IPP_ERR_BAD_ARG, "ipp_crop_batch_u8: NULL pointer");
+    IPP_REQUIRE(bpp >= 1 && bpp <= 16 && n >= 1, IPP_ERR_BAD_ARG, "ipp_crop_batch_u8: bpp=%d n=%d", bpp, n);
+    IPP_REQUIRE(out_w >= 0 && out_h >= 0 && out_w <= src_w && out_h <= src_h, IPP_ERR_BAD_SHAPE,
+                "ipp_crop_batch_u8: crop %dx%d larger than %dx%d", out_w, out_h, src_w, src_h);
+    IPP_REQUIRE(src_pitch >= (int64_t)src_w * bpp && dst_pitch >= (int64_t)out_w * bpp, IPP_ERR_BAD_SHAPE,
+                "ipp_crop_batch_u8: pitch smaller than a row");
+    if (out_w == 0 || out_h == 0) return IPP_OK;
+    RowsParams p{};
+    p.src = src; p.src_pitch = src_pitch; p.src_img_stride = src_image_stride;
+    p.bpp = bpp; p.out_w = out_w; p.out_h = out_h;
+    p.dst[0] = dst;
+    p.dst_pitch = dst_pitch; p.dst_img_stride = dst_image_stride;
+    p.xy = xy_offsets;
+    p.x0 = src_w - out_w; p.y0 = src_h - out_h;      // clamp limits of the per-image offsets
     return launch_rows(p, n, (cudaStream_t)stream);
 }
 

@@ -40,7 +40,9 @@ def _req(t: torch.Tensor, name: str = "image"):
         t = t.unsqueeze(-1)
     if t.dim() != 3:
         raise ValueError(f"{name} must be HW or HWC")
-    if t.stride(2) != 1 or (t.shape[2] > 1 and t.stride(1) != t.shape[2]):
+    # pixels must be dense inside a row for EVERY channel count (a column-strided gray view gray[:, ::2] is
+    # unsqueezed to HWC with stride(1) != 1): the kernels take a row pitch only
+    if t.stride(1) != t.shape[2] or (t.shape[2] > 1 and t.stride(2) != 1):
         t = t.contiguous()
     return t
 
@@ -191,14 +193,19 @@ def _tables(in_size: int, out_size: int, device):
     return ksize, torch.from_numpy(bounds).to(device), torch.from_numpy(kk).to(device)
 
 
-def resize_lanczos(rgba: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
-    """``Image.resize(size, LANCZOS)`` on RGBA (reference overlays.py:129); bit-exact."""
+def resize_lanczos(rgba: torch.Tensor, size: Tuple[int, int], scalar_kernels: bool = False) -> torch.Tensor:
+    """``Image.resize(size, LANCZOS)`` on RGBA (reference overlays.py:129); bit-exact.  Runs the tensor-core passes of
+    the batched path (batch.resize_lanczos_batch with one sprite); ``scalar_kernels=True`` keeps the two scalar
+    integer passes of resample.cu (ipp_resample_rgba_u8, caller-provided tables)."""
     t = _req(rgba, "rgba")
     if t.shape[2] != 4:
         raise ValueError("resize_lanczos expects an RGBA image")
     nw, nh = int(size[0]), int(size[1])
     if nw <= 0 or nh <= 0:
         raise ValueError("height and width must be > 0")          # PIL's message for empty sizes
+    if not scalar_kernels:
+        from . import batch
+        return batch.resize_lanczos_batch(t.contiguous().unsqueeze(0), [(nw, nh)])[0]
     ptr, pitch, W, H, _ = _geom(t)
     dev = t.device
     out = torch.empty((nh, nw, 4), dtype=torch.uint8, device=dev)

@@ -374,6 +374,78 @@ int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t 
                              const ipp_chain_item* items_host, int n_items, int out_size,
                              uint8_t* windows_dev, void* stream);
 
+/* =================================================================================
+ * Batched entry points of the stand-alone operators: n images per call, per-item parameter
+ * arrays on the device, flat tile lists (one launch per batch whatever the item sizes).
+ * These are what a ProcessingStep that maps one transform over a whole directory calls
+ * (reference pipeline.py:304-437 runs the same process function over every file).
+ * ================================================================================= */
+
+/* -- crop with per-image offsets (crop_square.py:192-196: x0, y0 are drawn per image).
+ *    xy_offsets: device int32[n][2] = {x0, y0} of image i; every crop is out_w x out_h. */
+int ipp_crop_batch_u8(const uint8_t* src, int64_t src_pitch, int64_t src_image_stride, int src_w, int src_h, int bpp,
+                      const int32_t* xy_offsets, int out_w, int out_h,
+                      uint8_t* dst, int64_t dst_pitch, int64_t dst_image_stride, int n, void* stream);
+
+/* -- rotation (rotations.py:55,96-99: convert("RGBA"), rotate(expand=True), getbbox) of n images.
+ *    One record per output canvas; 104 bytes. */
+typedef struct ipp_rot_item {
+    int32_t src;                        /* source image index                                       */
+    int32_t kind;                       /* 0 affine, 1 copy, 2 rot180, 3 rot90, 4 rot270            */
+    int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (NEAREST, kind 0)          */
+    int32_t dst_w, dst_h;               /* expanded canvas                                          */
+    int32_t tile_start;                 /* first 32 x 32 output tile of this canvas in the flat grid */
+    int32_t tiles_x;                    /* ceil(dst_w / 32)                                         */
+    int64_t dst_off;                    /* byte offset of the canvas in dst_pool (256-byte aligned);
+                                           rows are ((dst_w + 3) & ~3) * 4 bytes apart              */
+    double m[6];                        /* PIL inverse matrix (BILINEAR, kind 0)                    */
+} ipp_rot_item;
+
+/*    Host plan: one `random.uniform(angle_min, angle_max)` per image from the Python generator state
+ *    (rotations.py:89), PIL's rotate parameter math, canvas offsets and tile starts.  angles_out: double[n].
+ *    totals_out[0] = bytes of dst_pool, totals_out[1] = tiles. */
+int ipp_plan_rotate_batch_host(int src_w, int src_h, int n, double angle_min, double angle_max,
+                               uint32_t* rng_mt624, int32_t* rng_index,
+                               ipp_rot_item* items_out, double* angles_out, int64_t* totals_out);
+
+/*    src: n_src images of src_w x src_h, src_channels 3 (RGB, alpha = 255 supplied: the convert("RGBA") of
+ *    rotations.py:55 folded into the load) or 4 (RGBA).  mode 0: NEAREST, bit-exact (16.16 fixed point);
+ *    mode 1: BILINEAR on premultiplied alpha, double-precision source coordinates, single-precision
+ *    interpolation: within 1 LSB per channel of Pillow (documented tolerance).  Every canvas is fully written
+ *    (0 outside the source, padding columns included); bbox_out int32[n_items][4] = PIL getbbox of canvas i
+ *    ({x0,y0,x1,y1}, empty <=> x1 == 0), reduced in the same launch. */
+int ipp_rotate_batch_u8(const uint8_t* src, int64_t src_pitch, int64_t src_image_stride, int src_w, int src_h,
+                        int src_channels, int n_src, const ipp_rot_item* items, int n_items, int total_tiles, int mode,
+                        uint8_t* dst_pool, int32_t* bbox_out, void* stream);
+
+/* -- overlay (overlays.py:104-149: LANCZOS resize of an RGBA sprite, paste onto an RGB background, YOLO label)
+ *    of n (sprite, background) pairs.  Items are ipp_chain_item records: frame = sprite index, bg = background
+ *    index, spr_w / spr_h = sprite size, new_w / new_h, pos_x / pos_y, sq_x0 = sq_y0 = 0.
+ *    Host plan: per pair `uniform(scale_min, scale_max)`, `randint(0, W - nw)`, `randint(0, H - nh)` in the
+ *    reference's order; pairs whose resize would fail are skipped (overlays.py:151-153 prints and returns None).
+ *    labels_out: '\0'-separated label texts "{cls} {cx:.6f} {cy:.6f} {w:.6f} {h:.6f}" (overlays.py:149). */
+int ipp_plan_overlay_batch_host(int spr_w, int spr_h, int n_sprites, int n_pairs, const ipp_plan_params* p,
+                                uint32_t* rng_mt624, int32_t* rng_index,
+                                ipp_chain_item* items_out, int32_t* n_items_out,
+                                char* labels_out, int labels_capacity, ipp_plan_totals* totals_out);
+/*    Like ipp_chain_layout_host with the gather and the horizontal pass as separate kernels (the planar
+ *    premultiplied sprite lives in the sprite workspace): the layout of the batched resize / overlay path. */
+int ipp_chain_layout_planar_host(ipp_chain_item* items_host, int n_items, ipp_plan_totals* totals_out);
+/*    Straight-alpha RGBA sprites -> premultiplied byte planes [R, G, B, A][spr_h][Wp] at items[i].rot_off
+ *    (Pillow's RGBA -> RGBa, MULDIV255): the input of ipp_chain_stage_b2 called with fused_smem_bytes = 0 and
+ *    gather_tiles = 0.  sprites: n_sprites images of spr_w x spr_h x 4 (items[i].frame selects one). */
+int ipp_sprite_planes_u8(const uint8_t* sprites, int64_t sprite_pitch, int64_t sprite_stride, int spr_w, int spr_h,
+                         int n_sprites, const ipp_chain_item* items, int n_items, uint8_t* sprite_ws, void* stream);
+/*    stage C on a rectangular window: out[i] (out_h x out_w x 3) = paste(background[bg], sprite_i, pos)[sq_y0:, sq_x0:]
+ *    (out_w x out_h = the whole background for the plain overlay step). */
+int ipp_chain_stage_c_rect(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h,
+                           const ipp_chain_item* items, int n_items, const uint8_t* sprite_ws,
+                           uint8_t* out, int64_t out_pitch, int64_t out_stride, int out_w, int out_h, void* stream);
+/*    Resized straight-alpha RGBA sprites out of the workspace: dst + i * dst_stride = sprite i
+ *    (new_h x new_w x 4, dense); used by the stand-alone batched resize. */
+int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const uint8_t* sprite_ws,
+                          uint8_t* dst, const int64_t* dst_offsets_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,7 @@ def test_resize_lanczos_bit_exact(dims):
     w, h, nw, nh = dims
     sp = rng(9).integers(0, 256, (h, w, 4), dtype=np.uint8)
     assert np.array_equal(host(ops.resize_lanczos(dev(sp), (nw, nh))), L.resize_lanczos(sp, (nw, nh)))
+    assert np.array_equal(host(ops.resize_lanczos(dev(sp), (nw, nh), scalar_kernels=True)), L.resize_lanczos(sp, (nw, nh)))
 
 
 @pytest.mark.parametrize("pos", [(0, 0), (10, 20), (70, 60), (-5, -7), (100, 90), (119, 99), (200, 5)])
@@ -263,3 +264,14 @@ def test_square_crop_boxes_and_overlay_label():
     xyxy = np.array([[413, 77, 413 + 300, 77 + 211], [0, 0, 1920, 1080], [5, 6, 7, 9]])
     got = ops.xyxy2xywhn(xyxy, 1920, 1080, DEV)
     assert np.array_equal(got.view(np.uint32), L.xyxy2xywhn(xyxy, 1920, 1080).view(np.uint32))
+
+
+def test_column_strided_gray_view_is_densified():
+    """A single-channel strided view (gray[:, ::2]) has pixels that are not dense inside a row; the ops must copy it
+    instead of reading dense bytes with the row pitch."""
+    img = rng(77).integers(0, 256, (40, 64), dtype=np.uint8)
+    view = dev(img)[:, ::2]
+    assert np.array_equal(host(ops.flip_crop(view, flip_h=True)), img[:, ::2][:, ::-1])
+    outs = ops.symmetries(view, ["o", "v"])
+    assert np.array_equal(host(outs[0]), img[:, ::2]) and np.array_equal(host(outs[1]), img[:, ::2][::-1])
+    assert ops.nonzero_bbox(view) == (0, 0, 32, 40) or ops.nonzero_bbox(view) is not None
