@@ -1,28 +1,35 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native transform chain.
+"""bench.py — benchmark of the B200-native transform chain and of its operators at the BASELINE.json configs.
 
 Metric (BASELINE.json): images/sec, 1080p RGB full chain, at 1/2/4/8 B200; % of HBM roofline.
-A "step" = one pass of the full chain (border crop -> HSV key -> largest component + fit ->
-rotate + fit -> flip -> LANCZOS overlay -> square crop, with YOLO labels) over one batch of
-synthetic 1920x1080 frames and backgrounds per GPU.
+A "step" = one pass of the hot path over one batch of synthetic inputs per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+                    [--config chain|c1|c2|c3|c4|c5]
 
-* value      frames/s, inputs resident in HBM, CUDA-event timed, max over ranks, all N GPUs.
-* e2e        same metric through the public host API (chain.run_chain_host): pinned host
-             frames/backgrounds -> H2D -> chain -> D2H of the outputs inside the timed region.
-* roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration
+--config (default ``chain`` = the headline; the others are BASELINE.json configs[0..4]):
+  chain  full chain (border crop -> HSV key -> largest component + fit -> rotate + fit -> flip -> LANCZOS
+         overlay -> square crop, YOLO labels), 1920x1080 frame + background -> 1080x1080
+  c5     the same chain over a 3840x2160 frame stream (backgrounds 3840x2160 -> 2160x2160)
+  c1     symmetry (o, h, v, hv) + crop_square on 1024x1024 RGB images
+  c2     rotations (one per image, expand + getbbox) on 1920x1080 RGB images: nearest and bilinear
+  c3     overlays: LANCZOS resize of RGBA sprites + alpha paste onto 1920x1080 backgrounds, labels
+  c4     filtres_liste HSV key + pixels_isolés keep-largest-component on 512x512 images
+
+Every line carries:
+* value      images/s, inputs resident in HBM, CUDA-event timed, max over ranks, all N GPUs.
+* e2e        the same metric through the public host API with pinned HOST buffers: H2D + work + D2H of the
+             results inside the timed region.
+* roofline   dominant streaming kernel: algorithmic bytes per launch / its mean CUDA-event duration
              (events on the launching stream around every launch, ipp_timing_* hooks).
-* cpu_baseline  the oracle chain (the reference's own cv2/Pillow call sequence, in memory)
-             on this box's host cores, bounded sample.  Rank 0, N=1 only.
---impl reference times that CPU path with all host cores (ProcessPoolExecutor, the
-reference's workers=-1 mode, pipeline.py:88-90,372).
+* cpu_baseline  the oracle (the reference's own cv2 / Pillow call sequence, in memory) on this box's host cores,
+             bounded sample.  Rank 0, N = 1 only.
+--impl reference times that CPU path with all host cores (ProcessPoolExecutor, the reference's workers=-1 mode,
+pipeline.py:88-90,372) on the same config.
 """
 from __future__ import annotations
 
 import argparse
-import collections
-import contextlib
 import json
 import os
 import random
@@ -39,10 +46,34 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FH, FW = 1080, 1920
-ALG_BYTES_PER_IMAGE = 3 * FW * FH + 3 * FW * FH + 3 * 1080 * 1080      # frame + background + output
-WORKLOAD = "full chain (border-crop + HSV key + largest component + rotate + flip + LANCZOS overlay + square crop + labels), 1920x1080 RGB frame + 1920x1080 background -> 1080x1080"
 CHAIN_KW = dict(num_rotations=1, include_original=False, pool=["o", "h", "v", "hv"], choose_random=1,
                 sym_include_original=False)
+GENERATOR = ("frames = synth.frame (dark backdrop, every byte < 120, keyed out by filter 0 of filtres_liste.py:186-190; one bright "
+             "textured ellipse ~15 % of the pixels with yellow patches the other filters remove; 1 % bright salt specks), "
+             "8 base frames multiplied by cyclic shifts; backgrounds = uniform noise")
+
+CONFIGS = {
+    "chain": dict(metric="images/sec 1080p RGB full chain", fh=1080, fw=1920, batch=1024, e2e_frames=512,
+                  workload="full chain (border-crop + HSV key + largest component + rotate + flip + LANCZOS overlay + square crop "
+                           "+ labels), 1920x1080 RGB frame + 1920x1080 background -> 1080x1080; " + GENERATOR),
+    "c5": dict(metric="images/sec 4K RGB full chain (video.py frame stream)", fh=2160, fw=3840, batch=128, e2e_frames=64,
+               workload="BASELINE configs[4]: full chain over a synthetic 3840x2160 frame stream + 3840x2160 backgrounds "
+                        "-> 2160x2160; " + GENERATOR),
+    "c1": dict(metric="images/sec symmetry x4 + crop_square, 1024x1024 RGB", batch=1000, e2e_frames=250,
+               workload="BASELINE configs[0]: generate_symmetries (o, h, v, hv: one read, four writes) then "
+                        "process_square_crop_around_bbox of every variant on 1024x1024x3 uniform-noise images"),
+    "c2": dict(metric="images/sec rotation (expand + getbbox), 1920x1080 RGB", batch=512, e2e_frames=128,
+               workload="BASELINE configs[1]: process_rotations, one rotation per image, angle ~ U(1, 359), RGB -> RGBA fused, "
+                        "expanded canvas + alpha bbox; value = NEAREST (the reference's mode, bit-exact), value_bilinear = "
+                        "BILINEAR (<= 1 LSB); 1920x1080x3 uniform-noise images"),
+    "c3": dict(metric="images/sec overlay (LANCZOS resize + alpha paste + label), 1920x1080 backgrounds", batch=512, e2e_frames=256,
+               workload="BASELINE configs[2]: paste_overlay_onto_background, 512x384 RGBA noise sprites with a radial alpha ramp "
+                        "(0 / 255 plateaus), scale ~ U(.15, .30) of the background diagonal, onto 1920x1080x3 uniform-noise backgrounds"),
+    "c4": dict(metric="images/sec HSV key + keep-largest-component, 512x512", batch=4096, e2e_frames=2048,
+               workload="BASELINE configs[3]: process_images_with_color_masks (filter list of filtres_liste.py:186-190) then "
+                        "keep_largest_component, fused (frame -> 1-bit mask -> largest component -> BGRA), on 512x512x3 synth.frame "
+                        "images (blob + 1 % salt specks)"),
+}
 
 
 def measured_peak():
@@ -55,48 +86,79 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _shifts(n: int, seed: int, first: int):
+def _shifts(n: int, seed: int, first: int, fh: int = FH, fw: int = FW):
     out = []
     for i in range(n):
         r = np.random.default_rng(seed * 7_000_003 + first + i)
-        out.append((int(r.integers(-120, 121)), int(r.integers(-300, 301)), int(r.integers(0, FH)), int(r.integers(0, FW))))
+        out.append((int(r.integers(-fh // 9, fh // 9 + 1)), int(r.integers(-fw * 5 // 32, fw * 5 // 32 + 1)), int(r.integers(0, fh)), int(r.integers(0, fw))))
     return out
 
 
-def make_inputs(n: int, seed: int, first: int = 0, base: int = 8):
+def make_inputs(n: int, seed: int, first: int = 0, base: int = 8, fh: int = FH, fw: int = FW):
     """n frames + n backgrounds (numpy, host).  `base` distinct synthetic frames are generated with numpy
-    (synth.frame, ~0.4 s each) and multiplied by cyclic shifts so that every frame of the
+    (synth.frame, ~0.4 s each at 1080p) and multiplied by cyclic shifts so that every frame of the
     batch has different content and object position at negligible generation cost."""
     from image_processor_pipeline_b200 import synth
-    bases = [synth.frame(seed, k, FH, FW) for k in range(base)]
-    bgb = [synth.background(seed, k, FH, FW) for k in range(base)]
-    frames = np.empty((n, FH, FW, 3), np.uint8)
-    bgs = np.empty((n, FH, FW, 3), np.uint8)
-    for i, (dy, dx, by, bx) in enumerate(_shifts(n, seed, first)):
+    bases = [synth.frame(seed, k, fh, fw) for k in range(base)]
+    bgb = [synth.background(seed, k, fh, fw) for k in range(base)]
+    frames = np.empty((n, fh, fw, 3), np.uint8)
+    bgs = np.empty((n, fh, fw, 3), np.uint8)
+    for i, (dy, dx, by, bx) in enumerate(_shifts(n, seed, first, fh, fw)):
         g = first + i
         frames[i] = np.roll(bases[g % base], (dy, dx), axis=(0, 1))
         bgs[i] = np.roll(bgb[g % base], (by, bx), axis=(0, 1))
     return frames, bgs
 
 
-def make_inputs_device(n: int, seed: int, first: int, dev, base: int = 8):
+def make_inputs_device(n: int, seed: int, first: int, dev, base: int = 8, fh: int = FH, fw: int = FW, noise_frames: bool = False):
     """The same n frames + backgrounds as make_inputs, built on the device: only the `base` images are generated on
-    the host; the cyclic shifts are torch.roll on the GPU (no n x 12 MB host copies per rank)."""
+    the host; the cyclic shifts are gathers on the GPU (no n x 12 MB host copies per rank).
+    noise_frames: frames are uniform noise (SURVEY.md §8d's generic generator) instead of synth.frame."""
     import torch
     from image_processor_pipeline_b200 import synth
-    bases = torch.from_numpy(np.stack([synth.frame(seed, k, FH, FW) for k in range(base)])).to(dev)
-    bgb = torch.from_numpy(np.stack([synth.background(seed, k, FH, FW) for k in range(base)])).to(dev)
-    frames = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
-    bgs = torch.empty((n, FH, FW, 3), dtype=torch.uint8, device=dev)
-    sh = torch.tensor(_shifts(n, seed, first), dtype=torch.int64, device=dev)          # [n, 4] = dy, dx, by, bx
+    mk = (lambda k: synth.noise(seed + 13, k, (fh, fw, 3))) if noise_frames else (lambda k: synth.frame(seed, k, fh, fw))
+    bases = torch.from_numpy(np.stack([mk(k) for k in range(base)])).to(dev)
+    bgb = torch.from_numpy(np.stack([synth.background(seed, k, fh, fw) for k in range(base)])).to(dev)
+    frames = torch.empty((n, fh, fw, 3), dtype=torch.uint8, device=dev)
+    bgs = torch.empty((n, fh, fw, 3), dtype=torch.uint8, device=dev)
+    sh = torch.tensor(_shifts(n, seed, first, fh, fw), dtype=torch.int64, device=dev)          # [n, 4] = dy, dx, by, bx
     which = (first + torch.arange(n, device=dev)) % base
-    ys, xs = torch.arange(FH, device=dev), torch.arange(FW, device=dev)
-    for lo in range(0, n, 64):                                                          # rolled[y, x] = src[(y - dy) % H, (x - dx) % W]: one gather per 64 images
-        sl = slice(lo, min(lo + 64, n))
+    ys, xs = torch.arange(fh, device=dev), torch.arange(fw, device=dev)
+    step = max(1, 64 * (FH * FW) // (fh * fw))
+    for lo in range(0, n, step):                                                        # rolled[y, x] = src[(y - dy) % H, (x - dx) % W]
+        sl = slice(lo, min(lo + step, n))
         w = which[sl, None, None]
-        frames[sl] = bases[w, ((ys[None, :] - sh[sl, 0:1]) % FH)[:, :, None], ((xs[None, :] - sh[sl, 1:2]) % FW)[:, None, :]]
-        bgs[sl] = bgb[w, ((ys[None, :] - sh[sl, 2:3]) % FH)[:, :, None], ((xs[None, :] - sh[sl, 3:4]) % FW)[:, None, :]]
+        frames[sl] = bases[w, ((ys[None, :] - sh[sl, 0:1]) % fh)[:, :, None], ((xs[None, :] - sh[sl, 1:2]) % fw)[:, None, :]]
+        bgs[sl] = bgb[w, ((ys[None, :] - sh[sl, 2:3]) % fh)[:, :, None], ((xs[None, :] - sh[sl, 3:4]) % fw)[:, None, :]]
     return frames, bgs
+
+
+def noise_images_device(n: int, shape, seed: int, first: int, dev, base: int = 16):
+    """n uniform-noise uint8 images [n, *shape] on the device: `base` images of SURVEY.md §8d's generator
+    (default_rng(seed * 1_000_003 + i).integers(0, 256)) multiplied by cyclic row shifts."""
+    import torch
+    from image_processor_pipeline_b200 import synth
+    bases = torch.from_numpy(np.stack([synth.noise(seed, k, shape) for k in range(base)])).to(dev)
+    out = torch.empty((n,) + tuple(shape), dtype=torch.uint8, device=dev)
+    for i in range(n):
+        g = first + i
+        out[i] = torch.roll(bases[g % base], shifts=(g * 37) % shape[0], dims=0)
+    return out
+
+
+def noise_images_host(n: int, shape, seed: int, first: int, base: int = 4):
+    from image_processor_pipeline_b200 import synth
+    bases = [synth.noise(seed, k, shape) for k in range(min(base, n))]
+    return [np.roll(bases[(first + i) % len(bases)], ((first + i) * 37) % shape[0], axis=0) for i in range(n)]
+
+
+def sprite_images(n: int, sh: int, sw: int, seed: int):
+    """RGBA noise sprites with alpha = radial ramp with 0 / 255 plateaus."""
+    r = np.random.default_rng(seed * 1_000_003 + 991)
+    spr = r.integers(0, 256, (n, sh, sw, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    spr[..., 3] = np.clip(255 * (1.2 - np.hypot((xx - sw / 2) / (sw / 2), (yy - sh / 2) / (sh / 2))), 0, 255).astype(np.uint8)
+    return spr
 
 
 class ClockSampler:
@@ -150,53 +212,114 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------ CPU arm
+# ------------------------------------------------------------------------------------ CPU arm (oracle; every config)
+C4_SHAPE, C1_SHAPE, C2_SHAPE, SPR = (512, 512), (1024, 1024, 3), (1080, 1920, 3), (384, 512)
 _WORKER = {}
 
 
-def _cpu_worker_init(seed, count):
-    """Per-process set-up, outside any timed region: imports, single-threaded cv2, and this
-    worker's own `count` synthetic frames/backgrounds."""
+def _c1_box(i: int):
+    r = np.random.default_rng(4242 + i)
+    return np.array([[r.uniform(.3, .7), r.uniform(.3, .7), r.uniform(.05, .3), r.uniform(.05, .3)]])
+
+
+def _cpu_worker_init(config, seed, count, worker_index):
+    """Per-process set-up, outside any timed region: imports, single-threaded cv2, and this worker's own `count`
+    synthetic inputs — seeded from the worker INDEX (reproducible; the process id plays no role)."""
     import cv2
     cv2.setNumThreads(1)
     from image_processor_pipeline_b200 import synth
-    from oracle import chain as OC
-    first = (os.getpid() * 7919) % 100_000
-    frames, bgs = make_inputs(count, seed, first, base=min(4, count))
-    _WORKER.update(frames=list(frames), bgs=list(bgs), OC=OC, filters=synth.REFERENCE_FILTERS, seed=seed + first)
+    from oracle import chain as OC, libcalls as L
+    first = 1000 * worker_index
+    w = dict(config=config, OC=OC, L=L, filters=synth.REFERENCE_FILTERS, seed=seed + first, count=count)
+    if config in ("chain", "c5"):
+        c = CONFIGS[config]
+        frames, bgs = make_inputs(count, seed, first, base=min(4, count), fh=c["fh"], fw=c["fw"])
+        w.update(frames=list(frames), bgs=list(bgs))
+    elif config == "c1":
+        w.update(imgs=noise_images_host(count, C1_SHAPE, seed, first), boxes=[_c1_box(first + i) for i in range(count)])
+    elif config == "c2":
+        w.update(imgs=noise_images_host(count, C2_SHAPE, seed, first))
+    elif config == "c3":
+        w.update(bgs=noise_images_host(count, C2_SHAPE, seed, first), sprites=list(sprite_images(min(4, count), SPR[0], SPR[1], seed)))
+    elif config == "c4":
+        w.update(imgs=[synth.frame(seed, first + i, *C4_SHAPE) for i in range(min(8, count))])
+    _WORKER.clear()
+    _WORKER.update(w)
 
 
 def _cpu_worker_run(step):
-    """One pass of the oracle chain (the reference's cv2/Pillow call sequence, in memory) over the
-    worker's frames.  Returns (images produced, seconds of chain work)."""
+    """One pass of the oracle (the reference's cv2 / Pillow call sequence, in memory) over the worker's inputs.
+    Returns (images produced, seconds of work)."""
     w = _WORKER
+    L = w["L"]
     random.seed(w["seed"] + step)
+    cfg = w["config"]
     t0 = time.perf_counter()
-    imgs, labels, _ = w["OC"].run_chain(w["frames"], w["bgs"], color_ranges_to_exclude_hsv=w["filters"], **CHAIN_KW)
-    return len(imgs), time.perf_counter() - t0
+    if cfg in ("chain", "c5"):
+        imgs, labels, _ = w["OC"].run_chain(w["frames"], w["bgs"], color_ranges_to_exclude_hsv=w["filters"], **CHAIN_KW)
+        n = len(imgs)
+    elif cfg == "c1":
+        n = 0
+        for img, box in zip(w["imgs"], w["boxes"]):
+            syms = L.select_symmetries(None, None, True)
+            for v in L.symmetries(img, syms):
+                L.square_crop(v, np.array([0]), box)
+            n += 1
+    elif cfg == "c2":
+        n = 0
+        for img in w["imgs"]:
+            L.rotate_and_fit(L.to_rgba(img), random.uniform(1.0, 359.0))
+            n += 1
+    elif cfg == "c3":
+        n = 0
+        for k, bg in enumerate(w["bgs"]):
+            L.overlay_onto_background(w["sprites"][k % len(w["sprites"])], bg)
+            n += 1
+    else:
+        n = 0
+        for i in range(w["count"]):
+            img = w["imgs"][i % len(w["imgs"])]
+            L.keep_largest_component(L.color_masks_to_alpha(img, list(w["filters"])))
+            n += 1
+    return n, time.perf_counter() - t0
 
 
-def cpu_chain_rate_single(n_images: int, seed: int = 1):
-    """images/s of the oracle chain in this process, cv2 single-threaded."""
-    _cpu_worker_init(seed, n_images)
-    _cpu_worker_run(0) if n_images <= 4 else None            # warm the libraries on tiny samples only
+CPU_SAMPLE = {"chain": 16, "c5": 4, "c1": 32, "c2": 16, "c3": 32, "c4": 128}
+REF_PER_WORKER = {"chain": 4, "c5": 1, "c1": 8, "c2": 4, "c3": 8, "c4": 64}
+
+
+def cpu_rate_single(config: str, n_images: int, seed: int = 1):
+    """images/s of the oracle in this process, cv2 single-threaded."""
+    _cpu_worker_init(config, seed, n_images, 0)
+    if config not in ("chain", "c5"):
+        _cpu_worker_run(0)                                    # warm the libraries (cheap configs only)
     done, dt = _cpu_worker_run(1)
     return done / dt, dt
+
+
+def _ref_pool_init(config, per_worker, counter):
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    _cpu_worker_init(config, 100, per_worker, idx)
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path on all host cores.  ProcessPoolExecutor(cpu_count)
     is the reference's own workers=-1 mode (pipeline.py:88-90, :372); every worker owns
-    `per_worker` frames and one step = every worker running the oracle chain over its frames."""
+    `per_worker` inputs and one step = every worker running the oracle over its inputs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    per_worker = 4
+    per_worker = REF_PER_WORKER[args.config]
     per_step = per_worker * cores
     elapsed, produced = 0.0, 0
-    with ProcessPoolExecutor(max_workers=cores, initializer=_cpu_worker_init, initargs=(100, per_worker)) as ex:
+    counter = mp.Value("i", 0)
+    with ProcessPoolExecutor(max_workers=cores, initializer=_ref_pool_init, initargs=(args.config, per_worker, counter)) as ex:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = list(ex.map(_cpu_worker_run, [s] * cores, chunksize=1))
@@ -205,39 +328,253 @@ def run_reference_arm(args):
                 elapsed += dt
                 produced += sum(r[0] for r in res)
     value = produced / elapsed
-    line = {"impl": "reference", "metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s",
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_step": per_step},
+            "config": {"workload": cfg["workload"], "name": args.config},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} frames per step ({per_worker} per worker) over a ProcessPoolExecutor({cores}); oracle chain = the reference's cv2/Pillow call sequence in memory (no file I/O), inputs generated outside the timed region"},
+                             "sample": f"{per_step} images per step ({per_worker} per worker) over a ProcessPoolExecutor({cores}); oracle = the reference's cv2/Pillow call sequence in memory (no file I/O), inputs generated outside the timed region, seeded per worker index"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm: workloads
+class Workload:
+    """One BASELINE config on one GPU: resident step, end-to-end step, roofline bookkeeping."""
+    pipelined = False
+
+    def extra(self):
+        return {}
+
+
+class ChainWorkload(Workload):
+    pipelined = True
+
+    def __init__(self, name, args, dev, rank):
+        import torch
+        from image_processor_pipeline_b200 import chain, synth
+        self.torch, self.chain = torch, chain
+        c = CONFIGS[name]
+        self.name, self.args, self.dev, self.rank = name, args, dev, rank
+        self.fh, self.fw = c["fh"], c["fw"]
+        self.cs = min(self.fh, self.fw)
+        self.B = args.batch or c["batch"]
+        self.params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
+        self.frames_d, self.bgs_d = make_inputs_device(self.B, 1, rank * self.B, dev, fh=self.fh, fw=self.fw)
+        self.pipe = chain.ChainStream(self.params, stage_a_stream=args.stage_a_stream)
+        self.alg_bytes_per_image = 2 * 3 * self.fw * self.fh + 3 * self.cs * self.cs       # SURVEY.md §8d: frame + background + output
+        self.alg = {"chain_mask_kernel": self.B * 3 * self.fw * self.fh,                   # frame read once
+                    "chain_mask_seg_kernel": self.B * 3 * self.fw * self.fh,
+                    "chain_paste_kernel": self.B * 2 * 3 * self.cs * self.cs}              # background crop read + output write
+        self.l2_note = f"inputs per step {2 * self.B * 3 * self.fw * self.fh / 1e6:.0f} MB >> 126 MB L2 (no flush needed)"
+
+    def step(self, s):
+        random.seed(1000 * self.rank + s)
+        return self.chain.run_chain(self.frames_d, self.bgs_d, self.params).images.shape[0]
+
+    def run_pipelined(self, first, count, frames=None, bgs=None, pipe=None):
+        """`count` steps through ChainStream.map: the four phases of consecutive steps are interleaved on one
+        stream (finish(s-2), prepare(s-1), plan(s), submit(s+1) ...), so the device never waits for the host's
+        planning or for the small read-backs.  Draw order = step after step (re-seeded per step)."""
+        frames = self.frames_d if frames is None else frames
+        bgs = self.bgs_d if bgs is None else bgs
+        n_out = 0
+        for res in (pipe or self.pipe).map(((frames, bgs) for _ in range(count)), random,
+                                           on_batch=lambda i: random.seed(1000 * self.rank + first + i)):
+            n_out += res.images.shape[0]
+        return n_out
+
+    def e2e_setup(self):
+        torch = self.torch
+        E = min(self.B, self.args.e2e_frames or CONFIGS[self.name]["e2e_frames"])
+        self.E = E
+        self.frames_pin = torch.empty((E, self.fh, self.fw, 3), dtype=torch.uint8).pin_memory()
+        self.bgs_pin = torch.empty((E, self.fh, self.fw, 3), dtype=torch.uint8).pin_memory()
+        self.frames_pin.copy_(self.frames_d[:E]); self.bgs_pin.copy_(self.bgs_d[:E])
+        self.out_pin = torch.empty((E, self.cs, self.cs, 3), dtype=torch.uint8).pin_memory()
+        self.last = {}
+
+    def e2e_step(self, s):
+        random.seed(1000 * self.rank + s)
+        r = self.chain.run_chain_host(self.frames_pin, self.bgs_pin, self.params, self.dev, self.out_pin, chunk=self.args.e2e_chunk,
+                                      background_windows=not self.args.no_bg_windows)
+        self.last["h2d"], self.last["d2h"] = r.h2d_bytes, int(r.images.numel())
+        return r.images.shape[0]
+
+    def e2e_info(self):
+        return {"pipelined_slice_frames": self.args.e2e_chunk, "frames_per_step": self.E,
+                "background_upload": "whole images" if self.args.no_bg_windows else
+                "square-crop windows only (planned offsets known before the copy; cudaMemcpy2DAsync per item)"}
+
+    def extra(self):
+        """Content sensitivity: the same chain on UNIFORM-NOISE frames (SURVEY.md §8d's generic generator).  The key
+        then keeps ~75 % of the pixels as one giant component: every pixel is classified, the sprite is the whole frame."""
+        torch = self.torch
+        if self.args.no_noise or self.name != "chain":
+            return {}
+        nb = min(self.B, 128)
+        frames, bgs = make_inputs_device(nb, 2, self.rank * nb, self.dev, fh=self.fh, fw=self.fw, noise_frames=True)
+        pipe = self.chain.ChainStream(self.params)
+        self.run_pipelined(0, 3, frames, bgs, pipe)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = self.run_pipelined(3, 6, frames, bgs, pipe)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        del frames, bgs
+        return {"value_noise_frames": n / (ms * 1e-3),
+                "noise_frames_note": f"same chain, frames = uniform noise (worst case: every pixel classified, ~75 % of the frame is one component and becomes the sprite), {nb} frames x 6 steps, this rank only"}
+
+
+class OpsWorkload(Workload):
+    """c1..c4: one transform (or two chained steps) mapped over a resident batch through the batched operators."""
+
+    def __init__(self, name, args, dev, rank):
+        import torch
+        from image_processor_pipeline_b200 import batch, ops, synth
+        self.torch, self.batch, self.ops, self.synth = torch, batch, ops, synth
+        self.name, self.args, self.dev, self.rank = name, args, dev, rank
+        self.B = B = args.batch or CONFIGS[name]["batch"]
+        first = rank * B
+        if name == "c1":
+            self.imgs = noise_images_device(B, C1_SHAPE, 1, first, dev)
+            H, W, _ = C1_SHAPE
+            self.alg_bytes_per_image = 5 * H * W * 3 + 4 * 2 * H * W * 3                    # symmetries 1 read + 4 writes; 4 crops read + write
+            self.alg = {"rows_kernel": None}
+        elif name == "c2":
+            self.imgs = noise_images_device(B, C2_SHAPE, 1, first, dev)
+            H, W, _ = C2_SHAPE
+            self.alg_bytes_per_image = 3 * W * H + 4 * (W * H + (W * W + H * H) / np.pi)    # SURVEY.md §8d, RGB -> RGBA fused, mean over the angle
+            self.alg = {"rotate_batch_nearest_kernel": B * self.alg_bytes_per_image, "rotate_batch_bilinear_kernel": B * self.alg_bytes_per_image}
+        elif name == "c3":
+            self.imgs = noise_images_device(B, C2_SHAPE, 1, first, dev)                     # the backgrounds
+            self.sprites = torch.from_numpy(sprite_images(64, SPR[0], SPR[1], 1)).to(dev)
+            H, W, _ = C2_SHAPE
+            self.alg_bytes_per_image = 2 * 3 * W * H + 4 * SPR[0] * SPR[1] + 4 * 0.047 * W * H   # bg read + composite write + sprite source + resized sprite (mean 4.7 % of the bg)
+            self.alg = {"chain_paste_kernel": B * 2 * 3 * W * H}
+        else:
+            base = torch.from_numpy(np.stack([synth.frame(1, first + k, *C4_SHAPE) for k in range(32)])).to(dev)
+            self.imgs = torch.empty((B,) + C4_SHAPE + (3,), dtype=torch.uint8, device=dev)
+            for i in range(B):
+                self.imgs[i] = torch.roll(base[i % 32], shifts=((i * 53) % 512, (i * 97) % 512), dims=(0, 1))
+            H, W = C4_SHAPE
+            self.alg_bytes_per_image = 3 * H * W + 4 * H * W                                 # BGR read + BGRA write (HSV key); the CCL works on bits
+            self.alg = {"chain_mask_seg_kernel": B * 3 * H * W, "chain_mask_kernel": B * 3 * H * W, "bgra_from_keep_kernel": B * 7 * H * W}
+        self.l2_note = f"inputs per step {self.imgs.numel() / 1e6:.0f} MB >> 126 MB L2 (no flush needed)"
+
+    # the work on device tensors (also used by the end-to-end leg on uploaded slices); returns (n images, result tensors)
+    def work(self, x, s, mode=None):
+        ops, batch = self.ops, self.batch
+        if self.name == "c1":
+            from image_processor_pipeline_b200 import _native
+            n, H, W, c = x.shape
+            outs = [self.torch.empty_like(x) for _ in range(4)]
+            for _ in range(n):
+                random.sample(["o", "h", "v", "hv"], 4)                       # symmetry.py:122: the draw fixes the output order only
+            _native.check(_native.load().ipp_symmetries_u8(x.data_ptr(), W * c, W, H, c, *[o.data_ptr() for o in outs], W * c, n, H * W * c, H * W * c,
+                                                           self.torch.cuda.current_stream().cuda_stream), "ipp_symmetries_u8")
+            cs = min(H, W)
+            res = []
+            for o in outs:                                                    # crop_square.py:172-196 per variant: two randint per image
+                xy = np.array([[random.randint(0, W - cs), random.randint(0, H - cs)] for _ in range(n)], dtype=np.int32)
+                res.append(batch.crop_batch(o, xy, cs, cs))
+            return n, res
+        if self.name == "c2":
+            r = batch.rotate_batch(x, random, 1.0, 359.0, resample=mode or "nearest")
+            return x.shape[0], [r.pool, r._bbox_d]
+        if self.name == "c3":
+            r = batch.overlay_batch(self.sprites, x, x.shape[0], random)
+            return r.images.shape[0], [r.images]
+        cleaned, info = batch.key_and_keep_largest(x, self.synth.REFERENCE_FILTERS)
+        return x.shape[0], [cleaned]
+
+    def step(self, s, mode=None):
+        random.seed(1000 * self.rank + s)
+        return self.work(self.imgs, s, mode)[0]
+
+    def e2e_setup(self):
+        torch = self.torch
+        E = min(self.B, self.args.e2e_frames or CONFIGS[self.name]["e2e_frames"])
+        self.E = E
+        self.in_pin = torch.empty((E,) + tuple(self.imgs.shape[1:]), dtype=torch.uint8).pin_memory()
+        self.in_pin.copy_(self.imgs[:E])
+        self.chunk = max(1, E // 8)
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(2)]
+        self.out_pin = {}
+        self.last = {}
+
+    def e2e_step(self, s):
+        """pinned host inputs -> H2D -> batched operators -> D2H of every result, slices alternating between two streams
+        (copies of one slice overlap the kernels of the other)."""
+        torch = self.torch
+        random.seed(1000 * self.rank + s)
+        n_out, h2d, d2h = 0, 0, 0
+        for ci, lo in enumerate(range(0, self.E, self.chunk)):
+            st = self.streams[ci % 2]
+            with torch.cuda.stream(st):
+                xin = self.in_pin[lo:lo + self.chunk].to(self.dev, non_blocking=True)
+                h2d += xin.numel()
+                n, outs = self.work(xin, s)
+                n_out += n
+                for k, o in enumerate(outs):
+                    key = (ci, k)
+                    buf = self.out_pin.get(key)
+                    if buf is None or buf.numel() < o.numel():
+                        buf = self.out_pin[key] = torch.empty(o.numel(), dtype=o.dtype).pin_memory()
+                    buf[:o.numel()].copy_(o.reshape(-1), non_blocking=True)
+                    d2h += o.numel() * o.element_size()
+        for st in self.streams:
+            st.synchronize()
+        self.last["h2d"], self.last["d2h"] = h2d, d2h
+        return n_out
+
+    def e2e_info(self):
+        return {"frames_per_step": self.E, "slice_frames": self.chunk, "streams": 2}
+
+    def extra(self):
+        if self.name != "c2":
+            return {}
+        torch = self.torch
+        for s in range(2):
+            self.step(s, "bilinear")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = sum(self.step(10 + s, "bilinear") for s in range(5))
+        e1.record()
+        torch.cuda.synchronize()
+        return {"value_bilinear": n / (e0.elapsed_time(e1) * 1e-3)}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: enough for >= 1 s of timed work)")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="chain", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default per config)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="do not overlap stage A of step s+1 with the tail of step s")
+    ap.add_argument("--no-noise", action="store_true", help="chain: skip the uniform-noise-frames line")
+    ap.add_argument("--no-pipeline", action="store_true", help="chain: one run_chain call per step (host waits inside the step)")
     ap.add_argument("--stage-a-stream", default="caller", choices=["side", "caller"], help="stage A of new batches on a second stream")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
-    ap.add_argument("--e2e-frames", type=int, default=512, help="frames of the batch used by the end-to-end leg (0 = all; 512 = 8 GB of pinned host memory per rank)")
-    ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the host-buffer entry point")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="images of the batch used by the end-to-end leg (default per config)")
+    ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per pipelined slice of the chain's host-buffer entry point")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"chain": 160, "c5": 60, "c1": 100, "c2": 100, "c3": 120, "c4": 100}[args.config] if args.impl == "b200" else 5
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from image_processor_pipeline_b200 import _native, chain, synth
+    from image_processor_pipeline_b200 import _native
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -261,11 +598,8 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     _native.load()
-    B = args.batch
-    params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
-
-    # each rank owns a contiguous slice of the global work list (weak scaling: B frames per GPU)
-    frames_d, bgs_d = make_inputs_device(B, seed=1, first=rank * B, dev=dev)
+    cfg = CONFIGS[args.config]
+    wl = (ChainWorkload if args.config in ("chain", "c5") else OpsWorkload)(args.config, args, dev, rank)
     torch.cuda.synchronize()
 
     def barrier():
@@ -273,21 +607,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(s):
-        random.seed(1000 * rank + s)
-        return chain.run_chain(frames_d, bgs_d, params)
-
-    pipe = chain.ChainStream(params, stage_a_stream=args.stage_a_stream)
-
-    def run_pipelined(first, count):
-        """`count` steps through ChainStream.map: the four phases of consecutive steps are interleaved on one
-        stream (finish(s-3), prepare(s-2), plan(s-1), submit(s)), so the device never waits for the host's
-        planning or for the small read-backs.  Draw order = step after step (re-seeded per step)."""
-        n_out = 0
-        for res in pipe.map(((frames_d, bgs_d) for _ in range(count)), random,
-                            on_batch=lambda i: random.seed(1000 * rank + first + i)):
-            n_out += res.images.shape[0]
-        return n_out
+    def reduce(ms, n_out):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            c = torch.tensor([n_out], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            n_out = int(c.item())
+        return ms, n_out
 
     def timed(fn, steps, warmup):
         for s in range(warmup):
@@ -298,121 +626,95 @@ def main():
         l0 = _native.launch_count()
         e0.record()
         for s in range(steps):
-            n_out += fn(warmup + s).images.shape[0]
+            n_out += fn(warmup + s)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        launches = _native.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            c = torch.tensor([n_out], dtype=torch.int64, device=dev)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            n_out = int(c.item())
-        return ms, n_out, launches
+        ms, n_out = reduce(e0.elapsed_time(e1), n_out)
+        return ms, n_out, _native.launch_count() - l0
 
     def timed_pipelined(steps, warmup):
-        run_pipelined(0, warmup)
+        wl.run_pipelined(0, warmup)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _native.launch_count()
         e0.record()
-        n_out = run_pipelined(warmup, steps)
+        n_out = wl.run_pipelined(warmup, steps)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        launches = _native.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            c = torch.tensor([n_out], dtype=torch.int64, device=dev)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            n_out = int(c.item())
-        return ms, n_out, launches
+        ms, n_out = reduce(e0.elapsed_time(e1), n_out)
+        return ms, n_out, _native.launch_count() - l0
 
-    # stages B2/C (the caller's stream) get a higher priority than stage A of the next batch (side stream):
-    # the big persistent mask CTAs then fill SMs as the finishing batch drains instead of delaying it
     with ClockSampler(local) as clk:
-        if args.no_pipeline:
-            ms, n_out, launches = timed(step_resident, args.steps, args.warmup)
-        else:
+        if wl.pipelined and not args.no_pipeline:
             ms, n_out, launches = timed_pipelined(args.steps, args.warmup)
+        else:
+            ms, n_out, launches = timed(wl.step, args.steps, args.warmup)
     clocks = clk.summary()
     value = n_out / (ms * 1e-3)
 
-    # per-kernel device time of the same steps (events around every launch) -> roofline
+    # per-kernel device time of a few of the same steps (events around every launch) -> roofline
     _native.timing_enable(True)
-    for s in range(args.steps):
-        step_resident(args.warmup + s)
+    ksteps = min(args.steps, 10)
+    for s in range(ksteps):
+        wl.step(args.warmup + s)
     torch.cuda.synchronize()
     rep = _native.timing_report()
     _native.timing_enable(False)
-    alg = {"chain_mask_kernel": B * 3 * FW * FH,                       # frame read once (generic mask kernel)
-           "chain_mask_seg_kernel": B * 3 * FW * FH,                   # frame read once (table-driven per-warp segment kernel)
-           "chain_paste_kernel": B * 2 * 3 * 1080 * 1080}              # background crop read + output write
     peak, peak_src = measured_peak()
     kern = {k: {"launches": c, "total_ms": round(t, 4), "avg_ms": round(t / c, 5)} for k, (c, t) in rep.items()}
     total_kernel_ms = sum(t for _, t in rep.values())
-    dom = max(alg, key=lambda k: rep.get(k, (1, 0.0))[1])
-    dcnt, dms = rep.get(dom, (1, float("nan")))
+    alg = dict(wl.alg)
+    if "rows_kernel" in alg:                                            # c1: five launches of the same kernel per step (symmetries + 4 crops)
+        alg["rows_kernel"] = wl.B * wl.alg_bytes_per_image / 5
+    alg = {k: v for k, v in alg.items() if k in rep}
+    dom = max(alg, key=lambda k: rep[k][1])
+    dcnt, dms = rep[dom]
     achieved = alg[dom] / (dms / dcnt * 1e-3) / 1e9
     traffic, traffic_src = None, None                                  # dram bytes per launch from the committed ncu --set full capture
     tp = ROOT / "profiles" / "traffic.json"
-    if tp.is_file():
+    if tp.is_file() and args.config == "chain":
         rec = json.loads(tp.read_text()).get(dom)
         if rec:
-            traffic = rec["dram_bytes_per_frame"] * B
+            traffic = rec["dram_bytes_per_frame"] * wl.B
             traffic_src = rec["source"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dms / dcnt,
                 "share_of_kernel_time": dms / total_kernel_ms if total_kernel_ms else None}
-    chain_gbs = ALG_BYTES_PER_IMAGE * (n_out / world / args.steps) / (ms / args.steps * 1e-3) / 1e9
+    alg_gbs = wl.alg_bytes_per_image * (n_out / world / args.steps) / (ms / args.steps * 1e-3) / 1e9
 
-    # end to end through the host API: pinned host inputs, H2D + chain + D2H inside the timed region
+    extra = wl.extra()
+
+    # end to end through the host API: pinned host inputs, H2D + work + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        # host buffers of the end-to-end leg: the same batch in pinned memory (B = 512: 8 GB per rank; the first slice's
-        # upload is not overlapped, so short batches under-report the PCIe-bound steady state: 4.80 k at 256, 5.05 k at 512)
-        E = min(B, args.e2e_frames) if args.e2e_frames else B
-        frames_pin = torch.empty((E, FH, FW, 3), dtype=torch.uint8).pin_memory()
-        bgs_pin = torch.empty((E, FH, FW, 3), dtype=torch.uint8).pin_memory()
-        frames_pin.copy_(frames_d[:E]); bgs_pin.copy_(bgs_d[:E])
-        out_pin = torch.empty((E, 1080, 1080, 3), dtype=torch.uint8).pin_memory()
-
-        last = {}
-
-        def step_e2e(s):
-            random.seed(1000 * rank + s)
-            r = chain.run_chain_host(frames_pin, bgs_pin, params, dev, out_pin, chunk=args.e2e_chunk,
-                                     background_windows=not args.no_bg_windows)
-            last["h2d"], last["d2h"] = r.h2d_bytes, int(r.images.numel())
-            return r
-
-        ems, en, _ = timed(step_e2e, max(2, args.steps // 2), 1)
-        e2e = {"value": en / (ems * 1e-3), "unit": "images/s", "pipelined_slice_frames": args.e2e_chunk,
-               "frames_per_step": E, "h2d_bytes_per_step": int(last["h2d"]), "d2h_bytes_per_step": int(last["d2h"]),
-               "background_upload": "whole images" if args.no_bg_windows else
-               "square-crop windows only (planned offsets known before the copy; cudaMemcpy2DAsync per item)"}
+        wl.e2e_setup()
+        esteps = {"chain": 6, "c5": 6}.get(args.config, 10)
+        ems, en, _ = timed(wl.e2e_step, esteps, 2)
+        e2e = {"value": en / (ems * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(wl.last["h2d"]), "d2h_bytes_per_step": int(wl.last["d2h"])}
+        e2e.update(wl.e2e_info())
 
     if rank == 0:
         cpu = None
         if world == 1:
-            rate, dt = cpu_chain_rate_single(args.cpu_sample)
+            sample = args.cpu_sample or CPU_SAMPLE[args.config]
+            rate, dt = cpu_rate_single(args.config, sample)
             cpu = {"value": rate, "unit": "images/s", "cores": 1, "kind": "port",
-                   "sample": f"{args.cpu_sample} frames of the same workload, oracle chain (the reference's cv2/Pillow call sequence in memory, cv2.setNumThreads(1)), {dt:.1f} s",
+                   "sample": f"{sample} images of the same workload, oracle (the reference's cv2/Pillow call sequence in memory, cv2.setNumThreads(1)), {dt:.1f} s",
                    "host_cores_available": os.cpu_count()}
-        line = {"metric": "images/sec 1080p RGB full chain", "value": value, "unit": "images/s", "n_gpus": world,
+        line = {"metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "software_pipelined_steps": not args.no_pipeline,
-                           "l2": f"inputs per step {2 * B * 3 * FW * FH / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
-                           "host_work_in_step": "C++ planner (Python-compatible MT19937 draws) + 3 small device->host read-backs per batch (RNG bounds depend on sprite sizes; table-ambiguity count)"},
+                "config": {"workload": cfg["workload"], "name": args.config},
+                "run": {"images_per_gpu_per_step": wl.B, "software_pipelined_steps": bool(wl.pipelined and not args.no_pipeline), "l2": wl.l2_note,
+                        "host_work_in_step": "native planner (Python-compatible MT19937 draws) + small pinned read-backs; the chain interleaves the phases of consecutive steps on one stream" if wl.pipelined else "draws from Python's random in the reference's order (native planner for rotations / overlays)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "chain_algorithmic_gbs": chain_gbs, "chain_frac_of_peak": chain_gbs / peak,
+                "roofline": roofline, "algorithmic_gbs": alg_gbs, "frac_of_peak": alg_gbs / peak,
+                "algorithmic_bytes_per_image": wl.alg_bytes_per_image,
                 "kernels": kern, "cpu_baseline": cpu}
+        if args.config == "chain":
+            line["chain_algorithmic_gbs"], line["chain_frac_of_peak"] = alg_gbs, alg_gbs / peak
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "ipp_sprite_planes_u8": (_int, [_u8p, _i64, _i64, _int, _int, _int, _vp, _int, _u8p, _vp]),
     "ipp_chain_stage_c_rect": (_int, [_u8p, _i64, _i64, _int, _int, _vp, _int, _u8p, _u8p, _i64, _i64, _int, _int, _vp]),
     "ipp_sprites_export_u8": (_int, [_vp, _int, _u8p, _u8p, _vp, _vp]),
+    "ipp_bgra_from_keep_u8": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _u8p, _i64, _i64, _int, _vp]),
 }
 
 EXCEPTION_FOR_CODE = {-1: ValueError, -2: ValueError, -3: MemoryError, -4: NotImplementedError}

@@ -131,6 +131,34 @@ def rotate_batch(imgs: torch.Tensor, rng=_random, angle_min: float = 1.0, angle_
     return RotateBatchResult(pool, items, bbox, ang)
 
 
+# --------------------------------------------------------------------------- HSV key + largest component
+def key_and_keep_largest(bgr: torch.Tensor, color_ranges, zones=None, use_gimp_scale: bool = False, crop_margins=(0, 0, 0, 0)):
+    """``process_images_with_color_masks`` then ``keep_largest_component`` (filtres_liste.py:90-134, pixels_isolés.py:29-58)
+    for a batch [N, H, W, 3] of BGR images WITHOUT the BGRA image in between: the frame is read once into a 1-bit mask, the
+    largest 8-connected component is found on bits, and the BGRA result is written once.  Returns (bgra [N, h, w, 4], info
+    int32 CPU [N, 8] = {x, y, w, h of the kept component, area, n_fg, 0, 0}); ``_crop_fit`` of the reference is the view
+    bgra[i, y:y+h, x:x+w] (w == 0: nothing left, the reference writes no file)."""
+    from . import hostmath
+    t = _check_batch(bgr, "bgr", (3,))
+    n, FH, FW, _ = t.shape
+    lib = _native.load()
+    rect = hostmath.border_crop_rect(FW, FH, crop_margins)
+    ranges = hostmath.pack_hsv_ranges(color_ranges, zones, use_gimp_scale)
+    geom = chain._geom_struct(FW, FH, rect, rect[2], rect[3], ranges)
+    w, h = rect[2], rect[3]
+    out = torch.empty((n, h, w, 4), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        ws_bytes = lib.ipp_chain_mask_workspace_bytes(C.byref(geom), n)
+        ws = chain._scratch("kk_mask", ws_bytes, t.device)
+        info = torch.empty((n, 8), dtype=torch.int32, device=t.device)
+        _native.check(lib.ipp_chain_stage_a(t.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), info.data_ptr(), ws.data_ptr(), ws_bytes, n,
+                                            _stream()), "ipp_chain_stage_a")
+        _native.check(lib.ipp_bgra_from_keep_u8(t.data_ptr(), FW * 3, FH * FW * 3, C.byref(geom), ws.data_ptr(), out.data_ptr(), w * 4, h * w * 4, n,
+                                                _stream()), "ipp_bgra_from_keep_u8")
+        info_h = info.cpu().numpy()
+    return out, info_h
+
+
 # --------------------------------------------------------------------------- LANCZOS resize / overlay
 def _resize_items(items: np.ndarray, sprites: torch.Tensor, device_tables: bool, eps: float):
     """Layout + tables + premultiplied planes + tensor-core passes for an item array over ``sprites``

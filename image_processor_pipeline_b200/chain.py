@@ -180,6 +180,7 @@ def release_scratch():
     _SCRATCH.clear()
     _PINNED.clear()
     _HOSTBUF.clear()
+    _WIN_FREE.clear()
 
 
 # Small host->device uploads (plan records) go through rotating PINNED staging buffers: a copy from
@@ -501,6 +502,7 @@ def amb_ints(capacity: int = AMB_CAPACITY) -> int:
 
 
 _HOSTBUF = {}
+_WIN_FREE = {}       # (window buffer name, device) -> event recorded after the stage C that last read it
 
 
 def _pinned(name: str, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
@@ -695,11 +697,18 @@ def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResul
         items_c["sq_x0"] = 0
         items_c["sq_y0"] = 0
         items_c_d = _upload("items_c" + b.tag, items_c, dev)
-        bg_dev = _scratch("bg_windows" + b.tag, K * cs * cs * 3, dev)
+        win_key = f"bg_windows{b.tag}/{b.slot}"
+        bg_dev = _scratch(win_key, K * cs * cs * 3, dev)
         geom_c = _geom_struct(b.FW, b.FH, b.rect, cs, cs, b.ranges)
         bg_pitch, bg_stride = cs * 3, cs * cs * 3
-        up = upload_stream if upload_stream is not None else _side_streams(dev)[0]
-        up.wait_stream(torch.cuda.current_stream())                   # previous readers of the window buffer
+        # the windows get their own copy stream: queued behind the frames of the NEXT slices (uploaded ahead on the frame
+        # stream) they would hold stage C — and everything behind it on the compute stream — for several slices of H2D time
+        up = upload_stream if upload_stream is not None else _side_streams(dev)[2]
+        prev = _WIN_FREE.get((win_key, dev.index))
+        if prev is not None:
+            up.wait_event(prev)                                       # stage C of the batch that last read this window buffer
+        else:
+            up.wait_stream(torch.cuda.current_stream())
         _native.check(lib.ipp_chain_upload_windows(backgrounds.data_ptr(), b.BW * 3, b.BH * b.BW * 3, b.BW, b.BH, b.m, items.ctypes.data, K, cs,
                                                    bg_dev.data_ptr(), up.cuda_stream), "ipp_chain_upload_windows")
         bg_ready = torch.cuda.Event()
@@ -720,6 +729,10 @@ def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResul
     _native.check(lib.ipp_chain_stage_c(bg_dev.data_ptr(), bg_pitch, bg_stride, C.byref(geom_c), items_c_d.data_ptr(), K,
                                         spr_ws.data_ptr(), b.out.data_ptr(), cs * 3, cs * cs * 3, cs, _stream()),
                   "ipp_chain_stage_c")
+    if bg_ready is not None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        _WIN_FREE[(win_key, dev.index)] = ev
     _mark("b2+c_issued")
     for t in (b.rot_d, b.items_d, items_c_d):
         if t is not None:
@@ -960,64 +973,68 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
         if m != n:
             raise ValueError("chunked run_chain_host pairs slice c with backgrounds[c*chunk:(c+1)*chunk]: pass one background per frame")
         compute = torch.cuda.current_stream()
-        up, down = _side_streams(dev)
-        n_slots, ahead = 3, 2                             # frames of two slices are queued ahead of the slice being chained
+        up, down, _ = _side_streams(dev)
+        bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        # slices flow through ChainStream.map (three slices between submit and finish) with their frames uploaded two
+        # slices ahead on the copy stream: the host only ever waits for read-backs of work queued an iteration earlier,
+        # so neither the copy engines nor the SMs drain while it plans
+        pipe = _HOST_PIPES.get((id(params), dev.index))
+        if pipe is None or pipe.params is not params or pipe._live:
+            pipe = ChainStream(params, slots=4, **kw)
+            _HOST_PIPES.clear()
+            _HOST_PIPES[(id(params), dev.index)] = pipe
+        ahead, n_slots = 3, 10                            # frame buffers: 3 in the chain + 1 being submitted + 3 ahead + spares (stage C of a slice waits for its windows, queued behind the frames uploaded ahead)
         slots = [dict(f=_scratch(f"h2d_f{i}", chunk * frames_host[0].numel(), dev).view((chunk,) + tuple(frames_host.shape[1:])),
                       b=None if windows else
                       _scratch(f"h2d_b{i}", chunk * backgrounds_host[0].numel(), dev).view((chunk,) + tuple(backgrounds_host.shape[1:])),
-                      ready=torch.cuda.Event(), free=torch.cuda.Event()) for i in range(n_slots)]
-        bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
-        h2d_bytes = 0
-        uploaded = [0]
-
-        def upload_next():
-            """Queue the frames of the next slice on the copy stream.  Called right before the host waits for a slice's
-            stage C (and its crop windows, already queued): the copy engine never drains while the host is blocked."""
-            c = uploaded[0]
-            if c >= len(bounds):
-                return
-            uploaded[0] += 1
-            lo, hi = bounds[c]
-            s = slots[c % n_slots]
-            up.wait_event(s["free"])                      # the chain that last used this slot has finished
-            with torch.cuda.stream(up):
-                s["f"][:hi - lo].copy_(frames_host[lo:hi], non_blocking=True)
-                if not windows:
-                    s["b"][:hi - lo].copy_(backgrounds_host[lo:hi], non_blocking=True)
-                s["ready"].record(up)
-
-        for s in slots:
-            s["free"].record(compute)
-        for _ in range(ahead):
-            upload_next()
-        labels: List[str] = []
-        arrays = []
-        k_total = 0
-        pending = []
+                      ready=torch.cuda.Event(), free=None) for i in range(n_slots)]
         cap = n * params.max_outputs_per_frame()
         if out_host is None:
             out_host = torch.empty((cap, cs, cs, 3), dtype=torch.uint8).pin_memory()
         elif out_host.shape[0] < cap:
             raise ValueError(f"out_host holds {out_host.shape[0]} images; {n} frames can yield up to {cap} with these parameters")
-        for c, (lo, hi) in enumerate(bounds):
+        state = dict(uploaded=0, h2d=0)
+
+        def upload(c):
+            lo, hi = bounds[c]
             s = slots[c % n_slots]
-            compute.wait_event(s["ready"])
-            bgs = backgrounds_host[lo:hi] if windows else s["b"][:hi - lo]
-            before = uploaded[0]
-            res = run_chain(s["f"][:hi - lo], bgs, params, rng, _upload_stream=up, _before_sync=upload_next, **kw)
-            if uploaded[0] == before:
-                upload_next()                             # the chain returned early (nothing to paste): keep the queue fed
-            s["free"].record(compute)
-            h2d_bytes += (hi - lo) * int(frames_host[0].numel())
-            h2d_bytes += res.h2d_background_bytes if windows else (hi - lo) * int(backgrounds_host[0].numel())
-            k = res.images.shape[0]
+            if s["free"] is not None:
+                up.wait_event(s["free"])                  # stages B2/C of the slice that last used this buffer are done
+            with torch.cuda.stream(up):
+                s["f"][:hi - lo].copy_(frames_host[lo:hi], non_blocking=True)
+                if not windows:
+                    s["b"][:hi - lo].copy_(backgrounds_host[lo:hi], non_blocking=True)
+                s["ready"].record(up)
+            state["h2d"] += (hi - lo) * int(frames_host[0].numel())
+            if not windows:
+                state["h2d"] += (hi - lo) * int(backgrounds_host[0].numel())
+
+        def slices():
+            for c, (lo, hi) in enumerate(bounds):
+                while state["uploaded"] < min(len(bounds), c + 1 + ahead):
+                    upload(state["uploaded"])
+                    state["uploaded"] += 1
+                s = slots[c % n_slots]
+                compute.wait_event(s["ready"])
+                yield s["f"][:hi - lo], (backgrounds_host[lo:hi] if windows else s["b"][:hi - lo])
+
+        labels: List[str] = []
+        arrays = []
+        k_total = 0
+        keep = []
+        for c, res in enumerate(pipe.map(slices(), rng)):
+            lo, hi = bounds[c]
             done = torch.cuda.Event()
             done.record(compute)
+            slots[c % n_slots]["free"] = done
+            k = res.images.shape[0]
             down.wait_event(done)
             with torch.cuda.stream(down):
                 out_host[k_total:k_total + k].copy_(res.images, non_blocking=True)
             res.images.record_stream(down)
-            pending.append(res.images)
+            keep.append(res.images)
+            if windows:
+                state["h2d"] += res.h2d_background_bytes
             labels += res.labels
             items, aux, rot_index, angles = res._arrays
             arrays.append((items, aux, rot_index, angles, lo))
@@ -1027,9 +1044,12 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
     merged = ChainResult(out_host[:k_total], labels, records=None, record_arrays=None)
     merged._chunks = arrays
     merged._records = None
-    merged.h2d_bytes = h2d_bytes
+    merged.h2d_bytes = state["h2d"]
     merged.__class__ = _ChunkedResult
     return merged
+
+
+_HOST_PIPES = {}
 
 
 class _ChunkedResult(ChainResult):
@@ -1053,5 +1073,5 @@ _SIDE = {}
 def _side_streams(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE:
-        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))      # frames up, results down, windows up
     return _SIDE[key]

@@ -12,10 +12,9 @@
 namespace ipp {
 
 // ===================================================================== rotation
-// CTA = 32 x 32 output tile of one canvas (8 lanes x 4 px wide, 4 rows per warp): the rotated source
-// footprint of a square tile is compact (<= 46 x 46 source pixels), so the gathers of a CTA share L1 lines
-// and every source byte leaves HBM once.  Canvas rows are padded to a multiple of four pixels: every lane
-// stores one aligned 16-byte vector.
+// CTA = one output tile of a canvas: the rotated source footprint of a compact tile is compact, so the gathers of
+// a CTA share L1 lines and every source byte leaves HBM once (ncu: DRAM read = the sources, once).  Canvas rows are
+// padded to a multiple of four pixels: every lane stores one aligned 16-byte vector.
 struct RotBatchParams {
     const uint8_t* src;
     int64_t src_pitch, src_stride;
@@ -55,29 +54,101 @@ __device__ __forceinline__ void premult_t(uint32_t v, T out[4]) {
 template <int CH> struct InterpType { typedef float type; };      // opaque sources: single precision, <= 1 LSB
 template <> struct InterpType<4> { typedef double type; };        // real alpha: libImaging's double (un-premultiply amplifies errors)
 
+// bilinear sample of canvas pixel (x, y) (MODE 1, affine): libImaging's affine_transform + bilinear_filter32RGB on premultiplied
+// alpha, source coordinates in double like C evaluates them (no fma contraction)
+template <int CH>
+__device__ __forceinline__ uint32_t bilinear_px(const uint8_t* img, int64_t pitch, int src_w, int src_h, const double* m, int x, int y) {
+    typedef typename InterpType<CH>::type T;
+    const double xo = (double)x + 0.5, yo = (double)y + 0.5;
+    double xin = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xo), __dmul_rn(m[1], yo)), m[2]);
+    double yin = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xo), __dmul_rn(m[4], yo)), m[5]);
+    if (!(xin >= 0.0 && xin < (double)src_w && yin >= 0.0 && yin < (double)src_h)) return 0u;
+    xin -= 0.5;
+    yin -= 0.5;
+    const int xi = (int)floor(xin), yi = (int)floor(yin);
+    const T dx = (T)(xin - (double)xi), dy = (T)(yin - (double)yi);
+    const int xa = min(max(xi, 0), src_w - 1), xb = min(max(xi + 1, 0), src_w - 1);
+    const int ya = min(max(yi, 0), src_h - 1), yb = min(max(yi + 1, 0), src_h - 1);
+    T s00[4], s01[4], s10[4], s11[4];
+    premult_t<T>(fetch_rgba<CH>(img, pitch, xa, ya), s00);
+    premult_t<T>(fetch_rgba<CH>(img, pitch, xb, ya), s01);
+    premult_t<T>(fetch_rgba<CH>(img, pitch, xa, yb), s10);
+    premult_t<T>(fetch_rgba<CH>(img, pitch, xb, yb), s11);
+    uint32_t c[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const T v1 = add_rn(s00[b], mul_rn(sub_rn(s01[b], s00[b]), dx));
+        const T v2 = add_rn(s10[b], mul_rn(sub_rn(s11[b], s10[b]), dx));
+        const T v = add_rn(v1, mul_rn(sub_rn(v2, v1), dy));
+        c[b] = (uint32_t)min(max((int)v, 0), 255);
+    }
+    const uint32_t a = c[3];
+    if (a != 0u && a != 255u) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) c[b] = min(255u, (255u * c[b]) / a);
+    }
+    return c[0] | (c[1] << 8) | (c[2] << 16) | (a << 24);
+}
+
+// CTA = 64 x 32 output tile of one canvas: 16 lanes x 4 px across, 16 rows per pass, two passes (rows y and y + 16).
+// The kernel is bound by issued instructions (ncu: 78 % issue slots, DRAM traffic = source once + canvas once), so the
+// per-pixel path is kept minimal: 32-bit source offsets, incremental fixed-point coordinates, the alpha bbox from a
+// 4-bit mask per thread, one block reduction per tile whose global atomics are skipped when they cannot change the box.
+constexpr int kRotTileW = 64, kRotTileH = 32;
 template <int MODE, int CH>
 __global__ void __launch_bounds__(256) rotate_batch_kernel(const RotBatchParams p) {
     __shared__ int s_rec;
+    __shared__ int s_bb[4];
     if (threadIdx.x < 32) {
         const int found = find_record(p.items, p.n_items, (int)blockIdx.x, [](const ipp_rot_item& r) { return r.tile_start; });
-        if (threadIdx.x == 0) s_rec = found;
+        if (threadIdx.x == 0) {
+            s_rec = found;
+            s_bb[0] = INT_MAX; s_bb[1] = INT_MAX; s_bb[2] = 0; s_bb[3] = 0;
+        }
     }
     __syncthreads();
     const int rec = s_rec;
     const ipp_rot_item& it = p.items[rec];
+    const int kind = it.kind, a0 = it.a0, a1 = it.a1, a3 = it.a3, a4 = it.a4;
+    const int dst_w = it.dst_w, dst_h = it.dst_h, tiles_x = it.tiles_x;
     const int tile = (int)blockIdx.x - it.tile_start;
-    const int ty = tile / it.tiles_x, tx = tile - ty * it.tiles_x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = tx * 32 + (lane & 7) * 4;
-    const int y = ty * 32 + warp * 4 + (lane >> 3);
-    const int dst_w = it.dst_w, dst_h = it.dst_h;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int tid = threadIdx.x;
+    const int x = tx * kRotTileW + (tid & 15) * 4;
     const int wpad = (dst_w + 3) & ~3;
     const uint8_t* img = p.src + (int64_t)it.src * p.src_stride;
+    const uint32_t pitch32 = (uint32_t)p.src_pitch;
+    const uint32_t img_lsb = (uint32_t)((uintptr_t)img & 3u);
+    const uint8_t* img_al = img - img_lsb;
+    uint8_t* dbase = p.dst_pool + it.dst_off;
     int minx = INT_MAX, miny = INT_MAX, maxx1 = 0, maxy1 = 0;
-    if (y < dst_h && x < wpad) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int y = ty * kRotTileH + (tid >> 4) + 16 * pass;
+        if (y >= dst_h || x >= wpad) continue;
         uint32_t px[4] = {0u, 0u, 0u, 0u};
-        if (MODE == 0 || it.kind != 0) {
-            const SrcMap m{it.kind, it.a0, it.a1, it.a2, it.a3, it.a4, it.a5, p.src_w, p.src_h};
+        if (MODE == 0 && kind == 0) {
+            int xx = it.a2 + y * a1 + x * a0, yy = it.a5 + y * a4 + x * a3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xin = xx >> 16, yin = yy >> 16;
+                xx += a0;
+                yy += a3;
+                const bool inside = ((unsigned)xin < (unsigned)p.src_w) & ((unsigned)yin < (unsigned)p.src_h) & (x + k < dst_w);
+                if (inside) {
+                    if (CH == 4) {
+                        px[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (uint32_t)yin * pitch32) + xin);
+                    } else {
+                        const uint32_t off = (uint32_t)yin * pitch32 + (uint32_t)xin * 3u + img_lsb;
+                        const uint32_t* aw = reinterpret_cast<const uint32_t*>(img_al + (off & ~3u));
+                        const uint32_t bsh = (off & 3u) * 8u;
+                        const uint32_t w0 = __ldg(aw), w1 = bsh > 8u ? __ldg(aw + 1) : 0u;     // every word read holds a byte of the pixel
+                        px[k] = __funnelshift_r(w0, w1, bsh) | 0xff000000u;
+                    }
+                }
+            }
+        } else if (MODE == 0 || kind != 0) {
+            const SrcMap m{kind, a0, a1, it.a2, a3, a4, it.a5, p.src_w, p.src_h};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int xin, yin;
@@ -85,56 +156,31 @@ __global__ void __launch_bounds__(256) rotate_batch_kernel(const RotBatchParams 
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (x + k >= dst_w) break;
-                // xin = m0*(x+.5) + m1*(y+.5) + m2 as C evaluates it (double, no fma contraction): the validity test and the
-                // sample position are Pillow's; the interpolation runs in single precision for opaque RGB sources (<= 1 LSB,
-                // no un-premultiply) and in double like libImaging for RGBA sources
-                typedef typename InterpType<CH>::type T;
-                const double xo = (double)(x + k) + 0.5, yo = (double)y + 0.5;
-                double xin = __dadd_rn(__dadd_rn(__dmul_rn(it.m[0], xo), __dmul_rn(it.m[1], yo)), it.m[2]);
-                double yin = __dadd_rn(__dadd_rn(__dmul_rn(it.m[3], xo), __dmul_rn(it.m[4], yo)), it.m[5]);
-                if (!(xin >= 0.0 && xin < (double)p.src_w && yin >= 0.0 && yin < (double)p.src_h)) continue;
-                xin -= 0.5;
-                yin -= 0.5;
-                const int xi = (int)floor(xin), yi = (int)floor(yin);
-                const T dx = (T)(xin - (double)xi), dy = (T)(yin - (double)yi);
-                const int xa = min(max(xi, 0), p.src_w - 1), xb = min(max(xi + 1, 0), p.src_w - 1);
-                const int ya = min(max(yi, 0), p.src_h - 1), yb = min(max(yi + 1, 0), p.src_h - 1);
-                T s00[4], s01[4], s10[4], s11[4];
-                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xa, ya), s00);
-                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xb, ya), s01);
-                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xa, yb), s10);
-                premult_t<T>(fetch_rgba<CH>(img, p.src_pitch, xb, yb), s11);
-                uint32_t c[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const T v1 = add_rn(s00[b], mul_rn(sub_rn(s01[b], s00[b]), dx));
-                    const T v2 = add_rn(s10[b], mul_rn(sub_rn(s11[b], s10[b]), dx));
-                    const T v = add_rn(v1, mul_rn(sub_rn(v2, v1), dy));
-                    c[b] = (uint32_t)min(max((int)v, 0), 255);
-                }
-                const uint32_t a = c[3];
-                if (a != 0u && a != 255u) {
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) c[b] = min(255u, (255u * c[b]) / a);
-                }
-                px[k] = c[0] | (c[1] << 8) | (c[2] << 16) | (a << 24);
-            }
+            for (int k = 0; k < 4; ++k)
+                if (x + k < dst_w) px[k] = bilinear_px<CH>(img, p.src_pitch, p.src_w, p.src_h, it.m, x + k, y);
         }
-        uint8_t* d = p.dst_pool + it.dst_off + ((int64_t)y * wpad + x) * 4;
-        stg_stream16(d, make_uint4(px[0], px[1], px[2], px[3]));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if ((px[k] >> 24) != 0u) {
-                minx = min(minx, x + k);
-                maxx1 = max(maxx1, x + k + 1);
-                miny = y;
-                maxy1 = y + 1;
-            }
+        stg_stream16(dbase + ((int64_t)y * wpad + x) * 4, make_uint4(px[0], px[1], px[2], px[3]));
+        const uint32_t nz = (px[0] >> 24 ? 1u : 0u) | (px[1] >> 24 ? 2u : 0u) | (px[2] >> 24 ? 4u : 0u) | (px[3] >> 24 ? 8u : 0u);
+        if (nz) {
+            minx = min(minx, x + __ffs(nz) - 1);
+            maxx1 = max(maxx1, x + 32 - __clz(nz));
+            miny = min(miny, y);
+            maxy1 = max(maxy1, y + 1);
         }
     }
-    bbox_block_reduce(p.bbox + 4 * rec, minx, miny, maxx1, maxy1);
+    // block reduction (s_bb was initialised before the first barrier); global atomics only where they can change the box
+    minx = warp_min(minx); miny = warp_min(miny); maxx1 = warp_max(maxx1); maxy1 = warp_max(maxy1);
+    if ((tid & 31) == 0 && maxx1 > 0) {
+        atomicMin(&s_bb[0], minx); atomicMin(&s_bb[1], miny); atomicMax(&s_bb[2], maxx1); atomicMax(&s_bb[3], maxy1);
+    }
+    __syncthreads();
+    if (tid == 0 && s_bb[2] > 0) {
+        int32_t* bb = p.bbox + 4 * rec;
+        if (s_bb[0] < __ldcg(bb + 0)) atomicMin(bb + 0, s_bb[0]);      // the box only grows: a stale read can only cause a redundant atomic
+        if (s_bb[1] < __ldcg(bb + 1)) atomicMin(bb + 1, s_bb[1]);
+        if (s_bb[2] > __ldcg(bb + 2)) atomicMax(bb + 2, s_bb[2]);
+        if (s_bb[3] > __ldcg(bb + 3)) atomicMax(bb + 3, s_bb[3]);
+    }
 }
 
 // ===================================================================== overlay: RGBA sprite -> premultiplied planes
@@ -234,3 +280,60 @@ int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const u
 }
 
 }  // extern "C"
+
+// ===================================================================== HSV key + largest component, fused (BASELINE configs[3])
+// filtres_liste.py:90-134 followed by pixels_isolés.py:29-58 without the BGRA image in between: stage A of the chain
+// (ipp_chain_stage_a: frame read once -> 1-bit mask -> keep-mask of the largest component + its bbox) and this kernel, which
+// writes the BGRA result: B, G, R of the (border-cropped) frame, alpha = 255 on the kept component, 0 elsewhere.
+// (The key's alpha is 0 or 255; pixels_isolés zeroes every pixel outside the largest component, and an image without any
+// foreground keeps its all-zero alpha.)  thread = 4 pixels: 12 source bytes, 4 mask bits, one 16-byte store.
+namespace ipp {
+__global__ void __launch_bounds__(256) bgra_from_keep_kernel(const uint8_t* __restrict__ frames, int64_t pitch, int64_t stride,
+                                                             int crop_l, int crop_t, int w, int h,
+                                                             const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
+                                                             uint8_t* __restrict__ out, int64_t out_pitch, int64_t out_stride, int n) {
+    const int q = (w + 3) >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)q * h;
+    if (idx >= per * n) return;
+    const int img = (int)(idx / per);
+    const int rem = (int)(idx - (int64_t)img * per);
+    const int y = rem / q, x = (rem - y * q) * 4;
+    const uint8_t* s = frames + (int64_t)img * stride + (int64_t)(crop_t + y) * pitch + (int64_t)(crop_l + x) * 3;
+    const uint32_t word = bits[(int64_t)img * bits_stride + (int64_t)y * wpr + (x >> 5)];
+    const uint32_t m = word >> (x & 31);                 // x is a multiple of 4: the four bits sit in one word
+    uint8_t* d = out + (int64_t)img * out_stride + (int64_t)y * out_pitch + (int64_t)x * 4;
+    if (x + 3 < w && ((((uintptr_t)s) & 3) == 0) && ((((uintptr_t)d) & 15) == 0)) {
+        const uint32_t a = ldg_stream4(s), b = ldg_stream4(s + 4), c = ldg_stream4(s + 8);     // b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+        uint4 v;
+        v.x = (a & 0x00ffffffu) | ((m & 1u) ? 0xff000000u : 0u);
+        v.y = __funnelshift_r(a, b, 24) & 0x00ffffffu; v.y |= (m & 2u) ? 0xff000000u : 0u;
+        v.z = __funnelshift_r(b, c, 16) & 0x00ffffffu; v.z |= (m & 4u) ? 0xff000000u : 0u;
+        v.w = (c >> 8) | ((m & 8u) ? 0xff000000u : 0u);
+        stg_stream16(d, v);
+    } else {
+        for (int k = 0; k < 4 && x + k < w; ++k) {
+            d[4 * k + 0] = s[3 * k + 0]; d[4 * k + 1] = s[3 * k + 1]; d[4 * k + 2] = s[3 * k + 2];
+            d[4 * k + 3] = ((m >> k) & 1u) ? 255 : 0;
+        }
+    }
+}
+}  // namespace ipp
+
+extern "C" int ipp_bgra_from_keep_u8(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride, const ipp_chain_geom* g,
+                                     const void* workspace, uint8_t* out, int64_t out_pitch, int64_t out_stride, int n, void* stream) {
+    using namespace ipp;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = chain_check_geom(g);
+    if (rc != IPP_OK) return rc;
+    IPP_REQUIRE(frames && workspace && out && n >= 1, IPP_ERR_BAD_ARG, "ipp_bgra_from_keep_u8: bad arguments");
+    IPP_REQUIRE(frame_pitch >= (int64_t)g->frame_w * 3 && out_pitch >= (int64_t)g->crop_w * 4, IPP_ERR_BAD_SHAPE, "ipp_bgra_from_keep_u8: pitch smaller than a row");
+    const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
+    const int64_t threads = (int64_t)((g->crop_w + 3) >> 2) * g->crop_h * n;
+    IPP_REQUIRE(threads / 256 < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_bgra_from_keep_u8: batch too large");
+    { ipp::LaunchTimer _lt("bgra_from_keep_kernel", st);
+      bgra_from_keep_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(frames, frame_pitch, frame_stride, g->crop_l, g->crop_t, g->crop_w, g->crop_h,
+                                                                               (const uint32_t*)workspace, cg.bits_stride, cg.wpr, out, out_pitch, out_stride, n); }
+    IPP_LAUNCH_CHECK();
+    return IPP_OK;
+}

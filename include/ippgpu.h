@@ -394,8 +394,8 @@ typedef struct ipp_rot_item {
     int32_t kind;                       /* 0 affine, 1 copy, 2 rot180, 3 rot90, 4 rot270            */
     int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (NEAREST, kind 0)          */
     int32_t dst_w, dst_h;               /* expanded canvas                                          */
-    int32_t tile_start;                 /* first 32 x 32 output tile of this canvas in the flat grid */
-    int32_t tiles_x;                    /* ceil(dst_w / 32)                                         */
+    int32_t tile_start;                 /* first 64 x 32 output tile of this canvas in the flat grid */
+    int32_t tiles_x;                    /* ceil(dst_w / 64); the canvas has tiles_x * ceil(dst_h / 32) tiles */
     int64_t dst_off;                    /* byte offset of the canvas in dst_pool (256-byte aligned);
                                            rows are ((dst_w + 3) & ~3) * 4 bytes apart              */
     double m[6];                        /* PIL inverse matrix (BILINEAR, kind 0)                    */
@@ -445,6 +445,13 @@ int ipp_chain_stage_c_rect(const uint8_t* backgrounds, int64_t bg_pitch, int64_t
  *    (new_h x new_w x 4, dense); used by the stand-alone batched resize. */
 int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const uint8_t* sprite_ws,
                           uint8_t* dst, const int64_t* dst_offsets_host, void* stream);
+
+/* -- HSV key + largest component of n frames without the BGRA image in between (filtres_liste.py:90-134 then
+ *    pixels_isolés.py:29-58): call ipp_chain_stage_a (mask + keep-mask + info = bbox of the kept component, what
+ *    _crop_fit of pixels_isolés.py:74-81 crops to), then this: out[i] (crop_h x crop_w x 4) = B, G, R of the
+ *    border-cropped frame, alpha = 255 on the kept component and 0 elsewhere.  `workspace` = stage A's. */
+int ipp_bgra_from_keep_u8(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride, const ipp_chain_geom* geom_host,
+                          const void* workspace, uint8_t* out, int64_t out_pitch, int64_t out_stride, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,3 +128,24 @@ def test_overlay_batch_equals_reference_calls(geom):
         assert label == res.labels[k]
         assert np.array_equal(out[k], comp)
     assert random.getstate() == state
+
+
+@pytest.mark.parametrize("shape", [(6, 96, 130), (4, 512, 512), (3, 61, 77)])
+def test_key_and_keep_largest_equals_the_two_reference_steps(shape):
+    """filtres_liste.py:90-134 then pixels_isolés.py:29-81 per image, fused on the device (frame -> bits -> CCL -> BGRA)."""
+    from image_processor_pipeline_b200 import synth
+    n, H, W = shape
+    frames = np.stack([synth.frame(70, i, H, W, speck_density=0.02) for i in range(n)])
+    frames[-1] = synth.frame(70, 99, H, W)
+    frames[-1][frames[-1] > 0] //= 3                                   # everything dark: the key removes the whole image
+    out, info = batch.key_and_keep_largest(dev(frames), synth.REFERENCE_FILTERS)
+    out = host(out)
+    for i in range(n):
+        keyed = L.color_masks_to_alpha(frames[i], list(synth.REFERENCE_FILTERS))
+        x, y, w, h = (int(v) for v in info[i, :4])
+        if not (keyed[..., 3] > 1).any():
+            assert w == 0 and h == 0 and not out[i, ..., 3].any()
+            continue
+        ref = L.keep_largest_component(keyed)
+        assert np.array_equal(out[i, y:y + h, x:x + w], ref)
+        assert np.array_equal(out[i, ..., :3], frames[i])
