@@ -21,6 +21,13 @@
  *    cudaError_t of a failed runtime call.  ipp_last_error_string() describes
  *    the last failure on the calling thread.  No exceptions cross the ABI.
  *  - sm_100a only.  There is no CPU fallback.
+ *  - memory access guarantee: 3-byte pixels are gathered through the aligned 32-bit word(s) that hold them
+ *    (stage B2 / the batched rotation) and bit masks through aligned 16-byte quads (stage B1, inside the
+ *    library-owned workspace).  Every word that is loaded contains at least one byte of the addressed pixel, so
+ *    a kernel never reads beyond the 4-byte-aligned extent of a caller's buffer — i.e. never outside the memory
+ *    page of its last valid byte; no padding is required of the caller.  (A buffer whose length is not a
+ *    multiple of four is read up to 3 bytes past its end inside that last word; CUDA allocations are at least
+ *    256-byte granular, so this is always backed memory.)
  */
 #ifndef IPPGPU_H
 #define IPPGPU_H

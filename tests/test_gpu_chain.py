@@ -89,6 +89,29 @@ def test_chain_1080p():
     _compare(*_run_both(frames, bgs, 23, **kw))
 
 
+def test_chain_1080p_uniform_noise_frames():
+    """SURVEY.md §8d's generic generator: uniform-noise frames.  The key then keeps ~3/4 of the pixels as one giant
+    component (plus thousands of small ones), the sprite is nearly the whole frame: the worst case of every stage."""
+    H, W = 1080, 1920
+    frames = [synth.noise(91, i, (H, W, 3)) for i in range(2)]
+    bgs = [synth.background(91, i, H, W) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=1, include_original=False,
+              pool=["o", "h", "v", "hv"], choose_random=1, sym_include_original=False)
+    _compare(*_run_both(frames, bgs, 24, **kw))
+
+
+def test_chain_odd_sizes_exact_length_buffers():
+    """Frames whose byte length is not a multiple of four (333 x 217 x 3 x n): the gathers fetch the aligned 32-bit word(s)
+    holding a pixel, and every such word holds at least one byte of the pixel, so nothing beyond the aligned extent of the
+    caller's buffer is ever read (run under compute-sanitizer without the caching allocator: profiles/r02/memcheck*)."""
+    H, W = 217, 333
+    frames = [synth.frame(93, i, H, W, speck_density=0.02) for i in range(3)]
+    bgs = [synth.background(93, i, 301, 275) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=2, include_original=True,
+              pool=["o", "h", "v", "hv"], choose_random=2)
+    _compare(*_run_both(frames, bgs, 25, **kw))
+
+
 def test_chain_4k_frames_config5():
     """BASELINE.json config 5: the full chain over 3840x2160 frames (a video.py frame stream) with 4K backgrounds:
     2160x2160 outputs, sprites that need more than one 64-wide super-block in the LANCZOS passes."""
@@ -394,9 +417,7 @@ def test_fused_gather_and_staged_lanczos_vs_pillow(sizes, flips):
     bits[:, :, :sw] = alpha
     words = np.packbits(bits.reshape(n, sh, wpr, 32), axis=-1, bitorder="little").view("<u4").reshape(n, sh, wpr)
     bits_d = torch.from_numpy(np.ascontiguousarray(words).view(np.uint8).reshape(-1)).to(DEV)
-    pad = torch.zeros(4096, dtype=torch.uint8, device=DEV)
-    bits_d = torch.cat([bits_d, pad])
-    frames_d = torch.cat([torch.from_numpy(frames.reshape(-1)).to(DEV), pad])     # aligned word loads may look past the last pixel
+    frames_d = torch.from_numpy(frames.reshape(-1)).to(DEV)                  # exact length: see the access guarantee in ippgpu.h
     ws = torch.zeros(tot["ws"], dtype=torch.uint8, device=DEV)
     geom = chain._geom_struct(sw, sh, (0, 0, sw, sh), max(nw, 8), max(nh, 8), hostmath.pack_hsv_ranges(synth.REFERENCE_FILTERS))
     items_d = torch.from_numpy(items.view(np.uint8)).to(DEV)

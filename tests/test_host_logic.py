@@ -128,3 +128,23 @@ def test_shard_ranges_partition_the_work_list():
             assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
     with pytest.raises(ValueError):
         sharding.shard_range(10, 2, 2)
+
+
+def test_word_gather_addresses_stay_inside_aligned_extent():
+    """The 3-byte-pixel gathers (chain.cu stage B2, batch.cu rotation) load the aligned 32-bit word holding a pixel's first
+    byte and, when the pixel spills over (byte offset 2 or 3 inside the word), the next word.  Enumerated over every base
+    alignment and pixel position: each loaded word contains at least one byte of the pixel, hence lies inside
+    [floor4(buffer start), ceil4(buffer end)) — the access guarantee stated in include/ippgpu.h.  (compute-sanitizer is
+    closed on the GPU pool of this build; this is the bounds check of our own.)"""
+    for base in range(0, 8):
+        for n_px in (1, 2, 5, 333 * 217):
+            end = base + 3 * n_px
+            lo_ok, hi_ok = base & ~3, (end + 3) & ~3
+            for px in (set(range(min(n_px, 64))) | {n_px - 1, n_px - 2}) - {-1}:
+                a = base + 3 * px
+                words = [a & ~3]
+                if (a & 3) * 8 > 8:
+                    words.append((a & ~3) + 4)
+                for w in words:
+                    assert lo_ok <= w and w + 4 <= hi_ok
+                    assert any(a <= b < a + 3 for b in range(w, w + 4)), "a loaded word without a byte of the pixel"
