@@ -115,6 +115,9 @@ PROTOTYPES = {
     "ipp_sprite_planes_u8": (_int, [_u8p, _i64, _i64, _int, _int, _int, _vp, _int, _u8p, _vp]),
     "ipp_chain_stage_c_rect": (_int, [_u8p, _i64, _i64, _int, _int, _vp, _int, _u8p, _u8p, _i64, _i64, _int, _int, _vp]),
     "ipp_sprites_export_u8": (_int, [_vp, _int, _u8p, _u8p, _vp, _vp]),
+    "ipp_plan_enhance_host": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ipp_enhance_workspace_bytes": (_i64, [_int, _int, _int, _int]),
+    "ipp_enhance_batch_u8": (_int, [_u8p, _u8p, _int, _int, _int, _vp, _u8p, _i32p, _int, _vp, _i64, _vp]),
     "ipp_bgra_from_keep_u8": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _u8p, _i64, _i64, _int, _vp]),
 }
 

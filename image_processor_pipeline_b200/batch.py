@@ -159,6 +159,63 @@ def key_and_keep_largest(bgr: torch.Tensor, color_ranges, zones=None, use_gimp_s
     return out, info_h
 
 
+# --------------------------------------------------------------------------- photometric jitter (tranfo.py)
+ENH_ITEM_DTYPE = np.dtype([("brightness", "<f4"), ("contrast", "<f4"), ("color", "<f4"), ("blur", "<i4"), ("box_radius", "<i4"),
+                           ("ww", "<u4"), ("fw", "<u4"), ("lut", "<i4")])
+assert ENH_ITEM_DTYPE.itemsize == 32
+
+
+def sample_flags(n: int, rng=_random):
+    """The 'sample' pairing of pipeline.py:209-225: two ``random.sample(files, int(n * 0.3))`` draws decide which of the n
+    files get the blur / the per-channel jitter.  Returns (do_blur, do_rgb) as bool arrays."""
+    files = list(range(n))
+    blur = set(rng.sample(files, int(n * 0.3)))
+    do_blur = np.array([i in blur for i in files], dtype=bool)
+    rgb = set(rng.sample(files, int(n * 0.3)))
+    do_rgb = np.array([i in rgb for i in files], dtype=bool)
+    return do_blur, do_rgb
+
+
+def plan_enhance(n: int, do_blur, do_rgb, rng=_random):
+    """Per-image draws of tranfo.py:38-51 in order (native planner on the generator's own state).
+    Returns (items, luts [n, 3, 256] uint8, draws [n, 4] float64)."""
+    do_blur = np.ascontiguousarray(np.asarray(do_blur, dtype=bool).astype(np.uint8))
+    do_rgb = np.ascontiguousarray(np.asarray(do_rgb, dtype=bool).astype(np.uint8))
+    if len(do_blur) != n or len(do_rgb) != n:
+        raise ValueError("one blur / rgb flag per image")
+    items = np.zeros(n, dtype=ENH_ITEM_DTYPE)
+    luts = np.zeros((n, 3, 256), dtype=np.uint8)
+    draws = np.zeros((n, 4), dtype=np.float64)
+    bridge = chain._RngBridge(rng)
+    _native.check(_native.load().ipp_plan_enhance_host(n, do_blur.ctypes.data, do_rgb.ctypes.data, bridge.mt.ctypes.data, bridge.idx.ctypes.data,
+                                                       items.ctypes.data, luts.ctypes.data, draws.ctypes.data), "ipp_plan_enhance_host")
+    bridge.commit()
+    return items, luts, draws
+
+
+def enhance_batch(images: torch.Tensor, do_blur, do_rgb, rng=_random, inplace: bool = False, plan=None) -> torch.Tensor:
+    """``enhance_image`` (tranfo.py:37-51) for a batch [N, H, W, 3] of RGB images: Brightness, Contrast, Color jitter, GaussianBlur
+    where ``do_blur[i]``, per-channel 256-entry tables where ``do_rgb[i]`` — draws per image in the reference's order from ``rng``.
+    Bit-exact against Pillow.  ``plan``: (items, luts) from ``plan_enhance`` (then nothing is drawn here)."""
+    t = _check_batch(images, "images", (3,))
+    n, H, W, _ = t.shape
+    items, luts = plan_enhance(n, do_blur, do_rgb, rng)[:2] if plan is None else plan
+    lib = _native.load()
+    out = t if inplace else torch.empty_like(t)
+    blur_idx = np.flatnonzero(items["blur"]).astype(np.int32)
+    with torch.cuda.device(t.device):
+        items_d = chain._upload("enh_items", items, t.device)
+        luts_d = chain._upload("enh_luts", luts, t.device)
+        blur_d = chain._upload("enh_blur", blur_idx if len(blur_idx) else np.zeros(1, np.int32), t.device)
+        ws_bytes = lib.ipp_enhance_workspace_bytes(W, H, n, len(blur_idx))
+        ws = chain._scratch("enh_ws", ws_bytes, t.device)
+        _native.check(lib.ipp_enhance_batch_u8(t.data_ptr(), out.data_ptr(), W, H, n, items_d.data_ptr(), luts_d.data_ptr(), blur_d.data_ptr(),
+                                               len(blur_idx), ws.data_ptr(), ws_bytes, _stream()), "ipp_enhance_batch_u8")
+        for x in (items_d, luts_d, blur_d):
+            x.record_stream(torch.cuda.current_stream())
+    return out
+
+
 # --------------------------------------------------------------------------- LANCZOS resize / overlay
 def _resize_items(items: np.ndarray, sprites: torch.Tensor, device_tables: bool, eps: float):
     """Layout + tables + premultiplied planes + tensor-core passes for an item array over ``sprites``

@@ -10,4 +10,5 @@
 #include "boxes.cu"
 #include "chain.cu"
 #include "batch.cu"
+#include "enhance.cu"
 #include "planner.cu"

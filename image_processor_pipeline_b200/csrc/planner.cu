@@ -601,6 +601,53 @@ int ipp_plan_overlay_batch_host(int spr_w, int spr_h, int n_sprites, int n_pairs
     return IPP_OK;
 }
 
+// Photometric jitter step (tranfo.py:37-51): the draws of n images in order, the GaussianBlur box parameters exactly as
+// libImaging derives them (BoxBlur.c: _gaussian_blur_radius with single-precision variables, ImagingHorizontalBoxBlur's
+// 8.24 weights) and the channel tables as Image.point builds them (round-half-even of the clamped product).
+int ipp_plan_enhance_host(int n, const uint8_t* do_blur, const uint8_t* do_rgb, uint32_t* rng_mt624, int32_t* rng_index,
+                          ipp_enhance_item* items_out, uint8_t* luts_out, double* draws_out) {
+    using namespace ipp;
+    using namespace ipp::plan;
+    IPP_REQUIRE(n >= 0 && do_blur && do_rgb && rng_mt624 && rng_index && items_out && luts_out && draws_out, IPP_ERR_BAD_ARG,
+                "ipp_plan_enhance_host: bad arguments");
+    PyRandom rng{rng_mt624, rng_index};
+    for (int i = 0; i < n; ++i) {
+        ipp_enhance_item* it = items_out + i;
+        memset(it, 0, sizeof(*it));
+        double* d = draws_out + 4 * i;
+        d[0] = rng.uniform(0.7, 1.3); d[1] = rng.uniform(0.7, 1.3); d[2] = rng.uniform(0.7, 1.3); d[3] = NAN;
+        it->brightness = (float)d[0]; it->contrast = (float)d[1]; it->color = (float)d[2];
+        if (do_blur[i]) {
+            d[3] = rng.uniform(0.5, 3.0);
+            const int passes = 3;
+            const float radius = (float)d[3];
+            const float sigma2 = radius * radius / passes;
+            const float L = (float)std::sqrt(12.0 * sigma2 + 1.0);
+            const float l = (float)std::floor((L - 1.0) / 2.0);
+            float a = (2 * l + 1) * (l * (l + 1) - 3 * sigma2);
+            a /= 6 * (sigma2 - (l + 1) * (l + 1));
+            const float box = l + a;
+            if (box != 0.0f) {
+                it->blur = 1;
+                it->box_radius = (int)box;
+                it->ww = (uint32_t)((uint32_t)(1 << 24) / (box * 2 + 1));
+                it->fw = (uint32_t)(((1 << 24) - (it->box_radius * 2 + 1) * (long long)it->ww) / 2);
+            }
+        }
+        uint8_t* lut = luts_out + (size_t)768 * i;
+        if (do_rgb[i]) {
+            it->lut = 1;
+            for (int j = 0; j < 768; ++j) {
+                const double v = (double)(j & 255) * rng.uniform(0.75, 1.25);
+                lut[j] = (uint8_t)std::nearbyint(std::fmax(0.0, std::fmin(255.0, v)));       // Python round(): half to even
+            }
+        } else {
+            for (int j = 0; j < 768; ++j) lut[j] = (uint8_t)(j & 255);
+        }
+    }
+    return IPP_OK;
+}
+
 // the planner's exact-decimal helpers, exported so that tests can hold them against Python's round() / "%.6f"
 double ipp_host_round15(double x) { return ipp::plan::round15(x); }
 int ipp_host_format6(double v, char* text_out48, double* parsed_out) {

@@ -460,6 +460,28 @@ int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const u
 int ipp_bgra_from_keep_u8(const uint8_t* frames, int64_t frame_pitch, int64_t frame_stride, const ipp_chain_geom* geom_host,
                           const void* workspace, uint8_t* out, int64_t out_pitch, int64_t out_stride, int n, void* stream);
 
+/* -- photometric jitter of n RGB images (tranfo.py:37-51; last step of the workflow, pairing mode 'sample'
+ *    pipeline.py:209-225): Brightness / Contrast / Color enhance (ImagingBlend in single precision), optional
+ *    GaussianBlur (three 8.24 fixed-point box passes per axis), optional per-channel 256-entry tables.  Bit-exact. */
+typedef struct ipp_enhance_item {
+    float brightness, contrast, color;  /* enhance factors (tranfo.py:38-40: uniform(0.7, 1.3) each)            */
+    int32_t blur;                       /* 1: GaussianBlur; box_radius / ww / fw as ImagingHorizontalBoxBlur derives them */
+    int32_t box_radius;
+    uint32_t ww, fw;
+    int32_t lut;                        /* 1: per-channel tables at luts[i][3][256] (tranfo.py:46-51)            */
+} ipp_enhance_item;
+/*    Host plan, image by image in order: three uniform(0.7, 1.3), then uniform(0.5, 3) when do_blur[i], then
+ *    3 x 256 uniform(0.75, 1.25) when do_rgb[i] (Image.point calls the lambda once per table entry), from the
+ *    Python generator state.  draws_out: double[n][4] = the three factors and the blur radius (NaN: none). */
+int ipp_plan_enhance_host(int n, const uint8_t* do_blur, const uint8_t* do_rgb, uint32_t* rng_mt624, int32_t* rng_index,
+                          ipp_enhance_item* items_out, uint8_t* luts_out, double* draws_out);
+int64_t ipp_enhance_workspace_bytes(int w, int h, int n, int n_blur);
+/*    src / dst: n dense images (h x w x 3), may be the same buffer; items / luts / blur_list (indices of the images
+ *    with blur == 1, n_blur of them) are DEVICE arrays. */
+int ipp_enhance_batch_u8(const uint8_t* src, uint8_t* dst, int w, int h, int n, const ipp_enhance_item* items,
+                         const uint8_t* luts, const int32_t* blur_list, int n_blur,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -436,3 +436,97 @@ def keep_largest_alpha(alpha: np.ndarray):
     rows = np.flatnonzero(nz.any(axis=1))
     cols = np.flatnonzero(nz.any(axis=0))
     return out, (int(cols[0]), int(rows[0]), int(cols[-1] - cols[0] + 1), int(rows[-1] - rows[0] + 1)), best_area
+
+
+# --------------------------------------------------------------------------- photometric jitter (tranfo.py -> Pillow)
+def luma_u8(rgb: np.ndarray) -> np.ndarray:
+    """Pillow convert("L") (libImaging Convert.c rgb2l): (R*19595 + G*38470 + B*7471 + 0x8000) >> 16."""
+    r, g, b = (rgb[..., i].astype(np.uint32) for i in range(3))
+    return ((r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16).astype(np.uint8)
+
+
+def blend_u8(a: np.ndarray, b: np.ndarray, alpha: float) -> np.ndarray:
+    """libImaging ImagingBlend (Blend.c): out = (UINT8)(a + alpha * (b - a)) in SINGLE precision, truncation;
+    outside [0, 1] the result is clipped to [0, 255] first.  ImageEnhance.*.enhance(f) = blend(degenerate, image, f)."""
+    alpha = np.float32(alpha)
+    a_i, b_i = a.astype(np.int32), b.astype(np.int32)
+    t = (a_i.astype(np.float32) + alpha * (b_i - a_i).astype(np.float32)).astype(np.float32)
+    if 0 <= alpha <= 1:
+        return t.astype(np.int32).astype(np.uint8)
+    return np.where(t <= 0, 0, np.where(t >= 255, 255, t.astype(np.int32))).astype(np.uint8)
+
+
+def enhance_brightness(rgb, f):
+    return blend_u8(np.zeros_like(rgb), rgb, f)                       # degenerate = black (ImageEnhance.Brightness)
+
+
+def contrast_mean(rgb) -> int:
+    lum = luma_u8(rgb)
+    return int(int(lum.astype(np.int64).sum()) / lum.size + 0.5)      # int(ImageStat.Stat(L).mean[0] + 0.5)
+
+
+def enhance_contrast(rgb, f):
+    return blend_u8(np.full_like(rgb, contrast_mean(rgb)), rgb, f)    # degenerate = mean gray (ImageEnhance.Contrast)
+
+
+def enhance_color(rgb, f):
+    return blend_u8(np.repeat(luma_u8(rgb)[..., None], 3, axis=2), rgb, f)    # degenerate = gray image (ImageEnhance.Color)
+
+
+def gaussian_box_radius(radius: float, passes: int = 3) -> np.float32:
+    """libImaging BoxBlur.c _gaussian_blur_radius: the box radius whose `passes` box blurs approximate a gaussian of
+    that sigma — single-precision variables, double-precision sqrt / floor as the C expression promotes them."""
+    import math
+    f32 = np.float32
+    radius = f32(radius)
+    sigma2 = f32(radius * radius / f32(passes))
+    L = f32(math.sqrt(12.0 * float(sigma2) + 1.0))
+    l = f32(math.floor((float(L) - 1.0) / 2.0))
+    a = f32(f32(2 * l + 1) * f32(f32(l * f32(l + 1)) - f32(3 * sigma2)))
+    a = f32(a / f32(6 * f32(sigma2 - f32(f32(l + 1) * f32(l + 1)))))
+    return f32(l + a)
+
+
+def box_blur_params(float_radius):
+    """ImagingHorizontalBoxBlur: integer radius, 8.24 fixed-point weight of a full pixel (ww) and of the two far pixels (fw)."""
+    f32 = np.float32
+    radius = int(float_radius)
+    ww = int(f32(16777216) / f32(f32(f32(float_radius) * f32(2)) + f32(1)))
+    fw = ((1 << 24) - (radius * 2 + 1) * ww) // 2
+    return radius, ww, fw
+
+
+def box_blur_rows(a: np.ndarray, float_radius) -> np.ndarray:
+    """One horizontal box-blur pass (ImagingLineBoxBlur32/8): window sum over [x-r, x+r] with clamped edges times ww plus the
+    two far pixels times fw, (v + 2^23) >> 24 in unsigned 32-bit arithmetic."""
+    H, W = a.shape[:2]
+    radius, ww, fw = box_blur_params(float_radius)
+    idx = np.arange(W)
+    ai = a.astype(np.int64)
+    acc = np.zeros_like(ai)
+    for d in range(-radius, radius + 1):
+        acc += ai[:, np.clip(idx + d, 0, W - 1)]
+    far = ai[:, np.clip(idx - radius - 1, 0, W - 1)] + ai[:, np.clip(idx + radius + 1, 0, W - 1)]
+    bulk = (acc * ww + far * fw) & 0xffffffff
+    return (((bulk + (1 << 23)) & 0xffffffff) >> 24).astype(np.uint8)
+
+
+def gaussian_blur(rgb: np.ndarray, radius: float) -> np.ndarray:
+    """ImageFilter.GaussianBlur(radius) = ImagingGaussianBlur(passes=3): three horizontal box passes (each rounded to 8
+    bits), transpose, three more, transpose back."""
+    br = gaussian_box_radius(radius)
+    out = rgb
+    if br != 0:
+        for _ in range(3):
+            out = box_blur_rows(out, br)
+        t = np.ascontiguousarray(out.transpose(1, 0, 2))
+        for _ in range(3):
+            t = box_blur_rows(t, br)
+        out = np.ascontiguousarray(t.transpose(1, 0, 2))
+    return out
+
+
+def point_lut(factors) -> np.ndarray:
+    """Image.point(lambda p: max(0, min(255, p * f_p))) with one factor per table entry: round-half-even of the clamped
+    product (Image.point rounds float tables with Python's round)."""
+    return np.array([round(max(0, min(255, p * f))) for p, f in enumerate(factors)], dtype=np.uint8)

@@ -317,3 +317,35 @@ def keep_largest_component(image_bgra: np.ndarray, min_component_size: int = 500
         bbox = cv2.boundingRect(nz)
         return cropped, cleaned, bbox, int(max_area)
     return cropped
+
+
+# --------------------------------------------------------------------------- photometric jitter (tranfo.py)
+def enhance_image(rgb: np.ndarray, apply_blur: bool, apply_rgb: bool) -> np.ndarray:
+    """reference transforms/tranfo.py:37-51 — the identical Pillow calls on an RGB array, draws from ``random``:
+    Brightness / Contrast / Color enhance(uniform(.7, 1.3)), optional GaussianBlur(uniform(.5, 3)), optional
+    per-channel ``point(lambda p: max(0, min(255, p * uniform(.75, 1.25))))`` (256 draws per channel)."""
+    from PIL import ImageEnhance, ImageFilter
+    img = Image.fromarray(rgb, "RGB")
+    img = ImageEnhance.Brightness(img).enhance(random.uniform(0.7, 1.3))
+    img = ImageEnhance.Contrast(img).enhance(random.uniform(0.7, 1.3))
+    img = ImageEnhance.Color(img).enhance(random.uniform(0.7, 1.3))
+    if apply_blur:
+        img = img.filter(ImageFilter.GaussianBlur(random.uniform(0.5, 3)))
+    if apply_rgb:
+        r, g, b = img.split()
+        r = r.point(lambda p: max(0, min(255, p * random.uniform(0.75, 1.25))))
+        g = g.point(lambda p: max(0, min(255, p * random.uniform(0.75, 1.25))))
+        b = b.point(lambda p: max(0, min(255, p * random.uniform(0.75, 1.25))))
+        img = Image.merge("RGB", (r, g, b))
+    return np.asarray(img)
+
+
+def sample_pairing_flags(n: int):
+    """reference pipeline.py:209-225 ('sample' pairing): which of n files get the blur / the RGB jitter — two
+    ``random.sample(files, int(n * 0.3))`` draws."""
+    files = list(range(n))
+    blur = set(random.sample(files, int(n * 0.3)))
+    do_blur = [i in blur for i in files]
+    rgb = set(random.sample(files, int(n * 0.3)))
+    do_rgb = [i in rgb for i in files]
+    return do_blur, do_rgb

@@ -68,6 +68,7 @@ def load():
     ns.filtres_liste = importlib.import_module(t + "filtres_liste")
     ns.labels = importlib.import_module(t + "labels")
     ns.video = importlib.import_module(t + "video")
+    ns.tranfo = importlib.import_module(t + "tranfo")
     ns.utils = importlib.import_module("image_processor_pipeline.utils.utils")
 
     src = (REFERENCE_ROOT / "transforms" / "crop_square.py").read_text(encoding="utf-8")

@@ -103,6 +103,17 @@ def main():
         save(f"rotations_{k}", input=img, angles=np.array(angles),
              meta={"seed": seed, "opts": opts, "names": [p.name for p in res]}, **outs)
 
+    # ---------------------------------------------------------------- tranfo (photometric jitter, pairing mode 'sample')
+    for k, (shape, seed, blur, rgb) in enumerate([((48, 70, 3), 61, False, False), ((40, 33, 3), 62, True, False),
+                                                  ((29, 64, 3), 63, False, True), ((56, 56, 3), 64, True, True)]):
+        d = tmp / f"tranfo{k}"; (d / "in").mkdir(parents=True); (d / "out").mkdir()
+        img = _rng(seed).integers(0, 256, shape, dtype=np.uint8)
+        Image.fromarray(img, "RGB").save(d / "in" / "img.png")
+        random.seed(seed)
+        res = ref.tranfo.enhance_image(d / "in" / "img.png", blur, rgb, [d / "out"])
+        save(f"tranfo_{k}", input=img, out=np.asarray(Image.open(res).convert("RGB")),
+             meta={"seed": seed, "apply_blur": blur, "apply_rgb": rgb, "name": res.name})
+
     # ---------------------------------------------------------------- crop_square (repaired copy)
     for k, (shape, seed, labels) in enumerate([
         ((50, 80, 3), 31, "0 0.5 0.5 0.2 0.3\n1 0.55 0.4 0.1 0.1\n"),

@@ -149,3 +149,39 @@ def test_key_and_keep_largest_equals_the_two_reference_steps(shape):
         ref = L.keep_largest_component(keyed)
         assert np.array_equal(out[i, y:y + h, x:x + w], ref)
         assert np.array_equal(out[i, ..., :3], frames[i])
+
+
+@pytest.mark.parametrize("shape", [(7, 48, 70), (5, 120, 90), (3, 1080, 1080), (4, 33, 5)])
+def test_enhance_batch_bit_exact(shape):
+    """tranfo.py:37-51 per image (Pillow ImageEnhance blends, GaussianBlur box passes, per-channel point tables): the batch on
+    the device equals the reference's calls, with the draws taken from the same generator in the same order."""
+    n, H, W = shape
+    r = np.random.default_rng(51)
+    imgs = r.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    imgs[0] = (imgs[0] // 16) + 100                                   # a low-contrast image: extrapolated blends get clipped
+    random.seed(17)
+    do_blur, do_rgb = batch.sample_flags(n, random)
+    do_blur[0], do_rgb[min(1, n - 1)], do_blur[-1], do_rgb[-1] = True, True, True, True
+    out = host(batch.enhance_batch(dev(imgs), do_blur, do_rgb, random))
+    state = random.getstate()
+    random.seed(17)
+    L.sample_pairing_flags(n)
+    for i in range(n):
+        assert np.array_equal(out[i], L.enhance_image(imgs[i], bool(do_blur[i]), bool(do_rgb[i]))), i
+    assert random.getstate() == state
+
+
+def test_enhance_image_drop_in_equals_reference_golden(tmp_path):
+    """The file-based drop-in against outputs of the REAL reference function (tests/golden/tranfo_*.npz)."""
+    from conftest import load_golden
+    from PIL import Image as PILImage
+    from image_processor_pipeline_b200.transforms import tranfo
+    for k in range(4):
+        g = load_golden(f"tranfo_{k}")
+        d_in, d_out = tmp_path / f"in{k}", tmp_path / f"out{k}"
+        d_in.mkdir(); d_out.mkdir()
+        PILImage.fromarray(g["input"], "RGB").save(d_in / "img.png")
+        random.seed(g["meta"]["seed"])
+        res = tranfo.enhance_image(d_in / "img.png", g["meta"]["apply_blur"], g["meta"]["apply_rgb"], [d_out])
+        assert res.name == g["meta"]["name"]
+        assert np.array_equal(np.asarray(PILImage.open(res).convert("RGB")), g["out"])

@@ -135,3 +135,37 @@ def test_exact_decimal_helpers_match_python():
         want = "%.6f" % float(v)
         assert buf.value.decode() == want and n == len(want), (v, buf.value, want)
         assert parsed.value == float(want), v
+
+
+def test_native_enhance_plan_equals_python_draws_and_pillow_models():
+    """ipp_plan_enhance_host: the draws of tranfo.py:38-51 from the generator's own state (state equal afterwards), the
+    GaussianBlur box parameters of libImaging and the Image.point tables — against Python's random + the integer models."""
+    import random
+    from image_processor_pipeline_b200 import batch
+    from oracle import intmodels as M
+    n = 23
+    rng = random.Random(41)
+    do_blur, do_rgb = batch.sample_flags(n, rng)
+    assert do_blur.sum() == int(n * 0.3) and do_rgb.sum() == int(n * 0.3)
+    ref = random.Random(41)
+    files = list(range(n))
+    rb = set(ref.sample(files, int(n * 0.3))); rr = set(ref.sample(files, int(n * 0.3)))
+    assert [i in rb for i in files] == do_blur.tolist() and [i in rr for i in files] == do_rgb.tolist()
+    items, luts, draws = batch.plan_enhance(n, do_blur, do_rgb, rng)
+    for i in range(n):
+        f = [ref.uniform(0.7, 1.3) for _ in range(3)]
+        assert f == draws[i, :3].tolist()
+        assert (np.float32(f[0]), np.float32(f[1]), np.float32(f[2])) == (items[i]["brightness"], items[i]["contrast"], items[i]["color"])
+        if do_blur[i]:
+            rad = ref.uniform(0.5, 3)
+            assert rad == draws[i, 3]
+            radius, ww, fw = M.box_blur_params(M.gaussian_box_radius(rad))
+            assert (items[i]["blur"], items[i]["box_radius"], items[i]["ww"], items[i]["fw"]) == (1, radius, ww, fw)
+        else:
+            assert np.isnan(draws[i, 3]) and items[i]["blur"] == 0
+        if do_rgb[i]:
+            for c in range(3):
+                assert np.array_equal(luts[i, c], M.point_lut([ref.uniform(0.75, 1.25) for _ in range(256)]))
+        else:
+            assert np.array_equal(luts[i], np.tile(np.arange(256, dtype=np.uint8), (3, 1)))
+    assert rng.getstate() == ref.getstate()

@@ -96,3 +96,12 @@ def test_filtres_liste_golden(k):
     assert np.array_equal(L.color_masks_to_alpha(g["input"], filters, zones, m["gimp"]), g["out"])
     scaled = [L.rescale_filter(f, m["gimp"]) for f in filters]
     assert np.array_equal(M.color_masks_to_alpha(g["input"], scaled, zones), g["out"])
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_tranfo_golden(k):
+    """transforms/tranfo.py:37-53 run for real (brightness / contrast / colour, optional blur, optional per-channel LUT)."""
+    g = load_golden(f"tranfo_{k}")
+    random.seed(g["meta"]["seed"])
+    out = L.enhance_image(g["input"], g["meta"]["apply_blur"], g["meta"]["apply_rgb"])
+    assert np.array_equal(out, g["out"])

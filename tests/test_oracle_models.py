@@ -118,3 +118,43 @@ def test_keep_largest_model_tie_break_block_raster():
     _, cleaned, bbox, area = L.keep_largest_component(img, with_info=True)
     out, bb, ar = M.keep_largest_alpha(alpha)
     assert np.array_equal(cleaned[..., 3], out) and tuple(bbox) == bb and area == ar == 2
+
+
+# ------------------------------------------------------------------ tranfo.py (photometric jitter)
+@pytest.mark.parametrize("shape", [(37, 53, 3), (5, 200, 3), (64, 7, 3), (120, 90, 3)])
+def test_enhance_models_equal_pillow(shape):
+    from PIL import ImageEnhance, ImageFilter
+    img = np.random.default_rng(3).integers(0, 256, shape, dtype=np.uint8)
+    im = Image.fromarray(img, "RGB")
+    for f in (0.7, 0.83, 1.0, 1.17, 1.3, 0.0, 2.5):
+        assert np.array_equal(np.asarray(ImageEnhance.Brightness(im).enhance(f)), M.enhance_brightness(img, f))
+        assert np.array_equal(np.asarray(ImageEnhance.Contrast(im).enhance(f)), M.enhance_contrast(img, f))
+        assert np.array_equal(np.asarray(ImageEnhance.Color(im).enhance(f)), M.enhance_color(img, f))
+    for rad in (0.5, 0.51, 0.77, 1.0, 1.5, 2.0, 2.37, 2.9, 3.0, 0.05, 7.3):
+        assert np.array_equal(np.asarray(im.filter(ImageFilter.GaussianBlur(rad))), M.gaussian_blur(img, rad)), rad
+    fac = np.random.default_rng(4).uniform(0.75, 1.25, 256)
+    lut = M.point_lut(fac)
+    ref = np.asarray(im.split()[0].point(lambda p: max(0, min(255, p * fac[p]))))
+    assert np.array_equal(ref, lut[img[..., 0]])
+
+
+def test_enhance_oracle_draw_order_matches_models():
+    """oracle.libcalls.enhance_image (the Pillow calls with draws from `random`) == the integer models fed with the same draws,
+    in the same order: 3 uniforms, optional blur radius, optional 3 x 256 LUT factors."""
+    import random
+    img = np.random.default_rng(5).integers(0, 256, (48, 70, 3), dtype=np.uint8)
+    for blur, rgb in ((False, False), (True, False), (False, True), (True, True)):
+        random.seed(9)
+        ref = L.enhance_image(img, blur, rgb)
+        state = random.getstate()
+        random.seed(9)
+        out = M.enhance_brightness(img, random.uniform(0.7, 1.3))
+        out = M.enhance_contrast(out, random.uniform(0.7, 1.3))
+        out = M.enhance_color(out, random.uniform(0.7, 1.3))
+        if blur:
+            out = M.gaussian_blur(out, random.uniform(0.5, 3))
+        if rgb:
+            luts = [M.point_lut([random.uniform(0.75, 1.25) for _ in range(256)]) for _ in range(3)]
+            out = np.stack([luts[c][out[..., c]] for c in range(3)], axis=2)
+        assert random.getstate() == state
+        assert np.array_equal(ref, out)
