@@ -52,6 +52,7 @@ GENERATOR = ("frames = synth.frame (dark backdrop, every byte < 120, keyed out b
              "textured ellipse ~15 % of the pixels with yellow patches the other filters remove; 1 % bright salt specks), "
              "8 base frames multiplied by cyclic shifts; backgrounds = uniform noise")
 
+ENHANCE_NOTE = "; + enhance_image (tranfo.py: brightness / contrast / colour jitter, GaussianBlur on 30 %, channel tables on 30 %) as the last step"
 CONFIGS = {
     "chain": dict(metric="images/sec 1080p RGB full chain", fh=1080, fw=1920, batch=1024, e2e_frames=512,
                   workload="full chain (border-crop + HSV key + largest component + rotate + flip + LANCZOS overlay + square crop "
@@ -222,7 +223,7 @@ def _c1_box(i: int):
     return np.array([[r.uniform(.3, .7), r.uniform(.3, .7), r.uniform(.05, .3), r.uniform(.05, .3)]])
 
 
-def _cpu_worker_init(config, seed, count, worker_index):
+def _cpu_worker_init(config, seed, count, worker_index, enhance=False):
     """Per-process set-up, outside any timed region: imports, single-threaded cv2, and this worker's own `count`
     synthetic inputs — seeded from the worker INDEX (reproducible; the process id plays no role)."""
     import cv2
@@ -230,7 +231,7 @@ def _cpu_worker_init(config, seed, count, worker_index):
     from image_processor_pipeline_b200 import synth
     from oracle import chain as OC, libcalls as L
     first = 1000 * worker_index
-    w = dict(config=config, OC=OC, L=L, filters=synth.REFERENCE_FILTERS, seed=seed + first, count=count)
+    w = dict(config=config, OC=OC, L=L, filters=synth.REFERENCE_FILTERS, seed=seed + first, count=count, enhance=enhance)
     if config in ("chain", "c5"):
         c = CONFIGS[config]
         frames, bgs = make_inputs(count, seed, first, base=min(4, count), fh=c["fh"], fw=c["fw"])
@@ -256,7 +257,7 @@ def _cpu_worker_run(step):
     cfg = w["config"]
     t0 = time.perf_counter()
     if cfg in ("chain", "c5"):
-        imgs, labels, _ = w["OC"].run_chain(w["frames"], w["bgs"], color_ranges_to_exclude_hsv=w["filters"], **CHAIN_KW)
+        imgs, labels, _ = w["OC"].run_chain(w["frames"], w["bgs"], color_ranges_to_exclude_hsv=w["filters"], enhance=w.get("enhance", False), **CHAIN_KW)
         n = len(imgs)
     elif cfg == "c1":
         n = 0
@@ -288,20 +289,20 @@ CPU_SAMPLE = {"chain": 16, "c5": 4, "c1": 32, "c2": 16, "c3": 32, "c4": 128}
 REF_PER_WORKER = {"chain": 4, "c5": 1, "c1": 8, "c2": 4, "c3": 8, "c4": 64}
 
 
-def cpu_rate_single(config: str, n_images: int, seed: int = 1):
+def cpu_rate_single(config: str, n_images: int, seed: int = 1, enhance: bool = False):
     """images/s of the oracle in this process, cv2 single-threaded."""
-    _cpu_worker_init(config, seed, n_images, 0)
+    _cpu_worker_init(config, seed, n_images, 0, enhance)
     if config not in ("chain", "c5"):
         _cpu_worker_run(0)                                    # warm the libraries (cheap configs only)
     done, dt = _cpu_worker_run(1)
     return done / dt, dt
 
 
-def _ref_pool_init(config, per_worker, counter):
+def _ref_pool_init(config, per_worker, counter, enhance=False):
     with counter.get_lock():
         idx = counter.value
         counter.value += 1
-    _cpu_worker_init(config, 100, per_worker, idx)
+    _cpu_worker_init(config, 100, per_worker, idx, enhance)
 
 
 def run_reference_arm(args):
@@ -319,7 +320,7 @@ def run_reference_arm(args):
     per_step = per_worker * cores
     elapsed, produced = 0.0, 0
     counter = mp.Value("i", 0)
-    with ProcessPoolExecutor(max_workers=cores, initializer=_ref_pool_init, initargs=(args.config, per_worker, counter)) as ex:
+    with ProcessPoolExecutor(max_workers=cores, initializer=_ref_pool_init, initargs=(args.config, per_worker, counter, bool(args.enhance))) as ex:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = list(ex.map(_cpu_worker_run, [s] * cores, chunksize=1))
@@ -331,7 +332,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "name": args.config},
+            "config": {"workload": cfg["workload"] + ENHANCE_NOTE * bool(args.enhance), "name": args.config + "+enhance" * bool(args.enhance)},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{per_step} images per step ({per_worker} per worker) over a ProcessPoolExecutor({cores}); oracle = the reference's cv2/Pillow call sequence in memory (no file I/O), inputs generated outside the timed region, seeded per worker index"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -360,7 +361,7 @@ class ChainWorkload(Workload):
         self.fh, self.fw = c["fh"], c["fw"]
         self.cs = min(self.fh, self.fw)
         self.B = args.batch or c["batch"]
-        self.params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, **CHAIN_KW)
+        self.params = chain.ChainParams(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, enhance=bool(args.enhance), **CHAIN_KW)
         self.frames_d, self.bgs_d = make_inputs_device(self.B, 1, rank * self.B, dev, fh=self.fh, fw=self.fw)
         self.pipe = chain.ChainStream(self.params, stage_a_stream=args.stage_a_stream)
         self.alg_bytes_per_image = 2 * 3 * self.fw * self.fh + 3 * self.cs * self.cs       # frame + background + output
@@ -561,6 +562,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-noise", action="store_true", help="chain: skip the uniform-noise-frames line")
+    ap.add_argument("--enhance", action="store_true", help="chain / c5: add tranfo.py's enhance_image (pairing 'sample') as the last step")
     ap.add_argument("--no-pipeline", action="store_true", help="chain: one run_chain call per step (host waits inside the step)")
     ap.add_argument("--stage-a-stream", default="caller", choices=["side", "caller"], help="stage A of new batches on a second stream")
     ap.add_argument("--no-bg-windows", action="store_true", help="e2e: upload whole backgrounds instead of the planned crop windows")
@@ -698,14 +700,14 @@ def main():
         cpu = None
         if world == 1:
             sample = args.cpu_sample or CPU_SAMPLE[args.config]
-            rate, dt = cpu_rate_single(args.config, sample)
+            rate, dt = cpu_rate_single(args.config, sample, enhance=bool(args.enhance))
             cpu = {"value": rate, "unit": "images/s", "cores": 1, "kind": "port",
                    "sample": f"{sample} images of the same workload, oracle (the reference's cv2/Pillow call sequence in memory, cv2.setNumThreads(1)), {dt:.1f} s",
                    "host_cores_available": os.cpu_count()}
         line = {"metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": cfg["workload"], "name": args.config},
+                "config": {"workload": cfg["workload"] + ENHANCE_NOTE * bool(args.enhance), "name": args.config + "+enhance" * bool(args.enhance)},
                 "run": {"images_per_gpu_per_step": wl.B, "software_pipelined_steps": bool(wl.pipelined and not args.no_pipeline), "l2": wl.l2_note,
                         "host_work_in_step": "native planner (Python-compatible MT19937 draws) + small pinned read-backs; the chain interleaves the phases of consecutive steps on one stream" if wl.pipelined else "draws from Python's random in the reference's order (native planner for rotations / overlays)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

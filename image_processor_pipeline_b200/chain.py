@@ -81,6 +81,9 @@ class ChainParams:
     yolo_class_id: int = 0
     scale_min: float = 0.15
     scale_max: float = 0.30
+    # enhance_image (tranfo.py:9-55) as a last step, with the 'sample' pairing of pipeline.py:209-225 (30 % of the images
+    # blurred, 30 % with per-channel tables)
+    enhance: bool = False
 
     def max_outputs_per_frame(self) -> int:
         """Upper bound of images one frame can yield: rotations (+ original) x symmetry variants."""
@@ -632,6 +635,13 @@ def _phase_items(b: _Batch, rng):
         items, aux = _python_plan_to_arrays(b.py_rots, finals)
         labels = [f["label"] for f in finals]
     own = np.flatnonzero((items["frame"] >= b.lo) & (items["frame"] < b.hi))
+    b.enh_plan = None
+    if b.params.enhance and len(items):
+        # last step of the workflow: its draws follow the square-crop draws of ALL items (steps run one after the other)
+        from . import batch as _batch
+        flags = _batch.sample_flags(len(items), rng)
+        e_items, e_luts, _ = _batch.plan_enhance(len(items), flags[0], flags[1], rng)
+        b.enh_plan = (e_items[own].copy(), e_luts[own].copy())
     if b.shard is not None:
         items, aux = items[own].copy(), aux[own].copy()
         labels = [labels[i] for i in own]
@@ -733,6 +743,9 @@ def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResul
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         _WIN_FREE[(win_key, dev.index)] = ev
+    if b.enh_plan is not None:
+        from . import batch as _batch
+        _batch.enhance_batch(b.out, None, None, inplace=True, plan=b.enh_plan)
     _mark("b2+c_issued")
     for t in (b.rot_d, b.items_d, items_c_d):
         if t is not None:

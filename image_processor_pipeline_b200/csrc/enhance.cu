@@ -15,9 +15,10 @@
 //   1. enh_luma_sum_kernel   one read: sum of L(brightness(px)) per image (the Contrast step needs the image mean)
 //   2. enh_point_kernel      one read + one write: brightness -> contrast (one 256-entry table per image, built per CTA) ->
 //                            colour (per pixel) -> channel tables when the image is not blurred
-//   3. enh_blur_h / enh_blur_v   only for the images drawn for the blur: the three horizontal passes of a row group and the
-//                            three vertical passes of a 64-byte column strip run from shared memory (one read + one write per
-//                            axis instead of three); the channel tables are applied in the last store.
+//   3. enh_blur_h / enh_blur_vwalk   only for the images drawn for the blur: the three horizontal passes of a group of 8 rows run
+//                            from shared memory; the three vertical passes are chained sliding windows in registers (a thread
+//                            walks down one 4-byte column word): one read + one write per axis instead of three.  The channel
+//                            tables are applied in the last store.  (enh_blur_v: generic radius / odd row lengths, shared memory.)
 #include "common.cuh"
 
 namespace ipp {
@@ -138,39 +139,65 @@ __device__ __forceinline__ uint8_t box_at(const uint8_t* line, int x, int n, int
     return (uint8_t)((acc * ww + far * fw + (1u << 23)) >> 24);
 }
 
-// three horizontal passes of `rows` image rows per CTA: element = one byte of a pixel, neighbours 3 bytes apart
-__global__ void __launch_bounds__(256) enh_blur_h_kernel(const EnhParams p, int rows) {
+// three horizontal passes of 8 image rows per CTA from shared memory: blockDim = (128, 8), thread (tx, ty) walks the pixels
+// tx, tx + 128, ... of row ty.  Rows are staged as one 32-bit word per pixel (R | G << 8 | B << 16): a neighbour is ONE shared
+// load and the three channels are summed at once in two 16-bit x 2 accumulators (the kernel was bound by byte loads before).
+constexpr int kBlurRows = 8;
+__global__ void __launch_bounds__(1024) enh_blur_h_kernel(const EnhParams p) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int img = p.blur_list[blockIdx.y];
     const ipp_enhance_item it = p.items[img];
     const int rowbytes = p.w * 3;
-    const int y0 = blockIdx.x * rows, nr = min(rows, p.h - y0);
-    uint8_t* a = sm;
-    uint8_t* b = sm + (size_t)rows * rowbytes;
+    const int y0 = blockIdx.x * kBlurRows, nr = min(kBlurRows, p.h - y0);
+    const int tid = threadIdx.y * 128 + threadIdx.x;
+    uint32_t* a = reinterpret_cast<uint32_t*>(sm);
+    uint32_t* b = a + (size_t)kBlurRows * p.w;
     const uint8_t* src = p.dst + (int64_t)img * p.stride + (int64_t)y0 * rowbytes;      // the point pass wrote dst
-    const int total = nr * rowbytes;
-    for (int i = threadIdx.x; i < total; i += 256) a[i] = src[i];
+    const int npx = nr * p.w;
+    for (int i = tid; i < npx; i += 1024) {
+        const uint8_t* q = src + 3 * i;
+        a[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+    }
     __syncthreads();
+    const int r = it.box_radius, last = p.w - 1;
+    const uint32_t ww = it.ww, fw = it.fw;
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-        for (int i = threadIdx.x; i < total; i += 256) {
-            const int r = i / rowbytes, xb = i - r * rowbytes;
-            const int x = xb / 3, ch = xb - 3 * x;
-            b[i] = box_at(a + r * rowbytes + ch, x, p.w, 3, it.box_radius, it.ww, it.fw);
+        if ((int)threadIdx.y < nr) {
+            const uint32_t* row = a + threadIdx.y * p.w;
+            uint32_t* out = b + threadIdx.y * p.w;
+            for (int x = threadIdx.x; x <= last; x += 128) {
+                uint32_t lo = 0, hi = 0;
+                for (int d = -r; d <= r; ++d) {
+                    const uint32_t v = row[min(max(x + d, 0), last)];
+                    lo += v & 0x00ff00ffu; hi += (v >> 8) & 0xffu;
+                }
+                const uint32_t fa = row[min(max(x - r - 1, 0), last)], fb = row[min(max(x + r + 1, 0), last)];
+                const uint32_t flo = (fa & 0x00ff00ffu) + (fb & 0x00ff00ffu), fhi = ((fa >> 8) & 0xffu) + ((fb >> 8) & 0xffu);
+                const uint32_t c0 = ((lo & 0xffffu) * ww + (flo & 0xffffu) * fw + (1u << 23)) >> 24;
+                const uint32_t c2 = ((lo >> 16) * ww + (flo >> 16) * fw + (1u << 23)) >> 24;
+                const uint32_t c1 = (hi * ww + fhi * fw + (1u << 23)) >> 24;
+                out[x] = (c0 & 255u) | ((c1 & 255u) << 8) | ((c2 & 255u) << 16);
+            }
         }
         __syncthreads();
-        uint8_t* t = a; a = b; b = t;
+        uint32_t* t = a; a = b; b = t;
     }
     uint8_t* dst = p.tmp + (int64_t)blockIdx.y * p.stride + (int64_t)y0 * rowbytes;
-    for (int i = threadIdx.x; i < total; i += 256) dst[i] = a[i];
+    const int total = nr * rowbytes;
+    for (int i = tid; i < total; i += 1024) {
+        const int px = i / 3;                      // constant divisor: a multiply
+        dst[i] = (uint8_t)(a[px] >> (8 * (i - 3 * px)));
+    }
 }
 
-// three vertical passes of a strip of `sw` bytes x all rows per CTA; channel tables in the last store
-__global__ void __launch_bounds__(256) enh_blur_v_kernel(const EnhParams p, int sw) {
+// three vertical passes, generic radius: a strip of `sw` bytes x all rows per CTA; channel tables in the last store
+__global__ void __launch_bounds__(256) enh_blur_v_kernel(const EnhParams p, int sw, int walker) {
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ uint8_t lc[768];
     const int img = p.blur_list[blockIdx.y];
     const ipp_enhance_item it = p.items[img];
+    if (walker && it.box_radius <= 3) return;                        // handled by the register walker below
     const int rowbytes = p.w * 3;
     const int b0 = blockIdx.x * sw, nb = min(sw, rowbytes - b0);
     if (it.lut)
@@ -201,6 +228,116 @@ __global__ void __launch_bounds__(256) enh_blur_v_kernel(const EnhParams p, int 
             if (it.lut) v = lc[256 * ((b0 + xb) % 3) + v];
             dst[(int64_t)y * rowbytes + xb] = v;
         }
+    }
+}
+
+// three vertical passes, radius <= 3 (every GaussianBlur radius tranfo.py draws): a thread owns one 4-byte column word and
+// walks down the image through three chained sliding windows held in registers — every byte is read once and written once,
+// a warp reads 128 contiguous bytes per row.  Four bytes are summed at once in two 16-bit x 2 accumulators.
+struct Walk {       // one box pass over a column word: ring of the last 2r + 3 inputs (rows y-r-1 .. y+r+1 around the output row)
+    uint32_t ring[9];
+    uint32_t lo, hi;    // window sums of bytes {0, 2} and {1, 3}
+};
+__device__ __forceinline__ uint32_t walk_emit(const Walk& w, int r, uint32_t ww, uint32_t fw) {
+    // ring[0] = row y-r-1 (far above), ring[2r+2] = row y+r+1 (far below); lo / hi = sums over ring[1 .. 2r+1]
+    const uint32_t fa = w.ring[0], fb = w.ring[2 * r + 2];
+    const uint32_t flo = (fa & 0x00ff00ffu) + (fb & 0x00ff00ffu), fhi = ((fa >> 8) & 0x00ff00ffu) + ((fb >> 8) & 0x00ff00ffu);
+    const uint32_t b0 = ((w.lo & 0xffffu) * ww + (flo & 0xffffu) * fw + (1u << 23)) >> 24;
+    const uint32_t b2 = ((w.lo >> 16) * ww + (flo >> 16) * fw + (1u << 23)) >> 24;
+    const uint32_t b1 = ((w.hi & 0xffffu) * ww + (fhi & 0xffffu) * fw + (1u << 23)) >> 24;
+    const uint32_t b3 = ((w.hi >> 16) * ww + (fhi >> 16) * fw + (1u << 23)) >> 24;
+    return (b0 & 255u) | ((b1 & 255u) << 8) | ((b2 & 255u) << 16) | (b3 << 24);
+}
+template <int R>
+__device__ __forceinline__ void walk_push(Walk& w, uint32_t v) {
+    // the window moves down one row: ring[1] leaves the sum, the old far-below element enters it, v becomes far-below
+    const uint32_t out = w.ring[1], in = w.ring[2 * R + 2];
+    w.lo += (in & 0x00ff00ffu) - (out & 0x00ff00ffu);
+    w.hi += ((in >> 8) & 0x00ff00ffu) - ((out >> 8) & 0x00ff00ffu);
+#pragma unroll
+    for (int i = 0; i < 2 * R + 2; ++i) w.ring[i] = w.ring[i + 1];
+    w.ring[2 * R + 2] = v;
+}
+template <int R>
+__device__ __forceinline__ void walk_init(Walk& w, uint32_t first) {
+    // state for output row -1 ... every ring entry = row 0 (clamped), sums over 2R+1 copies
+#pragma unroll
+    for (int i = 0; i < 2 * R + 3; ++i) w.ring[i] = first;
+    w.lo = (first & 0x00ff00ffu) * (2 * R + 1);
+    w.hi = ((first >> 8) & 0x00ff00ffu) * (2 * R + 1);
+}
+__device__ __forceinline__ uint32_t lut_word(const uint8_t* lc, uint32_t v, int ch0) {
+    // channel of byte k of this word = (ch0 + k) % 3
+    const int c1 = ch0 == 2 ? 0 : ch0 + 1, c2 = c1 == 2 ? 0 : c1 + 1;
+    return (uint32_t)lc[256 * ch0 + (v & 255u)] | ((uint32_t)lc[256 * c1 + ((v >> 8) & 255u)] << 8) |
+           ((uint32_t)lc[256 * c2 + ((v >> 16) & 255u)] << 16) | ((uint32_t)lc[256 * ch0 + (v >> 24)] << 24);
+}
+// Rows [y0, y1) are produced by a walk that starts 3 (R + 1) rows above y0 (as if that row were the top: the outputs that are
+// wrong for it are exactly the ones not stored — pass k is correct from k (R + 1) rows below the start) and clamps at the true
+// bottom.  The caller passes src / dst already offset to the start row s; h = rows from s to the bottom, first = y0 - s.
+template <int R>
+__device__ __forceinline__ void walk_column(const uint32_t* src, uint32_t* dst, int pitch_w, int h, int first, int count, uint32_t ww, uint32_t fw,
+                                            const uint8_t* lc, bool lut, int ch0) {
+    // Pass k sees the output rows of pass k-1 as its input rows.  A pass can emit output row y once its input row
+    // y + R + 1 (clamped to h - 1) has been pushed; feeding the last row again beyond the end reproduces the clamped edge.
+    Walk w1, w2, w3;
+    const uint32_t f0 = src[0];
+    walk_init<R>(w1, f0);
+    // prime pass 1 with input rows 0 .. R (ring then holds rows -R-1 .. R+1 around output row 0 after R + 2 pushes in total)
+    int in1 = 0;                       // next input row of pass 1
+    auto next1 = [&]() { const uint32_t v = src[(int64_t)min(in1, h - 1) * pitch_w]; ++in1; return v; };
+    // after walk_init the ring models output row -1 - ... we push R + 2 rows (rows 0 .. R+1) to reach output row 0:
+    // ring = {row -R-1 .. row R+1} = {0 x (R+2) clamped, 1 .. R+1}
+    // walk_init put row 0 everywhere = state "output row -(R+2)+... "; pushing rows 1 .. R+1 yields output row 0.
+    next1();                           // row 0 is already everywhere
+    for (int i = 0; i < R + 1; ++i) walk_push<R>(w1, next1());
+    int out1 = 0;                      // next output row of pass 1
+    auto emit1 = [&]() { const uint32_t v = walk_emit(w1, R, ww, fw); walk_push<R>(w1, next1()); ++out1; return v; };
+    // pass 2 primed from pass 1's outputs 0 .. R+1
+    const uint32_t g0 = emit1();
+    walk_init<R>(w2, g0);
+    for (int i = 0; i < R + 1; ++i) walk_push<R>(w2, out1 < h ? emit1() : w2.ring[2 * R + 2]);
+    int out2 = 0;
+    auto next2 = [&]() { return out1 < h ? emit1() : w2.ring[2 * R + 2]; };        // beyond the end: the last row again
+    auto emit2 = [&]() { const uint32_t v = walk_emit(w2, R, ww, fw); walk_push<R>(w2, next2()); ++out2; return v; };
+    const uint32_t h0 = emit2();
+    walk_init<R>(w3, h0);
+    for (int i = 0; i < R + 1; ++i) walk_push<R>(w3, out2 < h ? emit2() : w3.ring[2 * R + 2]);
+    auto next3 = [&]() { return out2 < h ? emit2() : w3.ring[2 * R + 2]; };
+    for (int y = 0; y < first + count; ++y) {
+        uint32_t v = walk_emit(w3, R, ww, fw);
+        walk_push<R>(w3, next3());
+        if (y >= first) {
+            if (lut) v = lut_word(lc, v, ch0);
+            dst[(int64_t)y * pitch_w] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) enh_blur_vwalk_kernel(const EnhParams p) {
+    __shared__ uint8_t lc[768];
+    const int img = p.blur_list[blockIdx.y];
+    const ipp_enhance_item it = p.items[img];
+    const int pitch_w = (p.w * 3) >> 2;
+    if (it.box_radius > 3) return;                                  // generic kernel
+    if (it.lut)
+        for (int i = threadIdx.x; i < 768; i += 128) lc[i] = p.luts[(int64_t)img * 768 + i];
+    __syncthreads();
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= pitch_w) return;
+    // the column is cut into gridDim.z segments (more threads in flight: a walk is a chain of dependent loads)
+    const int seg_h = (p.h + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int y0 = (int)blockIdx.z * seg_h, y1 = min(y0 + seg_h, p.h);
+    if (y0 >= y1) return;
+    const int s0 = max(y0 - 3 * (it.box_radius + 1), 0);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.tmp + (int64_t)blockIdx.y * p.stride) + col + (int64_t)s0 * pitch_w;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.dst + (int64_t)img * p.stride) + col + (int64_t)s0 * pitch_w;
+    const int ch0 = (4 * col) % 3;
+    const int hh = p.h - s0, first = y0 - s0, count = y1 - y0;
+    switch (it.box_radius) {
+        case 0: walk_column<0>(src, dst, pitch_w, hh, first, count, it.ww, it.fw, lc, it.lut != 0, ch0); break;
+        case 1: walk_column<1>(src, dst, pitch_w, hh, first, count, it.ww, it.fw, lc, it.lut != 0, ch0); break;
+        case 2: walk_column<2>(src, dst, pitch_w, hh, first, count, it.ww, it.fw, lc, it.lut != 0, ch0); break;
+        default: walk_column<3>(src, dst, pitch_w, hh, first, count, it.ww, it.fw, lc, it.lut != 0, ch0); break;
     }
 }
 
@@ -239,10 +376,7 @@ int ipp_enhance_batch_u8(const uint8_t* src, uint8_t* dst, int w, int h, int n, 
     IPP_LAUNCH_CHECK();
     if (n_blur > 0) {
         const int rowbytes = w * 3;
-        int rows = 24576 / rowbytes;
-        if (rows < 1) rows = 1;
-        if (rows > h) rows = h;
-        const size_t smem_h = 2 * (size_t)rows * rowbytes;
+        const size_t smem_h = 2 * (size_t)kBlurRows * w * 4;
         IPP_REQUIRE(smem_h <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_enhance_batch_u8: row too long for the blur");
         int sw = 64;
         while (sw > 4 && 2 * (size_t)h * sw > 200 * 1024) sw >>= 1;
@@ -259,9 +393,16 @@ int ipp_enhance_batch_u8(const uint8_t* src, uint8_t* dst, int w, int h, int n, 
             IPP_CUDA(cudaFuncSetAttribute(enh_blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_v, 48 * 1024)));
             if (dev_id >= 0 && dev_id < 64) set_v[dev_id] = smem_v;
         }
-        { ipp::LaunchTimer _lt("enh_blur_h_kernel", st); enh_blur_h_kernel<<<dim3(ceil_div(h, rows), n_blur), 256, smem_h, st>>>(p, rows); }
+        { ipp::LaunchTimer _lt("enh_blur_h_kernel", st); enh_blur_h_kernel<<<dim3(ceil_div(h, kBlurRows), n_blur), dim3(128, kBlurRows), smem_h, st>>>(p); }
         IPP_LAUNCH_CHECK();
-        { ipp::LaunchTimer _lt("enh_blur_v_kernel", st); enh_blur_v_kernel<<<dim3(ceil_div(rowbytes, sw), n_blur), 256, smem_v, st>>>(p, sw); }
+        // vertical passes: the register walker takes the images with a box radius <= 3 (and 4-byte-multiple rows), the generic
+        // shared-memory kernel the others; each kernel returns at once for the images of the other
+        const int walker = rowbytes % 4 == 0 && (((uintptr_t)dst | (uintptr_t)p.tmp) & 3) == 0 && (p.stride & 3) == 0;
+        if (walker) {
+            { ipp::LaunchTimer _lt("enh_blur_vwalk_kernel", st); enh_blur_vwalk_kernel<<<dim3(ceil_div(rowbytes / 4, 128), n_blur, h >= 256 ? 8 : 1), 128, 0, st>>>(p); }
+            IPP_LAUNCH_CHECK();
+        }
+        { ipp::LaunchTimer _lt("enh_blur_v_kernel", st); enh_blur_v_kernel<<<dim3(ceil_div(rowbytes, sw), n_blur), 256, smem_v, st>>>(p, sw, walker); }
         IPP_LAUNCH_CHECK();
     }
     return IPP_OK;

@@ -25,7 +25,7 @@ SYM_FILE_ORDER = {"h": 0, "hv": 1, "o": 2, "v": 3}
 def run_chain(frames_bgr, backgrounds_rgb, *, crop_margins=(0, 0, 0, 0), color_ranges_to_exclude_hsv=(), zones=None,
               use_gimp_scale=False, num_rotations=10, include_original=True, angle_min=1.0, angle_max=359.0,
               pool=None, choose_random=None, sym_include_original=True, yolo_class_id=0, scale_min=0.15,
-              scale_max=0.30, fast_cc=True):
+              scale_max=0.30, fast_cc=True, enhance=False):
     """Returns (images [list of HxWx3 RGB arrays], labels [list of str], records [list of dict])."""
     # step 1+2+3: border crop, HSV key, largest component (+ fit)
     sprites = []
@@ -83,4 +83,9 @@ def run_chain(frames_bgr, backgrounds_rgb, *, crop_margins=(0, 0, 0, 0), color_r
         labels.append(L.format_label_rows(ncls, nboxes))
         records.append(dict(frame=c["frame"], rot_index=c["rot_index"], angle=c["angle"], sym=c["sym"], bg=c["bg"],
                             new=c["new"], pos=c["pos"], sq=(x0, y0, cropped.shape[0])))
+
+    # step 8 (optional): photometric jitter, 'sample' pairing (pipeline.py:209-225, tranfo.py:37-51)
+    if enhance and images:
+        do_blur, do_rgb = L.sample_pairing_flags(len(images))
+        images = [L.enhance_image(np.ascontiguousarray(img), bl, rg) for img, bl, rg in zip(images, do_blur, do_rgb)]
     return images, labels, records

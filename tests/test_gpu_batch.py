@@ -171,6 +171,23 @@ def test_enhance_batch_bit_exact(shape):
     assert random.getstate() == state
 
 
+def test_enhance_blur_generic_radius_and_odd_rows():
+    """GaussianBlur outside the fast path of the vertical pass: box radius > 3 (radius 9) and rows whose byte length is not a
+    multiple of four — against the integer model of libImaging's box blur (itself proven equal to Pillow)."""
+    from oracle import intmodels as M
+    r = np.random.default_rng(53)
+    for (n, H, W), rad in (((2, 64, 48), 9.0), ((2, 40, 33), 2.2), ((1, 37, 50), 0.6)):
+        imgs = r.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+        items = np.zeros(n, dtype=batch.ENH_ITEM_DTYPE)
+        items["brightness"] = items["contrast"] = items["color"] = 1.0
+        radius, ww, fw = M.box_blur_params(M.gaussian_box_radius(rad))
+        items["blur"], items["box_radius"], items["ww"], items["fw"] = 1, radius, ww, fw
+        luts = np.tile(np.arange(256, dtype=np.uint8), (n, 3, 1))
+        out = host(batch.enhance_batch(dev(imgs), None, None, plan=(items, luts)))
+        for i in range(n):
+            assert np.array_equal(out[i], M.gaussian_blur(imgs[i], rad)), (H, W, rad)
+
+
 def test_enhance_image_drop_in_equals_reference_golden(tmp_path):
     """The file-based drop-in against outputs of the REAL reference function (tests/golden/tranfo_*.npz)."""
     from conftest import load_golden

@@ -100,6 +100,27 @@ def test_chain_1080p_uniform_noise_frames():
     _compare(*_run_both(frames, bgs, 24, **kw))
 
 
+def test_chain_with_enhance_step():
+    """The chain followed by tranfo.py's enhance_image under the 'sample' pairing (30 % blurred, 30 % channel tables):
+    images, labels and the generator state equal the oracle's — plain and software-pipelined."""
+    H, W = 200, 320
+    frames = [synth.frame(95, i, H, W) for i in range(4)]
+    bgs = [synth.background(95, i, 240, 300) for i in range(3)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=2, include_original=True,
+              pool=["o", "h", "v", "hv"], choose_random=2, enhance=True)
+    res, ref_imgs, ref_labels, ref_recs = _run_both(frames, bgs, 26, **kw)
+    _compare(res, ref_imgs, ref_labels, ref_recs)
+    assert len(ref_imgs) >= 10
+    fd, bd = torch.from_numpy(np.stack(frames)).to(DEV), torch.from_numpy(np.stack(bgs)).to(DEV)
+    random.seed(26)
+    pipe = chain.ChainStream(chain.ChainParams(**kw))
+    outs = list(pipe.map([(fd, bd), (fd, bd), (fd, bd)]))
+    random.seed(26)
+    for r in outs:
+        imgs, labels, _ = OC.run_chain(frames, bgs, **kw)
+        assert labels == r.labels and all(np.array_equal(a, b) for a, b in zip(r.images.cpu().numpy(), imgs))
+
+
 def test_chain_odd_sizes_exact_length_buffers():
     """Frames whose byte length is not a multiple of four (333 x 217 x 3 x n): the gathers fetch the aligned 32-bit word(s)
     holding a pixel, and every such word holds at least one byte of the pixel, so nothing beyond the aligned extent of the
