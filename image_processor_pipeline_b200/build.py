@@ -43,6 +43,22 @@ def build(force: bool = False, verbose: bool = False, out: Path = OUT, defines=(
     return out
 
 
+JPEG_OUT = HERE / "libippjpeg.so"
+JPEG_SRC = HERE / "csrc_jpeg" / "ippjpeg.cpp"
+
+
+def build_jpeg(force: bool = False) -> Path:
+    """libippjpeg.so: the nvJPEG codec layer (include/ippjpeg.h), its own library so that libippgpu does not depend on libnvjpeg."""
+    srcs = [JPEG_SRC, HERE.parent / "include" / "ippjpeg.h"]
+    if not force and JPEG_OUT.is_file() and all(p.stat().st_mtime <= JPEG_OUT.stat().st_mtime for p in srcs):
+        return JPEG_OUT
+    cmd = ["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", str(JPEG_OUT), str(JPEG_SRC), "-lnvjpeg"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    return JPEG_OUT
+
+
 if __name__ == "__main__":
     if "--variant" in sys.argv:                       # python -m ...build --variant NAME -DX=1 -DY=2
         name = sys.argv[sys.argv.index("--variant") + 1]
@@ -50,3 +66,4 @@ if __name__ == "__main__":
                     defines=[a for a in sys.argv if a.startswith("-D")]))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+        print(build_jpeg(force="--force" in sys.argv))

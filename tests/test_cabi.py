@@ -68,3 +68,14 @@ def test_product_path_has_no_cpu_fallback():
     src = (ROOT / "image_processor_pipeline_b200").rglob("*.py")
     for f in src:
         assert "oracle" not in f.read_text().replace("oracle/", ""), f"{f} must not import the oracle"
+
+
+def test_jpeg_library_exports_every_declared_symbol():
+    """include/ippjpeg.h (the nvJPEG codec layer, its own shared library) — symbols only, no device work."""
+    import ctypes
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "ippjpeg.h").read_text(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(ippjpeg_[a-z0-9_]+)\s*\(", text)))
+    assert len(syms) >= 8
+    lib = ctypes.CDLL(str(ROOT / "image_processor_pipeline_b200" / "libippjpeg.so"))
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in ippjpeg.h but not exported"
