@@ -356,9 +356,9 @@ def _python_plan_to_arrays(rots: List[dict], finals: List[dict]):
 # =========================================================================== native planner
 def _plan_params(p: ChainParams, BW: int, BH: int, m: int) -> _native.PlanParams:
     pool, choose = p.resolved_pool()
-    if len(pool) > 4 or len(set(pool)) != len(pool):
-        raise NotImplementedError("symmetry pool must hold at most four distinct entries")
     pp = _native.PlanParams()
+    if len(pool) > 4 or len(set(pool)) != len(pool):
+        pool, choose = [], 0                   # planned by the Python planner (see _begin); the record is not used for the symmetry step
     pp.num_rotations, pp.include_original = int(p.num_rotations), int(bool(p.include_original))
     pp.angle_min, pp.angle_max = float(p.angle_min), float(p.angle_max)
     for i, s in enumerate(pool):
@@ -534,6 +534,13 @@ def _begin(frames, backgrounds, params, planner, device_tables, ambiguity_eps, s
         raise TypeError("frames / backgrounds must be uint8 [N, H, W, 3]")
     if planner not in ("native", "python"):
         raise ValueError("planner must be 'native' or 'python'")
+    pool, _ = params.resolved_pool()
+    if planner == "native" and (len(pool) > 4 or len(set(pool)) != len(pool)):
+        # symmetry.py:97-122 accepts any pool, repeated entries included (random.sample then draws among positions); the native
+        # planner's record holds four distinct entries: such pools are planned by the Python twin (same draws, same results)
+        planner = "python"
+        if device_tables is None:
+            device_tables = True
     if host_bgs and not backgrounds.is_contiguous():
         raise ValueError("host backgrounds must be contiguous")
     b = _Batch()

@@ -43,17 +43,29 @@ def fit_crop(image_path: Path, output_dirs: List[Path], **options: Any) -> Optio
     (reference recadrages.py:63-82).  The bbox is a device reduction."""
     output_dir = output_dirs[0]
     image = Image.open(image_path)
-    if image.mode not in ("L", "LA", "RGB", "RGBA"):
-        raise NotImplementedError(f"fit_crop: PIL mode {image.mode} is not supported on the GPU path")
     arr = np.asarray(image)
-    dev = _io.to_device(arr)
-    bbox = ops.nonzero_bbox(dev)
-    if not bbox:
-        new_image = image.copy()
+    if image.mode in ("L", "LA", "RGB", "RGBA"):
+        dev = _io.to_device(arr)
+        bbox = ops.nonzero_bbox(dev)
+        if not bbox:
+            new_image = image.copy()
+        else:
+            x0, y0, x1, y1 = bbox
+            out = _io.to_host(ops.flip_crop(dev, x0, y0, x1 - x0, y1 - y0), like=arr)
+            new_image = Image.fromarray(out, image.mode)
     else:
-        x0, y0, x1, y1 = bbox
-        out = _io.to_host(ops.flip_crop(dev, x0, y0, x1 - x0, y1 - y0), like=arr)
-        new_image = Image.fromarray(out, image.mode)
+        # any other PIL mode (P, PA, 1, CMYK, YCbCr, I;16, I, F, La, RGBa ...): getbbox tests the alpha band for modes that have
+        # one and "any byte of the pixel non-zero" otherwise (libImaging GetBBox.c works on the raw pixel bytes) — the same
+        # device reduction on the byte view; the crop itself stays with PIL so that palette / info travel like in the reference
+        raw = np.ascontiguousarray(arr.astype(np.uint8) if arr.dtype == bool else arr)
+        byts = raw.view(np.uint8).reshape(raw.shape[0], raw.shape[1], -1)
+        if image.mode.startswith("I;16"):
+            # libImaging keeps I;16 rows in its 8-bit plane and GetBBox.c scans `xsize` BYTES of each row there: Pillow's bbox of a
+            # 16-bit image is the bbox of the first `width` bytes of every row, one byte = one column.  Reproduced as is.
+            byts = np.ascontiguousarray(byts.reshape(raw.shape[0], -1)[:, :raw.shape[1], None])
+        alpha_only = image.mode in ("PA", "La", "RGBa")
+        bbox = ops.nonzero_bbox(_io.to_device(byts), alpha_only=alpha_only)
+        new_image = image.crop(bbox) if bbox else image.copy()
     output_path = output_dir / image_path.name
     new_image.save(output_path)
     return output_path

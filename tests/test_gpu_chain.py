@@ -100,6 +100,17 @@ def test_chain_1080p_uniform_noise_frames():
     _compare(*_run_both(frames, bgs, 24, **kw))
 
 
+def test_chain_symmetry_pool_with_repeated_entries():
+    """symmetry.py:97-122 takes any pool: repeated entries are positions random.sample draws among (a variant drawn twice is
+    written twice under the same name).  Such pools are planned by the Python planner automatically."""
+    H, W = 160, 240
+    frames = [synth.frame(97, i, H, W) for i in range(3)]
+    bgs = [synth.background(97, i, 200, 260) for i in range(2)]
+    kw = dict(color_ranges_to_exclude_hsv=synth.REFERENCE_FILTERS, num_rotations=2, include_original=False,
+              pool=["h", "h", "v", "hv", "o", "v"], choose_random=3, sym_include_original=False)
+    _compare(*_run_both(frames, bgs, 27, **kw))
+
+
 def test_chain_with_enhance_step():
     """The chain followed by tranfo.py's enhance_image under the 'sample' pairing (30 % blurred, 30 % channel tables):
     images, labels and the generator state equal the oracle's — plain and software-pipelined."""

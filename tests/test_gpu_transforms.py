@@ -188,3 +188,36 @@ def test_pipeline_end_to_end_on_gpu(tmp_path):
         assert all(l["status"] == "Success" for s in pipe.steps for l in s.process_logs)
     a = cv2.imread(str(tmp_path / "s1" / "im0_h.png"), cv2.IMREAD_UNCHANGED)
     assert np.array_equal(a, cv2.flip(cv2.imread(str(tmp_path / "raw" / "im0.png"), cv2.IMREAD_UNCHANGED), 1))
+
+
+@pytest.mark.parametrize("mode", ["P", "1", "CMYK", "I;16", "F"])
+def test_fit_crop_other_pil_modes(tmp_path, mode):
+    """recadrages.py:71-77 takes whatever Image.open returns: getbbox + crop for every PIL mode (device bbox on the pixel
+    bytes), compared with Pillow's own getbbox / crop."""
+    from PIL import Image
+    r = np.random.default_rng(3)
+    h, w = 23, 31
+    base = np.zeros((h, w), np.uint8)
+    base[5:17, 7:22] = r.integers(1, 255, (12, 15))
+    if mode == "P":
+        im = Image.fromarray(base, "L").convert("P")
+    elif mode == "1":
+        im = Image.fromarray((base > 0).astype(np.uint8) * 255, "L").convert("1")
+    elif mode == "CMYK":
+        im = Image.merge("CMYK", [Image.fromarray(base, "L")] * 4)
+    elif mode == "I;16":
+        im = Image.fromarray(base.astype(np.uint16) * 200, "I;16")
+    elif mode == "PA":
+        im = Image.merge("LA", [Image.fromarray(np.full((h, w), 9, np.uint8), "L"), Image.fromarray(base, "L")]).convert("PA")
+    else:
+        im = Image.fromarray(base.astype(np.float32) * 0.5, "F")
+    ext = {"F": "tiff", "CMYK": "tiff", "I;16": "png", "PA": "png"}.get(mode, "png")
+    din, dout = tmp_path / "in", tmp_path / "out"
+    din.mkdir(); dout.mkdir()
+    im.save(din / f"x.{ext}")
+    opened = Image.open(din / f"x.{ext}")
+    ref = opened.crop(opened.getbbox()) if opened.getbbox() else opened.copy()
+    res = recadrages.fit_crop(din / f"x.{ext}", [dout])
+    out = Image.open(res)
+    assert out.size == ref.size and out.mode == ref.mode
+    assert np.array_equal(np.asarray(out), np.asarray(ref))
