@@ -678,15 +678,23 @@ def _phase_items(b: _Batch, rng):
 
 
 def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResult":
-    """Exact-row confirmation of the device tables (patches them where the C library's sin() decides
-    otherwise — before anything has read them), then stages B2 + C."""
+    """Exact-row confirmation of the device tables, then stages B2 + C (see _phase_b2 / _phase_c)."""
+    _phase_b2(b, upload_stream, before_sync)
+    return _phase_c(b)
+
+
+def _phase_b2(b: _Batch, upload_stream=None, before_sync=None):
+    """Exact-row confirmation of the device tables (patches them where the C library's sin() decides otherwise — before
+    anything has read them), the upload of the background crop windows (host backgrounds) on their copy stream, stage B2."""
     lib, dev, items, tot, K, cs = b.lib, b.dev, b.items, b.tot, b.K, b.cs
     res = ChainResult(b.out, b.labels, record_arrays=(b.items, b.aux, b.rot_index, b.angles))
     res.tables_flagged_rows = res.tables_fixed_items = 0
     res.h2d_background_bytes = 0
     b.phase = 4
+    b.res = res
+    b.c_args = None
     if K == 0:
-        return res
+        return
     if b.ev_amb is not None:
         if before_sync is not None:
             before_sync()                                             # e.g. queue the next uploads before the host waits
@@ -741,6 +749,19 @@ def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResul
                                          tot["gt"], tot["ht"], tot["vt"], b.tab_d.data_ptr(), band_d.data_ptr(), tot["max_band_warps"],
                                          tot["fused_smem"], tot["vstaged_smem"], b.ws.data_ptr(), spr_ws.data_ptr(), _stream()),
                   "ipp_chain_stage_b2")
+    b.c_args = (bg_ready, bg_dev, bg_pitch, bg_stride, geom_c, items_c_d, spr_ws, win_key if bg_ready is not None else None)
+    _mark("b2_issued")
+
+
+def _phase_c(b: _Batch) -> "ChainResult":
+    """Stage C (paste + square crop; waits for the crop windows when the backgrounds live on the host), then the optional
+    enhance step.  Queued LAST in a pipelined iteration: nothing the host waits for sits behind the window transfer."""
+    b.phase = 5
+    res = b.res
+    if b.c_args is None:
+        return res
+    lib, dev, K, cs = b.lib, b.dev, b.K, b.cs
+    bg_ready, bg_dev, bg_pitch, bg_stride, geom_c, items_c_d, spr_ws, win_key = b.c_args
     if bg_ready is not None:
         torch.cuda.current_stream().wait_event(bg_ready)              # the windows have landed (copied while B2 ran)
     _native.check(lib.ipp_chain_stage_c(bg_dev.data_ptr(), bg_pitch, bg_stride, C.byref(geom_c), items_c_d.data_ptr(), K,
@@ -753,10 +774,11 @@ def _phase_paste(b: _Batch, upload_stream=None, before_sync=None) -> "ChainResul
     if b.enh_plan is not None:
         from . import batch as _batch
         _batch.enhance_batch(b.out, None, None, inplace=True, plan=b.enh_plan)
-    _mark("b2+c_issued")
+    _mark("c_issued")
     for t in (b.rot_d, b.items_d, items_c_d):
         if t is not None:
             t.record_stream(torch.cuda.current_stream())
+    b.c_args = None
     return res
 
 
@@ -829,7 +851,10 @@ class ChainStream:
     a caller can interleave consecutive batches: while the host waits for the small read-back of one phase
     and plans, the GPU still has the later phases of older batches queued.  ``map`` does exactly that:
 
-        iteration s:  finish(s-3)   prepare(s-2)   plan(s-1)   submit(s)
+        iteration s:  gather(s-3)   prepare(s-2)   plan(s-1)   submit(s)   finish(s-3)
+
+    (stage C of the oldest batch is queued last: with host backgrounds it waits for the crop windows to cross PCIe, and
+    nothing the host needs next sits behind that wait)
 
     Every wait then targets work that was queued a whole iteration earlier and is followed by several
     milliseconds of queued kernels: the device never idles on the host.  ``finish`` runs the earlier
@@ -900,10 +925,17 @@ class ChainStream:
             with torch.cuda.device(b.dev):
                 _phase_items(b, rng)
 
-    def finish(self, b: _Batch, rng=_random) -> "ChainResult":
+    def gather(self, b: _Batch, rng=_random):
+        """Phase 4: confirm the flagged table rows, queue the crop-window upload (host backgrounds) and stage B2."""
         self.prepare(b, rng)
+        if b.phase < 4:
+            with torch.cuda.device(b.dev):
+                _phase_b2(b)
+
+    def finish(self, b: _Batch, rng=_random) -> "ChainResult":
+        self.gather(b, rng)
         with torch.cuda.device(b.dev):
-            res = _phase_paste(b)
+            res = _phase_c(b)
             if self.stage_a_stream == "side":
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())
@@ -926,9 +958,10 @@ class ChainStream:
         exhausted = False
         while True:
             # oldest first: finish(s-3), prepare(s-2), plan(s-1), then submit(s)
-            out = None
+            out = oldest = None
             if q and q[0].phase >= 3 and (len(q) >= 3 or exhausted):
-                out = self.finish(q.popleft(), rng)
+                oldest = q.popleft()
+                self.gather(oldest, rng)                             # stage B2 now, stage C at the end of the iteration
             for b in q:
                 if b.phase == 2:
                     self.prepare(b, rng)
@@ -948,6 +981,8 @@ class ChainStream:
                     q.append(b)
                 except StopIteration:
                     exhausted = True
+            if oldest is not None:
+                out = self.finish(oldest, rng)
             if out is not None:
                 yield out
             if exhausted and not q:
@@ -956,7 +991,7 @@ class ChainStream:
 
 def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, params: ChainParams, device,
                    out_host: Optional[torch.Tensor] = None, rng=_random, chunk: Optional[int] = None,
-                   background_windows: bool = True, **kw) -> ChainResult:
+                   background_windows: bool = True, passes: int = 1, **kw) -> ChainResult:
     """End-to-end entry for HOST buffers (what a pipeline step does after decoding): pinned host
     frames / backgrounds -> H2D -> chain -> D2H of the output images.
 
@@ -970,7 +1005,10 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
     then only the crop windows are copied (22 % fewer H2D bytes per 1080p image).  False: whole
     backgrounds are uploaded up front.
     ``out_host`` (pinned, [>= K, cs, cs, 3]) receives the images; ChainResult.images is that host
-    tensor (first K rows).  ChainResult.h2d_bytes = bytes that crossed PCIe host->device."""
+    tensor (first K rows).  ChainResult.h2d_bytes = bytes that crossed PCIe host->device.
+    ``passes`` (chunked mode): stream the host batch that many times back to back as ONE pipeline (what a decoder that keeps
+    refilling the same pinned buffers produces): the copy engines never drain between passes.  The result describes the last
+    pass; ``images_total`` / ``h2d_bytes`` / ``d2h_bytes`` count all of them."""
     dev = torch.device(device)
     n = frames_host.shape[0]
     m = backgrounds_host.shape[0]
@@ -994,7 +1032,8 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
             raise ValueError("chunked run_chain_host pairs slice c with backgrounds[c*chunk:(c+1)*chunk]: pass one background per frame")
         compute = torch.cuda.current_stream()
         up, down, _ = _side_streams(dev)
-        bounds = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        per_pass = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+        bounds = per_pass * max(1, int(passes))
         # slices flow through ChainStream.map (three slices between submit and finish) with their frames uploaded two
         # slices ahead on the copy stream: the host only ever waits for read-backs of work queued an iteration earlier,
         # so neither the copy engines nor the SMs drain while it plans
@@ -1041,9 +1080,12 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
         labels: List[str] = []
         arrays = []
         k_total = 0
+        k_all = d2h = 0
         keep = []
         for c, res in enumerate(pipe.map(slices(), rng)):
             lo, hi = bounds[c]
+            if c % len(per_pass) == 0:                    # a new pass over the host batch: its results overwrite the previous pass's
+                labels, arrays, k_total = [], [], 0
             done = torch.cuda.Event()
             done.record(compute)
             slots[c % n_slots]["free"] = done
@@ -1059,12 +1101,15 @@ def run_chain_host(frames_host: torch.Tensor, backgrounds_host: torch.Tensor, pa
             items, aux, rot_index, angles = res._arrays
             arrays.append((items, aux, rot_index, angles, lo))
             k_total += k
+            k_all += k
+            d2h += int(res.images.numel())
         down.synchronize()
         compute.synchronize()
     merged = ChainResult(out_host[:k_total], labels, records=None, record_arrays=None)
     merged._chunks = arrays
     merged._records = None
     merged.h2d_bytes = state["h2d"]
+    merged.images_total, merged.d2h_bytes = k_all, d2h
     merged.__class__ = _ChunkedResult
     return merged
 
