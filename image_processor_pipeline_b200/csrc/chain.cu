@@ -1418,14 +1418,21 @@ __global__ void __launch_bounds__(128) chain_tables_kernel(const TabParams p) {
     int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
     if (xmax > in_size) xmax = in_size;
     xmax -= xmin;
+    // every weight is evaluated ONCE (two double-precision sin() each): windows of up to kTabKeep taps stay in registers /
+    // local memory between the normalisation sum and the quantisation; longer windows are re-evaluated
+    constexpr int kTabKeep = 24;
+    double wv[kTabKeep];
     double ww = 0.0;
-    for (int x = 0; x < xmax; ++x)
-        ww = __dadd_rn(ww, d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss)));
+    for (int x = 0; x < xmax; ++x) {
+        const double w = d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+        if (x < kTabKeep) wv[x] = w;
+        ww = __dadd_rn(ww, w);
+    }
     bool amb = false;
     for (int x = 0; x < ksize; ++x) {
         int c = 0;
         if (x < xmax) {
-            double w = d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+            double w = x < kTabKeep ? wv[x] : d_lanczos(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
             if (ww != 0.0) w = __ddiv_rn(w, ww);
             const double v = __dmul_rn(w, 4194304.0);
             const double t = (w < 0) ? __dadd_rn(-0.5, v) : __dadd_rn(0.5, v);
