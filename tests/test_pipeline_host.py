@@ -139,3 +139,25 @@ def test_parallel_workers_process_pool_for_host_functions(tmp_path):
     step = ProcessingStep("par", flaky_fn, tmp_path / "in", tmp_path / "out", workers=2)
     step.run()
     assert sorted(l["status"] for l in step.process_logs) == ["Success"] * 6
+
+
+def test_copy_helpers_follow_the_reference(tmp_path):
+    """transforms/copy.py:6-67 — pure file plumbing, kept for drop-in imports."""
+    from image_processor_pipeline_b200.transforms import copy as C
+    src = tmp_path / "src"; a = tmp_path / "a"; b = tmp_path / "b"
+    for d in (src, a, b):
+        d.mkdir()
+    (src / "img_0001.png").write_bytes(b"png")
+    (src / "img_0001.txt").write_text("0 0.5 0.5 0.1 0.1\n")
+    out = C.copy_img_with_labels(src / "img_0001.png", src / "img_0001.txt", [a, b])
+    assert out == [a / "img_0001.png", b / "img_0001.txt"] and (b / "img_0001.txt").read_text().startswith("0 0.5")
+    with pytest.raises(ValueError):
+        C.copy_img_with_labels(src / "img_0001.png", src / "img_0001.txt", [a])
+    assert C.copy_img_with_labels(src / "absent.png", src / "img_0001.txt", [a, b]) is None
+    assert C.copy_files(src / "img_0001.png", [a], suffix="v2") == a / "img_0001_v2.png"
+    assert C.copy_files(src / "img_0001.png", [a], replace_params=("img", "pic")) == a / "pic_0001.png"
+    assert C.copy_files(src / "img_0001.txt", [b]) == b / "img_0001.txt"
+    with pytest.raises(ValueError):
+        C.copy_files(src / "img_0001.png", [a], suffix="x", replace_params=("a", "b"))
+    with pytest.raises(IndexError):
+        C.copy_files(src / "img_0001.png", [])
