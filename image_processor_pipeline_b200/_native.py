@@ -103,6 +103,8 @@ PROTOTYPES = {
                                   _i32p, _vp, _int, _int, _int, _vp, _u8p, _vp]),
     "ipp_chain_layout_host": (_int, [_vp, _int, C.POINTER(PlanTotals)]),
     "ipp_host_round15": (C.c_double, [C.c_double]),
+    "ipp_host_hypot": (C.c_double, [C.c_double, C.c_double]),
+    "ipp_host_overlay_size": (_int, [_int, _int, _int, _int, C.c_double, _vp]),
     "ipp_host_format6": (_int, [C.c_double, C.c_char_p, C.POINTER(C.c_double)]),
     "ipp_chain_stage_c": (_int, [_u8p, _i64, _i64, C.POINTER(ChainGeom), _vp, _int, _u8p, _u8p, _i64, _i64, _int, _vp]),
     "ipp_chain_upload_windows": (_int, [_vp, _i64, _i64, _int, _int, _int, _vp, _int, _int, _u8p, _vp]),

@@ -17,6 +17,7 @@
 // (records, labels and the RNG state afterwards).
 #include "common.cuh"
 
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -202,16 +203,59 @@ static int rotation_plan(int w, int h, double angle, ipp_chain_rot* r, double* m
     return 0;
 }
 
+// math.hypot of CPython >= 3.10 for two finite arguments (Modules/mathmodule.c vector_norm): scaling by a power of two,
+// lossless squaring (fma) and addition (two-sum), a square root and one differential correction step.  It is NOT the C
+// library's hypot(): the two differ in the last bit now and then, and overlays.py:125 truncates a value derived from it with
+// int() — for a sprite that is limited by the background's height the expression is mathematically an integer, so the last
+// bit decides between h and h - 1.  (Found by tests/fuzz_parity.py: seed 705192.)
+static double py_hypot2(double a, double b) {
+    a = std::fabs(a);
+    b = std::fabs(b);
+    const double mx = a > b ? a : b;
+    if (std::isinf(mx)) return mx;
+    if (a != a || b != b) return NAN;
+    if (mx == 0.0) return mx;
+    int max_e;
+    std::frexp(mx, &max_e);
+    if (max_e < -1023) return DBL_MIN * py_hypot2(a / DBL_MIN, b / DBL_MIN);
+    const double scale = std::ldexp(1.0, -max_e);
+    double csum = 1.0, frac1 = 0.0, frac2 = 0.0;
+    const double v[2] = {a, b};
+    for (int i = 0; i < 2; ++i) {
+        const double x = v[i] * scale;                       // lossless scaling
+        const double hi = x * x, lo = std::fma(x, x, -hi);   // lossless squaring
+        const double sx = csum + hi, sy = (csum - sx) + hi;  // lossless addition (|csum| >= |hi|)
+        csum = sx;
+        frac1 += lo;
+        frac2 += sy;
+    }
+    double h = std::sqrt(csum - 1.0 + (frac1 + frac2));
+    {
+        const double hi = -h * h, lo = std::fma(-h, h, -hi);
+        const double sx = csum + hi, sy = (csum - sx) + hi;
+        csum = sx;
+        frac1 += lo;
+        frac2 += sy;
+    }
+    const double x = csum - 1.0 + (frac1 + frac2);
+    h += x / (2.0 * h);                                      // differential correction
+    return h / scale;
+}
+
 // reference transforms/overlays.py:106-126; false when PIL's resize would raise (size <= 0)
 static bool overlay_size(int ow, int oh, int bw, int bh, double ratio, int* nw, int* nh) {
     if (oh == 0) return false;
-    const double bg_diag = std::hypot((double)bw, (double)bh);
+    const double bg_diag = py_hypot2((double)bw, (double)bh);
     const double target = bg_diag * ratio;
     const double ar = (double)ow / (double)oh;
     const double h_max = std::fmin((double)bw / ar, (double)bh);
-    const double max_diag = std::hypot(ar * h_max, h_max);
+    const double max_diag = py_hypot2(ar * h_max, h_max);
     const double d = std::fmin(target, max_diag);
-    const double hh = std::sqrt(std::pow(d, 2.0) / (std::pow(ar, 2.0) + 1.0));
+    // Python's `x ** 2` is libm's pow(x, 2.0), which is NOT always x * x (glibc's pow is within 1 ulp, not correctly rounded:
+    // 1968.445400028335 ** 2 differs from the product in the last bit, and int() of the root then gives 1967 instead of 1968).
+    // The call goes through a volatile pointer so that the compiler cannot fold it into a multiplication.
+    static double (*volatile libm_pow)(double, double) = static_cast<double (*)(double, double)>(::pow);
+    const double hh = std::sqrt(libm_pow(d, 2.0) / (libm_pow(ar, 2.0) + 1.0));
     if (!(hh == hh)) return false;
     *nh = (int)hh;
     *nw = (int)(ar * (double)*nh);
@@ -650,6 +694,14 @@ int ipp_plan_enhance_host(int n, const uint8_t* do_blur, const uint8_t* do_rgb, 
 
 // the planner's exact-decimal helpers, exported so that tests can hold them against Python's round() / "%.6f"
 double ipp_host_round15(double x) { return ipp::plan::round15(x); }
+double ipp_host_hypot(double a, double b) { return ipp::plan::py_hypot2(a, b); }
+int ipp_host_overlay_size(int ow, int oh, int bw, int bh, double ratio, int32_t* nw_nh_out) {
+    if (!nw_nh_out) return -1;
+    int nw = 0, nh = 0;
+    const bool ok = ipp::plan::overlay_size(ow, oh, bw, bh, ratio, &nw, &nh);
+    nw_nh_out[0] = nw; nw_nh_out[1] = nh;
+    return ok ? 1 : 0;
+}
 int ipp_host_format6(double v, char* text_out48, double* parsed_out) {
     if (!text_out48) return -1;
     const int len = ipp::plan::fmt6(text_out48, v, parsed_out);

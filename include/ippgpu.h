@@ -312,6 +312,10 @@ int ipp_lanczos_row_host(int in_size, int out_size, int xx, int32_t* bounds2_hos
  * path): Python's round(x, 15) (PIL:Image.py:2541-2548 rounds the rotation matrix) and "%.6f" of a label number
  * together with the float64 np.loadtxt reads back from that text (overlays.py:149, crop_square.py:62-65,98-101). */
 double ipp_host_round15(double x);
+/* CPython's math.hypot (two arguments) and the overlay size math of overlays.py:106-126 built on it, exported for tests:
+ * returns 1 and {new_w, new_h} in nw_nh_out, or 0 when the resize would fail (size <= 0). */
+double ipp_host_hypot(double a, double b);
+int ipp_host_overlay_size(int ow, int oh, int bw, int bh, double ratio, int32_t* nw_nh_out);
 int ipp_host_format6(double v, char* text_out48, double* parsed_out);
 /* Device-side schedule of an item array (sizes, kind, flips, positions already set): coefficient-table
  * and fragment-table offsets, flat tile starts, sprite-workspace offsets, out_slot = index.  Called by

@@ -169,3 +169,28 @@ def test_native_enhance_plan_equals_python_draws_and_pillow_models():
         else:
             assert np.array_equal(luts[i], np.tile(np.arange(256, dtype=np.uint8), (3, 1)))
     assert rng.getstate() == ref.getstate()
+
+
+def test_native_hypot_and_overlay_size_equal_python():
+    """The planner's math.hypot (CPython's vector_norm, not libm's hypot) and the overlay size built on it (overlays.py:106-126)
+    against Python, on random inputs and on the height-limited cases where the expression is mathematically an integer and the
+    last bit of hypot decides int() (the fuzz case that exposed it: sprite 198 x 308 on a 319 x 105 background)."""
+    import math
+    import random
+    from image_processor_pipeline_b200 import hostmath
+    lib = _native.load()
+    rnd = random.Random(5)
+    for _ in range(20000):
+        a, b = rnd.uniform(0, 5000), rnd.uniform(0, 5000)
+        if rnd.random() < 0.3:
+            a, b = float(int(a)), float(int(b))
+        assert lib.ipp_host_hypot(a, b) == math.hypot(a, b)
+    out = np.zeros(2, dtype=np.int32)
+    cases = [(198, 308, 319, 105, 0.4329757405351776), (12, 564, 3595, 1968, 0.6696314906938445)]
+    for _ in range(20000):
+        cases.append((rnd.randint(1, 900), rnd.randint(1, 900), rnd.randint(8, 4000), rnd.randint(8, 2200), rnd.uniform(0.02, 1.2)))
+    for ow, oh, bw, bh, ratio in cases:
+        ok = lib.ipp_host_overlay_size(ow, oh, bw, bh, ratio, out.ctypes.data)
+        nw, nh = hostmath.overlay_size(ow, oh, bw, bh, ratio)
+        assert (int(out[0]), int(out[1])) == (nw, nh), (ow, oh, bw, bh, ratio)
+        assert bool(ok) == (nw > 0 and nh > 0)
