@@ -435,8 +435,15 @@ class ChainWorkload(Workload):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        from image_processor_pipeline_b200 import _native
+        _native.timing_report()
+        _native.timing_enable(True)                      # per-kernel device time of one more (untimed) noise step
+        self.run_pipelined(9, 1, frames, bgs, pipe)
+        rep = _native.timing_report()
+        _native.timing_enable(False)
         del frames, bgs
         return {"value_noise_frames": n / (ms * 1e-3),
+                "noise_frames_kernels_ms_per_step": {k: round(v[1], 4) for k, v in sorted(rep.items())},
                 "noise_frames_note": f"same chain, frames = uniform noise (worst case: every pixel classified, ~75 % of the frame is one component and becomes the sprite), {nb} frames x 6 steps, this rank only"}
 
 

@@ -122,7 +122,11 @@ def rotate_batch(imgs: torch.Tensor, rng=_random, angle_min: float = 1.0, angle_
             off += int(t2[0]); tiles += int(t2[1])
         totals[:] = (off, tiles)
     with torch.cuda.device(t.device):
-        pool = torch.empty(max(int(totals[0]), 256), dtype=torch.uint8, device=t.device)
+        # the pool's size follows the drawn angles: rounded up to an eighth of its power of two, so that consecutive batches ask the
+        # caching allocator for a size it has seen (a fresh multi-GB cudaMalloc per call cost more than the kernel)
+        need = max(int(totals[0]), 256)
+        gran = max(1 << 21, 1 << max(need.bit_length() - 4, 0))
+        pool = torch.empty((need + gran - 1) // gran * gran, dtype=torch.uint8, device=t.device)
         bbox = torch.empty((n, 4), dtype=torch.int32, device=t.device)
         items_d = chain._upload("rot_items", items, t.device)
         _native.check(lib.ipp_rotate_batch_u8(t.data_ptr(), W * c, H * W * c, W, H, c, n, items_d.data_ptr(), n, int(totals[1]), mode,

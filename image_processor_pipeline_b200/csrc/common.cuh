@@ -51,6 +51,12 @@ struct LaunchTimer {
     int slot_;
 };
 
+// output tile of rotate_batch_kernel (batch.cu); the host planner (planner.cu) counts the same tiles
+#ifndef IPP_ROT_TILE_H
+#define IPP_ROT_TILE_H 256
+#endif
+constexpr int kRotTileW = 64, kRotTileH = IPP_ROT_TILE_H;
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------- device helpers

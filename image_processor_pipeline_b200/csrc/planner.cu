@@ -581,9 +581,9 @@ int ipp_plan_rotate_batch_host(int src_w, int src_h, int n, double angle_min, do
         it->src = i; it->kind = r.kind;
         it->a0 = r.a0; it->a1 = r.a1; it->a2 = r.a2; it->a3 = r.a3; it->a4 = r.a4; it->a5 = r.a5;
         it->dst_w = r.canvas_w; it->dst_h = r.canvas_h;
-        it->tiles_x = (r.canvas_w + 63) / 64;                      // rotate_batch_kernel: 64 x 32 output tiles
+        it->tiles_x = (r.canvas_w + kRotTileW - 1) / kRotTileW;    // rotate_batch_kernel's output tiles
         it->tile_start = (int32_t)tiles;
-        tiles += (int64_t)it->tiles_x * ((r.canvas_h + 31) / 32);
+        tiles += (int64_t)it->tiles_x * ((r.canvas_h + kRotTileH - 1) / kRotTileH);
         IPP_REQUIRE(tiles < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_plan_rotate_batch_host: too many tiles; use a smaller batch");
         it->dst_off = off;
         off = align_up(off + (int64_t)((r.canvas_w + 3) & ~3) * 4 * r.canvas_h, 256);

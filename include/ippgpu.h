@@ -405,8 +405,8 @@ typedef struct ipp_rot_item {
     int32_t kind;                       /* 0 affine, 1 copy, 2 rot180, 3 rot90, 4 rot270            */
     int32_t a0, a1, a2, a3, a4, a5;     /* libImaging 16.16 coefficients (NEAREST, kind 0)          */
     int32_t dst_w, dst_h;               /* expanded canvas                                          */
-    int32_t tile_start;                 /* first 64 x 32 output tile of this canvas in the flat grid */
-    int32_t tiles_x;                    /* ceil(dst_w / 64); the canvas has tiles_x * ceil(dst_h / 32) tiles */
+    int32_t tile_start;                 /* first 64 x 256 output tile of this canvas in the flat grid */
+    int32_t tiles_x;                    /* ceil(dst_w / 64); the canvas has tiles_x * ceil(dst_h / 256) tiles */
     int64_t dst_off;                    /* byte offset of the canvas in dst_pool (256-byte aligned);
                                            rows are ((dst_w + 3) & ~3) * 4 bytes apart              */
     double m[6];                        /* PIL inverse matrix (BILINEAR, kind 0)                    */

@@ -1,12 +1,12 @@
 """Randomised parity sweep (not collected by pytest: run it by hand on a GPU box):
 
-    python tests/fuzz_parity.py [cases] [seed]  > profiles/r02/fuzz_r02.txt
+    python tests/fuzz_parity.py [cases] [seed] [--quiet]  > profiles/r02/fuzz_r02.txt
 
 Random frame / background sizes, border margins, filter lists (with zones / GIMP scale), rotation counts and angle ranges,
 symmetry pools, scale ranges, the enhance step on or off — the fused chain against the oracle chain (images bit-exact, labels
 string-equal, generator state equal), plus random batches through the batched operators (rotation nearest, overlay, key + keep
-largest, enhance) against the reference's cv2 / Pillow calls.  Prints one line per case and a summary; exits non-zero on the
-first mismatch."""
+largest, enhance) against the reference's cv2 / Pillow calls.  Prints one line per case (unless --quiet) and a summary; goes on after a mismatch (up to ten) and
+exits non-zero if there was one."""
 import random
 import sys
 import time
@@ -133,8 +133,10 @@ def ops_case(r: np.random.Generator, seed: int):
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    quiet = "--quiet" in sys.argv
     t0 = time.time()
     done = {"chain": 0, "ops": 0}
+    bad = []
     for c in range(cases):
         seed = seed0 * 100_000 + c
         r = np.random.default_rng(seed)
@@ -142,11 +144,18 @@ def main():
         try:
             line = fn(r, seed)
         except AssertionError as e:
-            print(f"case {c} seed {seed}: MISMATCH: {e}")
-            raise SystemExit(1)
+            print(f"case {c} seed {seed}: MISMATCH: {e}", flush=True)
+            bad.append(seed)
+            if len(bad) >= 10:
+                break
+            continue
         done[key] += 1
-        print(f"case {c:4d} ok  {line}")
-    print(f"SUMMARY: {done['chain']} random chain cases and {done['ops']} random batched-operator cases bit-exact against the oracle in {time.time() - t0:.0f} s")
+        if not quiet:
+            print(f"case {c:4d} ok  {line}")
+    print(f"SUMMARY: {done['chain']} random chain cases and {done['ops']} random batched-operator cases bit-exact against the oracle in {time.time() - t0:.0f} s"
+          + (f"; MISMATCHES at seeds {bad}" if bad else ""))
+    if bad:
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":
