@@ -208,7 +208,8 @@ constexpr int kSegBatch = IPP_SEG_BATCH;
 #define IPP_SEG_REFINE 20
 #endif
 constexpr int kSegRefine = IPP_SEG_REFINE;          // more cheaply-flagged groups than this: run the exact dark test
-constexpr size_t kSegSmem = 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192;
+constexpr size_t kSegSmem = 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192 + (size_t)kSegWarps * kSegBatch * 16;
+static_assert(kSegBatch >= 1 && kSegBatch <= 32, "a batch's descriptors are computed by one lane each");
 
 __global__ void __launch_bounds__(kSegThreads, 1024 / kSegThreads) chain_mask_seg_kernel(const MaskSegParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -235,11 +236,12 @@ __global__ void __launch_bounds__(kSegThreads, 1024 / kSegThreads) chain_mask_se
     for (int i = tid; i < 256; i += kSegThreads) hdiv[i] = g_hsv_hdiv[i];
     __syncthreads();
 
-    // ---- issue side: position of the next segment to request (warp-uniform registers)
-    uint32_t is_left = 0;                        // segments left in the drawn batch
-    int is_row = 0, is_sx = 0;
-    const uint8_t* is_rowptr = nullptr;          // first wanted byte of the current row
-    uint32_t is_outrow = 0;                      // word index of the current row's first mask word
+    // ---- issue side.  The descriptors of a drawn batch (source window, geometry, first mask word) are computed by its first
+    // lanes in parallel, one segment each, and parked in shared memory; requesting a segment is then one broadcast load plus
+    // lane 0's bulk copy (walking row / frame boundaries with warp-uniform pointer arithmetic cost ~45 instructions per segment,
+    // an eighth of the kernel).
+    uint4* desc = reinterpret_cast<uint4*>(smem + 65536 + (size_t)kSegWarps * kSegStages * kSegStageBytes + (size_t)kSegWarps * 192) + warp * kSegBatch;
+    uint32_t is_left = 0, is_k = 0;              // segments left in the drawn batch, next descriptor
     bool is_done = false;
     // per stage: word index of the segment's first mask word, and npx | shift << 16 (npx == 0: no segment)
     uint32_t d_out[kSegStages], d_geo[kSegStages];
@@ -253,41 +255,39 @@ __global__ void __launch_bounds__(kSegThreads, 1024 / kSegThreads) chain_mask_se
                 is_done = true;
             } else {
                 is_left = min((uint32_t)kSegBatch, p.n_segs - b);
-                const int frame = (int)(b / (uint32_t)p.segs_per_frame);
-                const int rem = (int)(b - (uint32_t)frame * (uint32_t)p.segs_per_frame);
-                is_row = rem / p.segs_per_row;
-                is_sx = rem - is_row * p.segs_per_row;
-                is_rowptr = p.frames + (int64_t)frame * p.stride + (int64_t)(p.crop_t + is_row) * p.pitch + (int64_t)p.crop_l * 3;
-                is_outrow = (uint32_t)((int64_t)frame * p.bits_stride + (int64_t)is_row * p.wpr);
+                is_k = 0;
+                __syncwarp();                    // every lane has read the last descriptor of the previous batch
+                if ((uint32_t)lane < is_left) {
+                    const uint32_t seg = b + (uint32_t)lane;
+                    const uint32_t frame = seg / (uint32_t)p.segs_per_frame;
+                    const uint32_t rem = seg - frame * (uint32_t)p.segs_per_frame;
+                    const uint32_t row = rem / (uint32_t)p.segs_per_row;
+                    const uint32_t sx = rem - row * (uint32_t)p.segs_per_row;
+                    const int x0 = (int)sx * kSegPx;
+                    const int npx = min(kSegPx, p.w - x0);
+                    const uint8_t* src = p.frames + (int64_t)frame * p.stride + (int64_t)(p.crop_t + (int)row) * p.pitch + (int64_t)(p.crop_l + x0) * 3;
+                    const uint32_t shift = (uint32_t)((uintptr_t)src & 15u);
+                    const uint64_t base = (uint64_t)(uintptr_t)(src - shift);
+                    desc[lane] = make_uint4((uint32_t)base, (uint32_t)(base >> 32), (uint32_t)npx | (shift << 16),
+                                            (uint32_t)((int64_t)frame * p.bits_stride + (int64_t)row * p.wpr) + sx * (kSegPx / 32));
+                }
+                __syncwarp();
             }
         }
         if (is_done) {
             d_geo[s] = 0;
             return;
         }
-        const int x0 = is_sx * kSegPx;
-        const int npx = min(kSegPx, p.w - x0);
-        const uint8_t* src = is_rowptr + x0 * 3;
-        const uint32_t shift = (uint32_t)((uintptr_t)src & 15u);
-        d_out[s] = is_outrow + (uint32_t)is_sx * (kSegPx / 32);
-        d_geo[s] = (uint32_t)npx | (shift << 16);
+        const uint4 d = desc[is_k];
+        d_out[s] = d.w;
+        d_geo[s] = d.z;
         if (lane == 0) {
-            const uint32_t bytes = (shift + (uint32_t)npx * 3u + 15u) & ~15u;
+            const uint32_t bytes = ((d.z >> 16) + (d.z & 0xffffu) * 3u + 15u) & ~15u;
             mbar_expect_tx(&full[warp][s], bytes);
-            bulk_g2s(ring + (size_t)s * kSegStageBytes, src - shift, bytes, &full[warp][s]);
+            bulk_g2s(ring + (size_t)s * kSegStageBytes, reinterpret_cast<const void*>((uintptr_t)(((uint64_t)d.y << 32) | d.x)), bytes, &full[warp][s]);
         }
+        ++is_k;
         --is_left;
-        if (++is_sx == p.segs_per_row) {
-            is_sx = 0;
-            is_outrow += (uint32_t)p.wpr;
-            if (++is_row == p.h) {               // next frame: rows are not contiguous across frames in general
-                is_row = 0;
-                is_rowptr += p.stride - (int64_t)(p.h - 1) * p.pitch;
-                is_outrow += (uint32_t)(p.bits_stride - (int64_t)p.h * p.wpr);
-            } else {
-                is_rowptr += p.pitch;
-            }
-        }
     };
 
     const int dark_mode = p.f.dark_mode;
@@ -346,8 +346,12 @@ __global__ void __launch_bounds__(kSegThreads, 1024 / kSegThreads) chain_mask_se
                     }
                 }
             }
-            reinterpret_cast<uint32_t*>(nib)[lane] = 0u;                    // 16 pixels keyed out unless pass 2 says otherwise
             const uint32_t balA = __ballot_sync(0xffffffffu, needA), balB = __ballot_sync(0xffffffffu, needB);
+            if ((balA | balB) == 0u) {                                      // nothing above the dark threshold: sixteen zero words
+                if (lane < 16 && 32 * lane < npx) p.bits[(size_t)d_out[s] + lane] = 0u;
+                continue;
+            }
+            reinterpret_cast<uint32_t*>(nib)[lane] = 0u;                    // 16 pixels keyed out unless pass 2 says otherwise
             const int nA = __popc(balA);
             const int ntasks = 2 * (nA + __popc(balB));
             if (needA) wq[__popc(balA & lt_mask)] = (uint8_t)g0;
