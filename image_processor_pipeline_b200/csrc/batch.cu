@@ -317,33 +317,61 @@ int ipp_sprites_export_u8(const ipp_chain_item* items_host, int n_items, const u
 // (The key's alpha is 0 or 255; pixels_isolés zeroes every pixel outside the largest component, and an image without any
 // foreground keeps its all-zero alpha.)  thread = 4 pixels: 12 source bytes, 4 mask bits, one 16-byte store.
 namespace ipp {
+#ifndef IPP_BGRA_QUADS
+#define IPP_BGRA_QUADS 2
+#endif
+constexpr int kBgraQuads = IPP_BGRA_QUADS;     // 4-pixel groups per thread: all their loads are in flight before the first store
+// grid = (groups of one image / (256 * kBgraQuads), images): 32-bit index arithmetic (a 64-bit division per thread made the
+// one-group-per-thread form of this kernel issue-bound at 0.64 of the copy peak)
 __global__ void __launch_bounds__(256) bgra_from_keep_kernel(const uint8_t* __restrict__ frames, int64_t pitch, int64_t stride,
                                                              int crop_l, int crop_t, int w, int h,
                                                              const uint32_t* __restrict__ bits, int64_t bits_stride, int wpr,
-                                                             uint8_t* __restrict__ out, int64_t out_pitch, int64_t out_stride, int n) {
-    const int q = (w + 3) >> 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = (int64_t)q * h;
-    if (idx >= per * n) return;
-    const int img = (int)(idx / per);
-    const int rem = (int)(idx - (int64_t)img * per);
-    const int y = rem / q, x = (rem - y * q) * 4;
-    const uint8_t* s = frames + (int64_t)img * stride + (int64_t)(crop_t + y) * pitch + (int64_t)(crop_l + x) * 3;
-    const uint32_t word = bits[(int64_t)img * bits_stride + (int64_t)y * wpr + (x >> 5)];
-    const uint32_t m = word >> (x & 31);                 // x is a multiple of 4: the four bits sit in one word
-    uint8_t* d = out + (int64_t)img * out_stride + (int64_t)y * out_pitch + (int64_t)x * 4;
-    if (x + 3 < w && ((((uintptr_t)s) & 3) == 0) && ((((uintptr_t)d) & 15) == 0)) {
-        const uint32_t a = ldg_stream4(s), b = ldg_stream4(s + 4), c = ldg_stream4(s + 8);     // b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-        uint4 v;
-        v.x = (a & 0x00ffffffu) | ((m & 1u) ? 0xff000000u : 0u);
-        v.y = __funnelshift_r(a, b, 24) & 0x00ffffffu; v.y |= (m & 2u) ? 0xff000000u : 0u;
-        v.z = __funnelshift_r(b, c, 16) & 0x00ffffffu; v.z |= (m & 4u) ? 0xff000000u : 0u;
-        v.w = (c >> 8) | ((m & 8u) ? 0xff000000u : 0u);
-        stg_stream16(d, v);
-    } else {
-        for (int k = 0; k < 4 && x + k < w; ++k) {
-            d[4 * k + 0] = s[3 * k + 0]; d[4 * k + 1] = s[3 * k + 1]; d[4 * k + 2] = s[3 * k + 2];
-            d[4 * k + 3] = ((m >> k) & 1u) ? 255 : 0;
+                                                             uint8_t* __restrict__ out, int64_t out_pitch, int64_t out_stride, int img0) {
+    const uint32_t q = (uint32_t)(w + 3) >> 2, per = q * (uint32_t)h;
+    const int img = img0 + (int)blockIdx.y;
+    const uint32_t rem0 = blockIdx.x * (256u * kBgraQuads) + threadIdx.x;
+    const uint8_t* fbase = frames + (int64_t)img * stride + (int64_t)crop_t * pitch + (int64_t)crop_l * 3;
+    uint8_t* obase = out + (int64_t)img * out_stride;
+    const uint32_t* bbase = bits + (int64_t)img * bits_stride;
+    const uint8_t* sp[kBgraQuads];
+    uint8_t* dp[kBgraQuads];
+    uint32_t a[kBgraQuads], b[kBgraQuads], c[kBgraQuads], m[kBgraQuads];
+    int left[kBgraQuads];                      // pixels of the group inside the row; 0 = no group; < 0 = slow path (unaligned / ragged)
+#pragma unroll
+    for (int k = 0; k < kBgraQuads; ++k) {
+        const uint32_t rem = rem0 + 256u * k;
+        left[k] = 0;
+        if (rem >= per) continue;
+        const uint32_t y = rem / q, x = (rem - y * q) * 4u;
+        const uint8_t* s = fbase + (int64_t)y * pitch + x * 3u;
+        uint8_t* d = obase + (int64_t)y * out_pitch + x * 4u;
+        sp[k] = s; dp[k] = d;
+        m[k] = __ldg(bbase + y * (uint32_t)wpr + (x >> 5)) >> (x & 31u);      // x is a multiple of 4: the four bits sit in one word
+        left[k] = min(4, w - (int)x);
+        if (left[k] == 4 && ((((uintptr_t)s) & 3) == 0) && ((((uintptr_t)d) & 15) == 0)) {
+            // three loads of one lane sit 12 bytes apart: the requests of a warp touch the same sectors, the second and third hit L1
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s);
+            a[k] = __ldg(s32); b[k] = __ldg(s32 + 1); c[k] = __ldg(s32 + 2);             // b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+        } else {
+            left[k] = -left[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kBgraQuads; ++k) {
+        if (left[k] == 4) {
+            uint4 v;
+            v.x = (a[k] & 0x00ffffffu) | ((m[k] & 1u) ? 0xff000000u : 0u);
+            v.y = __funnelshift_r(a[k], b[k], 24) & 0x00ffffffu; v.y |= (m[k] & 2u) ? 0xff000000u : 0u;
+            v.z = __funnelshift_r(b[k], c[k], 16) & 0x00ffffffu; v.z |= (m[k] & 4u) ? 0xff000000u : 0u;
+            v.w = (c[k] >> 8) | ((m[k] & 8u) ? 0xff000000u : 0u);
+            stg_stream16(dp[k], v);
+        } else if (left[k] < 0) {
+            const uint8_t* s = sp[k];
+            uint8_t* d = dp[k];
+            for (int j = 0; j < -left[k]; ++j) {
+                d[4 * j + 0] = s[3 * j + 0]; d[4 * j + 1] = s[3 * j + 1]; d[4 * j + 2] = s[3 * j + 2];
+                d[4 * j + 3] = ((m[k] >> j) & 1u) ? 255 : 0;
+            }
         }
     }
 }
@@ -358,11 +386,14 @@ extern "C" int ipp_bgra_from_keep_u8(const uint8_t* frames, int64_t frame_pitch,
     IPP_REQUIRE(frames && workspace && out && n >= 1, IPP_ERR_BAD_ARG, "ipp_bgra_from_keep_u8: bad arguments");
     IPP_REQUIRE(frame_pitch >= (int64_t)g->frame_w * 3 && out_pitch >= (int64_t)g->crop_w * 4, IPP_ERR_BAD_SHAPE, "ipp_bgra_from_keep_u8: pitch smaller than a row");
     const CclGeom cg = make_ccl_geom(g->crop_w, g->crop_h);
-    const int64_t threads = (int64_t)((g->crop_w + 3) >> 2) * g->crop_h * n;
-    IPP_REQUIRE(threads / 256 < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_bgra_from_keep_u8: batch too large");
-    { ipp::LaunchTimer _lt("bgra_from_keep_kernel", st);
-      bgra_from_keep_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(frames, frame_pitch, frame_stride, g->crop_l, g->crop_t, g->crop_w, g->crop_h,
-                                                                               (const uint32_t*)workspace, cg.bits_stride, cg.wpr, out, out_pitch, out_stride, n); }
+    const int64_t per = (int64_t)((g->crop_w + 3) >> 2) * g->crop_h;
+    IPP_REQUIRE(per < (1LL << 31), IPP_ERR_UNSUPPORTED, "ipp_bgra_from_keep_u8: image too large");
+    for (int img0 = 0; img0 < n; img0 += 65535) {
+        const dim3 grid((unsigned)ceil_div(per, 256 * kBgraQuads), (unsigned)std::min(65535, n - img0));
+        ipp::LaunchTimer _lt("bgra_from_keep_kernel", st);
+        bgra_from_keep_kernel<<<grid, 256, 0, st>>>(frames, frame_pitch, frame_stride, g->crop_l, g->crop_t, g->crop_w, g->crop_h,
+                                                    (const uint32_t*)workspace, cg.bits_stride, cg.wpr, out, out_pitch, out_stride, img0);
+    }
     IPP_LAUNCH_CHECK();
     return IPP_OK;
 }
