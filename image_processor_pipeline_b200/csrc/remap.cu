@@ -52,6 +52,29 @@ __device__ __forceinline__ uint4 gather_reversed16(const uint8_t* win, uint32_t 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// 3-byte pixels, mirrored: 16 pixels = 48 bytes at a time.  The 48 output bytes starting at pixel 16 u of the mirrored row are the
+// 16 source pixels that END at pixel out_w - 1 - 16 u, in reverse pixel order: three unaligned 16-byte window loads, then the
+// pixels of every 12-byte group swap places with four byte permutes (b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3 ->
+// b3 g3 r3 b2 | g2 r2 b1 g1 | r1 b0 g0 r0) and the four groups leave in reverse order — ~50 instructions per 48 bytes where the
+// byte-wise gather needs ~330 (the mirrored variants made the kernel issue-bound).
+__device__ __forceinline__ void reverse_group3(uint32_t x, uint32_t y, uint32_t z, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+    o0 = __byte_perm(y, z, 0x2765);
+    o1 = __byte_perm(__byte_perm(y, z, 0x0043), x, 0x3710);
+    o2 = __byte_perm(x, y, 0x2105);
+}
+__device__ __forceinline__ void store_reversed48(const uint8_t* win, uint32_t src_off, uint8_t* d) {
+    const uint4 a = window_load16(win, src_off), b = window_load16(win, src_off + 16), c = window_load16(win, src_off + 32);
+    // source groups g0 = a.xyz, g1 = a.w b.xy, g2 = b.zw c.x, g3 = c.yzw; output = rev(g3) rev(g2) rev(g1) rev(g0)
+    uint4 o0, o1, o2;
+    reverse_group3(c.y, c.z, c.w, o0.x, o0.y, o0.z);
+    reverse_group3(b.z, b.w, c.x, o0.w, o1.x, o1.y);
+    reverse_group3(a.w, b.x, b.y, o1.z, o1.w, o2.x);
+    reverse_group3(a.x, a.y, a.z, o2.y, o2.z, o2.w);
+    stg_stream16(d, o0);
+    stg_stream16(d + 16, o1);
+    stg_stream16(d + 32, o2);
+}
+
 __global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -89,6 +112,22 @@ __global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) 
         if (dimg == nullptr) continue;
         dimg += (int64_t)img * p.dst_img_stride;
         const bool rev = (v & 1) != 0;
+        // mirrored 3-byte pixels with 16-byte aligned destination rows: 48-byte units (16 pixels); the generic loop below then
+        // only sees the bytes behind the last whole unit
+        const bool fast_rev = rev && p.bpp == 3 && ((((uintptr_t)dimg) | (uintptr_t)p.dst_pitch) & 15) == 0;
+        const uint32_t upr = fast_rev ? rowbytes / 48u : 0u;     // units per row
+        if (fast_rev) {
+            for (uint32_t it = tid; it < (uint32_t)nrows * upr; it += kRowsThreads) {
+                const uint32_t r = it / upr, u = it - r * upr;
+                const int y = row0 + (int)r;
+                const int drow = (v & 2) ? (p.out_h - 1 - y) : y;
+                const uint8_t* s = src_img + (int64_t)(y0 + y) * p.src_pitch + (int64_t)x0 * 3;
+                const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
+                store_reversed48(smem + (size_t)r * p.smem_row_stride, shift + (uint32_t)(p.out_w - 16 - 16 * (int)u) * 3u,
+                                 dimg + (int64_t)drow * p.dst_pitch + 48u * u);
+            }
+        }
+        const uint32_t c_first = upr * 3u;                       // first 16-byte chunk the generic loop still owns (head == 0 here)
         for (uint32_t it = tid; it < items; it += kRowsThreads) {
             const uint32_t r = it / cpr;
             const uint32_t c = it - r * cpr;
@@ -100,6 +139,7 @@ __global__ void __launch_bounds__(kRowsThreads) rows_kernel(const RowsParams p) 
             const uint32_t shift = (uint32_t)((uintptr_t)s & 15);
             const RowSplit sp = split_row(d, rowbytes);
             if (c < sp.nb) {
+                if (c < c_first) continue;
                 const uint32_t ob = sp.head + (c << 4);
                 uint4 val;
                 if (!rev) {
@@ -139,8 +179,11 @@ static int launch_rows(RowsParams& p, int n, cudaStream_t st) {
     p.smem_row_stride = staged_row_stride(rowbytes);
     IPP_REQUIRE(p.smem_row_stride <= 200 * 1024, IPP_ERR_UNSUPPORTED,
                 "remap: a row of %u bytes does not fit the shared-memory staging buffer", rowbytes);
-    // ~16 KB of rows per CTA: enough bytes in flight per SM with several resident CTAs
-    int rows = (int)(16384 / p.smem_row_stride);
+    // ~48 KB of rows per CTA (4 resident CTAs: ~190 KB in flight per SM).  Measured on C1 (1024 x 1024 x 3, one read + four
+    // writes): 16 / 24 / 32 / 48 / 64 KB = 0.74 / 0.81 / 0.82 / 0.86 / 0.83 of the copy peak — a CTA loads, waits and then writes,
+    // so the bytes in flight come from the other resident CTAs, and at 16 KB the register file allowed only 6 of them
+    static const int budget_env = getenv("IPP_ROWS_SMEM") ? atoi(getenv("IPP_ROWS_SMEM")) : 0;
+    int rows = (int)((budget_env > 0 ? budget_env : 49152) / p.smem_row_stride);
     if (rows < 1) rows = 1;
     if (rows > p.out_h) rows = p.out_h;
     // keep the grid at >= ~4 waves of CTAs when the image is small
