@@ -692,11 +692,11 @@ def main():
     achieved = alg[dom] / (dms / dcnt * 1e-3) / 1e9
     traffic, traffic_src = None, None                                  # dram bytes per launch from the committed ncu --set full capture
     tp = ROOT / "profiles" / "traffic.json"
-    if tp.is_file() and args.config == "chain":
+    if tp.is_file() and args.config in ("chain", "c5", "c2", "c4"):      # per-frame figures of 1080p / C2 / C4 captures (c5: 4K frames = 4 x the bytes)
         rec = json.loads(tp.read_text()).get(dom)
         if rec:
-            traffic = rec["dram_bytes_per_frame"] * wl.B
-            traffic_src = rec["source"]
+            traffic = rec["dram_bytes_per_frame"] * wl.B * (4 if args.config == "c5" else 1)
+            traffic_src = rec["source"] + (" — scaled x4 from the 1080p capture to 3840x2160 frames" if args.config == "c5" else "")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": dms / dcnt,
