@@ -69,10 +69,24 @@ __global__ void __launch_bounds__(256) enh_luma_sum_kernel(const EnhParams p) {
         lb[c] = (uint8_t)blend_byte(0.0f, (float)c, it.brightness, it.brightness >= 0.0f && it.brightness <= 1.0f);
     }
     __syncthreads();
-    const int64_t npx = (int64_t)p.w * p.h, ngrp = (npx + 3) >> 2;
+    const int64_t npx = (int64_t)p.w * p.h;
     const uint8_t* src = p.src + (int64_t)img * p.stride;
-    unsigned long long sum = 0;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * blockDim.x) {
+    // whole 4-pixel groups (12 aligned bytes) without per-pixel bounds tests, 32-bit indices and a 32-bit partial sum (a thread
+    // sees a few dozen pixels); the ragged tail / an unaligned image goes through the checked loader
+    const uint32_t nfull = ((((uintptr_t)src) & 3) == 0 && npx < (1ll << 31)) ? (uint32_t)(npx >> 2) : 0u;
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t part = 0;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfull; t += gridDim.x * blockDim.x) {
+        const uint32_t a = ldg_stream4(src32 + 3 * t), b = ldg_stream4(src32 + 3 * t + 1), d = ldg_stream4(src32 + 3 * t + 2);
+        // a = r0 g0 b0 r1 | b = g1 b1 r2 g2 | d = b2 r3 g3 b3
+        part += luma(lb[a & 255u], lb[(a >> 8) & 255u], lb[(a >> 16) & 255u]);
+        part += luma(lb[a >> 24], lb[b & 255u], lb[(b >> 8) & 255u]);
+        part += luma(lb[(b >> 16) & 255u], lb[b >> 24], lb[d & 255u]);
+        part += luma(lb[(d >> 8) & 255u], lb[(d >> 16) & 255u], lb[d >> 24]);
+    }
+    unsigned long long sum = part;
+    const int64_t ngrp = (npx + 3) >> 2;
+    for (int64_t t = (int64_t)nfull + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * blockDim.x) {
         uint8_t c[12];
         load_px4(src, t, npx, c);
 #pragma unroll
@@ -105,28 +119,41 @@ __global__ void __launch_bounds__(256) enh_point_kernel(const EnhParams p) {
     const bool col_in = it.color >= 0.0f && it.color <= 1.0f;
     const uint8_t* src = p.src + (int64_t)img * p.stride;
     uint8_t* dst = p.dst + (int64_t)img * p.stride;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * blockDim.x) {
+    auto pixel = [&](uint32_t c0, uint32_t c1, uint32_t c2, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+        const uint32_t r = l1[c0], g = l1[c1], b = l1[c2];
+        const float L = (float)luma(r, g, b);
+        o0 = blend_byte(L, (float)r, it.color, col_in);
+        o1 = blend_byte(L, (float)g, it.color, col_in);
+        o2 = blend_byte(L, (float)b, it.color, col_in);
+        if (lut_here) { o0 = lc[o0]; o1 = lc[256 + o1]; o2 = lc[512 + o2]; }
+    };
+    // whole 4-pixel groups: three aligned words in, three out, 32-bit indices, no per-pixel bounds tests
+    const uint32_t nfull = ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0 && npx < (1ll << 31)) ? (uint32_t)(npx >> 2) : 0u;
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfull; t += gridDim.x * blockDim.x) {
+        const uint32_t a = ldg_stream4(src32 + 3 * t), b = ldg_stream4(src32 + 3 * t + 1), d = ldg_stream4(src32 + 3 * t + 2);
+        uint32_t o[12];
+        pixel(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, o[0], o[1], o[2]);
+        pixel(a >> 24, b & 255u, (b >> 8) & 255u, o[3], o[4], o[5]);
+        pixel((b >> 16) & 255u, b >> 24, d & 255u, o[6], o[7], o[8]);
+        pixel((d >> 8) & 255u, (d >> 16) & 255u, d >> 24, o[9], o[10], o[11]);
+        dst32[3 * t] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        dst32[3 * t + 1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+        dst32[3 * t + 2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
+    }
+    for (int64_t t = (int64_t)nfull + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ngrp; t += (int64_t)gridDim.x * blockDim.x) {
         uint8_t c[12];
         load_px4(src, t, npx, c);
         uint8_t o[12];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t r = l1[c[3 * k]], g = l1[c[3 * k + 1]], b = l1[c[3 * k + 2]];
-            const float L = (float)luma(r, g, b);
-            uint32_t r2 = blend_byte(L, (float)r, it.color, col_in), g2 = blend_byte(L, (float)g, it.color, col_in),
-                     b2 = blend_byte(L, (float)b, it.color, col_in);
-            if (lut_here) { r2 = lc[r2]; g2 = lc[256 + g2]; b2 = lc[512 + b2]; }
+            uint32_t r2, g2, b2;
+            pixel(c[3 * k], c[3 * k + 1], c[3 * k + 2], r2, g2, b2);
             o[3 * k] = (uint8_t)r2; o[3 * k + 1] = (uint8_t)g2; o[3 * k + 2] = (uint8_t)b2;
         }
         uint8_t* d = dst + 12 * t;
-        if (4 * t + 3 < npx && ((((uintptr_t)d) & 3) == 0)) {
-            uint32_t w[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) w[j] = o[4 * j] | (o[4 * j + 1] << 8) | (o[4 * j + 2] << 16) | ((uint32_t)o[4 * j + 3] << 24);
-            reinterpret_cast<uint32_t*>(d)[0] = w[0]; reinterpret_cast<uint32_t*>(d)[1] = w[1]; reinterpret_cast<uint32_t*>(d)[2] = w[2];
-        } else {
-            for (int k = 0; k < 12 && 4 * t + k / 3 < npx; ++k) d[k] = o[k];
-        }
+        for (int k = 0; k < 12 && 4 * t + k / 3 < npx; ++k) d[k] = o[k];
     }
 }
 
@@ -143,9 +170,10 @@ __device__ __forceinline__ uint8_t box_at(const uint8_t* line, int x, int n, int
 // tx, tx + 128, ... of row ty.  Rows are staged as one 32-bit word per pixel (R | G << 8 | B << 16): a neighbour is ONE shared
 // load and the three channels are summed at once in two 16-bit x 2 accumulators (the kernel was bound by byte loads before).
 constexpr int kBlurRows = 8;
-__global__ void __launch_bounds__(1024) enh_blur_h_kernel(const EnhParams p) {
+__global__ void __launch_bounds__(1024) enh_blur_h_kernel(const EnhParams p, int walker) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int img = p.blur_list[blockIdx.y];
+    if (walker && p.items[img].box_radius <= 3) return;               // handled by the register walker (enh_blur_hwalk_kernel)
     const ipp_enhance_item it = p.items[img];
     const int rowbytes = p.w * 3;
     const int y0 = blockIdx.x * kBlurRows, nr = min(kBlurRows, p.h - y0);
@@ -341,6 +369,67 @@ __global__ void __launch_bounds__(128) enh_blur_vwalk_kernel(const EnhParams p) 
     }
 }
 
+// three horizontal passes, radius <= 3: the vertical walker turned by 90 degrees.  Eight image rows are staged as one 32-bit word
+// per pixel (R | G << 8 | B << 16: the byte lanes of a word are the channels, exactly what walk_column sums in parallel); one warp
+// per row, lane = a segment of the row, which it walks through the three chained sliding windows in registers — one shared load
+// and one shared store per pixel and pass chain, where the windowed kernel above re-reads 2r + 3 neighbours per pixel and pass.
+// A segment starts 3 (r + 1) pixels early (walk_column's warm-up); its length is odd so that the 32 lanes of a warp sit in
+// different banks.
+constexpr int kHwRows = 8;
+__global__ void __launch_bounds__(32 * kHwRows) enh_blur_hwalk_kernel(const EnhParams p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int img = p.blur_list[blockIdx.y];
+    const ipp_enhance_item it = p.items[img];
+    if (it.box_radius > 3) return;                                    // generic kernel
+    const int rowbytes = p.w * 3;
+    const int y0 = blockIdx.x * kHwRows, nr = min(kHwRows, p.h - y0);
+    const int tid = threadIdx.x;
+    uint32_t* a = reinterpret_cast<uint32_t*>(sm);
+    uint32_t* b = a + (size_t)kHwRows * p.w;
+    const uint8_t* src = p.dst + (int64_t)img * p.stride + (int64_t)y0 * rowbytes;      // the point pass wrote dst
+    const int npx = nr * p.w;
+    for (int i = tid; i < npx; i += 32 * kHwRows) {
+        const uint8_t* q = src + 3 * i;
+        a[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+    }
+    __syncthreads();
+    {
+        const int row = tid >> 5, seg = tid & 31;
+        const int S = ((p.w + 31) >> 5) | 1;
+        const int x0 = seg * S, x1 = min(x0 + S, p.w);
+        if (row < nr && x0 < x1) {
+            const int s0 = max(x0 - 3 * (it.box_radius + 1), 0);
+            const uint32_t* ws = a + (size_t)row * p.w + s0;
+            uint32_t* wd = b + (size_t)row * p.w + s0;
+            const int hh = p.w - s0, first = x0 - s0, count = x1 - x0;
+            switch (it.box_radius) {
+                case 0: walk_column<0>(ws, wd, 1, hh, first, count, it.ww, it.fw, nullptr, false, 0); break;
+                case 1: walk_column<1>(ws, wd, 1, hh, first, count, it.ww, it.fw, nullptr, false, 0); break;
+                case 2: walk_column<2>(ws, wd, 1, hh, first, count, it.ww, it.fw, nullptr, false, 0); break;
+                default: walk_column<3>(ws, wd, 1, hh, first, count, it.ww, it.fw, nullptr, false, 0); break;
+            }
+        }
+    }
+    __syncthreads();
+    uint8_t* dst = p.tmp + (int64_t)blockIdx.y * p.stride + (int64_t)y0 * rowbytes;
+    const int total = nr * rowbytes;
+    if ((((uintptr_t)dst) & 3) == 0 && (total & 3) == 0) {
+        // word j of the packed rows = bytes 4j .. 4j+3 = channels (4j + t) % 3 of pixels (4j + t) / 3
+        for (int j = tid; j < (total >> 2); j += 32 * kHwRows) {
+            const int px = (4 * j) / 3, ph = 4 * j - 3 * px;          // ph = 0, 1, 2
+            const uint32_t v0 = b[px], v1 = b[min(px + 1, npx - 1)];
+            // 6 candidate bytes: v0 channels 0..2 then v1 channels 0..2; the word takes 4 of them starting at ph
+            const uint64_t six = (uint64_t)(v0 & 0x00ffffffu) | ((uint64_t)(v1 & 0x00ffffffu) << 24);
+            reinterpret_cast<uint32_t*>(dst)[j] = (uint32_t)(six >> (8 * ph));
+        }
+    } else {
+        for (int i = tid; i < total; i += 32 * kHwRows) {
+            const int px = i / 3;                      // constant divisor: a multiply
+            dst[i] = (uint8_t)(b[px] >> (8 * (i - 3 * px)));
+        }
+    }
+}
+
 }  // namespace ipp
 
 extern "C" {
@@ -393,7 +482,19 @@ int ipp_enhance_batch_u8(const uint8_t* src, uint8_t* dst, int w, int h, int n, 
             IPP_CUDA(cudaFuncSetAttribute(enh_blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_v, 48 * 1024)));
             if (dev_id >= 0 && dev_id < 64) set_v[dev_id] = smem_v;
         }
-        { ipp::LaunchTimer _lt("enh_blur_h_kernel", st); enh_blur_h_kernel<<<dim3(ceil_div(h, kBlurRows), n_blur), dim3(128, kBlurRows), smem_h, st>>>(p); }
+        // horizontal passes: the register walker takes the images with a box radius <= 3, the windowed kernel the others
+        static const bool h_walker = getenv("IPP_ENH_NO_HWALK") == nullptr;
+        if (h_walker) {
+            const size_t smem_w = 2 * (size_t)kHwRows * w * 4;
+            static size_t set_w[64] = {};
+            if (dev_id < 0 || dev_id >= 64 || smem_w > set_w[dev_id]) {
+                IPP_CUDA(cudaFuncSetAttribute(enh_blur_hwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_w, 48 * 1024)));
+                if (dev_id >= 0 && dev_id < 64) set_w[dev_id] = smem_w;
+            }
+            { ipp::LaunchTimer _lt("enh_blur_hwalk_kernel", st); enh_blur_hwalk_kernel<<<dim3(ceil_div(h, kHwRows), n_blur), 32 * kHwRows, smem_w, st>>>(p); }
+            IPP_LAUNCH_CHECK();
+        }
+        { ipp::LaunchTimer _lt("enh_blur_h_kernel", st); enh_blur_h_kernel<<<dim3(ceil_div(h, kBlurRows), n_blur), dim3(128, kBlurRows), smem_h, st>>>(p, h_walker ? 1 : 0); }
         IPP_LAUNCH_CHECK();
         // vertical passes: the register walker takes the images with a box radius <= 3 (and 4-byte-multiple rows), the generic
         // shared-memory kernel the others; each kernel returns at once for the images of the other
