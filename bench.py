@@ -416,7 +416,7 @@ class ChainWorkload(Workload):
         return {"pipelined_slice_frames": self.args.e2e_chunk, "frames_per_step": self.E,
                 "steps_streamed_back_to_back": bool(self.args.e2e_stream),
                 "background_upload": "whole images" if self.args.no_bg_windows else
-                "square-crop windows only (planned offsets known before the copy; cudaMemcpy2DAsync per item)"}
+                "square-crop windows only (planned offsets known before the copy; rows <= 4 KB: gathered from the pinned host buffer by a small kernel over PCIe, longer rows: cudaMemcpy2DAsync per item)"}
 
     def extra(self):
         """Content sensitivity: the same chain on UNIFORM-NOISE frames (SURVEY.md §8d's generic generator).  The key

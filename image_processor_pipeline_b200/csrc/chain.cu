@@ -1381,6 +1381,59 @@ __global__ void __launch_bounds__(kPasteThreads) chain_paste_kernel(const CParam
     }
 }
 
+// ---- crop windows straight out of pinned host memory.  The copy engines move the 2-D windows (3240 of 5760 bytes per row) at
+// ~36 GB/s next to the contiguous frame uploads; here the SMs read the rows themselves (zero-copy loads over PCIe, every aligned
+// 16-byte vector of a row exactly once, staged per warp in shared memory and re-cut to the destination's alignment).  A small
+// persistent grid: the bytes in flight (8 warps x ~3 KB per CTA) are what the link needs, not the SMs.
+constexpr int kWinMaxItems = 256;
+struct WinGatherParams {
+    const uint8_t* src[kWinMaxItems];      // first byte of every item's window (host, device-accessible)
+    int64_t bg_pitch;
+    uint8_t* dst;
+    int out_size, n;
+    uint32_t smem_row_stride;
+};
+__global__ void __launch_bounds__(256) window_gather_kernel(const __grid_constant__ WinGatherParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* buf = smem + (size_t)warp * p.smem_row_stride;
+    const uint32_t rowbytes = (uint32_t)p.out_size * 3u;
+    const int total_rows = p.n * p.out_size;
+    for (int r = blockIdx.x * 8 + warp; r < total_rows; r += gridDim.x * 8) {
+        const int i = r / p.out_size, y = r - i * p.out_size;
+        const uint8_t* s = p.src[i] + (int64_t)y * p.bg_pitch;
+        const Window w = make_window(s, rowbytes);
+        // eight vectors per lane requested before the first is parked: a PCIe round trip is microseconds, the loads of a row must
+        // all be in flight together
+        const uint32_t nv = w.bytes >> 4;
+        for (uint32_t c0 = lane; c0 < nv; c0 += 32 * 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + 32 * k < nv) v[k] = ldg_stream16(w.base + ((c0 + 32 * k) << 4));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + 32 * k < nv) *reinterpret_cast<uint4*>(buf + ((c0 + 32 * k) << 4)) = v[k];
+        }
+        __syncwarp();
+        uint8_t* d = p.dst + ((int64_t)i * p.out_size + y) * rowbytes;
+        const RowSplit sp = split_row(d, rowbytes);
+        const uint32_t off0 = w.shift + sp.head;
+        switch ((off0 & 15u) >> 2) {
+            case 0: copy_row_body<0>(buf, off0, d, sp.head, sp.nb, lane); break;
+            case 1: copy_row_body<1>(buf, off0, d, sp.head, sp.nb, lane); break;
+            case 2: copy_row_body<2>(buf, off0, d, sp.head, sp.nb, lane); break;
+            default: copy_row_body<3>(buf, off0, d, sp.head, sp.nb, lane); break;
+        }
+        if ((uint32_t)lane < sp.head) d[lane] = buf[w.shift + lane];
+        if (lane >= 16 && (uint32_t)(lane - 16) < sp.tail) {
+            const uint32_t b = sp.head + (sp.nb << 4) + (uint32_t)(lane - 16);
+            d[b] = buf[w.shift + b];
+        }
+        __syncwarp();
+    }
+}
+
 // ===================================================================== device LANCZOS tables
 struct TabParams {
     const ipp_chain_item* items;
@@ -1767,6 +1820,53 @@ int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t 
         IPP_REQUIRE(it.bg >= 0 && it.bg < n_bgs && it.sq_size == out_size && it.sq_x0 >= 0 && it.sq_y0 >= 0 &&
                         it.sq_x0 + out_size <= bg_w && it.sq_y0 + out_size <= bg_h,
                     IPP_ERR_BAD_ARG, "ipp_chain_upload_windows: item %d has a window outside its background", i);
+    }
+    // SM-driven gather: needs rows whose aligned 16-byte cover stays inside the row (pitch and base multiples of 16) and host
+    // memory the device can address (pinned; unified addressing)
+    // Short window rows are where the copy engines lose (1080p: 3240 of 5760 bytes per row, 36 GB/s next to the frame uploads;
+    // gather 4.37 k -> 4.75 k images/s end to end); with 4K rows (6480 of 11520 bytes) they win (1.16 k vs 1.09-1.11 k).
+    // IPP_WINDOWS_COPY=dma / sm forces one or the other.
+    static const char* mode_env = getenv("IPP_WINDOWS_COPY");
+    static const int ctas_env = getenv("IPP_WINDOWS_CTAS") ? atoi(getenv("IPP_WINDOWS_CTAS")) : 32;
+    const bool want_sm = mode_env ? mode_env[0] == 's' : row <= 4096;
+    const bool sm_copy = want_sm && (bg_pitch % 16) == 0 && (bg_stride % 16) == 0 && (((uintptr_t)bgs_host) & 15) == 0 &&
+                         (int64_t)bg_w * 3 <= bg_pitch;
+    const uint8_t* bgs_dev_view = nullptr;       // the host buffer as the device addresses it (pageable memory: none -> copy engines)
+    if (sm_copy) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, bgs_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+            bgs_dev_view = static_cast<const uint8_t*>(pa.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
+    if (sm_copy && bgs_dev_view) {
+        const uint32_t stride = staged_row_stride((uint32_t)row);
+        const size_t smem = 8 * (size_t)stride;
+        IPP_REQUIRE(smem <= 200 * 1024, IPP_ERR_UNSUPPORTED, "ipp_chain_upload_windows: row too long");
+        static size_t set_w[64] = {};
+        int dev_id = 0;
+        IPP_CUDA(cudaGetDevice(&dev_id));
+        if (smem > 48 * 1024 && (dev_id < 0 || dev_id >= 64 || smem > set_w[dev_id])) {
+            IPP_CUDA(cudaFuncSetAttribute(window_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev_id >= 0 && dev_id < 64) set_w[dev_id] = smem;
+        }
+        for (int i0 = 0; i0 < n_items; i0 += kWinMaxItems) {
+            WinGatherParams wp{};
+            wp.n = std::min(kWinMaxItems, n_items - i0);
+            for (int i = 0; i < wp.n; ++i) {
+                const ipp_chain_item& it = items_host[i0 + i];
+                wp.src[i] = bgs_dev_view + (int64_t)it.bg * bg_stride + (int64_t)it.sq_y0 * bg_pitch + (int64_t)it.sq_x0 * 3;
+            }
+            wp.bg_pitch = bg_pitch; wp.out_size = out_size; wp.smem_row_stride = stride;
+            wp.dst = windows_dev + (size_t)i0 * row * out_size;
+            const int grid = (int)std::min<int64_t>(ctas_env, ceil_div((int64_t)wp.n * out_size, 8));
+            { ipp::LaunchTimer _lt("window_gather_kernel", st); window_gather_kernel<<<grid, 256, smem, st>>>(wp); }
+            IPP_LAUNCH_CHECK();
+        }
+        return IPP_OK;
+    }
+    for (int i = 0; i < n_items; ++i) {
+        const ipp_chain_item& it = items_host[i];
         const uint8_t* src = bgs_host + (int64_t)it.bg * bg_stride + (int64_t)it.sq_y0 * bg_pitch + (int64_t)it.sq_x0 * 3;
         IPP_CUDA(cudaMemcpy2DAsync(windows_dev + (size_t)i * row * out_size, row, src, (size_t)bg_pitch, row, (size_t)out_size,
                                    cudaMemcpyHostToDevice, st));

@@ -380,7 +380,9 @@ int ipp_chain_stage_c(const uint8_t* backgrounds, int64_t bg_pitch, int64_t bg_s
  * — the final square crop (crop_square.py:196) folded into the host->device copy, so the
  * columns/rows the crop throws away never cross PCIe.  Stage C is then called on windows_dev with
  * items whose bg = i, sq_x0 = sq_y0 = 0 and pos_x/pos_y shifted by the window origin.
- * items_host is a HOST array. */
+ * items_host is a HOST array.  bgs_host must be PINNED host memory: short window rows (<= 4 KB) are gathered by a small kernel that
+ * reads the host rows over PCIe itself (zero-copy loads; the copy engines move such 2-D windows at ~70 % of their contiguous
+ * rate), longer rows go through cudaMemcpy2DAsync. */
 int ipp_chain_upload_windows(const uint8_t* bgs_host, int64_t bg_pitch, int64_t bg_stride, int bg_w, int bg_h, int n_bgs,
                              const ipp_chain_item* items_host, int n_items, int out_size,
                              uint8_t* windows_dev, void* stream);
