@@ -59,6 +59,24 @@ def build_jpeg(force: bool = False) -> Path:
     return JPEG_OUT
 
 
+VIDEO_OUT = HERE / "libippvideo.so"
+VIDEO_SRC = HERE / "csrc_video" / "ippvideo.cu"
+
+
+def build_video(force: bool = False) -> Path:
+    """libippvideo.so: the NVDEC frame source (include/ippvideo.h).  libnvcuvid belongs to the driver and is opened at run time
+    (dlopen): the library builds and loads on machines without it."""
+    srcs = [VIDEO_SRC, HERE.parent / "include" / "ippvideo.h"]
+    if not force and VIDEO_OUT.is_file() and all(p.stat().st_mtime <= VIDEO_OUT.stat().st_mtime for p in srcs):
+        return VIDEO_OUT
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           "-o", str(VIDEO_OUT), str(VIDEO_SRC), "-ldl"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    return VIDEO_OUT
+
+
 if __name__ == "__main__":
     if "--variant" in sys.argv:                       # python -m ...build --variant NAME -DX=1 -DY=2
         name = sys.argv[sys.argv.index("--variant") + 1]
@@ -67,3 +85,4 @@ if __name__ == "__main__":
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
         print(build_jpeg(force="--force" in sys.argv))
+        print(build_video(force="--force" in sys.argv))

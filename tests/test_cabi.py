@@ -79,3 +79,21 @@ def test_jpeg_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(str(ROOT / "image_processor_pipeline_b200" / "libippjpeg.so"))
     for name in syms:
         assert hasattr(lib, name), f"{name} declared in ippjpeg.h but not exported"
+
+
+def test_video_library_exports_every_declared_symbol_and_reports_unavailability():
+    """include/ippvideo.h (the NVDEC frame source, its own shared library; libnvcuvid is opened at run time) — symbols, and the
+    loud failure where there is no decoder: no device work."""
+    import ctypes
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "ippvideo.h").read_text(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(ippvideo_[a-z0-9_]+)\s*\(", text)))
+    assert len(syms) >= 6
+    lib = ctypes.CDLL(str(ROOT / "image_processor_pipeline_b200" / "libippvideo.so"))
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in ippvideo.h but not exported"
+    lib.ippvideo_last_error_string.restype = ctypes.c_char_p
+    import torch
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        assert lib.ippvideo_create(ctypes.byref(h), 10) != 0 and not h.value
+        assert lib.ippvideo_last_error_string()
